@@ -1,0 +1,16 @@
+class Registry:
+    def __init__(self, name):
+        self._name = name
+        self._obj_map = {}
+
+    def register(self, obj=None):
+        if obj is None:
+            def deco(fn):
+                self._obj_map[fn.__name__] = fn
+                return fn
+            return deco
+        self._obj_map[obj.__name__] = obj
+        return obj
+
+    def get(self, name):
+        return self._obj_map[name]
