@@ -1,0 +1,219 @@
+"""The stage-1 AFI-GAN training step on pre-extracted features: AFIGAN_Trainer.run_step of the reference
+(afigan/engine/stage1_trainer.py:305-435) minus the guide-model forward and the logging plumbing.
+
+Per level l in p2..p6:
+  D phase  tr = crop(G(lr_l)).detach(); d_l = BCE(D0(hr_l), 1) + BCE(D0(tr), 0)   (real BEFORE fake, :349-350)
+           D.zero_grad(); sum(d_l).backward(); SGD(D)
+  G phase  tr = crop(G(lr_l)); adv = BCE(D0(tr).detach(), 1) [no gradient, :399-408]; _ = D0(hr_l) (fake BEFORE real)
+           g_l = 1e-3 * adv + L1(tr, hr_l); G.zero_grad(); sum(g_l).backward(); SGD(G)
+
+This fast path drives the C-ABI directly (no autograd graph, no per-level host syncs, losses stay on the device),
+keeps packed gradient accumulators across the five levels, and all-reduces ONE flat gradient buffer per optimiser
+(the DDP semantics the reference intended: stage1_trainer.py:80-89).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .. import native as N
+from ..functional import _u8, d_grad_struct, d_param_struct, g_param_struct
+
+CH = 256
+
+
+class Stage1Step:
+    def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
+                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None):
+        self.G, self.D = G, D
+        self.Dstack = D.Discriminators[0]
+        self.lr, self.momentum, self.wd, self.wd_norm = lr, momentum, weight_decay, weight_decay_norm
+        self.precision = precision or G.precision or N.default_precision()
+        self.prec = N.PRECISIONS[self.precision]
+        self.pg = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
+            if distributed is None else distributed
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.g_params: List[torch.nn.Parameter] = G._params()
+        self.d_params: List[torch.nn.Parameter] = self.Dstack._params()
+        dev = self.g_params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("Stage1Step needs the modules on an sm_100a CUDA device (no CPU fallback)")
+        self.dev = dev
+        self.n_rdb = G.n_residual_dense_blocks
+        self.lib, self.ctx = N.lib(), N.context(dev)
+        # flat gradient buffers: param.grad are views, so one all-reduce per optimiser covers every parameter
+        self.g_flat, self.g_grads = self._flat_grads(self.g_params)
+        self.d_flat, self.d_grads = self._flat_grads(self.d_params)
+        self.g_mom = [torch.zeros_like(p) for p in self.g_params]
+        self.d_mom = [torch.zeros_like(p) for p in self.d_params]
+        self.steps_done = 0
+        self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
+        self.d_acc = _u8(self.lib.afi_d_gradacc_bytes(), dev)
+        self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
+        self.d_packed = _u8(self.lib.afi_d_packed_bytes(self.prec), dev)
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+        self.losses = torch.zeros(4, 8, dtype=torch.float32, device=dev)   # rows: d_loss, g_loss, adv, content ; cols: levels
+        self._tmp = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._pack_g()
+        self._pack_d()
+
+    # ---- helpers --------------------------------------------------------------------------------------
+    def _flat_grads(self, params):
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        views, off = [], 0
+        for p in params:
+            v = flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            views.append(v)
+            off += p.numel()
+        return flat, views
+
+    def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool) -> torch.Tensor:
+        key = (kind, n, h, w, save)
+        if key not in self._ws:
+            if kind == "g":
+                nb = self.lib.afi_g_workspace_bytes(self.prec, n, h, w, self.n_rdb, 0, int(save))
+            else:
+                nb = self.lib.afi_d_workspace_bytes(self.prec, n, h, w, int(save))
+            self._ws[key] = _u8(nb, self.dev)
+        return self._ws[key]
+
+    def _buf(self, name: str, shape) -> torch.Tensor:
+        key = (name, tuple(shape))
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(shape, dtype=torch.float32, device=self.dev)
+        return self._bufs[key]
+
+    def _gs(self):
+        return g_param_struct(self.g_params, self.n_rdb)
+
+    def _ds(self):
+        return d_param_struct(self.d_params, self.Dstack._buffers_list())
+
+    def _pack_g(self):
+        ps = self._gs()
+        N.check(self.lib.afi_g_pack(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.stream_ptr()))
+
+    def _pack_d(self):
+        ps = self._ds()
+        N.check(self.lib.afi_d_pack(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), N.stream_ptr()))
+
+    def _g_forward(self, lr_f: torch.Tensor, oh: int, ow: int, save: bool, tag: str) -> torch.Tensor:
+        n, _, h, w = lr_f.shape
+        ws = self._ws_for("g", n, h, w, save)
+        y = self._buf("tr" + tag, (n, CH, oh, ow))
+        ps = self._gs()
+        N.check(self.lib.afi_g_forward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.view4(lr_f), n, h, w, y.data_ptr(),
+                                       oh, ow, None, ws.data_ptr(), ws.numel(), int(save), N.stream_ptr()))
+        return y
+
+    def _d_forward(self, x: torch.Tensor, save: bool, tag: str) -> torch.Tensor:
+        n, _, h, w = x.shape
+        ws = self._ws_for("d", n, h, w, save)
+        logits = self._buf("logit" + tag, (n, 1, h, w))
+        ps = self._ds()
+        bn = self.Dstack[0][0].norm
+        N.check(self.lib.afi_d_forward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), N.view4(x), n, h, w, logits.data_ptr(),
+                                       1, 0.1 if bn.momentum is None else bn.momentum, bn.eps, ws.data_ptr(), ws.numel(), int(save),
+                                       N.stream_ptr()))
+        return logits
+
+    def _d_backward(self, dlogits: torch.Tensor, n: int, h: int, w: int):
+        ws = self._ws_for("d", n, h, w, True)
+        ps = self._ds()
+        N.check(self.lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), dlogits.data_ptr(), n, h, w,
+                                        ws.data_ptr(), ws.numel(), self.d_acc.data_ptr(), None, N.stream_ptr()))
+
+    def _bce(self, logits: torch.Tensor, target: float, out_slot: int, sum_ptr: Optional[int], weight: float,
+             dlogits: Optional[torch.Tensor]):
+        N.check(self.lib.afi_bce_with_logits(logits.data_ptr(), logits.numel(), target, self._tmp[out_slot:].data_ptr(), sum_ptr, weight,
+                                             N.ptr(dlogits), 1.0, N.stream_ptr()))
+
+    def _sgd(self, params, grads, moms, is_norm):
+        first = int(self.steps_done == 0)
+        for p, g, m, nrm in zip(params, grads, moms, is_norm):
+            N.check(self.lib.afi_sgd_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel(), self.lr, self.momentum,
+                                          self.wd_norm if nrm else self.wd, 1.0 / self.world, first, N.stream_ptr()))
+            p._version  # parameters are updated in place behind torch's back; packed copies are refreshed explicitly below
+
+    def _allreduce(self, flat: torch.Tensor):
+        if self.distributed:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+
+    # ---- the step ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_step(self, lr_feats: Sequence[torch.Tensor], hr_feats: Sequence[torch.Tensor], apply_updates: bool = True):
+        """Returns the device tensor `losses` [4, 8]: row 0 d_loss_p*, 1 g_loss_p*, 2 adv_loss_p*, 3 content_loss_p* (cols = levels)."""
+        lib, st = self.lib, N.stream_ptr
+        nl = len(lr_feats)
+        assert nl == len(hr_feats) and nl <= 8
+        self.losses.zero_()
+        lp = self.losses.data_ptr()
+
+        def slot(row, col):
+            return lp + 4 * (row * 8 + col)
+
+        # ------------------------------ D phase (stage1_trainer.py:334-381)
+        N.check(lib.afi_zero(self.d_acc.data_ptr(), self.d_acc.numel(), st()))
+        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
+            n, _, h, w = lo.shape
+            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))
+            tr = self._g_forward(lo, oh, ow, False, f"d{l}")
+            hi_c = hi[:, :, :oh, :ow]
+            dl = self._buf("dlogit", (n, 1, oh, ow))
+            logit_real = self._d_forward(hi_c, True, "r")
+            self._bce(logit_real, 1.0, 0, slot(0, l), 1.0, dl)
+            self._d_backward(dl, n, oh, ow)
+            logit_fake = self._d_forward(tr, True, "f")
+            self._bce(logit_fake, 0.0, 1, slot(0, l), 1.0, dl)
+            self._d_backward(dl, n, oh, ow)
+        gs = d_grad_struct(self.d_grads)
+        N.check(lib.afi_d_unpack_grads(self.ctx, self.prec, self.d_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
+        self._allreduce(self.d_flat)
+        if apply_updates:
+            self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
+            self._pack_d()
+
+        # ------------------------------ G phase (stage1_trainer.py:384-433)
+        N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
+        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
+            n, _, h, w = lo.shape
+            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))
+            tr = self._g_forward(lo, oh, ow, True, f"g{l}")
+            hi_c = hi[:, :, :oh, :ow]
+            logit_fake = self._d_forward(tr, False, "f")
+            self._bce(logit_fake, 1.0, 2, slot(2, l), 1.0, None)           # adv: no gradient (logit is .detach()-ed, :399)
+            self._d_forward(hi_c, False, "r")                              # dead compute kept for its BN running-stat side effect (:400)
+            dtr = self._buf("dtr", (n, CH, oh, ow))
+            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), n, CH, oh, ow, self._tmp[3:].data_ptr(), slot(3, l), 1.0, dtr.data_ptr(),
+                                    1.0, st()))
+            ps = self._gs()
+            ws = self._ws_for("g", n, h, w, True)
+            N.check(lib.afi_g_backward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.view4(dtr), n, h, w, oh, ow,
+                                       ws.data_ptr(), ws.numel(), self.g_acc.data_ptr(), None, None, None, None, None, st()))
+        self.losses[1, :nl] = 1e-3 * self.losses[2, :nl] + self.losses[3, :nl]
+        gs = g_param_struct(self.g_grads, self.n_rdb)
+        N.check(lib.afi_g_unpack_grads(self.ctx, self.prec, self.g_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
+        self._allreduce(self.g_flat)
+        if apply_updates:
+            self._sgd(self.g_params, self.g_grads, self.g_mom, [False] * len(self.g_params))
+            self._pack_g()
+            self.steps_done += 1
+        return self.losses
+
+    def metrics(self, n_levels: int = 5) -> Dict[str, float]:
+        """Host copy of the per-level losses under the reference's metric names (stage1_trainer.py:357,409)."""
+        v = self.losses.cpu()
+        out = {}
+        for l in range(n_levels):
+            out[f"d_loss_p{l + 2}"] = float(v[0, l])
+            out[f"g_loss_p{l + 2}"] = float(v[1, l])
+            out[f"adv_loss_p{l + 2}"] = float(v[2, l])
+            out[f"content_loss_p{l + 2}"] = float(v[3, l])
+        return out

@@ -1,0 +1,202 @@
+"""torch.autograd glue around the C-ABI: parameter marshalling, packed-weight caching, workspaces."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import native as N
+
+CH = 256
+
+
+def _u8(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def g_param_struct(tensors: Sequence[Optional[torch.Tensor]], n_rdb: int) -> N.GParams:
+    """tensors in state-dict order: head_w, head_b, (rdb r: conv1..conv5 weights)*, post_w, post_b, up_w, up_b, out_w, out_b."""
+    s = N.GParams()
+    s.n_rdb = n_rdb
+    it = iter(tensors)
+    s.head_w, s.head_b = N.ptr(next(it)), N.ptr(next(it))
+    for r in range(n_rdb):
+        for i in range(5):
+            s.rdb_w[r][i] = N.ptr(next(it))
+    s.post_w, s.post_b = N.ptr(next(it)), N.ptr(next(it))
+    s.up_w, s.up_b = N.ptr(next(it)), N.ptr(next(it))
+    s.out_w, s.out_b = N.ptr(next(it)), N.ptr(next(it))
+    return s
+
+
+def d_param_struct(params: Sequence[torch.Tensor], buffers: Sequence[Optional[torch.Tensor]]) -> N.DParams:
+    """params: (w, b, gamma, beta) x 3, w4, b4 ; buffers: (running_mean, running_var, num_batches_tracked) x 3."""
+    s = N.DParams()
+    for i in range(3):
+        s.w[i], s.b[i], s.gamma[i], s.beta[i] = (N.ptr(params[4 * i + k]) for k in range(4))
+        s.running_mean[i], s.running_var[i], s.num_batches_tracked[i] = (N.ptr(buffers[3 * i + k]) for k in range(3))
+    s.w[3], s.b[3] = N.ptr(params[12]), N.ptr(params[13])
+    return s
+
+
+def d_grad_struct(grads: Sequence[Optional[torch.Tensor]]) -> N.DGrads:
+    s = N.DGrads()
+    for i in range(3):
+        s.w[i], s.b[i], s.gamma[i], s.beta[i] = (N.ptr(grads[4 * i + k]) for k in range(4))
+    s.w[3], s.b[3] = N.ptr(grads[12]), N.ptr(grads[13])
+    return s
+
+
+class PackedWeights:
+    """Packed GEMM-layout copy of a module's parameters, refreshed when any parameter version changes."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.key = None
+
+    def get(self, kind: str, prec: int, params: Sequence[torch.Tensor], struct, n_rdb: int = 0) -> torch.Tensor:
+        dev = params[0].device
+        key = (kind, prec, dev, tuple((p.data_ptr(), p._version) for p in params))
+        if self.buf is None or self.key != key:
+            ctx = N.context(dev)
+            if kind == "g":
+                nbytes = N.lib().afi_g_packed_bytes(prec, n_rdb)
+                self.buf = _u8(nbytes, dev)
+                N.check(N.lib().afi_g_pack(ctx, prec, C.byref(struct), self.buf.data_ptr(), N.stream_ptr()))
+            else:
+                nbytes = N.lib().afi_d_packed_bytes(prec)
+                self.buf = _u8(nbytes, dev)
+                N.check(N.lib().afi_d_pack(ctx, prec, C.byref(struct), self.buf.data_ptr(), N.stream_ptr()))
+            self.key = key
+        return self.buf
+
+
+class AFInterpolatorFn(torch.autograd.Function):
+    """Generator.forward (reference generator_rdb.py:123-130) with the stage-1 top-left crop folded in."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, holder, prec: int, out_hw: Optional[Tuple[int, int]], *params: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
+        if x.dim() != 4 or x.size(1) != CH:
+            raise ValueError(f"AF interpolator expects [N,{CH},H,W], got {tuple(x.shape)}")
+        x = x.float()
+        n, _, h, w = x.shape
+        oh, ow = out_hw if out_hw is not None else (2 * h, 2 * w)
+        n_rdb = holder.n_rdb
+        dev = x.device
+        ps = g_param_struct(params, n_rdb)
+        packed = holder.packed.get("g", prec, params, ps, n_rdb)
+        need_bwd = any(ctx.needs_input_grad[4:]) or ctx.needs_input_grad[0]
+        lib, actx = N.lib(), N.context(dev)
+        ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, n_rdb, 0, int(need_bwd)), dev)
+        y = torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev)
+        N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), N.view4(x), n, h, w, y.data_ptr(), oh, ow, None,
+                                  ws.data_ptr(), ws.numel(), int(need_bwd), N.stream_ptr()))
+        ctx.holder, ctx.prec, ctx.shape, ctx.n_rdb = holder, prec, (n, h, w, oh, ow), n_rdb
+        ctx.ws, ctx.packed = ws, packed
+        ctx.save_for_backward(*params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        params = ctx.saved_tensors
+        n, h, w, oh, ow = ctx.shape
+        dev = dy.device
+        lib, actx = N.lib(), N.context(dev)
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("AF interpolator: gradient w.r.t. the input feature is not implemented yet")
+        dy = dy.float()
+        acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
+        N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
+        ps = g_param_struct(params, ctx.n_rdb)
+        N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), N.view4(dy), n, h, w, oh, ow, ctx.ws.data_ptr(),
+                                   ctx.ws.numel(), acc.data_ptr(), None, None, None, None, None, N.stream_ptr()))
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[4 + i] else None for i, p in enumerate(params)]
+        gs = g_param_struct(grads, ctx.n_rdb)
+        N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
+        ctx.ws = None
+        return (None, None, None, None, *grads)
+
+
+class PatchDiscriminatorFn(torch.autograd.Function):
+    """Discriminators[0](x) (reference feature_patch_discriminator.py:32-41)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, holder, prec: int, training: bool, momentum: float, eps: float, buffers, *params: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("feature-patch discriminator: input must live on an sm_100a CUDA device (no CPU fallback)")
+        if x.dim() != 4 or x.size(1) != CH:
+            raise ValueError(f"discriminator expects [N,{CH},H,W], got {tuple(x.shape)}")
+        x = x.float()
+        n, _, h, w = x.shape
+        dev = x.device
+        ps = d_param_struct(params, buffers)
+        packed = holder.packed.get("d", prec, params, ps)
+        need_bwd = any(ctx.needs_input_grad[7:]) or ctx.needs_input_grad[0]
+        if need_bwd and not training:
+            raise NotImplementedError("discriminator backward in eval mode is not implemented")
+        lib, actx = N.lib(), N.context(dev)
+        ws = _u8(lib.afi_d_workspace_bytes(prec, n, h, w, int(need_bwd)), dev)
+        logits = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
+        N.check(lib.afi_d_forward(actx, prec, C.byref(ps), packed.data_ptr(), N.view4(x), n, h, w, logits.data_ptr(), int(training),
+                                  momentum, eps, ws.data_ptr(), ws.numel(), int(need_bwd), N.stream_ptr()))
+        ctx.prec, ctx.shape, ctx.ws, ctx.packed, ctx.buffers = prec, (n, h, w), ws, packed, buffers
+        ctx.save_for_backward(*params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits: torch.Tensor):
+        params = ctx.saved_tensors
+        n, h, w = ctx.shape
+        dev = dlogits.device
+        lib, actx = N.lib(), N.context(dev)
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("discriminator: gradient w.r.t. the input feature is not implemented "
+                                      "(the stage-1/2 trainers detach it: stage1_trainer.py:339,399)")
+        dl = dlogits.float().contiguous()
+        acc = _u8(lib.afi_d_gradacc_bytes(), dev)
+        N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
+        ps = d_param_struct(params, ctx.buffers)
+        N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), dl.data_ptr(), n, h, w, ctx.ws.data_ptr(),
+                                   ctx.ws.numel(), acc.data_ptr(), None, N.stream_ptr()))
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[7 + i] else None for i, p in enumerate(params)]
+        gs = d_grad_struct(grads)
+        N.check(lib.afi_d_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
+        ctx.ws = None
+        return (None, None, None, None, None, None, None, *grads)
+
+
+def bce_with_logits(logits: torch.Tensor, target: float) -> torch.Tensor:
+    """nn.BCEWithLogitsLoss()(logits, full_like(logits, target)) -- forward only (stage-1 G phase: stage1_trainer.py:408)."""
+    out = torch.zeros((), dtype=torch.float32, device=logits.device)
+    lg = logits.detach().float().contiguous()
+    N.check(N.lib().afi_bce_with_logits(lg.data_ptr(), lg.numel(), float(target), out.data_ptr(), None, 0.0, None, 0.0, N.stream_ptr()))
+    return out
+
+
+def conv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], lrelu: bool, precision: str) -> torch.Tensor:
+    """Single 3x3/s1/p1 convolution through the library's GEMM engine (unit tests, kernel benchmarks)."""
+    prec = N.PRECISIONS[precision]
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    lib, actx = N.lib(), N.context(x.device)
+    ws = _u8(lib.afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout), x.device)
+    y = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+    N.check(lib.afi_conv3x3(actx, prec, N.view4(x), n, cin, h, w, weight.data_ptr(), N.ptr(bias), cout, int(lrelu), y.data_ptr(),
+                            ws.data_ptr(), ws.numel(), N.stream_ptr()))
+    return y
+
+
+def conv3x3_backward(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, precision: str, need_dx: bool = True):
+    prec = N.PRECISIONS[precision]
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    lib, actx = N.lib(), N.context(x.device)
+    ws = _u8(lib.afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout), x.device)
+    dw = torch.empty_like(weight)
+    dx = torch.empty_like(x) if need_dx else None
+    N.check(lib.afi_conv3x3_backward(actx, prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(dx),
+                                     ws.data_ptr(), ws.numel(), N.stream_ptr()))
+    return dw, dx

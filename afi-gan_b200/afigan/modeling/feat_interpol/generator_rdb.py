@@ -1,0 +1,97 @@
+"""AF interpolator ("Generator"): drop-in for reference afigan/modeling/feat_interpol/generator_rdb.py.
+
+Same constructor signature, parameter names / shapes / creation order and RNG consumption as the reference
+(generator_rdb.py:34-62, :75-121; state-dict layout SURVEY.md App. B), so optimisers, DDP, freezing
+(fpn_sr.py:67-69) and both checkpointers see the module they expect.  The modules below only HOLD parameters:
+`Generator.forward` runs the whole trunk in libafigan_b200.so (afi_g_forward / afi_g_backward).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from .. import _holder
+from ... import native
+from ...functional import AFInterpolatorFn, PackedWeights
+
+
+class ResidualDenseBlock(nn.Module):
+    """Parameter holder for one dense block: conv1..conv4 (C+32i -> 32, LeakyReLU) and conv5 (C+128 -> C), all bias-free."""
+
+    def __init__(self, in_features, growth_rate, residual_scale, kw, stw, padw):
+        super().__init__()
+        self.residual_scale = residual_scale
+        for i in range(4):
+            setattr(self, f"conv{i + 1}", nn.Sequential(
+                nn.Conv2d(in_features + i * growth_rate, growth_rate, kw, stw, padw, bias=False),
+                nn.LeakyReLU(negative_slope=0.2, inplace=True)))
+        self.conv5 = nn.Conv2d(in_features + 4 * growth_rate, in_features, kw, stw, padw, bias=False)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                m.weight.data *= 0.1
+
+    def weights(self) -> List[nn.Parameter]:
+        return [self.conv1[0].weight, self.conv2[0].weight, self.conv3[0].weight, self.conv4[0].weight, self.conv5.weight]
+
+    def forward(self, x):
+        raise RuntimeError("ResidualDenseBlock is evaluated inside Generator.forward by the CUDA library")
+
+
+class ResidualInResidual(nn.Module):
+    def __init__(self, n_residual_dense_blocks, in_features, growth_rate, residual_scale, kw, stw, padw):
+        super().__init__()
+        self.RDBs = nn.Sequential(*[ResidualDenseBlock(in_features, growth_rate, residual_scale, kw, stw, padw)
+                                    for _ in range(n_residual_dense_blocks)])
+        self.residual_scale = residual_scale
+
+    def forward(self, x):
+        raise RuntimeError("ResidualInResidual is evaluated inside Generator.forward by the CUDA library")
+
+
+class Generator(nn.Module):
+    def __init__(self, in_channels=256, n_residual_dense_blocks=2, growth_rate=32, residual_scale=0.2, scale=2,
+                 precision: Optional[str] = None):
+        super().__init__()
+        if in_channels != 256 or growth_rate != 32 or residual_scale != 0.2 or scale != 2:
+            raise ValueError("the sm_100a kernels are specialised for in_channels=256, growth_rate=32, residual_scale=0.2, "
+                             "scale=2 (every caller in the reference uses these: fpn_sr.py:65, stage1_trainer.py:505)")
+        if not 1 <= n_residual_dense_blocks <= native.MAX_RDB:
+            raise ValueError(f"n_residual_dense_blocks must be in [1, {native.MAX_RDB}]")
+        self.in_channels, self.n_residual_dense_blocks = in_channels, n_residual_dense_blocks
+        self.growth_rate, self.residual_scale, self.scale = growth_rate, residual_scale, scale
+        self.kw, self.padw, self.stw = 3, 1, 1
+        self.precision = precision
+
+        stages = [
+            nn.Sequential(nn.Conv2d(in_channels, in_channels, 3, 1, 1), nn.LeakyReLU(0.2, True)),
+            ResidualInResidual(n_residual_dense_blocks, in_channels, growth_rate, residual_scale, 3, 1, 1),
+            nn.Sequential(nn.Conv2d(in_channels, in_channels, 3, 1, 1), nn.LeakyReLU(0.2, True)),
+            nn.Sequential(nn.ConvTranspose2d(in_channels, in_channels, kernel_size=6, stride=2, padding=2), nn.LeakyReLU(0.2, True)),
+            nn.Sequential(nn.Conv2d(in_channels, in_channels, 3, 1, 1)),
+        ]
+        for st in stages:
+            if isinstance(st, ResidualInResidual):
+                continue
+            layer = st[0]
+            nn.init.kaiming_normal_(layer.weight)
+            layer.weight.data *= 0.1
+            layer.bias.data.zero_()
+        self.Generators = nn.ModuleList([nn.Sequential(*stages)])
+        self._native = _holder.Holder(n_rdb=n_residual_dense_blocks)
+
+    def _params(self) -> List[nn.Parameter]:
+        g = self.Generators[0]
+        ps = [g[0][0].weight, g[0][0].bias]
+        for rdb in g[1].RDBs:
+            ps += rdb.weights()
+        for i in (2, 3, 4):
+            ps += [g[i][0].weight, g[i][0].bias]
+        return ps
+
+    def forward(self, features: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """features [N,256,H,W] -> [N,256,2H,2W] (or its top-left out_hw crop: the _reshape_stage1 of the trainers)."""
+        prec = native.PRECISIONS[self.precision or native.default_precision()]
+        return AFInterpolatorFn.apply(features, self._native, prec, out_hw, *self._params())

@@ -1,0 +1,148 @@
+"""ctypes binding of libafigan_b200.so (include/afigan_b200.h).  PyTorch only supplies device memory and streams.
+
+There is NO CPU or eager-PyTorch fallback: if the shared library is missing, or the device is not an sm_100
+GPU, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libafigan_b200.so")
+
+PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT}
+MAX_RDB = 4
+
+
+def default_precision() -> str:
+    """AFIGAN_PRECISION = fp32 (parity mode) | bf16 (tcgen05 throughput mode) | bf16_simt (cross-check)."""
+    p = os.environ.get("AFIGAN_PRECISION", "bf16").lower()
+    if p not in PRECISIONS:
+        raise ValueError(f"AFIGAN_PRECISION={p!r}; expected one of {sorted(PRECISIONS)}")
+    return p
+
+
+class View4(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("sn", C.c_longlong), ("sc", C.c_longlong), ("sh", C.c_longlong), ("sw", C.c_longlong)]
+
+
+class GParams(C.Structure):
+    _fields_ = [("n_rdb", C.c_int), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("rdb_w", (C.c_void_p * 5) * MAX_RDB),
+                ("post_w", C.c_void_p), ("post_b", C.c_void_p), ("up_w", C.c_void_p), ("up_b", C.c_void_p),
+                ("out_w", C.c_void_p), ("out_b", C.c_void_p)]
+
+
+GGrads = GParams  # same layout (non-const pointers)
+
+
+class Lateral(C.Structure):
+    _fields_ = [("lat_x", View4), ("lat_c", C.c_int), ("lat_w", C.c_void_p), ("lat_b", C.c_void_p), ("scale", C.c_float)]
+
+
+class DParams(C.Structure):
+    _fields_ = [("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("gamma", C.c_void_p * 3), ("beta", C.c_void_p * 3),
+                ("running_mean", C.c_void_p * 3), ("running_var", C.c_void_p * 3), ("num_batches_tracked", C.c_void_p * 3)]
+
+
+class DGrads(C.Structure):
+    _fields_ = [("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("gamma", C.c_void_p * 3), ("beta", C.c_void_p * 3)]
+
+
+_SIGNATURES = {
+    "afi_abi_version": (C.c_int, []),
+    "afi_last_error": (C.c_char_p, []),
+    "afi_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "afi_destroy": (None, [C.c_void_p]),
+    "afi_g_packed_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "afi_g_gradacc_bytes": (C.c_size_t, [C.c_int]),
+    "afi_g_workspace_bytes": (C.c_size_t, [C.c_int] * 7),
+    "afi_g_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, C.c_void_p]),
+    "afi_g_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                C.c_int, C.c_int, C.POINTER(Lateral), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "afi_g_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(Lateral), C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "afi_g_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(GGrads), C.c_float, C.c_int, C.c_void_p]),
+    "afi_d_packed_bytes": (C.c_size_t, [C.c_int]),
+    "afi_d_gradacc_bytes": (C.c_size_t, []),
+    "afi_d_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "afi_d_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.c_void_p]),
+    "afi_d_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afi_d_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(DGrads), C.c_float, C.c_int, C.c_void_p]),
+    "afi_bce_with_logits": (C.c_int, [C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
+                                      C.c_void_p]),
+    "afi_l1_loss": (C.c_int, [View4, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
+                              C.c_void_p]),
+    "afi_sgd_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                               C.c_void_p]),
+    "afi_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "afi_conv3x3": (C.c_int, [C.c_void_p, C.c_int, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "afi_conv3x3_backward": (C.c_int, [C.c_void_p, C.c_int, View4, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "afi_conv3x3_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "afi_launch_count": (C.c_longlong, [C.c_int]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib: Optional[C.CDLL] = None
+_ctx = {}
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python afi-gan_b200/build.py` "
+                               "(there is no CPU / PyTorch fallback for the AFI-GAN hot path)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+class AfiError(RuntimeError):
+    pass
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise AfiError(f"libafigan_b200 error {code}: {lib().afi_last_error().decode()}")
+
+
+def context(device: torch.device) -> C.c_void_p:
+    """One afi_ctx per CUDA device of this process."""
+    if device.type != "cuda":
+        raise RuntimeError("the AFI-GAN hot path runs on sm_100a CUDA devices only (no CPU fallback); got device " + str(device))
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _ctx:
+        with torch.cuda.device(idx):
+            h = C.c_void_p()
+            check(lib().afi_create(C.byref(h)))
+            _ctx[idx] = h
+    return _ctx[idx]
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def view4(t: torch.Tensor) -> View4:
+    if t.dtype != torch.float32 or t.dim() != 4:
+        raise TypeError(f"expected a 4-D float32 tensor, got {tuple(t.shape)} {t.dtype}")
+    s = t.stride()
+    return View4(t.data_ptr(), s[0], s[1], s[2], s[3])
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,158 @@
+// Internal declarations shared by the translation units of libafigan_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/afigan_b200.h"
+
+namespace afi {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern long long g_launches;
+#define AFI_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            afi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return AFI_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+#define AFI_LAUNCH_CHECK()                                                                     \
+    do {                                                                                       \
+        afi::g_launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            afi::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return AFI_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+#define AFI_TRY(expr)                \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != AFI_OK) return _r; \
+    } while (0)
+#define AFI_REQUIRE(cond, ...)        \
+    do {                              \
+        if (!(cond)) {                \
+            afi::set_error(__VA_ARGS__); \
+            return AFI_ERR_INVALID;   \
+        }                             \
+    } while (0)
+
+// ---- pixel-major (NHWC) views -------------------------------------------------------------------------
+// addr(n, y, x, c) = ptr + n*sn + y*sy + x*sx + c, strides in ELEMENTS of the view's dtype.
+struct PView {
+    void* ptr;
+    long long sn, sy, sx;
+};
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+
+static inline PView pview(void* p, int h, int w, int cs) {
+    PView v; v.ptr = p; v.sx = cs; v.sy = (long long)w * cs; v.sn = (long long)h * w * cs; return v;
+}
+static inline PView pview_null() { PView v; v.ptr = nullptr; v.sn = v.sy = v.sx = 0; return v; }
+// channel-offset sub-view
+static inline PView pview_ch(PView v, int coff, int elem_bytes) {
+    v.ptr = (char*)v.ptr + (size_t)coff * elem_bytes; return v;
+}
+
+struct Tap { int dy, dx, view, slab; };
+#define AFI_MAX_TAPS 36
+
+// One implicit-GEMM convolution:  out[n,y,x,co] = epi( sum_taps sum_ci in[view][n,y+dy,x+dx,ci] * W[slab][.][.] )
+// Epilogue order:  v = acc + bias;  v = act ? lrelu(v) : v;  v *= alpha;  v += beta1*r1 + beta2*r2 + accin;
+//                  v *= mask > 0 ? 1 : mask_slope;   store (bf16/f32 as out_dt says).
+struct ConvArgs {
+    int N, H, W;          // logical pixel grid (output pixels; every input view has the same grid)
+    int cin, cout;
+    int ntaps;
+    Tap taps[AFI_MAX_TAPS];
+    PView in[4];          // dtype = storage dtype T
+    const void* w;        // packed slabs, dtype T.  SIMT engine: [slab][cin][cout]; tensor-core engine: [slab][cout][cin]
+    PView out; int out_dt;
+    const float* bias;
+    int act; float slope;
+    float alpha;
+    PView r1; int r1_dt; float beta1;
+    PView r2; int r2_dt; float beta2;
+    PView accin;          // f32
+    PView mask; float mask_slope;   // dtype T
+};
+
+// dW[slab][..] += sum_p dY[p][co] * X[p + tap][ci]   (fp32 atomics into a pre-zeroed accumulator)
+// SIMT engine layout: [slab][cin][cout]; tensor-core engine: [slab][cout][cin].
+struct WgradArgs {
+    int N, H, W;
+    int cin, cout;
+    int ntaps;
+    Tap taps[9];          // .view unused, .slab = output slab
+    PView x;              // T
+    PView dy;             // T
+    float* dw;
+};
+
+void conv_args_init(ConvArgs& a);
+void set_std_taps(Tap* taps, int view, int slab0);
+
+// engines
+template <typename T> int conv_simt(const ConvArgs& a, cudaStream_t st);
+template <typename T> int wgrad_simt(const WgradArgs& a, cudaStream_t st);
+int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st);
+int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st);
+int tc_init(afi_ctx* ctx);
+
+// ---- elementwise / layout kernels (elementwise.cu) ------------------------------------------------------
+template <typename T> int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st);
+// dst[n,c,y,x] (contiguous [n,c,oh,ow]) = scale * ( a[n,y,x,c] (T) [+ lat[n,y,x,c] (T)] [+ bilinear2x(skip)[n,c,y,x]] )
+template <typename T> int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale,
+                                       int n, int c, int oh, int ow, float* dst, cudaStream_t st);
+// dst = scale * (a + b) * mask ; a,b f32 or T views (dtype flags), mask T view (optional), dst T or f32
+int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt, float mask_slope,
+               float scale, int n, int h, int w, int c, cudaStream_t st);
+// per-channel sums over all pixels of a view: sum[c] += x, sumsq[c] += x*x (double accumulators, sumsq may be null)
+int col_stats(PView x, int dt, int n, int h, int w, int c, double* sum, double* sumsq, cudaStream_t st);
+// float accumulate variant for bias gradients: out[c] += sum_p x[p][c]
+int col_sum_f32(PView x, int dt, int n, int h, int w, int c, float* out, cudaStream_t st);
+// weight re-layout: dst[slab][r][c] from torch [co][ci][k][k] (see pack modes in elementwise.cu)
+enum PackMode { PACK_FWD_KN = 0, PACK_FWD_NK = 1, PACK_DGRAD_KN = 2, PACK_DGRAD_NK = 3,
+                PACK_DECONV_FWD_KN = 4, PACK_DECONV_FWD_NK = 5, PACK_DECONV_DGRAD_KN = 6, PACK_DECONV_DGRAD_NK = 7,
+                PACK_1X1_KN = 8, PACK_1X1_NK = 9 };
+int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st);
+// gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
+int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);
+int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st);
+
+// BatchNorm helpers (stats buffers: double sum[C], sumsq[C])
+int bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum, int training,
+                float* mean, float* rstd, float* running_mean, float* running_var, long long* nbt, cudaStream_t st);
+// a = lrelu(gamma * (z - mean) * rstd + beta)
+int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   float slope, int n, int h, int w, int c, cudaStream_t st);
+// reduce: s_dy[c] += dy, s_dyx[c] += dy * xhat (double);  apply: dz = gamma*rstd*(dy - s_dy/M - xhat*s_dyx/M) (in place on dy)
+int bn_bwd_reduce(PView dy, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
+                  double* s_dy, double* s_dyx, cudaStream_t st);
+int bn_bwd_apply(PView dy, PView z, int dt, const float* mean, const float* rstd, const float* gamma, const double* s_dy,
+                 const double* s_dyx, float* dgamma_acc, float* dbeta_acc, int n, int h, int w, int c, cudaStream_t st);
+// discriminator head (1024 -> 1 conv): t9[p][tap] = <a3[p], w4[tap]>, logits = b + 3x3 shift-sum of t9
+int dhead_forward(PView a3, int dt, const float* w4 /*[c][9] torch layout*/, const float* b4, int n, int h, int w, int c,
+                  float* t9, float* logits, cudaStream_t st);
+// dW4 += , db4 += , dy3 = (sum_tap g[q-tap] w4[tap]) * lrelu'(a3)
+int dhead_backward(PView a3, int dt, const float* w4, const float* g, int n, int h, int w, int c, float* dw4_acc, float* db4_acc,
+                   PView dy3, cudaStream_t st);
+
+template <typename T> struct dt_of;
+template <> struct dt_of<float> { static const int v = DT_F32; };
+template <> struct dt_of<bf16> { static const int v = DT_BF16; };
+
+}  // namespace afi
+
+struct afi_ctx {
+    int device;
+    int sm_count;
+    void* encode_tiled;   // cuTensorMapEncodeTiled entry point
+    int* tile_counter;    // reserved
+};

@@ -1,0 +1,534 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine (AFI_PREC_BF16): the throughput path of the library.
+//
+//   conv  : D[128 pixels x bn couts] += A[128 px x 64 ci] * B[bn co x 64 ci]^T per (tap, 64-channel chunk).
+//           The M tile is a TH x TW spatial patch of ONE image; the A operand of tap (dy,dx) is the same patch
+//           shifted by (dy,dx), fetched by a 4-D tiled TMA box {64 ch, TW, TH, 1}: out-of-image coordinates are
+//           zero-filled by the TMA unit, which IS the conv padding (and handles ragged 13x21 / 7x11 levels).
+//           Box rows land as 128-byte, 128B-swizzled rows = the UMMA K-major SWIZZLE_128B canonical layout.
+//   wgrad : D[128 couts x bn cins] += dY[64 px x 128 co]^T * X_shift[64 px x bn ci]: both operands MN-major
+//           (channels contiguous), K = pixels; same TMA boxes, split-K over spatial patches, fp32 RED into dW.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over a static tile list):
+//   warp 0 : TMA producer (one lane)      -- 4-stage smem ring, mbarrier full/empty
+//   warp 1 : TMEM allocator + MMA issuer  -- tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128, N=bn
+//   warp 2-5: epilogue                    -- tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x 256 cols)
+//                                            so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace afi {
+
+namespace tc {
+constexpr int STAGES = 4;
+constexpr int A_BYTES = 16384;          // 128 rows x 128 B
+constexpr int B_BYTES_MAX = 32768;      // 256 rows x 128 B
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int NUM_THREADS = 192;
+constexpr int ACC_COLS = 256;
+
+struct alignas(64) Maps {
+    CUtensorMap a[4];
+    CUtensorMap b;
+};
+struct Tiling {
+    int TH, TW, tiles_x, tiles_y;   // spatial patch and patch grid per image
+    int bn, n_tiles;                // N tile (multiple of 16, <= 256)
+    int kchunks;                    // ceil(cin / 64)
+    int total;                      // work items
+    int m_tiles, ksplit, ktiles;    // wgrad only
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ unsigned int g_tc_timeout_flag = 0;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if ((++spins & 1023u) == 0) {   // watchdog: a pipeline bug must trap, never hang the GPU
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) {
+                atomicExch(&g_tc_timeout_flag, 0x100u + (unsigned)who);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// UMMA shared-memory descriptor, SWIZZLE_128B, version 1 (sm_100).  Offsets in bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;     // descriptor version
+    d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor kind::f16: D=f32, A=B=bf16, M=128
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Smem {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int nmaps_a, int warp, int lane) {
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < nmaps_a; i++) prefetch_tmap(&maps.a[i]);
+        prefetch_tmap(&maps.b);
+        for (int i = 0; i < STAGES; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return s.tmem_base;
+}
+__device__ __forceinline__ void teardown(uint32_t tmem_base, int warp) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+__device__ __forceinline__ void ld16(const void* base, long long off, int dt, float* v) {
+    if (dt == DT_F32) {
+        const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { float4 t = p[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+    } else {
+        const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            uint4 u = p[i];
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[8 * i + 2 * j] = __uint_as_float(w[j] << 16); v[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+        }
+    }
+}
+__device__ __forceinline__ void st16(void* base, long long off, int dt, const float* v) {
+    if (dt == DT_F32) {
+        float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 4; i++) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+        uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            p[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// convolution kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Smem s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tmem_base = setup(s, maps, 4, warp, lane);
+    const int iters = a.ntaps * tl.kchunks;
+    const int tiles_per_img = tl.tiles_x * tl.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = A_BYTES + tl.bn * 128;
+            for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+                int nt = tile % tl.n_tiles, mt = tile / tl.n_tiles;
+                int img = mt / tiles_per_img, r = mt % tiles_per_img;
+                int y0 = (r / tl.tiles_x) * tl.TH, x0 = (r % tl.tiles_x) * tl.TW;
+                int n0 = nt * tl.bn;
+                for (int tp = 0; tp < a.ntaps; tp++) {
+                    const Tap t = a.taps[tp];
+                    for (int kc = 0; kc < tl.kchunks; kc++) {
+                        mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 1);
+                        uint32_t fb = smem_u32(&s.full[stage]);
+                        uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                        mbar_expect_tx(fb, tx_bytes);
+                        tma_load_4d(&maps.a[t.view], fb, sa, kc * 64, x0 + t.dx, y0 + t.dy, img);
+                        tma_load_3d(&maps.b, fb, sa + A_BYTES, kc * 64, n0, t.slab);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            const uint32_t idesc = make_idesc(tl.bn, 0, 0);
+            for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+                mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                for (int it = 0; it < iters; it++) {
+                    mbar_wait(smem_u32(&s.full[stage]), phase, 3);
+                    tc_fence_after();
+                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+                    umma_commit(smem_u32(&s.empty[stage]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(&s.acc_full[as]));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ty = row / tl.TW, tx = row % tl.TW;
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+            int nt = tile % tl.n_tiles, mt = tile / tl.n_tiles;
+            int img = mt / tiles_per_img, r = mt % tiles_per_img;
+            int y = (r / tl.tiles_x) * tl.TH + ty, x = (r % tl.tiles_x) * tl.TW + tx;
+            const bool ok = (y < a.H) && (x < a.W);
+            const int n0 = nt * tl.bn;
+            mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < tl.bn; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                const int col = n0 + c0;
+                if (ok && col < a.cout) {
+                    if (a.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += __ldg(a.bias + col + i);
+                    }
+                    if (a.act) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * a.slope;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] *= a.alpha;
+                    float t[16];
+                    if (a.r1.ptr) {
+                        ld16(a.r1.ptr, img * a.r1.sn + y * a.r1.sy + x * a.r1.sx + col, a.r1_dt, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
+                    }
+                    if (a.r2.ptr) {
+                        ld16(a.r2.ptr, img * a.r2.sn + y * a.r2.sy + x * a.r2.sx + col, a.r2_dt, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
+                    }
+                    if (a.accin.ptr) {
+                        ld16(a.accin.ptr, img * a.accin.sn + y * a.accin.sy + x * a.accin.sx + col, DT_F32, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += t[i];
+                    }
+                    if (a.mask.ptr) {
+                        ld16(a.mask.ptr, img * a.mask.sn + y * a.mask.sy + x * a.mask.sx + col, DT_BF16, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
+                    }
+                    st16(a.out.ptr, img * a.out.sn + y * a.out.sy + x * a.out.sx + col, a.out_dt, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[as]));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    teardown(tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel.  Work item = (tap, cout tile of 128, cin tile of bn, k split); K tile = TH x TW = 64 pixels.
+// smem stage: A = two [64 px][64 co] SW128 boxes (8 KB each), B = bn/64 [64 px][64 ci] boxes.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs a, const __grid_constant__ Tiling tl) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ Smem s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t tmem_base = setup(s, maps, 1, warp, lane);
+    const int tiles_per_img = tl.tiles_x * tl.tiles_y;
+    const int nb = tl.bn / 64;    // B boxes per stage
+    const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx_bytes = A_BYTES + nb * 8192;
+            for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
+                int ks = item % tl.ksplit; int r = item / tl.ksplit;
+                int nt = r % tl.n_tiles; r /= tl.n_tiles;
+                int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
+                const Tap t = a.taps[tp];
+                int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+                for (int kt = k0; kt < k1; kt++) {
+                    int img = kt / tiles_per_img, rr = kt % tiles_per_img;
+                    int y0 = (rr / tl.tiles_x) * tl.TH, x0 = (rr % tl.tiles_x) * tl.TW;
+                    mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
+                    uint32_t fb = smem_u32(&s.full[stage]);
+                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    mbar_expect_tx(fb, tx_bytes);
+                    tma_load_4d(&maps.a[0], fb, sa, mt * 128, x0, y0, img);
+                    tma_load_4d(&maps.a[0], fb, sa + 8192, mt * 128 + 64, x0, y0, img);
+                    for (int j = 0; j < nb; j++)
+                        tma_load_4d(&maps.b, fb, sa + A_BYTES + j * 8192, nt * tl.bn + j * 64, x0 + t.dx, y0 + t.dy, img);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            const uint32_t idesc = make_idesc(tl.bn, 1, 1);
+            for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
+                int ks = item % tl.ksplit;
+                int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+                mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 12);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                for (int kt = k0; kt < k1; kt++) {
+                    mbar_wait(smem_u32(&s.full[stage]), phase, 13);
+                    tc_fence_after();
+                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    // MN-major SW128: LBO = stride between 64-channel groups (8192 B), SBO = stride between 8-pixel groups (1024 B)
+                    uint64_t ad = make_desc(sa, 8192, 1024), bd = make_desc(sa + A_BYTES, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)     // 16 pixels = 2048 B per MMA
+                        umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
+                    umma_commit(smem_u32(&s.empty[stage]));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(smem_u32(&s.acc_full[as]));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int as = 0; uint32_t aphase = 0;
+        for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
+            int ks = item % tl.ksplit; int r = item / tl.ksplit;
+            int nt = r % tl.n_tiles; r /= tl.n_tiles;
+            int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
+            int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+            const int co = mt * 128 + row;
+            float* dst = a.dw + ((long long)a.taps[tp].slab * a.cout + co) * a.cin;
+            mbar_wait(smem_u32(&s.acc_full[as]), aphase, 14);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < tl.bn; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                const int ci = nt * tl.bn + c0;
+                if (k1 > k0 && co < a.cout && ci < a.cin) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) atomicAdd(dst + ci + i, v[i]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[as]));
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+    teardown(tmem_base, warp);
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(afi_ctx* ctx, CUtensorMap* m, void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    AFI_REQUIRE(((uintptr_t)ptr & 15) == 0, "TMA: global address not 16-byte aligned");
+    for (int i = 0; i < rank - 1; i++) AFI_REQUIRE(strides_bytes[i] % 16 == 0, "TMA: stride %d (%llu B) not a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+    CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, ptr, dims, strides_bytes, box, es,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AFI_ERR_CUDA; }
+    return AFI_OK;
+}
+static int encode_view(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int W, int H, int N, int TW, int TH) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    return encode_map(ctx, m, v.ptr, 4, dims, strides, box);
+}
+
+static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
+    // spatial patch of `pixels` (= GEMM rows per tile) minimising padded area; TW multiple of 8 keeps swizzle atoms whole
+    long long best = -1; int bh = pixels / 16, bw = 16;
+    for (int tw = 8; tw <= pixels; tw *= 2) {
+        int th = pixels / tw;
+        if (th < 1 || tw > 256 || th > 256) continue;
+        long long padded = (long long)((H + th - 1) / th) * th * (long long)((W + tw - 1) / tw) * tw;
+        if (best < 0 || padded < best || (padded == best && tw == 16)) { best = padded; bh = th; bw = tw; }
+    }
+    *TH = bh; *TW = bw;
+}
+
+}  // namespace tc
+
+int tc_init(afi_ctx* ctx) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+        return AFI_ERR_CUDA;
+    }
+    ctx->encode_tiled = fn;
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    return AFI_OK;
+}
+
+int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
+    using namespace tc;
+    AFI_REQUIRE(ctx && ctx->encode_tiled, "conv_tc: context not initialised");
+    AFI_REQUIRE(a.cin % 16 == 0 && a.cout % 16 == 0, "conv_tc: cin %d / cout %d must be multiples of 16", a.cin, a.cout);
+    if ((long long)a.N * a.H * a.W == 0) return AFI_OK;
+    Tiling tl{};
+    pick_patch(a.H, a.W, 128, &tl.TH, &tl.TW);
+    tl.tiles_x = (a.W + tl.TW - 1) / tl.TW;
+    tl.tiles_y = (a.H + tl.TH - 1) / tl.TH;
+    tl.n_tiles = (a.cout + 255) / 256;
+    tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
+    tl.kchunks = (a.cin + 63) / 64;
+    tl.total = a.N * tl.tiles_x * tl.tiles_y * tl.n_tiles;
+    Maps maps;
+    int nviews = 0;
+    for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
+    AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc: bad view count");
+    for (int i = 0; i < 4; i++) {
+        const PView& v = a.in[i < nviews ? i : 0];
+        AFI_TRY(encode_view(ctx, &maps.a[i], v, a.cin, a.W, a.H, a.N, tl.TW, tl.TH));
+    }
+    int nslab = 0;
+    for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab};
+        cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)tl.bn, 1};
+        AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
+    }
+    int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    k_conv_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
+    using namespace tc;
+    AFI_REQUIRE(ctx && ctx->encode_tiled, "wgrad_tc: context not initialised");
+    AFI_REQUIRE(a.cin % 16 == 0 && a.cout % 16 == 0, "wgrad_tc: cin %d / cout %d must be multiples of 16", a.cin, a.cout);
+    if ((long long)a.N * a.H * a.W == 0) return AFI_OK;
+    Tiling tl{};
+    pick_patch(a.H, a.W, 64, &tl.TH, &tl.TW);
+    tl.tiles_x = (a.W + tl.TW - 1) / tl.TW;
+    tl.tiles_y = (a.H + tl.TH - 1) / tl.TH;
+    tl.ktiles = a.N * tl.tiles_x * tl.tiles_y;
+    tl.m_tiles = (a.cout + 127) / 128;
+    tl.n_tiles = (a.cin + 255) / 256;
+    tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
+    int base = a.ntaps * tl.m_tiles * tl.n_tiles;
+    int ks = (2 * ctx->sm_count + base - 1) / base;
+    if (ks > tl.ktiles) ks = tl.ktiles;
+    if (ks < 1) ks = 1;
+    int kper = (tl.ktiles + ks - 1) / ks;
+    tl.ksplit = (tl.ktiles + kper - 1) / kper;
+    tl.total = base * tl.ksplit;
+    Maps maps;
+    AFI_TRY(encode_view(ctx, &maps.a[0], a.dy, a.cout, a.W, a.H, a.N, tl.TW, tl.TH));
+    for (int i = 1; i < 4; i++) maps.a[i] = maps.a[0];
+    AFI_TRY(encode_view(ctx, &maps.b, a.x, a.cin, a.W, a.H, a.N, tl.TW, tl.TH));
+    int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    k_wgrad_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+}  // namespace afi

@@ -1,0 +1,628 @@
+// HBM-bound passes of the AFI-GAN hot path: layout changes, weight (un)packing, BatchNorm statistics /
+// apply / backward, the 1024->1 discriminator head, the BCE / L1 losses and the SGD update.
+// All kernels are coalesced along the channel (innermost NHWC) dimension, 4 channels per thread,
+// reductions are warp/block-reduced before one atomic per channel per block.
+#include "common.cuh"
+
+namespace afi {
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const void* base, long long off, int dt) {
+    if (dt == DT_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + off);
+    float4 r;
+    r.x = __uint_as_float(u.x << 16); r.y = __uint_as_float(u.x & 0xffff0000u);
+    r.z = __uint_as_float(u.y << 16); r.w = __uint_as_float(u.y & 0xffff0000u);
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st4(void* base, long long off, int dt, float4 v) {
+    if (dt == DT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off) = v;
+    } else {
+        uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(base) + off) = u;
+    }
+}
+__device__ __forceinline__ float lmaskf(float a, float slope) { return a > 0.f ? 1.f : slope; }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// decode a flat (pixel, channel-quad) index
+struct PixIdx { int n, y, x; };
+__device__ __forceinline__ PixIdx decode_pixel(long long p, int H, int W) {
+    PixIdx r; r.x = (int)(p % W); long long t = p / W; r.y = (int)(t % H); r.n = (int)(t / H); return r;
+}
+__device__ __forceinline__ long long voff(const PView& v, PixIdx q) { return q.n * v.sn + q.y * v.sy + q.x * v.sx; }
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW fp32 (strided) -> NHWC T
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_nchw_to_nhwc(afi_view4 src, int c, int h, int w, PView dst) {
+    __shared__ float tile[32][33];
+    int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int n = blockIdx.z / h, y = blockIdx.z % h;
+    int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int cc = c0 + ty + 8 * i, xx = x0 + tx;
+        float v = 0.f;
+        if (cc < c && xx < w) v = src.ptr[n * src.sn + cc * src.sc + y * src.sh + xx * src.sw];
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+    T* d = reinterpret_cast<T*>(dst.ptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int xx = x0 + ty + 8 * i, cc = c0 + tx;
+        if (cc < c && xx < w) d[n * dst.sn + y * dst.sy + xx * dst.sx + cc] = (T)tile[tx][ty + 8 * i];
+    }
+}
+template <typename T>
+int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st) {
+    dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
+    k_nchw_to_nhwc<T><<<grid, block, 0, st>>>(src, c, h, w, dst);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+template int nchw_to_nhwc<float>(afi_view4, int, int, int, int, PView, cudaStream_t);
+template int nchw_to_nhwc<bf16>(afi_view4, int, int, int, int, PView, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// NHWC T -> contiguous NCHW fp32, fused with the bilinear x2 skip (generator_rdb.py:125,130), the lateral
+// add and the merge scale (fpn_sr.py:154-157), and the top-left crop (stage1_trainer.py:437-443).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_coord(int o, int size, int& i0, int& i1, float& l0, float& l1) {
+    // area_pixel_compute_source_index(scale=0.5, align_corners=False) as ATen's upsample_bilinear2d does
+    float s = (o + 0.5f) * 0.5f - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    i1 = i0 + (i0 < size - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+    l0 = 1.f - l1;
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int sh, int sw_, float scale, int c, int oh, int ow,
+                               float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int n = blockIdx.z / oh, y = blockIdx.z % oh;
+    int tx = threadIdx.x, ty = threadIdx.y;
+    const T* ap = reinterpret_cast<const T*>(a.ptr);
+    const T* lp = reinterpret_cast<const T*>(lat.ptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int xx = x0 + ty + 8 * i, cc = c0 + tx;
+        float v = 0.f;
+        if (cc < c && xx < ow) {
+            v = (float)ap[n * a.sn + y * a.sy + xx * a.sx + cc];
+            if (lp) v += (float)lp[n * lat.sn + y * lat.sy + xx * lat.sx + cc];
+        }
+        tile[ty + 8 * i][tx] = v;   // [x][c]
+    }
+    __syncthreads();
+    int y0, y1; float ly0, ly1;
+    bilin_coord(y, sh, y0, y1, ly0, ly1);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int cc = c0 + ty + 8 * i, xx = x0 + tx;
+        if (cc < c && xx < ow) {
+            float v = tile[tx][ty + 8 * i];
+            if (skip.ptr) {
+                int xa, xb; float lx0, lx1;
+                bilin_coord(xx, sw_, xa, xb, lx0, lx1);
+                const float* s = skip.ptr + n * skip.sn + cc * skip.sc;
+                float v00 = s[y0 * skip.sh + xa * skip.sw], v01 = s[y0 * skip.sh + xb * skip.sw];
+                float v10 = s[y1 * skip.sh + xa * skip.sw], v11 = s[y1 * skip.sh + xb * skip.sw];
+                v += ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+            }
+            dst[(((long long)n * c + cc) * oh + y) * ow + xx] = v * scale;
+        }
+    }
+}
+template <typename T>
+int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale, int n, int c, int oh, int ow,
+                 float* dst, cudaStream_t st) {
+    dim3 grid(cdiv(ow, 32), cdiv(c, 32), n * oh), block(32, 8);
+    k_nhwc_to_nchw<T><<<grid, block, 0, st>>>(a, lat, skip, skip_h, skip_w, scale, c, oh, ow, dst);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+template int nhwc_to_nchw<float>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t);
+template int nhwc_to_nchw<bf16>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// dst = scale * (a + b) * lrelu'(mask)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt,
+                             float mslope, float scale, int H, int W, int cq, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % cq) * 4;
+    PixIdx q = decode_pixel(i / cq, H, W);
+    float4 v = ld4(a.ptr, voff(a, q) + c, a_dt);
+    if (b.ptr) { float4 t = ld4(b.ptr, voff(b, q) + c, b_dt); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (mask.ptr) {
+        float4 m = ld4(mask.ptr, voff(mask, q) + c, mask_dt);
+        v.x *= lmaskf(m.x, mslope); v.y *= lmaskf(m.y, mslope); v.z *= lmaskf(m.z, mslope); v.w *= lmaskf(m.w, mslope);
+    }
+    st4(dst.ptr, voff(dst, q) + c, dst_dt, v);
+}
+int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt, float mask_slope,
+               float scale, int n, int h, int w, int c, cudaStream_t st) {
+    long long total = (long long)n * h * w * (c / 4);
+    if (total == 0) return AFI_OK;
+    k_ew_combine<<<cdiv(total, 256), 256, 0, st>>>(dst, dst_dt, a, a_dt, b, b_dt, mask, mask_dt, mask_slope, scale, h, w, c / 4, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-channel reductions over pixels.  Block = 256 threads = (c/4 channel quads) x (pixel lanes); each block
+// owns a chunk of pixels, accumulates in fp32 registers, reduces lanes through shared memory and issues one
+// atomic per channel.  MODE 0: sum, sumsq of x (double).  MODE 1: sum dy, sum dy*xhat (double).  MODE 2: sum x (float).
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void k_col_reduce(PView x, PView z, int dt, const float* __restrict__ mean, const float* __restrict__ rstd,
+                             int H, int W, int cq, long long npix, int chunk, double* o0, double* o1, float* of) {
+    __shared__ float4 s0[256];
+    __shared__ float4 s1[256];
+    int lanes = blockDim.x / cq;
+    int q4 = threadIdx.x % cq, lane = threadIdx.x / cq;
+    long long p0 = (long long)blockIdx.x * chunk, p1 = p0 + chunk;
+    if (p1 > npix) p1 = npix;
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = make_float4(0, 0, 0, 0);
+    float4 mu = make_float4(0, 0, 0, 0), rs = make_float4(1, 1, 1, 1);
+    if (MODE == 1 && lane < lanes) { mu = *reinterpret_cast<const float4*>(mean + q4 * 4); rs = *reinterpret_cast<const float4*>(rstd + q4 * 4); }
+    if (lane < lanes) {
+        for (long long p = p0 + lane; p < p1; p += lanes) {
+            PixIdx q = decode_pixel(p, H, W);
+            float4 v = ld4(x.ptr, voff(x, q) + q4 * 4, dt);
+            if (MODE == 0) {
+                a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+                a1.x += v.x * v.x; a1.y += v.y * v.y; a1.z += v.z * v.z; a1.w += v.w * v.w;
+            } else if (MODE == 1) {
+                float4 zz = ld4(z.ptr, voff(z, q) + q4 * 4, dt);
+                a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+                a1.x += v.x * (zz.x - mu.x) * rs.x; a1.y += v.y * (zz.y - mu.y) * rs.y;
+                a1.z += v.z * (zz.z - mu.z) * rs.z; a1.w += v.w * (zz.w - mu.w) * rs.w;
+            } else {
+                a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+            }
+        }
+    }
+    s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+    __syncthreads();
+    if (lane == 0) {
+        for (int l = 1; l < lanes; l++) {
+            float4 t = s0[l * cq + q4]; a0.x += t.x; a0.y += t.y; a0.z += t.z; a0.w += t.w;
+            if (MODE != 2) { float4 u = s1[l * cq + q4]; a1.x += u.x; a1.y += u.y; a1.z += u.z; a1.w += u.w; }
+        }
+        int c = q4 * 4;
+        if (MODE == 2) {
+            atomicAdd(of + c, a0.x); atomicAdd(of + c + 1, a0.y); atomicAdd(of + c + 2, a0.z); atomicAdd(of + c + 3, a0.w);
+        } else {
+            atomicAdd(o0 + c, (double)a0.x); atomicAdd(o0 + c + 1, (double)a0.y); atomicAdd(o0 + c + 2, (double)a0.z); atomicAdd(o0 + c + 3, (double)a0.w);
+            if (o1) { atomicAdd(o1 + c, (double)a1.x); atomicAdd(o1 + c + 1, (double)a1.y); atomicAdd(o1 + c + 2, (double)a1.z); atomicAdd(o1 + c + 3, (double)a1.w); }
+        }
+    }
+}
+static int col_reduce_launch(int mode, PView x, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
+                             double* o0, double* o1, float* of, cudaStream_t st) {
+    AFI_REQUIRE(c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0, "col_reduce: unsupported channel count %d", c);
+    long long npix = (long long)n * h * w;
+    if (npix == 0) return AFI_OK;
+    int chunk = 128;   // pixels per block: short fp32 partial sums (<= 128 terms per lane) keep BN statistics at ~1e-7
+    int grid = cdiv(npix, chunk);
+    if (mode == 0) k_col_reduce<0><<<grid, 256, 0, st>>>(x, z, dt, mean, rstd, h, w, c / 4, npix, chunk, o0, o1, of);
+    else if (mode == 1) k_col_reduce<1><<<grid, 256, 0, st>>>(x, z, dt, mean, rstd, h, w, c / 4, npix, chunk, o0, o1, of);
+    else k_col_reduce<2><<<grid, 256, 0, st>>>(x, z, dt, mean, rstd, h, w, c / 4, npix, chunk, o0, o1, of);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+int col_stats(PView x, int dt, int n, int h, int w, int c, double* sum, double* sumsq, cudaStream_t st) {
+    return col_reduce_launch(0, x, pview_null(), dt, nullptr, nullptr, n, h, w, c, sum, sumsq, nullptr, st);
+}
+int col_sum_f32(PView x, int dt, int n, int h, int w, int c, float* out, cudaStream_t st) {
+    return col_reduce_launch(2, x, pview_null(), dt, nullptr, nullptr, n, h, w, c, nullptr, nullptr, out, st);
+}
+int bn_bwd_reduce(PView dy, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
+                  double* s_dy, double* s_dyx, cudaStream_t st) {
+    return col_reduce_launch(1, dy, z, dt, mean, rstd, n, h, w, c, s_dy, s_dyx, nullptr, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BatchNorm finalize / apply / backward-apply
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum,
+                              int training, float* mean, float* rstd, float* rmean, float* rvar, long long* nbt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    if (training) {
+        double m = sum[i] / (double)count;
+        double var = sumsq[i] / (double)count - m * m;
+        if (var < 0) var = 0;
+        mean[i] = (float)m;
+        rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+        if (rmean) rmean[i] = (1.f - momentum) * rmean[i] + momentum * (float)m;
+        if (rvar) {
+            double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
+            rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unb;
+        }
+        if (i == 0 && nbt) *nbt += 1;
+    } else {
+        mean[i] = rmean[i];
+        rstd[i] = 1.f / sqrtf(rvar[i] + eps);
+    }
+}
+int bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum, int training,
+                float* mean, float* rstd, float* running_mean, float* running_var, long long* nbt, cudaStream_t st) {
+    if (!training) AFI_REQUIRE(running_mean && running_var, "bn_finalize: eval mode needs running statistics");
+    k_bn_finalize<<<cdiv(c, 256), 256, 0, st>>>(sum, sumsq, count, c, eps, momentum, training, mean, rstd, running_mean, running_var, nbt);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+__global__ void k_bn_apply_lrelu(PView z, PView a, int dt, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float slope, int H, int W,
+                                 int cq, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % cq) * 4;
+    PixIdx q = decode_pixel(i / cq, H, W);
+    float4 v = ld4(z.ptr, voff(z, q) + c, dt);
+    float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+    float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    // same operation order as ATen's batch_norm: (x - mean) * invstd * weight + bias
+    v.x = (v.x - mu.x) * rs.x * g.x + b.x; v.y = (v.y - mu.y) * rs.y * g.y + b.y;
+    v.z = (v.z - mu.z) * rs.z * g.z + b.z; v.w = (v.w - mu.w) * rs.w * g.w + b.w;
+    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+    st4(a.ptr, voff(a, q) + c, dt, v);
+}
+int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   float slope, int n, int h, int w, int c, cudaStream_t st) {
+    long long total = (long long)n * h * w * (c / 4);
+    if (total == 0) return AFI_OK;
+    k_bn_apply_lrelu<<<cdiv(total, 256), 256, 0, st>>>(z, a, dt, mean, rstd, gamma, beta, slope, h, w, c / 4, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+__global__ void k_bn_bwd_apply(PView dy, PView z, int dt, const float* __restrict__ mean, const float* __restrict__ rstd,
+                               const float* __restrict__ gamma, const double* __restrict__ s_dy, const double* __restrict__ s_dyx,
+                               float* dgamma_acc, float* dbeta_acc, int H, int W, int cq, long long total, float inv_m) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) {   // parameter gradients of the affine part: d gamma = sum dy*xhat, d beta = sum dy
+        for (int c = threadIdx.x; c < cq * 4; c += blockDim.x) {
+            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)s_dyx[c]);
+            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)s_dy[c]);
+        }
+    }
+    if (i >= total) return;
+    int c = (int)(i % cq) * 4;
+    PixIdx q = decode_pixel(i / cq, H, W);
+    long long o = voff(dy, q) + c;
+    float4 g = ld4(dy.ptr, o, dt);
+    float4 zz = ld4(z.ptr, voff(z, q) + c, dt);
+    float r[4] = {g.x, g.y, g.z, g.w}, zv[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float xhat = (zv[k] - mean[c + k]) * rstd[c + k];
+        float m_dy = (float)s_dy[c + k] * inv_m, m_dyx = (float)s_dyx[c + k] * inv_m;
+        r[k] = gamma[c + k] * rstd[c + k] * (r[k] - m_dy - xhat * m_dyx);
+    }
+    st4(dy.ptr, o, dt, make_float4(r[0], r[1], r[2], r[3]));
+}
+int bn_bwd_apply(PView dy, PView z, int dt, const float* mean, const float* rstd, const float* gamma, const double* s_dy,
+                 const double* s_dyx, float* dgamma_acc, float* dbeta_acc, int n, int h, int w, int c, cudaStream_t st) {
+    long long total = (long long)n * h * w * (c / 4);
+    if (total == 0) return AFI_OK;
+    k_bn_bwd_apply<<<cdiv(total, 256), 256, 0, st>>>(dy, z, dt, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, h, w, c / 4,
+                                                   total, 1.f / (float)((long long)n * h * w));
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// discriminator head: Conv2d 1024 -> 1, 3x3 (feature_patch_discriminator.py:40-41).  GEMV-like, HBM-bound:
+// forward = 9 per-pixel dot products (one read of a3) + a 3x3 shift-sum; backward fuses the weight gradient,
+// the input gradient and the LeakyReLU mask of layer 3 in one pass over a3.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_dhead_dots(PView a3, int dt, const float* __restrict__ w4, int H, int W, int c, long long npix, float* __restrict__ t9) {
+    extern __shared__ float ws[];   // [9][c]
+    for (int i = threadIdx.x; i < 9 * c; i += blockDim.x) { int cc = i / 9, t = i % 9; ws[t * c + cc] = w4[i]; }
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (long long p = (long long)blockIdx.x * nwarp + warp; p < npix; p += (long long)gridDim.x * nwarp) {
+        PixIdx q = decode_pixel(p, H, W);
+        long long base = voff(a3, q);
+        float acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) acc[t] = 0.f;
+        for (int cc = lane * 4; cc < c; cc += 128) {
+            float4 v = ld4(a3.ptr, base + cc, dt);
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                float4 wv = *reinterpret_cast<const float4*>(ws + t * c + cc);
+                acc[t] += v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; t++) t9[p * 9 + t] = acc[t];
+        }
+    }
+}
+__global__ void k_dhead_stencil(const float* __restrict__ t9, const float* __restrict__ b4, int H, int W, long long npix, float* __restrict__ logits) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    PixIdx q = decode_pixel(p, H, W);
+    float v = b4 ? b4[0] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        int yy = q.y + t / 3 - 1, xx = q.x + t % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v += t9[(((long long)q.n * H + yy) * W + xx) * 9 + t];
+    }
+    logits[p] = v;
+}
+int dhead_forward(PView a3, int dt, const float* w4, const float* b4, int n, int h, int w, int c, float* t9, float* logits, cudaStream_t st) {
+    long long npix = (long long)n * h * w;
+    if (npix == 0) return AFI_OK;
+    AFI_REQUIRE(c % 128 == 0, "dhead: channels must be a multiple of 128");
+    size_t smem = (size_t)9 * c * sizeof(float);
+    AFI_CUDA(cudaFuncSetAttribute(k_dhead_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((npix + 7) / 8); if (grid > 148 * 8) grid = 148 * 8;
+    k_dhead_dots<<<grid, 256, smem, st>>>(a3, dt, w4, h, w, c, npix, t9);
+    AFI_LAUNCH_CHECK();
+    k_dhead_stencil<<<cdiv(npix, 256), 256, 0, st>>>(t9, b4, h, w, npix, logits);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// block = c/4 threads (256 for c = 1024); each thread owns 4 channels and keeps its 4x9 weight-gradient partials in registers
+__global__ void k_dhead_backward(PView a3, int dt, const float* __restrict__ w4, const float* __restrict__ g, int H, int W, int c,
+                                 long long npix, int chunk, float* dw4_acc, float* db4_acc, PView dy3, float slope) {
+    __shared__ float g9s[9];
+    int c0 = threadIdx.x * 4;
+    float wr[4][9], dw[4][9];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int t = 0; t < 9; t++) { wr[k][t] = w4[(c0 + k) * 9 + t]; dw[k][t] = 0.f; }
+    float db = 0.f;
+    long long p0 = (long long)blockIdx.x * chunk, p1 = p0 + chunk;
+    if (p1 > npix) p1 = npix;
+    for (long long p = p0; p < p1; p++) {
+        PixIdx q = decode_pixel(p, H, W);
+        __syncthreads();
+        if (threadIdx.x < 9) {   // g9[t] = g[q - tap_t]
+            int t = threadIdx.x;
+            int yy = q.y - (t / 3 - 1), xx = q.x - (t % 3 - 1);
+            g9s[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? g[((long long)q.n * H + yy) * W + xx] : 0.f;
+        }
+        __syncthreads();
+        float g9[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) g9[t] = g9s[t];
+        long long o = voff(a3, q) + c0;
+        float4 a = ld4(a3.ptr, o, dt);
+        float av[4] = {a.x, a.y, a.z, a.w}, r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; t++) { s += g9[t] * wr[k][t]; dw[k][t] += av[k] * g9[t]; }
+            r[k] = s * lmaskf(av[k], slope);
+        }
+        st4(dy3.ptr, voff(dy3, q) + c0, dt, make_float4(r[0], r[1], r[2], r[3]));
+        if (threadIdx.x == 0) db += g9[4];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int t = 0; t < 9; t++) atomicAdd(dw4_acc + (c0 + k) * 9 + t, dw[k][t]);
+    if (threadIdx.x == 0 && db4_acc) atomicAdd(db4_acc, db);
+}
+int dhead_backward(PView a3, int dt, const float* w4, const float* g, int n, int h, int w, int c, float* dw4_acc, float* db4_acc,
+                   PView dy3, cudaStream_t st) {
+    long long npix = (long long)n * h * w;
+    if (npix == 0) return AFI_OK;
+    AFI_REQUIRE(c % 4 == 0 && c / 4 <= 1024, "dhead_backward: unsupported channel count");
+    int chunk = (int)((npix + 148 * 4 - 1) / (148 * 4)); if (chunk < 16) chunk = 16;
+    k_dhead_backward<<<cdiv(npix, chunk), c / 4, 0, st>>>(a3, dt, w4, g, h, w, c, npix, chunk, dw4_acc, db4_acc, dy3, 0.2f);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing: torch layouts -> GEMM slabs
+//   KN: dst[slab][k = gemm-cin][n = gemm-cout]   (CUDA-core engine, N contiguous)
+//   NK: dst[slab][n = gemm-cout][k = gemm-cin]   (tensor-core engine, K contiguous = UMMA K-major B operand)
+// forward conv : w[co][ci][ky][kx], slab = ky*3+kx, gemm-cin = ci, gemm-cout = co
+// dgrad conv   : slab t=(e+1)*3+(f+1) <- w[co][ci][1-e][1-f], gemm-cin = co, gemm-cout = ci
+// deconv fwd   : w[ci][co][6][6], slab = phase*9 + t, phase = a*2+b, t=(dy+1)*3+(dx+1) <- [2(1-dy)+a][2(1-dx)+b]
+// deconv dgrad : slab = phase*9 + t, t=(e+1)*3+(f+1) <- w[ci][co][2(1+e)+a][2(1+f)+b], gemm-cin = co, gemm-cout = ci
+// 1x1 forward  : w[co][ci] (lateral conv of the FPN merge), one slab (mode kind 4)
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int nk = mode & 1, kind = mode >> 1;
+    int gk = (kind == 0 || kind == 2 || kind == 4) ? ci : co;   // gemm-cin
+    int gn = (kind == 0 || kind == 2 || kind == 4) ? co : ci;   // gemm-cout
+    int inner = (int)(i % (nk ? gk : gn));
+    long long t2 = i / (nk ? gk : gn);
+    int outer = (int)(t2 % (nk ? gn : gk));
+    int slab = (int)(t2 / (nk ? gn : gk));
+    int k = nk ? inner : outer, n = nk ? outer : inner;
+    float v;
+    if (kind == 0) {            // fwd: k = ci, n = co
+        v = w[((long long)n * ci + k) * 9 + slab];
+    } else if (kind == 1) {     // dgrad: k = co, n = ci
+        v = w[((long long)k * ci + n) * 9 + (8 - slab)];
+    } else if (kind == 4) {     // 1x1 forward: w[co][ci], k = ci, n = co
+        v = w[(long long)n * ci + k];
+    } else {
+        int ph = slab / 9, t = slab % 9, a = ph >> 1, b = ph & 1, d0 = t / 3 - 1, d1 = t % 3 - 1;
+        if (kind == 2) {        // deconv fwd: k = ci, n = co
+            int ky = 2 * (1 - d0) + a, kx = 2 * (1 - d1) + b;
+            v = w[(((long long)k * co + n) * 6 + ky) * 6 + kx];
+        } else {                // deconv dgrad: k = co, n = ci
+            int ky = 2 * (1 + d0) + a, kx = 2 * (1 + d1) + b;
+            v = w[(((long long)n * co + k) * 6 + ky) * 6 + kx];
+        }
+    }
+    dst[i] = (T)v;
+}
+int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st) {
+    int kind = mode >> 1;
+    int slabs = kind == 4 ? 1 : (kind >= 2 ? 36 : 9);
+    long long total = (long long)slabs * co * ci;
+    if (dst_dt == DT_F32) k_pack<float><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (float*)dst, total);
+    else k_pack<bf16><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (bf16*)dst, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// packed fp32 weight gradient -> torch layout.  Conv: dst[co][ci][t]; deconv: dst[ci][co][ky][kx] (forward tap mapping).
+__global__ void k_unpack_wgrad(const float* __restrict__ packed, int co, int ci, int nk, int deconv, float* __restrict__ dst,
+                               float scale, int accumulate, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int slab, c_o, c_i;
+    if (!deconv) {
+        slab = (int)(i % 9); long long t = i / 9; c_i = (int)(t % ci); c_o = (int)(t / ci);
+    } else {
+        int kx = (int)(i % 6); long long t = i / 6; int ky = (int)(t % 6); t /= 6; c_o = (int)(t % co); c_i = (int)(t / co);
+        int a = ky & 1, b = kx & 1, d0 = 1 - (ky >> 1), d1 = 1 - (kx >> 1);
+        slab = (a * 2 + b) * 9 + (d0 + 1) * 3 + (d1 + 1);
+    }
+    long long src = nk ? ((long long)slab * co + c_o) * ci + c_i : ((long long)slab * ci + c_i) * co + c_o;
+    float v = packed[src] * scale;
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st) {
+    long long total = (long long)co * ci * (deconv ? 36 : 9);
+    k_unpack_wgrad<<<cdiv(total, 256), 256, 0, st>>>(packed, co, ci, layout_nk, deconv, dst, scale, accumulate, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+__global__ void k_axpby(const float* __restrict__ src, float* __restrict__ dst, long long n, float scale, int accumulate) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = accumulate ? dst[i] + scale * src[i] : scale * src[i];
+}
+int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st) {
+    if (n == 0) return AFI_OK;
+    k_axpby<<<cdiv(n, 256), 256, 0, st>>>(src, dst, n, scale, accumulate);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// losses and the optimiser step
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    if (warp == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void k_bce(const float* __restrict__ x, long long count, float target, float* loss_out, float* loss_sum, float weight,
+                      float* __restrict__ dlogits, float gscale) {
+    double acc = 0.0;
+    float inv = 1.f / (float)count;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        float l = fmaxf(v, 0.f) - v * target + log1pf(expf(-fabsf(v)));
+        acc += (double)l;
+        if (dlogits) dlogits[i] = gscale * (1.f / (1.f + expf(-v)) - target) * inv;
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) {
+        float m = (float)(acc / (double)count);
+        if (loss_out) atomicAdd(loss_out, m);
+        if (loss_sum) atomicAdd(loss_sum, weight * m);
+    }
+}
+extern "C" int afi_bce_with_logits(const float* logits, long long count, float target, float* loss_out, float* loss_sum,
+                                   float weight, float* dlogits, float grad_scale, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_REQUIRE(count > 0, "bce: empty logits");
+    if (loss_out) AFI_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    int grid = cdiv(count, 256); if (grid > 592) grid = 592;
+    k_bce<<<grid, 256, 0, st>>>(logits, count, target, loss_out, loss_sum, weight, dlogits, grad_scale);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+__global__ void k_l1(afi_view4 a, afi_view4 b, int c, int h, int w, long long total, float* loss_out, float* loss_sum, float weight,
+                     float* __restrict__ da, float gscale) {
+    double acc = 0.0;
+    float ginv = gscale / (float)total;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % w); long long t = i / w; int y = (int)(t % h); t /= h; int cc = (int)(t % c); int n = (int)(t / c);
+        float d = a.ptr[n * a.sn + cc * a.sc + y * a.sh + x * a.sw] - b.ptr[n * b.sn + cc * b.sc + y * b.sh + x * b.sw];
+        acc += (double)fabsf(d);
+        if (da) da[i] = d > 0.f ? ginv : (d < 0.f ? -ginv : 0.f);
+    }
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) {
+        float m = (float)(acc / (double)total);
+        if (loss_out) atomicAdd(loss_out, m);
+        if (loss_sum) atomicAdd(loss_sum, weight * m);
+    }
+}
+extern "C" int afi_l1_loss(afi_view4 a, afi_view4 b, int n, int c, int h, int w, float* loss_out, float* loss_sum, float weight,
+                           float* da, float grad_scale, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = (long long)n * c * h * w;
+    AFI_REQUIRE(total > 0, "l1: empty tensors");
+    if (loss_out) AFI_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    int grid = cdiv(total, 256 * 8); if (grid > 148 * 8) grid = 148 * 8;
+    k_l1<<<grid, 256, 0, st>>>(a, b, c, h, w, total, loss_out, loss_sum, weight, da, grad_scale);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+__global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, long long n, float lr, float mom,
+                      float wd, float gscale, int first) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = gscale * g[i] + wd * p[i];
+    float b = first ? d : mom * m[i] + d;
+    m[i] = b;
+    p[i] = p[i] - lr * b;
+}
+extern "C" int afi_sgd_step(float* p, const float* g, float* m, long long count, float lr, float momentum, float wd,
+                            float grad_scale, int first, void* stream) {
+    if (count == 0) return AFI_OK;
+    k_sgd<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, count, lr, momentum, wd, grad_scale, first);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+extern "C" int afi_zero(void* ptr, size_t bytes, void* stream) {
+    if (bytes) AFI_CUDA(cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream));
+    return AFI_OK;
+}
+
+}  // namespace afi

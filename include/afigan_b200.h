@@ -1,0 +1,174 @@
+/*
+ * afigan_b200.h -- C ABI of libafigan_b200.so: the B200 (sm_100a) implementation of AFI-GAN's hot path.
+ *
+ * The reference (inhavl-shlee/AFI-GAN) has no FFI of its own: its "operator API" for this path is the
+ * nn.Module contract of Generator / Discriminator plus the loss block of the stage-1/2 trainers.  Each
+ * entry point below names the reference interface it replaces (file:line under /root/reference).
+ * The Python side (afi-gan_b200/afigan) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain C: device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ *  - every function returns 0 on success or a negative AFI_ERR_* code; afi_last_error() gives the text
+ *    (thread-local).  Unsupported shapes / precision / architecture are hard errors: there is no fallback.
+ *  - all work is enqueued on the caller's stream; nothing synchronises; nothing is allocated: the caller
+ *    provides workspaces sized by the *_bytes() queries (torch owns all memory).
+ *  - tensors cross the boundary as strided fp32 NCHW-logical views (afi_view4: element strides), so both
+ *    contiguous and channels_last torch tensors and top-left crops are accepted without copies.
+ *  - parameters and gradients use the reference's state-dict layouts.
+ */
+#ifndef AFIGAN_B200_H
+#define AFIGAN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFI_ABI_VERSION 1
+
+#define AFI_OK 0
+#define AFI_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define AFI_ERR_CUDA (-2)      /* a CUDA runtime/driver call failed */
+#define AFI_ERR_ARCH (-3)      /* device is not sm_100 */
+#define AFI_ERR_WORKSPACE (-4) /* workspace too small */
+
+/* Operand modes (bf16 operands cannot meet 1e-3 on gradients, fp32 products can). */
+#define AFI_PREC_FP32 0      /* fp32 storage + fp32 FFMA implicit GEMM: the parity mode              */
+#define AFI_PREC_BF16 1      /* bf16 storage + tcgen05/TMEM implicit GEMM fed by TMA: throughput mode */
+#define AFI_PREC_BF16_SIMT 2 /* bf16 storage + CUDA-core GEMM: on-device cross-check of mode 1        */
+
+#define AFI_MAX_RDB 4
+#define AFI_CH 256 /* feature channels of the AF interpolator and of the discriminator input */
+
+typedef struct afi_ctx afi_ctx;
+
+/* Strided fp32 view of a logical [N, C, H, W] tensor; strides in elements. */
+typedef struct {
+    const float* ptr;
+    long long sn, sc, sh, sw;
+} afi_view4;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int afi_abi_version(void);
+const char* afi_last_error(void);
+/* Binds to the CURRENT device; fails with AFI_ERR_ARCH unless it is compute capability 10.x. */
+int afi_create(afi_ctx** out);
+void afi_destroy(afi_ctx* ctx);
+
+/* ---- AF interpolator ("Generator")  generator_rdb.py:75-130 ---------------------------------------- */
+typedef struct { /* device pointers, fp32, torch layouts:  Generators.0.* of App. B */
+    int n_rdb;
+    const float* head_w; const float* head_b;   /* Generators.0.0.0  [256,256,3,3] [256]   generator_rdb.py:91-93  */
+    const float* rdb_w[AFI_MAX_RDB][5];          /* ...1.RDBs.r.conv{1..4}.0 / conv5        generator_rdb.py:39-55  */
+    const float* post_w; const float* post_b;   /* Generators.0.2.0                        generator_rdb.py:97-99  */
+    const float* up_w; const float* up_b;       /* Generators.0.3.0  ConvTranspose [256,256,6,6]   :101-105         */
+    const float* out_w; const float* out_b;     /* Generators.0.4.0                        generator_rdb.py:107-108 */
+} afi_g_params;
+
+typedef struct { /* where gradients are written (same layouts); any pointer may be NULL to skip it */
+    int n_rdb;
+    float* head_w; float* head_b;
+    float* rdb_w[AFI_MAX_RDB][5];
+    float* post_w; float* post_b;
+    float* up_w; float* up_b;
+    float* out_w; float* out_b;
+} afi_g_grads;
+
+/* Optional fused lateral for the FPN/PAFPN top-down merge (fpn_sr.py:151-157, pafpn_sr.py:175-181):
+ * y = (conv1x1(lat_x; lat_w, lat_b) + G(x)) * scale, scale = 0.5 for FUSE_TYPE "avg".  lat_x is [N, lat_c, 2h, 2w]. */
+typedef struct {
+    afi_view4 lat_x; int lat_c;
+    const float* lat_w; const float* lat_b; /* [256, lat_c, 1, 1], [256] or NULL */
+    float scale;
+} afi_lateral;
+
+size_t afi_g_packed_bytes(int prec, int n_rdb);                  /* packed forward+dgrad weights          */
+size_t afi_g_gradacc_bytes(int n_rdb);                           /* packed fp32 gradient accumulator      */
+/* lat_c: channels of the fused lateral input (0 = no lateral) */
+size_t afi_g_workspace_bytes(int prec, int n, int h, int w, int n_rdb, int lat_c, int save_for_backward);
+
+/* Re-layout the parameters for the GEMM kernels.  Call again whenever the parameters change. */
+int afi_g_pack(afi_ctx*, int prec, const afi_g_params*, void* packed, void* stream);
+
+/* Generator.forward (generator_rdb.py:123-130): y[:, :, :oh, :ow] of Generators[0](x) + bilinear2x(x), x = [n,256,h,w],
+ * oh <= 2h, ow <= 2w (the top-left crop of _reshape_stage1, stage1_trainer.py:437-443, folded in).
+ * y is contiguous [n,256,oh,ow] fp32.  lateral may be NULL. */
+int afi_g_forward(afi_ctx*, int prec, const afi_g_params*, const void* packed, afi_view4 x, int n, int h, int w,
+                  float* y, int oh, int ow, const afi_lateral* lateral, void* ws, size_t ws_bytes,
+                  int save_for_backward, void* stream);
+
+/* Backward of the call that filled `ws`.  dy = dL/dy, view of [n,256,oh,ow].  Weight/bias gradients are ADDED
+ * into `gradacc` (packed, zero it with afi_zero first); dx (contiguous [n,256,h,w], may be NULL) is overwritten.
+ * lat_dx / lat_gw / lat_gb (may be NULL) receive the lateral's input / weight / bias gradients (overwritten). */
+int afi_g_backward(afi_ctx*, int prec, const afi_g_params*, const void* packed, afi_view4 dy, int n, int h, int w,
+                   int oh, int ow, void* ws, size_t ws_bytes, float* gradacc, float* dx,
+                   const afi_lateral* lateral, float* lat_dx, float* lat_gw, float* lat_gb, void* stream);
+
+/* grads (torch layouts) = [grads +] scale * unpack(gradacc) */
+int afi_g_unpack_grads(afi_ctx*, int prec, const float* gradacc, const afi_g_grads*, float scale, int accumulate, void* stream);
+
+/* ---- feature-patch discriminator  feature_patch_discriminator.py:18-55 -------------------------------- */
+typedef struct { /* Discriminators.0.* of App. B */
+    const float* w[4]; const float* b[4];            /* [512,256,3,3] [1024,512,3,3] [1024,1024,3,3] [1,1024,3,3] */
+    const float* gamma[3]; const float* beta[3];     /* ...norm.weight / norm.bias                                  */
+    float* running_mean[3]; float* running_var[3];   /* updated in training mode (momentum, unbiased var); may be NULL */
+    long long* num_batches_tracked[3];               /* +1 per training forward; may be NULL                         */
+} afi_d_params;
+
+typedef struct {
+    float* w[4]; float* b[4]; float* gamma[3]; float* beta[3];
+} afi_d_grads;
+
+size_t afi_d_packed_bytes(int prec);
+size_t afi_d_gradacc_bytes(void);
+size_t afi_d_workspace_bytes(int prec, int n, int h, int w, int save_for_backward);
+int afi_d_pack(afi_ctx*, int prec, const afi_d_params*, void* packed, void* stream);
+
+/* Discriminators[0](x) (feature_patch_discriminator.py:32-41 as called at stage1_trainer.py:349-353): x = [n,256,h,w],
+ * logits = contiguous [n,1,h,w].  training != 0: BatchNorm uses this call's batch statistics (biased var, eps) and
+ * updates the running buffers; training == 0: running statistics are used. */
+int afi_d_forward(afi_ctx*, int prec, const afi_d_params*, const void* packed, afi_view4 x, int n, int h, int w,
+                  float* logits, int training, float momentum, float eps, void* ws, size_t ws_bytes,
+                  int save_for_backward, void* stream);
+
+/* Backward of the (training-mode) call that filled ws.  dlogits contiguous [n,1,h,w].  Gradients are ADDED into
+ * gradacc (packed); dx (contiguous [n,256,h,w]) may be NULL -- stage 1/2 never need it (inputs are detached). */
+int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const float* dlogits, int n, int h, int w,
+                   void* ws, size_t ws_bytes, float* gradacc, float* dx, void* stream);
+int afi_d_unpack_grads(afi_ctx*, int prec, const float* gradacc, const afi_d_grads*, float scale, int accumulate, void* stream);
+
+/* ---- losses of the stage-1/2 trainers ---------------------------------------------------------------- */
+/* nn.BCEWithLogitsLoss() against a constant target map (stage1_trainer.py:154,355-359,408):
+ * *loss_out = mean(max(x,0) - x t + log1p(exp(-|x|))); if loss_sum: *loss_sum += weight * mean;
+ * if dlogits: dlogits = grad_scale * (sigmoid(x) - t) / count. */
+int afi_bce_with_logits(const float* logits, long long count, float target, float* loss_out, float* loss_sum,
+                        float weight, float* dlogits, float grad_scale, void* stream);
+/* F.l1_loss(a, b) on [n,c,h,w] views (stage1_trainer.py:410): *loss_out = mean|a-b|; if loss_sum: += weight*mean;
+ * if da: da (contiguous [n,c,h,w]) = grad_scale * sign(a-b) / numel. */
+int afi_l1_loss(afi_view4 a, afi_view4 b, int n, int c, int h, int w, float* loss_out, float* loss_sum, float weight,
+                float* da, float grad_scale, void* stream);
+
+/* ---- optimiser step + helpers ------------------------------------------------------------------------- */
+/* torch.optim.SGD as detectron2's build_optimizer configures it [upstream]: d = grad_scale*g + wd*p;
+ * m = first ? d : momentum*m + d;  p -= lr*m.  grad_scale folds the 1/world_size of the gradient all-reduce. */
+int afi_sgd_step(float* p, const float* g, float* m, long long count, float lr, float momentum, float wd,
+                 float grad_scale, int first, void* stream);
+int afi_zero(void* ptr, size_t bytes, void* stream);
+
+/* ---- single-layer entry points (unit tests and kernel benchmarks call the GEMM kernels through these) ---- */
+/* y = [lrelu](conv3x3(x, w) + b) with stride 1, pad 1; x [n,cin,h,w] view, w [cout,cin,3,3], y contiguous [n,cout,h,w]. */
+int afi_conv3x3(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, const float* weight, const float* bias,
+                int cout, int lrelu, float* y, void* ws, size_t ws_bytes, void* stream);
+/* dw [cout,cin,3,3] = wgrad of the same conv for upstream gradient dy [n,cout,h,w] (contiguous), dxo = dgrad (may be NULL) */
+int afi_conv3x3_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
+                         int cout, float* dw, float* dxo, void* ws, size_t ws_bytes, void* stream);
+size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
+
+/* Kernel launches issued by this library since the last call with reset != 0 (bench.py's gpu_launches). */
+long long afi_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFIGAN_B200_H */

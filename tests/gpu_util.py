@@ -1,0 +1,23 @@
+import torch
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cosine(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# tolerances per operand mode for END-TO-END quantities: (features, logits, loss_rel, grads)
+TOL = {
+    "fp32": dict(feat=1e-4, logit=2e-4, loss=1e-5, grad=1e-3, cos=0.999999),
+    "bf16": dict(feat=1e-3, logit=3e-2, loss=5e-3, grad=0.15, cos=0.985),
+    "bf16_simt": dict(feat=1e-3, logit=3e-2, loss=5e-3, grad=0.15, cos=0.985),
+}

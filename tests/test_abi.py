@@ -1,0 +1,68 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/afigan_b200.h
+declares (no compute calls without a GPU), and the Python modules expose the reference's state-dict contract."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "afigan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(afi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from afigan import native
+    names = _header_functions()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/afigan_b200.h but not exported"
+    assert set(native.EXPORTED_SYMBOLS) == set(names), set(native.EXPORTED_SYMBOLS) ^ set(names)
+    assert native.lib().afi_abi_version() == 1
+
+
+def test_size_queries_without_gpu():
+    from afigan import native
+    lib = native.lib()
+    assert lib.afi_g_gradacc_bytes(3) >= 7_834_624 * 4
+    assert lib.afi_d_gradacc_bytes() >= 15_352_321 * 4
+    assert lib.afi_g_packed_bytes(native.PREC_BF16, 3) * 2 == lib.afi_g_packed_bytes(native.PREC_FP32, 3)
+    small = lib.afi_g_workspace_bytes(native.PREC_BF16, 2, 7, 11, 3, 0, 0)
+    big = lib.afi_g_workspace_bytes(native.PREC_BF16, 2, 7, 11, 3, 0, 1)
+    assert 0 < small < big
+    assert lib.afi_d_workspace_bytes(native.PREC_FP32, 2, 13, 21, 1) > lib.afi_d_workspace_bytes(native.PREC_BF16, 2, 13, 21, 1)
+
+
+def test_state_dict_contract_matches_reference_layout():
+    from afigan.modeling import Discriminator, Generator
+    from oracle import afigan_oracle as O
+    torch.manual_seed(0)
+    G, D = Generator(n_residual_dense_blocks=3), Discriminator()
+    g_sd, d_sd = O.init_states(0)
+    assert list(G.state_dict()) == list(g_sd) and list(D.state_dict()) == list(d_sd)
+    for k, v in g_sd.items():
+        assert torch.equal(G.state_dict()[k], v), k      # same seed => same weights as the reference (bit exact)
+    for k, v in d_sd.items():
+        assert torch.equal(D.state_dict()[k], v), k
+    # optimisers are built over Generators[0] / Discriminators[0] only (stage1_trainer.py:109-114)
+    assert sum(p.numel() for p in G.Generators[0].parameters()) == 7_834_624
+    assert sum(p.numel() for p in D.Discriminators[0].parameters()) == 15_352_321
+    assert D.current_step == 0
+    G.load_state_dict(g_sd)
+    D.load_state_dict(d_sd)
+
+
+def test_no_cpu_fallback():
+    from afigan.modeling import Discriminator, Generator
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Generator(n_residual_dense_blocks=3)(torch.zeros(1, 256, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Discriminator().Discriminators[0](torch.zeros(1, 256, 4, 4))
+    with pytest.raises(ValueError):
+        Generator(in_channels=128)

@@ -1,0 +1,67 @@
+"""Per-kernel parity of the implicit-GEMM engines against torch CPU fp32 conv on the SAME bf16-representable inputs:
+every product is then exact in fp32, only the accumulation order differs (SURVEY.md App. F guidance (1)), so all three
+operand modes must agree with the oracle op to ~1e-5 -- a tight, well-posed gate for the tcgen05 descriptors."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import bf16_round, rel
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # n, cin, cout, h, w
+    (1, 256, 256, 8, 16),      # exactly one 128-pixel tile
+    (2, 256, 256, 13, 21),     # ragged (p6-sized level)
+    (1, 256, 32, 7, 11),       # dense-block growth conv (N = 32)
+    (2, 288, 32, 9, 10),       # K not a multiple of 64
+    (1, 384, 256, 12, 20),     # dense-block fusion conv
+    (1, 32, 352, 6, 9),        # dense-block dgrad shape (K = 32, N split 2 x 176)
+    (1, 256, 512, 25, 42),     # discriminator layer 1
+    (1, 512, 1024, 10, 12),    # discriminator layer 2 (4 N tiles)
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_forward(shape, precision):
+    from afigan.functional import conv3x3
+    n, cin, cout, h, w = shape
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.2)
+    y = conv3x3(x.cuda(), wt.cuda(), b.cuda(), True, precision).cpu()
+    tol = 2e-5 if precision == "fp32" else 6e-3   # bf16 modes round the OUTPUT to bf16 (2^-9 relative)
+    assert rel(y, ref) < tol, f"{precision} {shape}: rel err {rel(y, ref):.3e}"
+    if precision != "fp32":
+        assert rel(y, bf16_round(ref)) < 2e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_simt", "bf16"])
+@pytest.mark.parametrize("shape", SHAPES[:6], ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_backward(shape, precision):
+    from afigan.functional import conv3x3_backward
+    n, cin, cout, h, w = shape
+    g = torch.Generator().manual_seed(1 + hash(shape) % 1000)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * 0.05).requires_grad_(True)
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    F.conv2d(x, wt, None, padding=1).backward(dy)
+    dw, dx = conv3x3_backward(x.detach().cuda(), dy.cuda(), wt.detach().cuda(), precision)
+    assert rel(dw, wt.grad) < 3e-5, f"wgrad {precision} {shape}: {rel(dw, wt.grad):.3e}"
+    assert rel(dx, x.grad) < 3e-5, f"dgrad {precision} {shape}: {rel(dx, x.grad):.3e}"
+
+
+def test_strided_and_channels_last_inputs():
+    from afigan.functional import conv3x3
+    g = torch.Generator().manual_seed(3)
+    big = bf16_round(torch.randn(2, 256, 14, 22, generator=g))
+    wt = bf16_round(torch.randn(256, 256, 3, 3, generator=g) * 0.05)
+    crop = big[:, :, :13, :21]                     # the _reshape_stage1 top-left crop: a strided view, no copy
+    ref = F.conv2d(crop, wt, None, padding=1)
+    y = conv3x3(big.cuda()[:, :, :13, :21], wt.cuda(), None, False, "fp32").cpu()
+    assert rel(y, ref) < 2e-5
+    y2 = conv3x3(crop.contiguous().cuda().to(memory_format=torch.channels_last), wt.cuda(), None, False, "fp32").cpu()
+    assert rel(y2, ref) < 2e-5

@@ -1,0 +1,98 @@
+"""One full stage-1 step (fused fast path, afigan.engine.Stage1Step) against the oracle and the committed golden
+fixture (made from the unmodified reference): losses, every G/D parameter gradient, BN running buffers, SGD update."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import TOL, cosine, rel
+from oracle import afigan_oracle as O
+
+pytestmark = pytest.mark.gpu
+FX = np.load(os.path.join(os.path.dirname(__file__), "golden", "stage1_small.npz"))
+
+
+def _build(precision):
+    from afigan.engine import Stage1Step
+    from afigan.modeling import Discriminator, Generator
+    torch.manual_seed(0)
+    G = Generator(n_residual_dense_blocks=3, precision=precision).cuda()
+    D = Discriminator(precision=precision).cuda()
+    D.Discriminators[0].train()
+    return G, D, Stage1Step(G, D, lr=1e-3, precision=precision)
+
+
+def _sample(t, n=257):
+    f = t.detach().reshape(-1).cpu()
+    idx = torch.linspace(0, f.numel() - 1, min(n, f.numel())).long()
+    return f[idx].numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stage1_step_vs_oracle_and_golden(precision):
+    tol = TOL[precision]
+    G, D, step = _build(precision)
+    lr_shapes = tuple(map(tuple, FX["s1_lr_shapes"]))
+    hr_shapes = tuple(map(tuple, FX["s1_hr_shapes"]))
+    lr_f, hr_f = O.synthetic_features(2, 0, lr_shapes, hr_shapes, seed=4321)
+    step.run_step([t.cuda() for t in lr_f], [t.cuda() for t in hr_f], apply_updates=False)
+    m = step.metrics(3)
+    d_loss = np.array([m[f"d_loss_p{l}"] for l in (2, 3, 4)])
+    g_loss = np.array([m[f"g_loss_p{l}"] for l in (2, 3, 4)])
+    # golden fixture from the unmodified reference
+    np.testing.assert_allclose(d_loss, FX["s1_d_loss"], rtol=tol["loss"])
+    np.testing.assert_allclose(g_loss, FX["s1_g_loss"], rtol=tol["loss"], atol=1e-4)
+    if precision == "fp32":
+        assert abs(d_loss.sum() - FX["s1_d_loss"].sum()) < 1e-4 * max(1.0, FX["s1_d_loss"].sum() / 10)
+    for (name, p) in D.Discriminators[0].named_parameters():
+        ref_norm = float(FX["s1_dgrad_norm/" + name])
+        if name.endswith("0.bias") and not name.startswith("3."):
+            assert float(p.grad.norm()) < 1e-3
+            continue
+        assert abs(float(p.grad.norm()) - ref_norm) <= tol["grad"] * ref_norm, name
+        if precision == "fp32":
+            np.testing.assert_allclose(_sample(p.grad), FX["s1_dgrad_sample/" + name], rtol=5e-2, atol=2e-3 * ref_norm / np.sqrt(p.numel()))
+    for (name, p) in G.Generators[0].named_parameters():
+        ref_norm = float(FX["s1_ggrad_norm/" + name])
+        assert abs(float(p.grad.norm()) - ref_norm) <= tol["grad"] * ref_norm, name
+    # oracle on the same inputs: every gradient, norm-wise
+    g_sd, d_sd = O.init_states(0)
+    res = O.stage1_step(g_sd, d_sd, lr_f, hr_f, lr=None)
+    worst_d = worst_g = 0.0
+    for k, p in zip(O.discriminator_param_keys(), step.d_params):
+        if k.endswith("0.bias") and ".3." not in k:
+            continue
+        r = rel(p.grad, res["d_grads"][k])
+        worst_d = max(worst_d, r)
+        assert r < tol["grad"] and cosine(p.grad, res["d_grads"][k]) > tol["cos"], f"{k}: {r:.3e}"
+    for k, p in zip(O.generator_param_keys(), step.g_params):
+        r = rel(p.grad, res["g_grads"][k])
+        worst_g = max(worst_g, r)
+        assert r < tol["grad"] and cosine(p.grad, res["g_grads"][k]) > tol["cos"], f"{k}: {r:.3e}"
+    print(f"[{precision}] stage-1 grads: worst rel err D {worst_d:.3e}  G {worst_g:.3e}; d_loss {d_loss.sum():.6f} vs {FX['s1_d_loss'].sum():.6f}")
+    sd = D.state_dict()
+    for n in range(3):
+        for b in ("running_mean", "running_var"):
+            k = f"Discriminators.0.{n}.0.norm.{b}"
+            assert rel(sd[k], torch.from_numpy(FX["s1_bn/" + k])) < (1e-4 if precision == "fp32" else 3e-2), k
+        assert int(sd[f"Discriminators.0.{n}.0.norm.num_batches_tracked"]) == 12   # 4 D calls x 3 levels
+
+
+def test_stage1_two_steps_with_sgd_fp32():
+    """Two consecutive steps WITH the optimiser updates (momentum, weight decay) against the oracle."""
+    G, D, step = _build("fp32")
+    lr_shapes, hr_shapes = ((7, 11), (4, 6)), ((13, 21), (7, 11))
+    g_sd, d_sd = O.init_states(0)
+    g_mom, d_mom = {}, {}
+    for it in range(2):
+        lr_f, hr_f = O.synthetic_features(2, it, lr_shapes, hr_shapes, seed=77)
+        step.run_step([t.cuda() for t in lr_f], [t.cuda() for t in hr_f])
+        res = O.stage1_step(g_sd, d_sd, lr_f, hr_f, lr=1e-3, g_mom=g_mom, d_mom=d_mom)
+        m = step.metrics(2)
+        assert abs(m["d_loss_p2"] - res["d_loss"]["d_loss_p2"]) < 1e-4 * abs(res["d_loss"]["d_loss_p2"])
+        assert abs(m["g_loss_p3"] - res["g_loss"]["g_loss_p3"]) < 1e-4
+    for k, p in zip(O.generator_param_keys(), step.g_params):
+        assert rel(p, g_sd[k]) < 1e-5, k
+    for k, p in zip(O.discriminator_param_keys(), step.d_params):
+        assert rel(p, d_sd[k]) < 1e-5, k
