@@ -76,7 +76,7 @@ class AFInterpolatorFn(torch.autograd.Function):
     """Generator.forward (reference generator_rdb.py:123-130) with the stage-1 top-left crop folded in."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, holder, prec: int, out_hw: Optional[Tuple[int, int]], *params: torch.Tensor):
+    def forward(ctx, x: torch.Tensor, holder, prec: int, out_hw: Optional[Tuple[int, int]], grad_enabled: bool, *params: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
         if x.dim() != 4 or x.size(1) != CH:
@@ -88,7 +88,7 @@ class AFInterpolatorFn(torch.autograd.Function):
         dev = x.device
         ps = g_param_struct(params, n_rdb)
         packed = holder.packed.get("g", prec, params, ps, n_rdb)
-        need_bwd = any(ctx.needs_input_grad[4:]) or ctx.needs_input_grad[0]
+        need_bwd = grad_enabled and (any(ctx.needs_input_grad[5:]) or ctx.needs_input_grad[0])
         lib, actx = N.lib(), N.context(dev)
         ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, n_rdb, 0, int(need_bwd)), dev)
         y = torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev)
@@ -113,18 +113,19 @@ class AFInterpolatorFn(torch.autograd.Function):
         ps = g_param_struct(params, ctx.n_rdb)
         N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), N.view4(dy), n, h, w, oh, ow, ctx.ws.data_ptr(),
                                    ctx.ws.numel(), acc.data_ptr(), None, None, None, None, None, N.stream_ptr()))
-        grads = [torch.empty_like(p) if ctx.needs_input_grad[4 + i] else None for i, p in enumerate(params)]
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[5 + i] else None for i, p in enumerate(params)]
         gs = g_param_struct(grads, ctx.n_rdb)
         N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
         ctx.ws = None
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class PatchDiscriminatorFn(torch.autograd.Function):
     """Discriminators[0](x) (reference feature_patch_discriminator.py:32-41)."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, holder, prec: int, training: bool, momentum: float, eps: float, buffers, *params: torch.Tensor):
+    def forward(ctx, x: torch.Tensor, holder, prec: int, training: bool, momentum: float, eps: float, buffers, grad_enabled: bool,
+                *params: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("feature-patch discriminator: input must live on an sm_100a CUDA device (no CPU fallback)")
         if x.dim() != 4 or x.size(1) != CH:
@@ -134,7 +135,7 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         dev = x.device
         ps = d_param_struct(params, buffers)
         packed = holder.packed.get("d", prec, params, ps)
-        need_bwd = any(ctx.needs_input_grad[7:]) or ctx.needs_input_grad[0]
+        need_bwd = grad_enabled and (any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[0])
         if need_bwd and not training:
             raise NotImplementedError("discriminator backward in eval mode is not implemented")
         lib, actx = N.lib(), N.context(dev)
@@ -161,11 +162,11 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         ps = d_param_struct(params, ctx.buffers)
         N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), dl.data_ptr(), n, h, w, ctx.ws.data_ptr(),
                                    ctx.ws.numel(), acc.data_ptr(), None, N.stream_ptr()))
-        grads = [torch.empty_like(p) if ctx.needs_input_grad[7 + i] else None for i, p in enumerate(params)]
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[8 + i] else None for i, p in enumerate(params)]
         gs = d_grad_struct(grads)
         N.check(lib.afi_d_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
         ctx.ws = None
-        return (None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, *grads)
 
 
 def bce_with_logits(logits: torch.Tensor, target: float) -> torch.Tensor:

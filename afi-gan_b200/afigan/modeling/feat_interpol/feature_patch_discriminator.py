@@ -59,7 +59,8 @@ class PatchDiscriminatorStack(nn.Sequential):
         prec = native.PRECISIONS[self.precision or native.default_precision()]
         bn = self[0][0].norm
         momentum = 0.1 if bn.momentum is None else bn.momentum
-        return PatchDiscriminatorFn.apply(feature, self._native, prec, bn.training, momentum, bn.eps, self._buffers_list(), *self._params())
+        return PatchDiscriminatorFn.apply(feature, self._native, prec, bn.training, momentum, bn.eps, self._buffers_list(),
+                                          torch.is_grad_enabled(), *self._params())
 
 
 class Discriminator(nn.Module):

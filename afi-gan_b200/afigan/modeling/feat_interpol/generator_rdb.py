@@ -94,4 +94,4 @@ class Generator(nn.Module):
     def forward(self, features: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """features [N,256,H,W] -> [N,256,2H,2W] (or its top-left out_hw crop: the _reshape_stage1 of the trainers)."""
         prec = native.PRECISIONS[self.precision or native.default_precision()]
-        return AFInterpolatorFn.apply(features, self._native, prec, out_hw, *self._params())
+        return AFInterpolatorFn.apply(features, self._native, prec, out_hw, torch.is_grad_enabled(), *self._params())

@@ -90,6 +90,10 @@ _SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "afi_conv3x3_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "afi_launch_count": (C.c_longlong, [C.c_int]),
+    "afi_profile_begin": (C.c_int, [C.c_int]),
+    "afi_profile_end": (C.c_int, [C.POINTER(C.c_int)]),
+    "afi_profile_get": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -3,6 +3,7 @@
 // SURVEY.md App. A, reference generator_rdb.py:15-130 and feature_patch_discriminator.py:18-55.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -15,6 +16,22 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- per-launch profiling -------------------------------------------------------------------------------
+struct ProfRec { int kind, cin, cout; long long pixels; double flops; cudaEvent_t e0, e1; float ms; };
+bool g_prof_on = false;
+static ProfRec* g_prof = nullptr;
+static int g_prof_n = 0, g_prof_cap = 0;
+void prof_begin(int kind, double flops, int cin, int cout, long long pixels, cudaStream_t st) {
+    if (g_prof_n >= g_prof_cap) { g_prof_on = false; return; }
+    ProfRec& r = g_prof[g_prof_n];
+    r.kind = kind; r.flops = flops; r.cin = cin; r.cout = cout; r.pixels = pixels; r.ms = 0.f;
+    if (!r.e0) { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); }
+    cudaEventRecord(r.e0, st);
+}
+void prof_end(cudaStream_t st) {
+    if (g_prof_n < g_prof_cap) { cudaEventRecord(g_prof[g_prof_n].e1, st); g_prof_n++; }
 }
 
 void conv_args_init(ConvArgs& a) {
@@ -150,6 +167,31 @@ extern "C" {
 int afi_abi_version(void) { return AFI_ABI_VERSION; }
 const char* afi_last_error(void) { return g_err; }
 long long afi_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+
+int afi_profile_begin(int max_launches) {
+    AFI_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), "afi_profile_begin: bad capacity");
+    if (max_launches > g_prof_cap) {
+        ProfRec* n = (ProfRec*)calloc(max_launches, sizeof(ProfRec));
+        if (g_prof) { memcpy(n, g_prof, sizeof(ProfRec) * g_prof_cap); free(g_prof); }
+        g_prof = n; g_prof_cap = max_launches;
+    }
+    g_prof_n = 0; g_prof_on = true;
+    return AFI_OK;
+}
+int afi_profile_end(int* n_launches) {
+    g_prof_on = false;
+    AFI_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < g_prof_n; i++) AFI_CUDA(cudaEventElapsedTime(&g_prof[i].ms, g_prof[i].e0, g_prof[i].e1));
+    if (n_launches) *n_launches = g_prof_n;
+    return AFI_OK;
+}
+int afi_profile_get(int i, int* kind, double* flops, float* ms, int* cin, int* cout, long long* pixels) {
+    AFI_REQUIRE(i >= 0 && i < g_prof_n, "afi_profile_get: index out of range");
+    const ProfRec& r = g_prof[i];
+    if (kind) *kind = r.kind; if (flops) *flops = r.flops; if (ms) *ms = r.ms;
+    if (cin) *cin = r.cin; if (cout) *cout = r.cout; if (pixels) *pixels = r.pixels;
+    return AFI_OK;
+}
 
 int afi_create(afi_ctx** out) {
     AFI_REQUIRE(out != nullptr, "afi_create: null output");
@@ -529,7 +571,8 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         AFI_TRY(bn_bwd_apply(DYi, Z, dt, W.mean[i], W.rstd[i], p->gamma[i], W.sums, W.sums + 1024, gradacc + GL.gamma[i], gradacc + GL.beta[i],
                              n, h, w, co, st));
         AFI_TRY(wgrad_std(ctx, prec, pview(W.A[i], h, w, ci), ci, DYi, co, n, h, w, gradacc + GL.w[i], st));
-        AFI_TRY(col_sum_f32(DYi, dt, n, h, w, co, gradacc + GL.b[i], st));
+        // bias gradient: this bias feeds a train-mode BatchNorm, so dL/db = sum_p dz = 0 identically (the reference gets
+        // ~1e-9 rounding noise there); the accumulator slot stays at its zero-initialised value.
         if (i > 0) {   // dA_{i} * lrelu'(a_i) -> DY[i-1]
             ConvArgs a;
             conv_args_init(a);
@@ -561,9 +604,10 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
 // =====================================================================================================
 // single-layer entry points (unit tests / kernel benchmarks)
 // =====================================================================================================
+static inline int pad64(int c) { return c <= 64 ? c : (c + 63) / 64 * 64; }
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) {
     size_t es = dt_size(prec_dt(prec)), P = (size_t)n * h * w;
-    return align_up(P * cin * es) + 2 * align_up(P * cout * es) + 2 * align_up((size_t)9 * cin * cout * es) +
+    return align_up(P * pad64(cin) * es) + 2 * align_up(P * pad64(cout) * es) + 2 * align_up((size_t)9 * cin * cout * es) +
            align_up((size_t)9 * cin * cout * 4) + align_up(P * cin * 4) + 4096;
 }
 int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
@@ -596,21 +640,25 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3_backward: workspace too small"); return AFI_ERR_WORKSPACE; }
     int dt = prec_dt(prec); size_t es = dt_size(dt), P = (size_t)n * h * w;
     Carver cv(ws);
-    void* X = cv.take(P * cin * es); void* DYb = cv.take(P * cout * es); cv.take(P * cout * es);
+    // pixel strides padded to whole 64-channel groups (the tensor-core wgrad reads operands through grouped TMA views)
+    const int xs = pad64(cin), ys = pad64(cout);
+    void* X = cv.take(P * xs * es); void* DYb = cv.take(P * ys * es); cv.take(P * ys * es);
     void* Wp = cv.take((size_t)9 * cin * cout * es); cv.take((size_t)9 * cin * cout * es);
     float* acc = (float*)cv.take((size_t)9 * cin * cout * 4);
     void* DX = cv.take(P * cin * 4);
-    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
-    AFI_TRY(to_nhwc(prec, dy, n, cout, h, w, pview(DYb, h, w, cout), st));
+    if (xs != cin) AFI_CUDA(cudaMemsetAsync(X, 0, P * xs * es, st));
+    if (ys != cout) AFI_CUDA(cudaMemsetAsync(DYb, 0, P * ys * es, st));
+    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, xs), st));
+    AFI_TRY(to_nhwc(prec, dy, n, cout, h, w, pview(DYb, h, w, ys), st));
     AFI_CUDA(cudaMemsetAsync(acc, 0, (size_t)9 * cin * cout * 4, st));
-    AFI_TRY(wgrad_std(ctx, prec, pview(X, h, w, cin), cin, pview(DYb, h, w, cout), cout, n, h, w, acc, st));
+    AFI_TRY(wgrad_std(ctx, prec, pview(X, h, w, xs), cin, pview(DYb, h, w, ys), cout, n, h, w, acc, st));
     AFI_TRY(unpack_wgrad(acc, cout, cin, prec_tc(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
     if (dxo) {
         AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, dt, st));
         ConvArgs a;
         conv_args_init(a);
         a.N = n; a.H = h; a.W = w; a.cin = cout; a.cout = cin; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-        a.in[0] = pview(DYb, h, w, cout); a.w = Wp; a.out = pview(DX, h, w, cin); a.out_dt = DT_F32;
+        a.in[0] = pview(DYb, h, w, ys); a.w = Wp; a.out = pview(DX, h, w, cin); a.out_dt = DT_F32;
         AFI_TRY(run_conv(ctx, prec, a, st));
         afi_view4 none; memset(&none, 0, sizeof(none));
         AFI_TRY(nhwc_to_nchw<float>(pview(DX, h, w, cin), pview_null(), none, 0, 0, 1.f, n, cin, h, w, dxo, st));

@@ -95,6 +95,19 @@ struct WgradArgs {
     float* dw;
 };
 
+// optional per-launch CUDA-event profiling of the GEMM kernels (afi_profile_begin/_end; bench.py's roofline leg)
+enum ProfKind { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_CONV_SIMT = 2, PROF_WGRAD_SIMT = 3 };
+extern bool g_prof_on;
+void prof_begin(int kind, double flops, int cin, int cout, long long pixels, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(int kind, double flops, int cin, int cout, long long pixels, cudaStream_t s) : st(s), on(g_prof_on) {
+        if (on) prof_begin(kind, flops, cin, cout, pixels, st);
+    }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+
 void conv_args_init(ConvArgs& a);
 void set_std_taps(Tap* taps, int view, int slab0);
 

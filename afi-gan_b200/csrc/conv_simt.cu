@@ -212,6 +212,7 @@ int conv_simt(const ConvArgs& a, cudaStream_t st) {
     AFI_REQUIRE(a.ntaps >= 1 && a.ntaps <= AFI_MAX_TAPS, "conv_simt: bad tap count");
     long long M = (long long)a.N * a.H * a.W;
     if (M == 0) return AFI_OK;
+    ProfScope prof(PROF_CONV_SIMT, 2.0 * M * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, M, st);
     if (a.cout % 128 == 0 || a.cout > 128) {
         dim3 grid((unsigned)((M + BM - 1) / BM), (a.cout + 127) / 128);
         k_conv_simt<T, 128><<<grid, 256, 0, st>>>(a);
@@ -328,6 +329,7 @@ int wgrad_simt(const WgradArgs& a, cudaStream_t st) {
     chunk = (chunk + BK - 1) / BK * BK;
     ksplit = (P + chunk - 1) / chunk;
     dim3 grid((a.cin + BM - 1) / BM, (a.cout + bn - 1) / bn, (unsigned)(a.ntaps * ksplit));
+    ProfScope prof(PROF_WGRAD_SIMT, 2.0 * P * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, P, st);
     if (bn == 128) k_wgrad_simt<T, 128><<<grid, 256, 0, st>>>(a, (int)ksplit, (int)chunk);
     else k_wgrad_simt<T, 32><<<grid, 256, 0, st>>>(a, (int)ksplit, (int)chunk);
     AFI_LAUNCH_CHECK();

@@ -83,6 +83,11 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -348,10 +353,9 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     uint32_t fb = smem_u32(&s.full[stage]);
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
                     mbar_expect_tx(fb, tx_bytes);
-                    tma_load_4d(&maps.a[0], fb, sa, mt * 128, x0, y0, img);
-                    tma_load_4d(&maps.a[0], fb, sa + 8192, mt * 128 + 64, x0, y0, img);
-                    for (int j = 0; j < nb; j++)
-                        tma_load_4d(&maps.b, fb, sa + A_BYTES + j * 8192, nt * tl.bn + j * 64, x0 + t.dx, y0 + t.dy, img);
+                    // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
+                    tma_load_5d(&maps.a[0], fb, sa, 0, x0, y0, mt * 2, img);
+                    tma_load_5d(&maps.b, fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -438,6 +442,16 @@ static int encode_view(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int 
     return encode_map(ctx, m, v.ptr, 4, dims, strides, box);
 }
 
+// channel-grouped 5-D view for the MN-major operands of the weight-gradient GEMM
+static int encode_view_grouped(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int W, int H, int N, int TW, int TH, int gbox) {
+    int G = (C + 63) / 64;
+    AFI_REQUIRE(C <= 64 || (long long)G * 64 <= v.sx, "wgrad_tc: %d channels need %d groups of 64 but the pixel stride is %lld", C, G, v.sx);
+    cuuint64_t dims[5] = {(cuuint64_t)(C < 64 ? C : 64), (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)G, (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, 128, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)gbox, 1};
+    return encode_map(ctx, m, v.ptr, 5, dims, strides, box);
+}
+
 static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
     // spatial patch of `pixels` (= GEMM rows per tile) minimising padded area; TW multiple of 8 keeps swizzle atoms whole
     long long best = -1; int bh = pixels / 16, bw = 16;
@@ -496,6 +510,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
     }
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    ProfScope prof(PROF_CONV_TC, 2.0 * a.N * a.H * a.W * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, (long long)a.N * a.H * a.W, st);
     k_conv_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -522,10 +537,11 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
     Maps maps;
-    AFI_TRY(encode_view(ctx, &maps.a[0], a.dy, a.cout, a.W, a.H, a.N, tl.TW, tl.TH));
+    AFI_TRY(encode_view_grouped(ctx, &maps.a[0], a.dy, a.cout, a.W, a.H, a.N, tl.TW, tl.TH, 2));
     for (int i = 1; i < 4; i++) maps.a[i] = maps.a[0];
-    AFI_TRY(encode_view(ctx, &maps.b, a.x, a.cin, a.W, a.H, a.N, tl.TW, tl.TH));
+    AFI_TRY(encode_view_grouped(ctx, &maps.b, a.x, a.cin, a.W, a.H, a.N, tl.TW, tl.TH, tl.bn / 64));
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    ProfScope prof(PROF_WGRAD_TC, 2.0 * a.N * a.H * a.W * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, (long long)a.N * a.H * a.W, st);
     k_wgrad_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;

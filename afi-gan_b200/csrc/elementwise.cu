@@ -214,11 +214,169 @@ __global__ void k_col_reduce(PView x, PView z, int dt, const float* __restrict__
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Dense fast paths.  Every BatchNorm / column-reduction operand of the discriminator is a dense [P][C] buffer, so these
+// kernels drop the per-element (n,y,x) decode: a thread owns 8 consecutive channels (one 16-byte bf16 / two 16-byte fp32
+// accesses), keeps the per-channel parameters in registers, and walks rows with an unrolled loop so that several
+// independent 16-byte loads are in flight per thread (HBM-bound kernels: memory-level parallelism is what matters).
+// ---------------------------------------------------------------------------------------------------
+template <typename T> struct V8;
+template <> struct V8<float> {
+    __device__ static __forceinline__ void ld(const float* p, float* v) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ static __forceinline__ void st(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct V8<bf16> {
+    __device__ static __forceinline__ void ld(const bf16* p, float* v) {
+        uint4 u = *reinterpret_cast<const uint4*>(p);
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+    __device__ static __forceinline__ void st(bf16* p, const float* v) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+static inline bool is_dense(const PView& v, int h, int w, int c) {
+    return v.sx == c && v.sy == (long long)w * c && v.sn == (long long)h * w * c;
+}
+static inline bool dense_ok(int c) { return c % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0; }
+constexpr int DENSE_ROWS = 64;     // rows per block of the elementwise passes
+constexpr int REDUCE_ROWS = 256;   // rows per block of the column reductions
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_apply_dense(const T* __restrict__ z, T* __restrict__ a, long long P, int C,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
+    const int tpr = C >> 3, rpb = 256 / tpr;
+    const int c0 = (threadIdx.x % tpr) * 8;
+    float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k]; }
+    long long r0 = (long long)blockIdx.x * DENSE_ROWS, r1 = r0 + DENSE_ROWS;
+    if (r1 > P) r1 = P;
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
+        float v[8];
+        V8<T>::ld(z + r * C + c0, v);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float t = (v[k] - mu[k]) * rs[k] * ga[k] + be[k];    // ATen order: (x - mean) * invstd * weight + bias
+            v[k] = t > 0.f ? t : t * slope;
+        }
+        V8<T>::st(a + r * C + c0, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_dense(T* __restrict__ dy, const T* __restrict__ z, long long P, int C,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const double* __restrict__ s_dy,
+                                                            const double* __restrict__ s_dyx, float* dgamma_acc, float* dbeta_acc, float inv_m) {
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)s_dyx[c]);
+            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)s_dy[c]);
+        }
+    }
+    const int tpr = C >> 3, rpb = 256 / tpr;
+    const int c0 = (threadIdx.x % tpr) * 8;
+    float mu[8], rs[8], gr[8], m1[8], m2[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; gr[k] = gamma[c0 + k] * rs[k];
+        m1[k] = (float)s_dy[c0 + k] * inv_m; m2[k] = (float)s_dyx[c0 + k] * inv_m;
+    }
+    long long r0 = (long long)blockIdx.x * DENSE_ROWS, r1 = r0 + DENSE_ROWS;
+    if (r1 > P) r1 = P;
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
+        float g[8], zz[8];
+        V8<T>::ld(dy + r * C + c0, g);
+        V8<T>::ld(z + r * C + c0, zz);
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[k] = gr[k] * (g[k] - m1[k] - (zz[k] - mu[k]) * rs[k] * m2[k]);
+        V8<T>::st(dy + r * C + c0, g);
+    }
+}
+
+// MODE 0: sum x, sum x^2 (double out).  MODE 1: sum dy, sum dy*xhat (double out).  MODE 2: sum x (float out).
+template <int MODE, typename T>
+__global__ void __launch_bounds__(256) k_col_reduce_dense(const T* __restrict__ x, const T* __restrict__ z, long long P, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          double* o0, double* o1, float* of) {
+    __shared__ float sm0[256 * 8];
+    __shared__ float sm1[MODE == 2 ? 8 : 256 * 8];
+    const int tpr = C >> 3, rpb = 256 / tpr;
+    const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
+    const int c0 = cq * 8;
+    float a0[8], a1[8], mu[8], rs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { a0[k] = 0.f; a1[k] = 0.f; mu[k] = 0.f; rs[k] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; }
+    }
+    long long r0 = (long long)blockIdx.x * REDUCE_ROWS, r1 = r0 + REDUCE_ROWS;
+    if (r1 > P) r1 = P;
+#pragma unroll 4
+    for (long long r = r0 + lane_r; r < r1; r += rpb) {
+        float v[8];
+        V8<T>::ld(x + r * C + c0, v);
+        if (MODE == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { a0[k] += v[k]; a1[k] = fmaf(v[k], v[k], a1[k]); }
+        } else if (MODE == 1) {
+            float zz[8];
+            V8<T>::ld(z + r * C + c0, zz);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { a0[k] += v[k]; a1[k] = fmaf(v[k], (zz[k] - mu[k]) * rs[k], a1[k]); }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a0[k] += v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        sm0[(lane_r * 8 + k) * tpr + cq] = a0[k];
+        if (MODE != 2) sm1[(lane_r * 8 + k) * tpr + cq] = a1[k];
+    }
+    __syncthreads();
+    // thread t < C finalises channel t: sum over the rpb row lanes
+    for (int c = threadIdx.x; c < C; c += 256) {
+        int q = c >> 3, k = c & 7;
+        float t0 = 0.f, t1 = 0.f;
+        for (int l = 0; l < rpb; l++) {
+            t0 += sm0[(l * 8 + k) * tpr + q];
+            if (MODE != 2) t1 += sm1[(l * 8 + k) * tpr + q];
+        }
+        if (MODE == 2) atomicAdd(of + c, t0);
+        else { atomicAdd(o0 + c, (double)t0); if (o1) atomicAdd(o1 + c, (double)t1); }
+    }
+}
+
 static int col_reduce_launch(int mode, PView x, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
                              double* o0, double* o1, float* of, cudaStream_t st) {
     AFI_REQUIRE(c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0, "col_reduce: unsupported channel count %d", c);
     long long npix = (long long)n * h * w;
     if (npix == 0) return AFI_OK;
+    if (is_dense(x, h, w, c) && dense_ok(c) && (mode != 1 || is_dense(z, h, w, c))) {
+        int grid = cdiv(npix, REDUCE_ROWS);
+#define AFI_CR(M, T) k_col_reduce_dense<M, T><<<grid, 256, 0, st>>>((const T*)x.ptr, (const T*)z.ptr, npix, c, mean, rstd, o0, o1, of)
+        if (dt == DT_F32) { if (mode == 0) AFI_CR(0, float); else if (mode == 1) AFI_CR(1, float); else AFI_CR(2, float); }
+        else { if (mode == 0) AFI_CR(0, bf16); else if (mode == 1) AFI_CR(1, bf16); else AFI_CR(2, bf16); }
+#undef AFI_CR
+        AFI_LAUNCH_CHECK();
+        return AFI_OK;
+    }
     int chunk = 128;   // pixels per block: short fp32 partial sums (<= 128 terms per lane) keep BN statistics at ~1e-7
     int grid = cdiv(npix, chunk);
     if (mode == 0) k_col_reduce<0><<<grid, 256, 0, st>>>(x, z, dt, mean, rstd, h, w, c / 4, npix, chunk, o0, o1, of);
@@ -291,6 +449,13 @@ int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rst
                    float slope, int n, int h, int w, int c, cudaStream_t st) {
     long long total = (long long)n * h * w * (c / 4);
     if (total == 0) return AFI_OK;
+    if (is_dense(z, h, w, c) && is_dense(a, h, w, c) && dense_ok(c)) {
+        long long P = (long long)n * h * w;
+        if (dt == DT_F32) k_bn_apply_dense<float><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((const float*)z.ptr, (float*)a.ptr, P, c, mean, rstd, gamma, beta, slope);
+        else k_bn_apply_dense<bf16><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((const bf16*)z.ptr, (bf16*)a.ptr, P, c, mean, rstd, gamma, beta, slope);
+        AFI_LAUNCH_CHECK();
+        return AFI_OK;
+    }
     k_bn_apply_lrelu<<<cdiv(total, 256), 256, 0, st>>>(z, a, dt, mean, rstd, gamma, beta, slope, h, w, c / 4, total);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -325,6 +490,14 @@ int bn_bwd_apply(PView dy, PView z, int dt, const float* mean, const float* rstd
                  const double* s_dyx, float* dgamma_acc, float* dbeta_acc, int n, int h, int w, int c, cudaStream_t st) {
     long long total = (long long)n * h * w * (c / 4);
     if (total == 0) return AFI_OK;
+    if (is_dense(dy, h, w, c) && is_dense(z, h, w, c) && dense_ok(c)) {
+        long long P = (long long)n * h * w;
+        float inv_m = 1.f / (float)P;
+        if (dt == DT_F32) k_bn_bwd_apply_dense<float><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((float*)dy.ptr, (const float*)z.ptr, P, c, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, inv_m);
+        else k_bn_bwd_apply_dense<bf16><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((bf16*)dy.ptr, (const bf16*)z.ptr, P, c, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, inv_m);
+        AFI_LAUNCH_CHECK();
+        return AFI_OK;
+    }
     k_bn_bwd_apply<<<cdiv(total, 256), 256, 0, st>>>(dy, z, dt, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, h, w, c / 4,
                                                    total, 1.f / (float)((long long)n * h * w));
     AFI_LAUNCH_CHECK();

@@ -165,6 +165,13 @@ int afi_conv3x3_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, i
                          int cout, float* dw, float* dxo, void* ws, size_t ws_bytes, void* stream);
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
+/* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
+ * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05,
+ * 1 wgrad tcgen05, 2 conv CUDA-core, 3 wgrad CUDA-core), algorithmic FLOPs (2*pixels*taps*cin*cout), milliseconds. */
+int afi_profile_begin(int max_launches);
+int afi_profile_end(int* n_launches);
+int afi_profile_get(int i, int* kind, double* flops, float* ms, int* cin, int* cout, long long* pixels);
+
 /* Kernel launches issued by this library since the last call with reset != 0 (bench.py's gpu_launches). */
 long long afi_launch_count(int reset);
 
