@@ -74,8 +74,8 @@ class Stage1Step:
             off += p.numel()
         return flat, views
 
-    def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool) -> torch.Tensor:
-        key = (kind, n, h, w, save)
+    def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool, tag="") -> torch.Tensor:
+        key = (kind, n, h, w, save, tag)
         if key not in self._ws:
             if kind == "g":
                 nb = self.lib.afi_g_workspace_bytes(self.prec, n, h, w, self.n_rdb, 0, int(save))
@@ -104,31 +104,76 @@ class Stage1Step:
         ps = self._ds()
         N.check(self.lib.afi_d_pack(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), N.stream_ptr()))
 
-    def _g_forward(self, lr_f: torch.Tensor, oh: int, ow: int, save: bool, tag: str) -> torch.Tensor:
-        n, _, h, w = lr_f.shape
-        ws = self._ws_for("g", n, h, w, save)
-        y = self._buf("tr" + tag, (n, CH, oh, ow))
-        ps = self._gs()
-        N.check(self.lib.afi_g_forward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.view4(lr_f), n, h, w, y.data_ptr(),
-                                       oh, ow, None, ws.data_ptr(), ws.numel(), int(save), N.stream_ptr()))
-        return y
+    # ---- grouped calls: ONE kernel launch per layer covers all pyramid levels (and real + fake for the discriminator)
+    def _g_calls(self, lr_feats, hr_feats, save: bool, tag: str, dys=None):
+        calls = (N.GCall * len(lr_feats))()
+        outs = []
+        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
+            n, _, h, w = lo.shape
+            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))          # _reshape_stage1: crop to the element-wise min
+            ws = self._ws_for("g", n, h, w, save, l)
+            y = self._buf(f"tr{tag}{l}", (n, CH, oh, ow))
+            c = calls[l]
+            c.x, c.n, c.h, c.w, c.y, c.oh, c.ow = N.view4(lo), n, h, w, y.data_ptr(), oh, ow
+            c.ws, c.ws_bytes = ws.data_ptr(), ws.numel()
+            if dys is not None:
+                c.dy = N.view4(dys[l])
+            outs.append(y)
+        return calls, outs
 
-    def _d_forward(self, x: torch.Tensor, save: bool, tag: str) -> torch.Tensor:
-        n, _, h, w = x.shape
-        ws = self._ws_for("d", n, h, w, save)
-        logits = self._buf("logit" + tag, (n, 1, h, w))
+    def _g_forward(self, lr_feats, hr_feats, save: bool, tag: str):
+        calls, outs = self._g_calls(lr_feats, hr_feats, save, tag)
+        ps = self._gs()
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_g_forward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
+                                           C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, int(save), N.stream_ptr()))
+        return outs
+
+    def _g_backward(self, lr_feats, hr_feats, dys, tag: str):
+        calls, _ = self._g_calls(lr_feats, hr_feats, True, tag, dys)
+        ps = self._gs()
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_g_backward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
+                                            C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, self.g_acc.data_ptr(),
+                                            N.stream_ptr()))
+
+    def _d_calls(self, xs, tags, save: bool, dlogits=None):
+        calls = (N.DCall * len(xs))()
+        logits = []
+        for i, (x, tag) in enumerate(zip(xs, tags)):
+            n, _, h, w = x.shape
+            ws = self._ws_for("d", n, h, w, save, tag)
+            lg = self._buf("logit" + tag, (n, 1, h, w))
+            c = calls[i]
+            c.x, c.n, c.h, c.w, c.logits = N.view4(x), n, h, w, lg.data_ptr()
+            c.ws, c.ws_bytes = ws.data_ptr(), ws.numel()
+            if dlogits is not None:
+                c.dlogits = dlogits[i].data_ptr()
+            logits.append(lg)
+        return calls, logits
+
+    def _d_forward(self, xs, tags, save: bool):
+        calls, logits = self._d_calls(xs, tags, save)
         ps = self._ds()
         bn = self.Dstack[0][0].norm
-        N.check(self.lib.afi_d_forward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), N.view4(x), n, h, w, logits.data_ptr(),
-                                       1, 0.1 if bn.momentum is None else bn.momentum, bn.eps, ws.data_ptr(), ws.numel(), int(save),
-                                       N.stream_ptr()))
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_d_forward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(),
+                                           C.cast(C.byref(calls, i * C.sizeof(N.DCall)), C.POINTER(N.DCall)), k, 1, mom, bn.eps, int(save),
+                                           N.stream_ptr()))
         return logits
 
-    def _d_backward(self, dlogits: torch.Tensor, n: int, h: int, w: int):
-        ws = self._ws_for("d", n, h, w, True)
+    def _d_backward(self, xs, tags, dlogits):
+        calls, _ = self._d_calls(xs, tags, True, dlogits)
         ps = self._ds()
-        N.check(self.lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), dlogits.data_ptr(), n, h, w,
-                                        ws.data_ptr(), ws.numel(), self.d_acc.data_ptr(), None, N.stream_ptr()))
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(),
+                                            C.cast(C.byref(calls, i * C.sizeof(N.DCall)), C.POINTER(N.DCall)), k, self.d_acc.data_ptr(),
+                                            N.stream_ptr()))
 
     def _bce(self, logits: torch.Tensor, target: float, out_slot: int, sum_ptr: Optional[int], weight: float,
              dlogits: Optional[torch.Tensor]):
@@ -161,18 +206,18 @@ class Stage1Step:
 
         # ------------------------------ D phase (stage1_trainer.py:334-381)
         N.check(lib.afi_zero(self.d_acc.data_ptr(), self.d_acc.numel(), st()))
-        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
-            n, _, h, w = lo.shape
-            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))
-            tr = self._g_forward(lo, oh, ow, False, f"d{l}")
-            hi_c = hi[:, :, :oh, :ow]
-            dl = self._buf("dlogit", (n, 1, oh, ow))
-            logit_real = self._d_forward(hi_c, True, "r")
-            self._bce(logit_real, 1.0, 0, slot(0, l), 1.0, dl)
-            self._d_backward(dl, n, oh, ow)
-            logit_fake = self._d_forward(tr, True, "f")
-            self._bce(logit_fake, 0.0, 1, slot(0, l), 1.0, dl)
-            self._d_backward(dl, n, oh, ow)
+        trs = self._g_forward(lr_feats, hr_feats, False, "d")                       # G(lr).detach(), cropped
+        xs, tags = [], []
+        for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
+            xs += [hi[:, :, :tr.size(2), :tr.size(3)], tr]                          # D0(hr) BEFORE D0(tr)  (:349-350)
+            tags += [f"r{l}", f"f{l}"]
+        logits = self._d_forward(xs, tags, True)
+        dls = []
+        for i, lg in enumerate(logits):
+            dl = self._buf(f"dlogit{i}", tuple(lg.shape))
+            self._bce(lg, 1.0 if i % 2 == 0 else 0.0, i % 2, slot(0, i // 2), 1.0, dl)   # d_loss_l = BCE(real,1) + BCE(fake,0)
+            dls.append(dl)
+        self._d_backward(xs, tags, dls)
         gs = d_grad_struct(self.d_grads)
         N.check(lib.afi_d_unpack_grads(self.ctx, self.prec, self.d_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
         self._allreduce(self.d_flat)
@@ -182,21 +227,21 @@ class Stage1Step:
 
         # ------------------------------ G phase (stage1_trainer.py:384-433)
         N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
-        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
-            n, _, h, w = lo.shape
-            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))
-            tr = self._g_forward(lo, oh, ow, True, f"g{l}")
-            hi_c = hi[:, :, :oh, :ow]
-            logit_fake = self._d_forward(tr, False, "f")
-            self._bce(logit_fake, 1.0, 2, slot(2, l), 1.0, None)           # adv: no gradient (logit is .detach()-ed, :399)
-            self._d_forward(hi_c, False, "r")                              # dead compute kept for its BN running-stat side effect (:400)
-            dtr = self._buf("dtr", (n, CH, oh, ow))
-            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), n, CH, oh, ow, self._tmp[3:].data_ptr(), slot(3, l), 1.0, dtr.data_ptr(),
-                                    1.0, st()))
-            ps = self._gs()
-            ws = self._ws_for("g", n, h, w, True)
-            N.check(lib.afi_g_backward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.view4(dtr), n, h, w, oh, ow,
-                                       ws.data_ptr(), ws.numel(), self.g_acc.data_ptr(), None, None, None, None, None, st()))
+        trs = self._g_forward(lr_feats, hr_feats, True, "g")
+        xs, tags = [], []
+        for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
+            xs += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                          # D0(tr) BEFORE D0(hr) here (:399-400)
+            tags += [f"f{l}", f"r{l}"]
+        logits = self._d_forward(xs, tags, False)      # D0(hr) is dead compute kept for its BN running-stat side effect (:400)
+        dtrs = []
+        for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
+            self._bce(logits[2 * l], 1.0, 2, slot(2, l), 1.0, None)                 # adv: no gradient (logit is .detach()-ed, :399)
+            dtr = self._buf(f"dtr{l}", tuple(tr.shape))
+            hi_c = hi[:, :, :tr.size(2), :tr.size(3)]
+            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), tr.size(0), CH, tr.size(2), tr.size(3), self._tmp[3:].data_ptr(),
+                                    slot(3, l), 1.0, dtr.data_ptr(), 1.0, st()))
+            dtrs.append(dtr)
+        self._g_backward(lr_feats, hr_feats, dtrs, "g")
         self.losses[1, :nl] = 1e-3 * self.losses[2, :nl] + self.losses[3, :nl]
         gs = g_param_struct(self.g_grads, self.n_rdb)
         N.check(lib.afi_g_unpack_grads(self.ctx, self.prec, self.g_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))

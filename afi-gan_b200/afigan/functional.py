@@ -92,8 +92,8 @@ class AFInterpolatorFn(torch.autograd.Function):
         lib, actx = N.lib(), N.context(dev)
         ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, n_rdb, 0, int(need_bwd)), dev)
         y = torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev)
-        N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), N.view4(x), n, h, w, y.data_ptr(), oh, ow, None,
-                                  ws.data_ptr(), ws.numel(), int(need_bwd), N.stream_ptr()))
+        call = N.GCall(x=N.view4(x), n=n, h=h, w=w, y=y.data_ptr(), oh=oh, ow=ow, ws=ws.data_ptr(), ws_bytes=ws.numel())
+        N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, int(need_bwd), N.stream_ptr()))
         ctx.holder, ctx.prec, ctx.shape, ctx.n_rdb = holder, prec, (n, h, w, oh, ow), n_rdb
         ctx.ws, ctx.packed = ws, packed
         ctx.save_for_backward(*params)
@@ -111,8 +111,8 @@ class AFInterpolatorFn(torch.autograd.Function):
         acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
         N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
         ps = g_param_struct(params, ctx.n_rdb)
-        N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), N.view4(dy), n, h, w, oh, ow, ctx.ws.data_ptr(),
-                                   ctx.ws.numel(), acc.data_ptr(), None, None, None, None, None, N.stream_ptr()))
+        call = N.GCall(n=n, h=h, w=w, oh=oh, ow=ow, dy=N.view4(dy), ws=ctx.ws.data_ptr(), ws_bytes=ctx.ws.numel())
+        N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, acc.data_ptr(), N.stream_ptr()))
         grads = [torch.empty_like(p) if ctx.needs_input_grad[5 + i] else None for i, p in enumerate(params)]
         gs = g_param_struct(grads, ctx.n_rdb)
         N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
@@ -141,8 +141,9 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         lib, actx = N.lib(), N.context(dev)
         ws = _u8(lib.afi_d_workspace_bytes(prec, n, h, w, int(need_bwd)), dev)
         logits = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
-        N.check(lib.afi_d_forward(actx, prec, C.byref(ps), packed.data_ptr(), N.view4(x), n, h, w, logits.data_ptr(), int(training),
-                                  momentum, eps, ws.data_ptr(), ws.numel(), int(need_bwd), N.stream_ptr()))
+        call = N.DCall(x=N.view4(x), n=n, h=h, w=w, logits=logits.data_ptr(), ws=ws.data_ptr(), ws_bytes=ws.numel())
+        N.check(lib.afi_d_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, int(training), momentum, eps, int(need_bwd),
+                                  N.stream_ptr()))
         ctx.prec, ctx.shape, ctx.ws, ctx.packed, ctx.buffers = prec, (n, h, w), ws, packed, buffers
         ctx.save_for_backward(*params)
         return logits
@@ -160,8 +161,8 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         acc = _u8(lib.afi_d_gradacc_bytes(), dev)
         N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
         ps = d_param_struct(params, ctx.buffers)
-        N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), dl.data_ptr(), n, h, w, ctx.ws.data_ptr(),
-                                   ctx.ws.numel(), acc.data_ptr(), None, N.stream_ptr()))
+        call = N.DCall(n=n, h=h, w=w, dlogits=dl.data_ptr(), ws=ctx.ws.data_ptr(), ws_bytes=ctx.ws.numel())
+        N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, acc.data_ptr(), N.stream_ptr()))
         grads = [torch.empty_like(p) if ctx.needs_input_grad[8 + i] else None for i, p in enumerate(params)]
         gs = d_grad_struct(grads)
         N.check(lib.afi_d_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))

@@ -44,6 +44,19 @@ class Lateral(C.Structure):
     _fields_ = [("lat_x", View4), ("lat_c", C.c_int), ("lat_w", C.c_void_p), ("lat_b", C.c_void_p), ("scale", C.c_float)]
 
 
+class GCall(C.Structure):
+    _fields_ = [("x", View4), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("y", C.c_void_p), ("oh", C.c_int), ("ow", C.c_int),
+                ("dy", View4), ("dx", C.c_void_p), ("lateral", C.POINTER(Lateral)), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+class DCall(C.Structure):
+    _fields_ = [("x", View4), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("logits", C.c_void_p), ("dlogits", C.c_void_p),
+                ("dx", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
+
+MAX_CALLS = 10
+
+
 class DParams(C.Structure):
     _fields_ = [("w", C.c_void_p * 4), ("b", C.c_void_p * 4), ("gamma", C.c_void_p * 3), ("beta", C.c_void_p * 3),
                 ("running_mean", C.c_void_p * 3), ("running_var", C.c_void_p * 3), ("num_batches_tracked", C.c_void_p * 3)]
@@ -62,20 +75,16 @@ _SIGNATURES = {
     "afi_g_gradacc_bytes": (C.c_size_t, [C.c_int]),
     "afi_g_workspace_bytes": (C.c_size_t, [C.c_int] * 7),
     "afi_g_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, C.c_void_p]),
-    "afi_g_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                C.c_int, C.c_int, C.POINTER(Lateral), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
-    "afi_g_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(Lateral), C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_void_p]),
+    "afi_g_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, C.POINTER(GCall), C.c_int, C.c_int, C.c_void_p]),
+    "afi_g_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(GParams), C.c_void_p, C.POINTER(GCall), C.c_int, C.c_void_p, C.c_void_p]),
     "afi_g_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(GGrads), C.c_float, C.c_int, C.c_void_p]),
     "afi_d_packed_bytes": (C.c_size_t, [C.c_int]),
     "afi_d_gradacc_bytes": (C.c_size_t, []),
     "afi_d_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "afi_d_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.c_void_p]),
-    "afi_d_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, View4, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
-    "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                 C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afi_d_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_int, C.c_float,
+                                C.c_float, C.c_int, C.c_void_p]),
+    "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_void_p, C.c_void_p]),
     "afi_d_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(DGrads), C.c_float, C.c_int, C.c_void_p]),
     "afi_bce_with_logits": (C.c_int, [C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
                                       C.c_void_p]),

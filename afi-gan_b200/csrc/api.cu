@@ -40,6 +40,7 @@ void conv_args_init(ConvArgs& a) {
     a.slope = 0.2f;
     a.mask_slope = 0.2f;
     a.out_dt = DT_F32;
+    a.nprob = 1;
 }
 void set_std_taps(Tap* taps, int view, int slab0) {
     int i = 0;
@@ -80,13 +81,24 @@ static int to_nchw(int prec, PView a, PView lat, afi_view4 skip, int sh, int sw,
 // forward / dgrad pack modes per engine
 static inline int pm(int prec, int kind) { return kind * 2 + (prec_tc(prec) ? 1 : 0); }
 
-static int wgrad_std(afi_ctx* ctx, int prec, PView x, int cin, PView dy, int cout, int n, int h, int w, float* dw, cudaStream_t st) {
+// standard 3x3 weight gradient over a group of problems (dims / views per problem)
+struct Dim3 { int n, h, w; };
+static int wgrad_std(afi_ctx* ctx, int prec, int nprob, const Dim3* d, const PView* x, int cin, const PView* dy, int cout, float* dw,
+                     cudaStream_t st) {
     WgradArgs g;
     memset(&g, 0, sizeof(g));
-    g.N = n; g.H = h; g.W = w; g.cin = cin; g.cout = cout; g.ntaps = 9;
+    g.cin = cin; g.cout = cout; g.ntaps = 9; g.nprob = nprob;
     set_std_taps(g.taps, 0, 0);
-    g.x = x; g.dy = dy; g.dw = dw;
+    for (int k = 0; k < nprob; k++) { g.p[k].N = d[k].n; g.p[k].H = d[k].h; g.p[k].W = d[k].w; g.p[k].x = x[k]; g.p[k].dy = dy[k]; }
+    g.dw = dw;
     return run_wgrad(ctx, prec, g, st);
+}
+// common part of a 3x3 conv over a group; the caller fills a.p[k].in/out/... afterwards
+static void conv_std(ConvArgs& a, int nprob, const Dim3* d, int cin, int cout, const void* w, int slab0 = 0) {
+    conv_args_init(a);
+    a.cin = cin; a.cout = cout; a.ntaps = 9; a.nprob = nprob; a.w = w;
+    set_std_taps(a.taps, 0, slab0);
+    for (int k = 0; k < nprob; k++) { a.p[k].N = d[k].n; a.p[k].H = d[k].h; a.p[k].W = d[k].w; }
 }
 
 // =====================================================================================================
@@ -242,189 +254,226 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     return AFI_OK;
 }
 
-int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* packed, afi_view4 x, int n, int h, int w, float* y,
-                  int oh, int ow, const afi_lateral* lat, void* ws, size_t ws_bytes, int save, void* stream) {
+int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* packed, const afi_g_call* calls, int ncalls, int save,
+                  void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && p && packed && x.ptr && y && ws, "afi_g_forward: null argument");
-    AFI_TRY(g_check(prec, n, h, w, p->n_rdb));
-    AFI_REQUIRE(oh >= 1 && ow >= 1 && oh <= 2 * h && ow <= 2 * w, "afi_g_forward: output crop %dx%d exceeds %dx%d", oh, ow, 2 * h, 2 * w);
+    AFI_REQUIRE(ctx && p && packed && calls, "afi_g_forward: null argument");
+    AFI_REQUIRE(ncalls >= 1 && ncalls <= AFI_MAX_PROB, "afi_g_forward: %d calls per group (max %d)", ncalls, AFI_MAX_PROB);
     const int nr = p->n_rdb, dt = prec_dt(prec);
     const int es = (int)dt_size(dt);
-    const int lat_c = lat ? lat->lat_c : 0;
-    if (lat) AFI_REQUIRE(lat_c % 32 == 0 && lat_c <= 2048 && lat->lat_x.ptr && lat->lat_w, "afi_g_forward: bad lateral");
-    GWs W = g_ws_layout(ws, prec, n, h, w, nr, lat_c, save);
-    if (W.total > ws_bytes) { set_error("afi_g_forward: workspace %zu B < required %zu B", ws_bytes, W.total); return AFI_ERR_WORKSPACE; }
-    if (n == 0) return AFI_OK;
+    GWs W[AFI_MAX_PROB];
+    Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) {
+        const afi_g_call& c = calls[k];
+        AFI_REQUIRE(c.x.ptr && c.y && c.ws, "afi_g_forward: call %d has a null pointer", k);
+        AFI_TRY(g_check(prec, c.n, c.h, c.w, nr));
+        AFI_REQUIRE(c.n >= 1, "afi_g_forward: empty batch");
+        AFI_REQUIRE(c.oh >= 1 && c.ow >= 1 && c.oh <= 2 * c.h && c.ow <= 2 * c.w, "afi_g_forward: output crop %dx%d exceeds %dx%d", c.oh, c.ow,
+                    2 * c.h, 2 * c.w);
+        const int lat_c = c.lateral ? c.lateral->lat_c : 0;
+        if (c.lateral) AFI_REQUIRE(lat_c % 32 == 0 && lat_c <= 2048 && c.lateral->lat_x.ptr && c.lateral->lat_w, "afi_g_forward: bad lateral");
+        W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, lat_c, save);
+        if (W[k].total > c.ws_bytes) { set_error("afi_g_forward: workspace %zu B < required %zu B", c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        d1[k] = {c.n, c.h, c.w};
+        d2[k] = {c.n, 2 * c.h, 2 * c.w};
+    }
     GPacked L = g_packed_layout(nr);
     const char* pk = (const char*)packed;
-    const int H2x = 2 * h, W2x = 2 * w;
-
-    AFI_TRY(to_nhwc(prec, x, n, C, h, w, pview(W.X0, h, w, C), st));
     ConvArgs a;
+
+    for (int k = 0; k < ncalls; k++) AFI_TRY(to_nhwc(prec, calls[k].x, calls[k].n, C, calls[k].h, calls[k].w, pview(W[k].X0, calls[k].h, calls[k].w, C), st));
     // [0] head conv + bias + LeakyReLU -> B0[:, 0:256]                                   generator_rdb.py:91-93
-    conv_args_init(a);
-    a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = pview(W.X0, h, w, C); a.w = pk + L.head_f * es; a.bias = p->head_b; a.act = 1;
-    a.out = pview(W.B[0], h, w, CB); a.out_dt = dt;
+    conv_std(a, ncalls, d1, C, C, pk + L.head_f * es);
+    a.bias = p->head_b; a.act = 1; a.out_dt = dt;
+    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].X0, d1[k].h, d1[k].w, C); a.p[k].out = pview(W[k].B[0], d1[k].h, d1[k].w, CB); }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [1] residual-in-residual: dense blocks write their growth channels into slices of one 384-ch buffer   :39-71
     for (int r = 0; r < nr; r++) {
-        PView Br = pview(W.B[r], h, w, CB);
         for (int i = 0; i < 4; i++) {
-            conv_args_init(a);
-            a.N = n; a.H = h; a.W = w; a.cin = C + GR * i; a.cout = GR; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-            a.in[0] = Br; a.w = pk + L.rdb_f[r][i] * es; a.act = 1;
-            a.out = pview_ch(Br, C + GR * i, es); a.out_dt = dt;
+            conv_std(a, ncalls, d1, C + GR * i, GR, pk + L.rdb_f[r][i] * es);
+            a.act = 1; a.out_dt = dt;
+            for (int k = 0; k < ncalls; k++) {
+                PView Br = pview(W[k].B[r], d1[k].h, d1[k].w, CB);
+                a.p[k].in[0] = Br; a.p[k].out = pview_ch(Br, C + GR * i, es);
+            }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
-        conv_args_init(a);
-        a.N = n; a.H = h; a.W = w; a.cin = CB; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-        a.in[0] = Br; a.w = pk + L.rdb_f[r][4] * es;
-        if (r + 1 < nr) {          // x_{r+1} = x_r + 0.2 * conv5
-            a.alpha = 0.2f; a.r1 = Br; a.r1_dt = dt; a.beta1 = 1.f;
-            a.out = pview(W.B[r + 1], h, w, CB);
-        } else {                   // h1 = 0.2 * (x + 0.2 conv5) + h0                         :27-30
-            a.alpha = 0.04f; a.r1 = Br; a.r1_dt = dt; a.beta1 = 0.2f;
-            a.r2 = pview(W.B[0], h, w, CB); a.r2_dt = dt; a.beta2 = 1.f;
-            a.out = pview(W.H1, h, w, C);
+        conv_std(a, ncalls, d1, CB, C, pk + L.rdb_f[r][4] * es);
+        a.out_dt = dt; a.r1_dt = dt; a.r2_dt = dt;
+        if (r + 1 < nr) { a.alpha = 0.2f; a.beta1 = 1.f; }           // x_{r+1} = x_r + 0.2 * conv5
+        else { a.alpha = 0.04f; a.beta1 = 0.2f; a.beta2 = 1.f; }      // h1 = 0.2 * (x + 0.2 conv5) + h0            :27-30
+        for (int k = 0; k < ncalls; k++) {
+            PView Br = pview(W[k].B[r], d1[k].h, d1[k].w, CB);
+            a.p[k].in[0] = Br; a.p[k].r1 = Br;
+            if (r + 1 < nr) a.p[k].out = pview(W[k].B[r + 1], d1[k].h, d1[k].w, CB);
+            else { a.p[k].r2 = pview(W[k].B[0], d1[k].h, d1[k].w, CB); a.p[k].out = pview(W[k].H1, d1[k].h, d1[k].w, C); }
         }
-        a.out_dt = dt;
         AFI_TRY(run_conv(ctx, prec, a, st));
     }
     // [2] post conv + bias + LeakyReLU                                                   :97-99
-    conv_args_init(a);
-    a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = pview(W.H1, h, w, C); a.w = pk + L.post_f * es; a.bias = p->post_b; a.act = 1;
-    a.out = pview(W.H2, h, w, C); a.out_dt = dt;
+    conv_std(a, ncalls, d1, C, C, pk + L.post_f * es);
+    a.bias = p->post_b; a.act = 1; a.out_dt = dt;
+    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H1, d1[k].h, d1[k].w, C); a.p[k].out = pview(W[k].H2, d1[k].h, d1[k].w, C); }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [3] ConvTranspose2d k6 s2 p2 == four 3x3 sub-pixel convs with interleaved stores      :101-105, App. G
     for (int ph = 0; ph < 4; ph++) {
         int pa = ph >> 1, pb = ph & 1;
-        conv_args_init(a);
-        a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 9 * ph);
-        a.in[0] = pview(W.H2, h, w, C); a.w = pk + L.up_f * es; a.bias = p->up_b; a.act = 1;
-        PView o; o.ptr = (char*)W.H3 + ((size_t)pa * W2x + pb) * C * es;
-        o.sx = 2 * C; o.sy = (long long)2 * W2x * C; o.sn = (long long)H2x * W2x * C;
-        a.out = o; a.out_dt = dt;
+        conv_std(a, ncalls, d1, C, C, pk + L.up_f * es, 9 * ph);
+        a.bias = p->up_b; a.act = 1; a.out_dt = dt;
+        for (int k = 0; k < ncalls; k++) {
+            const int H2x = d2[k].h, W2x = d2[k].w;
+            a.p[k].in[0] = pview(W[k].H2, d1[k].h, d1[k].w, C);
+            PView o; o.ptr = (char*)W[k].H3 + ((size_t)pa * W2x + pb) * C * es;
+            o.sx = 2 * C; o.sy = (long long)2 * W2x * C; o.sn = (long long)H2x * W2x * C;
+            a.p[k].out = o;
+        }
         AFI_TRY(run_conv(ctx, prec, a, st));
     }
     // [4] output conv + bias on the 2h x 2w grid                                           :107-108
-    conv_args_init(a);
-    a.N = n; a.H = H2x; a.W = W2x; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = pview(W.H3, H2x, W2x, C); a.w = pk + L.out_f * es; a.bias = p->out_b;
-    a.out = pview(W.Yb, H2x, W2x, C); a.out_dt = dt;
+    conv_std(a, ncalls, d2, C, C, pk + L.out_f * es);
+    a.bias = p->out_b; a.out_dt = dt;
+    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H3, d2[k].h, d2[k].w, C); a.p[k].out = pview(W[k].Yb, d2[k].h, d2[k].w, C); }
     AFI_TRY(run_conv(ctx, prec, a, st));
-    // optional lateral 1x1 conv of the FPN merge (fpn_sr.py:152)
-    PView latv = pview_null();
-    float scale = 1.f;
-    if (lat) {
-        AFI_TRY(to_nhwc(prec, lat->lat_x, n, lat_c, oh, ow, pview(W.LX, oh, ow, lat_c), st));
-        // 1x1 weight [256, lat_c, 1, 1] is already [co][ci]; KN engines want [ci][co]
-        AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W.LW, dt, st));
-        conv_args_init(a);
-        a.N = n; a.H = oh; a.W = ow; a.cin = lat_c; a.cout = C; a.ntaps = 1;
-        a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0;
-        a.in[0] = pview(W.LX, oh, ow, lat_c); a.w = W.LW; a.bias = lat->lat_b;
-        a.out = pview(W.LAT, oh, ow, C); a.out_dt = dt;
-        AFI_TRY(run_conv(ctx, prec, a, st));
-        latv = pview(W.LAT, oh, ow, C);
-        scale = lat->scale;
+    for (int k = 0; k < ncalls; k++) {
+        const afi_g_call& c = calls[k];
+        PView latv = pview_null();
+        float scale = 1.f;
+        if (c.lateral) {   // lateral 1x1 conv of the FPN merge (fpn_sr.py:152), one problem per call
+            const afi_lateral* lat = c.lateral;
+            const int lat_c = lat->lat_c;
+            AFI_TRY(to_nhwc(prec, lat->lat_x, c.n, lat_c, c.oh, c.ow, pview(W[k].LX, c.oh, c.ow, lat_c), st));
+            AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W[k].LW, dt, st));
+            conv_args_init(a);
+            a.cin = lat_c; a.cout = C; a.ntaps = 1; a.nprob = 1;
+            a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0;
+            a.p[0].N = c.n; a.p[0].H = c.oh; a.p[0].W = c.ow;
+            a.p[0].in[0] = pview(W[k].LX, c.oh, c.ow, lat_c); a.w = W[k].LW; a.bias = lat->lat_b;
+            a.p[0].out = pview(W[k].LAT, c.oh, c.ow, C); a.out_dt = dt;
+            AFI_TRY(run_conv(ctx, prec, a, st));
+            latv = pview(W[k].LAT, c.oh, c.ow, C);
+            scale = lat->scale;
+        }
+        // y = (branch + bilinear2x(x) [+ lateral]) * scale, cropped to oh x ow            :125,130; stage1_trainer.py:437-443
+        AFI_TRY(to_nchw(prec, pview(W[k].Yb, d2[k].h, d2[k].w, C), latv, c.x, c.h, c.w, scale, c.n, C, c.oh, c.ow, c.y, st));
     }
-    // y = (branch + bilinear2x(x) [+ lateral]) * scale, cropped to oh x ow                  :125,130; stage1_trainer.py:437-443
-    AFI_TRY(to_nchw(prec, pview(W.Yb, H2x, W2x, C), latv, x, h, w, scale, n, C, oh, ow, y, st));
     return AFI_OK;
 }
 
-int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* packed, afi_view4 dy, int n, int h, int w, int oh,
-                   int ow, void* ws, size_t ws_bytes, float* gradacc, float* dx, const afi_lateral* lat, float* lat_dx, float* lat_gw,
-                   float* lat_gb, void* stream) {
+int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* packed, const afi_g_call* calls, int ncalls, float* gradacc,
+                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && p && packed && dy.ptr && ws && gradacc, "afi_g_backward: null argument");
-    AFI_TRY(g_check(prec, n, h, w, p->n_rdb));
-    AFI_REQUIRE(!lat, "afi_g_backward: lateral backward is not implemented yet (use torch autograd around the lateral conv)");
-    (void)lat_dx; (void)lat_gw; (void)lat_gb;
+    AFI_REQUIRE(ctx && p && packed && calls && gradacc, "afi_g_backward: null argument");
+    AFI_REQUIRE(ncalls >= 1 && ncalls <= AFI_MAX_PROB, "afi_g_backward: %d calls per group (max %d)", ncalls, AFI_MAX_PROB);
     const int nr = p->n_rdb, dt = prec_dt(prec);
     const int es = (int)dt_size(dt);
-    GWs W = g_ws_layout(ws, prec, n, h, w, nr, 0, 1);
-    if (W.total > ws_bytes) { set_error("afi_g_backward: workspace %zu B < required %zu B", ws_bytes, W.total); return AFI_ERR_WORKSPACE; }
-    if (n == 0) return AFI_OK;
+    GWs W[AFI_MAX_PROB];
+    Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
+    PView X0[AFI_MAX_PROB], H1[AFI_MAX_PROB], H2[AFI_MAX_PROB], H3[AFI_MAX_PROB], G0[AFI_MAX_PROB], G1[AFI_MAX_PROB], G2[AFI_MAX_PROB],
+        dH1[AFI_MAX_PROB], DC5[AFI_MAX_PROB], GC[AFI_MAX_PROB], GH[AFI_MAX_PROB], tmpx[AFI_MAX_PROB], tmpy[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) {
+        const afi_g_call& c = calls[k];
+        AFI_REQUIRE(c.dy.ptr && c.ws, "afi_g_backward: call %d has a null pointer", k);
+        AFI_REQUIRE(!c.lateral, "afi_g_backward: lateral backward is not implemented yet (wrap the lateral conv in torch autograd)");
+        AFI_REQUIRE(!c.dx, "afi_g_backward: input gradient is not implemented yet");
+        AFI_TRY(g_check(prec, c.n, c.h, c.w, nr));
+        W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, 0, 1);
+        if (W[k].total > c.ws_bytes) { set_error("afi_g_backward: workspace %zu B < required %zu B", c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        const int h = c.h, w = c.w, H2x = 2 * h, W2x = 2 * w;
+        d1[k] = {c.n, h, w};
+        d2[k] = {c.n, H2x, W2x};
+        X0[k] = pview(W[k].X0, h, w, C); H1[k] = pview(W[k].H1, h, w, C); H2[k] = pview(W[k].H2, h, w, C); H3[k] = pview(W[k].H3, H2x, W2x, C);
+        G0[k] = pview(W[k].G0, H2x, W2x, C); G1[k] = pview(W[k].G1, H2x, W2x, C); G2[k] = pview(W[k].G2, h, w, C);
+        dH1[k] = pview(W[k].dH1, h, w, C); DC5[k] = pview(W[k].DC5, h, w, C); GC[k] = pview(W[k].GC, h, w, GR); GH[k] = pview(W[k].GH, h, w, C);
+    }
     GPacked L = g_packed_layout(nr);
     GGradAcc GL = g_gradacc_layout(nr);
     const char* pk = (const char*)packed;
-    const int H2x = 2 * h, W2x = 2 * w;
-    const size_t P = (size_t)n * h * w;
-    PView X0 = pview(W.X0, h, w, C), H1 = pview(W.H1, h, w, C), H2 = pview(W.H2, h, w, C), H3 = pview(W.H3, H2x, W2x, C);
-    PView G0 = pview(W.G0, H2x, W2x, C), G1 = pview(W.G1, H2x, W2x, C), G2 = pview(W.G2, h, w, C);
-    PView dH1 = pview(W.dH1, h, w, C), DC5 = pview(W.DC5, h, w, C), GC = pview(W.GC, h, w, GR), GH = pview(W.GH, h, w, C);
     ConvArgs a;
 
     // dL/d(branch) on the full 2h x 2w grid: the crop's complement gets zero gradient
-    AFI_CUDA(cudaMemsetAsync(W.G0, 0, 4 * P * C * es, st));
-    AFI_TRY(to_nhwc(prec, dy, n, C, oh, ow, G0, st));
+    for (int k = 0; k < ncalls; k++) {
+        const afi_g_call& c = calls[k];
+        AFI_CUDA(cudaMemsetAsync(W[k].G0, 0, (size_t)4 * c.n * c.h * c.w * C * es, st));
+        AFI_TRY(to_nhwc(prec, c.dy, c.n, C, c.oh, c.ow, G0[k], st));
+    }
     // output conv
-    AFI_TRY(wgrad_std(ctx, prec, H3, C, G0, C, n, H2x, W2x, gradacc + GL.out_w, st));
-    AFI_TRY(col_sum_f32(G0, dt, n, H2x, W2x, C, gradacc + GL.out_b, st));
-    conv_args_init(a);
-    a.N = n; a.H = H2x; a.W = W2x; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = G0; a.w = pk + L.out_d * es; a.mask = H3; a.out = G1; a.out_dt = dt;
+    AFI_TRY(wgrad_std(ctx, prec, ncalls, d2, H3, C, G0, C, gradacc + GL.out_w, st));
+    for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G0[k], dt, d2[k].n, d2[k].h, d2[k].w, C, gradacc + GL.out_b, st));
+    conv_std(a, ncalls, d2, C, C, pk + L.out_d * es);
+    a.out_dt = dt;
+    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = G0[k]; a.p[k].mask = H3[k]; a.p[k].out = G1[k]; }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // transposed conv: wgrad per phase, bias, and dgrad as ONE 36-tap conv over the four phase views of G1
-    PView ph[4];
+    PView ph[AFI_MAX_PROB][4];
     for (int i = 0; i < 4; i++) {
         int pa = i >> 1, pb = i & 1;
-        ph[i].ptr = (char*)W.G1 + ((size_t)pa * W2x + pb) * C * es;
-        ph[i].sx = 2 * C; ph[i].sy = (long long)2 * W2x * C; ph[i].sn = (long long)H2x * W2x * C;
-        AFI_TRY(wgrad_std(ctx, prec, H2, C, ph[i], C, n, h, w, gradacc + GL.up_w + (size_t)i * 9 * C * C, st));
+        for (int k = 0; k < ncalls; k++) {
+            const int H2x = d2[k].h, W2x = d2[k].w;
+            ph[k][i].ptr = (char*)W[k].G1 + ((size_t)pa * W2x + pb) * C * es;
+            ph[k][i].sx = 2 * C; ph[k][i].sy = (long long)2 * W2x * C; ph[k][i].sn = (long long)H2x * W2x * C;
+            tmpy[k] = ph[k][i];
+        }
+        AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, H2, C, tmpy, C, gradacc + GL.up_w + (size_t)i * 9 * C * C, st));
     }
-    AFI_TRY(col_sum_f32(G1, dt, n, H2x, W2x, C, gradacc + GL.up_b, st));
+    for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G1[k], dt, d2[k].n, d2[k].h, d2[k].w, C, gradacc + GL.up_b, st));
     conv_args_init(a);
-    a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = C; a.ntaps = 36;
-    for (int i = 0; i < 4; i++) { set_std_taps(a.taps + 9 * i, i, 9 * i); a.in[i] = ph[i]; }
-    a.w = pk + L.up_d * es; a.mask = H2; a.out = G2; a.out_dt = dt;
+    a.cin = C; a.cout = C; a.ntaps = 36; a.nprob = ncalls; a.w = pk + L.up_d * es; a.out_dt = dt;
+    for (int i = 0; i < 4; i++) set_std_taps(a.taps + 9 * i, i, 9 * i);
+    for (int k = 0; k < ncalls; k++) {
+        a.p[k].N = d1[k].n; a.p[k].H = d1[k].h; a.p[k].W = d1[k].w;
+        for (int i = 0; i < 4; i++) a.p[k].in[i] = ph[k][i];
+        a.p[k].mask = H2[k]; a.p[k].out = G2[k];
+    }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // post conv
-    AFI_TRY(wgrad_std(ctx, prec, H1, C, G2, C, n, h, w, gradacc + GL.post_w, st));
-    AFI_TRY(col_sum_f32(G2, dt, n, h, w, C, gradacc + GL.post_b, st));
-    conv_args_init(a);
-    a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = C; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = G2; a.w = pk + L.post_d * es; a.out = dH1; a.out_dt = DT_F32;
+    AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, H1, C, G2, C, gradacc + GL.post_w, st));
+    for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G2[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.post_b, st));
+    conv_std(a, ncalls, d1, C, C, pk + L.post_d * es);
+    a.out_dt = DT_F32;
+    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = G2[k]; a.p[k].out = dH1[k]; }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // residual-in-residual: h1 = 0.2 * x_nr + h0.  d_out (fp32 view) = 0.2 * dH1 entering the last dense block.
-    PView d_out = dH1; float d_scale = 0.2f; int cur = 0;
+    float d_scale = 0.2f; int cur = 0;
+    PView d_out[AFI_MAX_PROB], GA[AFI_MAX_PROB], Br[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) d_out[k] = dH1[k];
     for (int r = nr - 1; r >= 0; r--) {
-        PView Br = pview(W.B[r], h, w, CB);
-        PView GA = pview(W.GA[cur], h, w, CB);
-        // dc5 = 0.2 * d_out (GEMM operand in storage dtype)
-        AFI_TRY(ew_combine(DC5, dt, d_out, DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, 0.2f * d_scale, n, h, w, C, st));
-        AFI_TRY(wgrad_std(ctx, prec, Br, CB, DC5, C, n, h, w, gradacc + GL.rdb_w[r][4], st));
-        // GA[:, 0:256] = d_out, GA[:, 256:384] = 0, then GA += dgrad(conv5)(dc5) over all 384 channels
-        AFI_CUDA(cudaMemsetAsync(W.GA[cur], 0, P * CB * 4, st));
-        AFI_TRY(ew_combine(GA, DT_F32, d_out, DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, d_scale, n, h, w, C, st));
-        conv_args_init(a);
-        a.N = n; a.H = h; a.W = w; a.cin = C; a.cout = CB; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-        a.in[0] = DC5; a.w = pk + L.rdb_d[r][4] * es; a.accin = GA; a.out = GA; a.out_dt = DT_F32;
+        for (int k = 0; k < ncalls; k++) {
+            const int n = d1[k].n, h = d1[k].h, w = d1[k].w;
+            Br[k] = pview(W[k].B[r], h, w, CB);
+            GA[k] = pview(W[k].GA[cur], h, w, CB);
+            // dc5 = 0.2 * d_out (GEMM operand in storage dtype)
+            AFI_TRY(ew_combine(DC5[k], dt, d_out[k], DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, 0.2f * d_scale, n, h, w, C, st));
+            // GA[:, 0:256] = d_out, GA[:, 256:384] = 0; the conv5 dgrad below accumulates over all 384 channels
+            AFI_CUDA(cudaMemsetAsync(W[k].GA[cur], 0, (size_t)n * h * w * CB * 4, st));
+            AFI_TRY(ew_combine(GA[k], DT_F32, d_out[k], DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, d_scale, n, h, w, C, st));
+        }
+        AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, CB, DC5, C, gradacc + GL.rdb_w[r][4], st));
+        conv_std(a, ncalls, d1, C, CB, pk + L.rdb_d[r][4] * es);
+        a.out_dt = DT_F32;
+        for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DC5[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
         AFI_TRY(run_conv(ctx, prec, a, st));
         for (int i = 3; i >= 0; i--) {
             int cin_f = C + GR * i;
             // g = GA[:, slice_i] * lrelu'(c_{i+1})
-            AFI_TRY(ew_combine(GC, dt, pview_ch(GA, cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br, cin_f, es), dt, 0.2f, 1.f, n, h, w, GR, st));
-            AFI_TRY(wgrad_std(ctx, prec, Br, cin_f, GC, GR, n, h, w, gradacc + GL.rdb_w[r][i], st));
-            conv_args_init(a);
-            a.N = n; a.H = h; a.W = w; a.cin = GR; a.cout = cin_f; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-            a.in[0] = GC; a.w = pk + L.rdb_d[r][i] * es; a.accin = GA; a.out = GA; a.out_dt = DT_F32;
+            for (int k = 0; k < ncalls; k++)
+                AFI_TRY(ew_combine(GC[k], dt, pview_ch(GA[k], cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br[k], cin_f, es), dt, 0.2f, 1.f,
+                                   d1[k].n, d1[k].h, d1[k].w, GR, st));
+            AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, cin_f, GC, GR, gradacc + GL.rdb_w[r][i], st));
+            conv_std(a, ncalls, d1, GR, cin_f, pk + L.rdb_d[r][i] * es);
+            a.out_dt = DT_F32;
+            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GC[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
-        d_out = GA; d_scale = 1.f; cur ^= 1;
+        for (int k = 0; k < ncalls; k++) d_out[k] = GA[k];
+        d_scale = 1.f; cur ^= 1;
     }
     // head conv: g_head = (d_out + dH1) * lrelu'(h0)
-    AFI_TRY(ew_combine(GH, dt, d_out, DT_F32, dH1, DT_F32, pview(W.B[0], h, w, CB), dt, 0.2f, 1.f, n, h, w, C, st));
-    AFI_TRY(wgrad_std(ctx, prec, X0, C, GH, C, n, h, w, gradacc + GL.head_w, st));
-    AFI_TRY(col_sum_f32(GH, dt, n, h, w, C, gradacc + GL.head_b, st));
-    if (dx) {
-        // dx = dgrad(head)(g_head) + bilinear2x^T(dy): conv into an NHWC fp32 buffer, then to NCHW (+ skip adjoint, TODO)
-        set_error("afi_g_backward: input gradient is not implemented yet");
-        return AFI_ERR_INVALID;
-    }
+    for (int k = 0; k < ncalls; k++)
+        AFI_TRY(ew_combine(GH[k], dt, d_out[k], DT_F32, dH1[k], DT_F32, pview(W[k].B[0], d1[k].h, d1[k].w, CB), dt, 0.2f, 1.f, d1[k].n, d1[k].h,
+                           d1[k].w, C, st));
+    AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, X0, C, GH, C, gradacc + GL.head_w, st));
+    for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(GH[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.head_b, st));
+    (void)tmpx;
     return AFI_OK;
 }
 
@@ -515,70 +564,94 @@ int afi_d_pack(afi_ctx* ctx, int prec, const afi_d_params* p, void* packed, void
     return AFI_OK;
 }
 
-int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, afi_view4 x, int n, int h, int w, float* logits,
-                  int training, float momentum, float eps, void* ws, size_t ws_bytes, int save, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && p && packed && x.ptr && logits && ws && prec_ok(prec), "afi_d_forward: bad argument");
-    AFI_REQUIRE(n >= 1 && h >= 1 && w >= 1, "afi_d_forward: bad shape n=%d h=%d w=%d", n, h, w);
-    const int dt = prec_dt(prec); const size_t es = dt_size(dt);
-    DWs W = d_ws_layout(ws, prec, n, h, w, save);
-    if (W.total > ws_bytes) { set_error("afi_d_forward: workspace %zu B < required %zu B", ws_bytes, W.total); return AFI_ERR_WORKSPACE; }
-    DPacked L = d_packed_layout();
-    AFI_TRY(to_nhwc(prec, x, n, DC[0], h, w, pview(W.A[0], h, w, DC[0]), st));
-    for (int i = 0; i < 3; i++) {
-        // Conv2d 3x3 + bias -> BatchNorm (batch statistics of THIS call) -> LeakyReLU(0.2)   feature_patch_discriminator.py:36-38
-        ConvArgs a;
-        conv_args_init(a);
-        a.N = n; a.H = h; a.W = w; a.cin = DC[i]; a.cout = DC[i + 1]; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-        a.in[0] = pview(W.A[i], h, w, DC[i]); a.w = (const char*)packed + L.f[i] * es; a.bias = p->b[i];
-        PView Z = pview(W.Z[i], h, w, DC[i + 1]);
-        a.out = Z; a.out_dt = dt;
-        AFI_TRY(run_conv(ctx, prec, a, st));
-        if (training) {
-            AFI_CUDA(cudaMemsetAsync(W.sums, 0, 2 * 1024 * sizeof(double), st));
-            AFI_TRY(col_stats(Z, dt, n, h, w, DC[i + 1], W.sums, W.sums + 1024, st));
-        }
-        AFI_TRY(bn_finalize(W.sums, W.sums + 1024, (long long)n * h * w, DC[i + 1], eps, momentum, training, W.mean[i], W.rstd[i],
-                            p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
-        AFI_TRY(bn_apply_lrelu(Z, pview(W.A[i + 1], h, w, DC[i + 1]), dt, W.mean[i], W.rstd[i], p->gamma[i], p->beta[i], 0.2f, n, h, w,
-                               DC[i + 1], st));
+static int d_calls_check(const char* who, int prec, const afi_d_call* calls, int ncalls, int save, DWs* W, Dim3* d) {
+    AFI_REQUIRE(prec_ok(prec) && calls, "%s: bad argument", who);
+    AFI_REQUIRE(ncalls >= 1 && ncalls <= AFI_MAX_PROB, "%s: %d calls per group (max %d)", who, ncalls, AFI_MAX_PROB);
+    for (int k = 0; k < ncalls; k++) {
+        const afi_d_call& c = calls[k];
+        AFI_REQUIRE(c.ws && c.n >= 1 && c.h >= 1 && c.w >= 1, "%s: call %d: bad shape n=%d h=%d w=%d or null workspace", who, k, c.n, c.h, c.w);
+        W[k] = d_ws_layout(c.ws, prec, c.n, c.h, c.w, save);
+        if (W[k].total > c.ws_bytes) { set_error("%s: workspace %zu B < required %zu B", who, c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        d[k] = {c.n, c.h, c.w};
     }
-    // Conv2d 1024 -> 1                                                                   feature_patch_discriminator.py:40-41
-    AFI_TRY(dhead_forward(pview(W.A[3], h, w, DC[3]), dt, p->w[3], p->b[3], n, h, w, DC[3], W.T9, logits, st));
     return AFI_OK;
 }
 
-int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, const float* dlogits, int n, int h, int w,
-                   void* ws, size_t ws_bytes, float* gradacc, float* dx, void* stream) {
+int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, const afi_d_call* calls, int ncalls, int training,
+                  float momentum, float eps, int save, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && p && packed && dlogits && ws && gradacc && prec_ok(prec), "afi_d_backward: bad argument");
-    AFI_REQUIRE(dx == nullptr, "afi_d_backward: input gradient is not implemented (stage 1/2 detach the discriminator input)");
+    AFI_REQUIRE(ctx && p && packed, "afi_d_forward: null argument");
+    DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
+    AFI_TRY(d_calls_check("afi_d_forward", prec, calls, ncalls, save, W, d));
     const int dt = prec_dt(prec); const size_t es = dt_size(dt);
-    DWs W = d_ws_layout(ws, prec, n, h, w, 1);
-    if (W.total > ws_bytes) { set_error("afi_d_backward: workspace %zu B < required %zu B", ws_bytes, W.total); return AFI_ERR_WORKSPACE; }
+    DPacked L = d_packed_layout();
+    for (int k = 0; k < ncalls; k++) {
+        AFI_REQUIRE(calls[k].x.ptr && calls[k].logits, "afi_d_forward: call %d has a null pointer", k);
+        AFI_TRY(to_nhwc(prec, calls[k].x, d[k].n, DC[0], d[k].h, d[k].w, pview(W[k].A[0], d[k].h, d[k].w, DC[0]), st));
+    }
+    for (int i = 0; i < 3; i++) {
+        // Conv2d 3x3 + bias (all calls in one grouped launch) -> per call: BatchNorm with THIS call's batch statistics
+        // -> LeakyReLU(0.2)                                                         feature_patch_discriminator.py:36-38
+        ConvArgs a;
+        conv_std(a, ncalls, d, DC[i], DC[i + 1], (const char*)packed + L.f[i] * es);
+        a.bias = p->b[i]; a.out_dt = dt;
+        for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].A[i], d[k].h, d[k].w, DC[i]); a.p[k].out = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); }
+        AFI_TRY(run_conv(ctx, prec, a, st));
+        for (int k = 0; k < ncalls; k++) {      // in call order: the running statistics see the calls sequentially
+            PView Z = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]);
+            if (training) {
+                AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+                AFI_TRY(col_stats(Z, dt, d[k].n, d[k].h, d[k].w, DC[i + 1], W[k].sums, W[k].sums + 1024, st));
+            }
+            AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, (long long)d[k].n * d[k].h * d[k].w, DC[i + 1], eps, momentum, training, W[k].mean[i],
+                                W[k].rstd[i], p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
+            AFI_TRY(bn_apply_lrelu(Z, pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]), dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], p->beta[i], 0.2f,
+                                   d[k].n, d[k].h, d[k].w, DC[i + 1], st));
+        }
+    }
+    // Conv2d 1024 -> 1                                                                   feature_patch_discriminator.py:40-41
+    for (int k = 0; k < ncalls; k++)
+        AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
+    return AFI_OK;
+}
+
+int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, const afi_d_call* calls, int ncalls, float* gradacc,
+                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_REQUIRE(ctx && p && packed && gradacc, "afi_d_backward: null argument");
+    DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
+    AFI_TRY(d_calls_check("afi_d_backward", prec, calls, ncalls, 1, W, d));
+    const int dt = prec_dt(prec); const size_t es = dt_size(dt);
     DPacked L = d_packed_layout();
     DGradAcc GL = d_gradacc_layout();
-    // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
-    PView DY = pview(W.DY[2], h, w, DC[3]);
-    AFI_TRY(dhead_backward(pview(W.A[3], h, w, DC[3]), dt, p->w[3], dlogits, n, h, w, DC[3], gradacc + GL.w[3], gradacc + GL.b[3], DY, st));
+    PView X[AFI_MAX_PROB], DYv[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) {
+        AFI_REQUIRE(calls[k].dlogits, "afi_d_backward: call %d has no dlogits", k);
+        AFI_REQUIRE(!calls[k].dx, "afi_d_backward: input gradient is not implemented (stage 1/2 detach the discriminator input)");
+        // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
+        AFI_TRY(dhead_backward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], calls[k].dlogits, d[k].n, d[k].h, d[k].w, DC[3],
+                               gradacc + GL.w[3], gradacc + GL.b[3], pview(W[k].DY[2], d[k].h, d[k].w, DC[3]), st));
+    }
     for (int i = 2; i >= 0; i--) {
         const int co = DC[i + 1], ci = DC[i];
-        PView Z = pview(W.Z[i], h, w, co);
-        PView DYi = pview(W.DY[i], h, w, co);
-        // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ)
-        AFI_CUDA(cudaMemsetAsync(W.sums, 0, 2 * 1024 * sizeof(double), st));
-        AFI_TRY(bn_bwd_reduce(DYi, Z, dt, W.mean[i], W.rstd[i], n, h, w, co, W.sums, W.sums + 1024, st));
-        AFI_TRY(bn_bwd_apply(DYi, Z, dt, W.mean[i], W.rstd[i], p->gamma[i], W.sums, W.sums + 1024, gradacc + GL.gamma[i], gradacc + GL.beta[i],
-                             n, h, w, co, st));
-        AFI_TRY(wgrad_std(ctx, prec, pview(W.A[i], h, w, ci), ci, DYi, co, n, h, w, gradacc + GL.w[i], st));
+        for (int k = 0; k < ncalls; k++) {
+            PView Z = pview(W[k].Z[i], d[k].h, d[k].w, co);
+            DYv[k] = pview(W[k].DY[i], d[k].h, d[k].w, co);
+            X[k] = pview(W[k].A[i], d[k].h, d[k].w, ci);
+            // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ)
+            AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+            AFI_TRY(bn_bwd_reduce(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], d[k].n, d[k].h, d[k].w, co, W[k].sums, W[k].sums + 1024, st));
+            AFI_TRY(bn_bwd_apply(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], W[k].sums, W[k].sums + 1024, gradacc + GL.gamma[i],
+                                 gradacc + GL.beta[i], d[k].n, d[k].h, d[k].w, co, st));
+        }
+        AFI_TRY(wgrad_std(ctx, prec, ncalls, d, X, ci, DYv, co, gradacc + GL.w[i], st));
         // bias gradient: this bias feeds a train-mode BatchNorm, so dL/db = sum_p dz = 0 identically (the reference gets
         // ~1e-9 rounding noise there); the accumulator slot stays at its zero-initialised value.
-        if (i > 0) {   // dA_{i} * lrelu'(a_i) -> DY[i-1]
+        if (i > 0) {   // dA_i * lrelu'(a_i) -> DY[i-1]
             ConvArgs a;
-            conv_args_init(a);
-            a.N = n; a.H = h; a.W = w; a.cin = co; a.cout = ci; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-            a.in[0] = DYi; a.w = (const char*)packed + L.d[i] * es; a.mask = pview(W.A[i], h, w, ci);
-            a.out = pview(W.DY[i - 1], h, w, ci); a.out_dt = dt;
+            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * es);
+            a.out_dt = dt;
+            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].mask = X[k]; a.p[k].out = pview(W[k].DY[i - 1], d[k].h, d[k].w, ci); }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
     }
@@ -618,15 +691,15 @@ int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int 
     if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3: workspace too small"); return AFI_ERR_WORKSPACE; }
     int dt = prec_dt(prec); size_t es = dt_size(dt), P = (size_t)n * h * w;
     Carver cv(ws);
-    void* X = cv.take(P * cin * es); void* Y = cv.take(P * cout * es); cv.take(P * cout * es);
+    void* X = cv.take(P * pad64(cin) * es); void* Y = cv.take(P * pad64(cout) * es); cv.take(P * pad64(cout) * es);
     void* Wp = cv.take((size_t)9 * cin * cout * es);
     AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
     AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, dt, st));
     ConvArgs a;
-    conv_args_init(a);
-    a.N = n; a.H = h; a.W = w; a.cin = cin; a.cout = cout; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-    a.in[0] = pview(X, h, w, cin); a.w = Wp; a.bias = bias; a.act = lrelu;
-    a.out = pview(Y, h, w, cout); a.out_dt = dt;
+    Dim3 d = {n, h, w};
+    conv_std(a, 1, &d, cin, cout, Wp);
+    a.bias = bias; a.act = lrelu; a.out_dt = dt;
+    a.p[0].in[0] = pview(X, h, w, cin); a.p[0].out = pview(Y, h, w, cout);
     AFI_TRY(run_conv(ctx, prec, a, st));
     afi_view4 none; memset(&none, 0, sizeof(none));
     AFI_TRY(to_nchw(prec, pview(Y, h, w, cout), pview_null(), none, 0, 0, 1.f, n, cout, h, w, y, st));
@@ -648,17 +721,19 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     void* DX = cv.take(P * cin * 4);
     if (xs != cin) AFI_CUDA(cudaMemsetAsync(X, 0, P * xs * es, st));
     if (ys != cout) AFI_CUDA(cudaMemsetAsync(DYb, 0, P * ys * es, st));
-    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, xs), st));
-    AFI_TRY(to_nhwc(prec, dy, n, cout, h, w, pview(DYb, h, w, ys), st));
+    PView Xv = pview(X, h, w, xs), DYv = pview(DYb, h, w, ys);
+    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, Xv, st));
+    AFI_TRY(to_nhwc(prec, dy, n, cout, h, w, DYv, st));
     AFI_CUDA(cudaMemsetAsync(acc, 0, (size_t)9 * cin * cout * 4, st));
-    AFI_TRY(wgrad_std(ctx, prec, pview(X, h, w, xs), cin, pview(DYb, h, w, ys), cout, n, h, w, acc, st));
+    Dim3 d = {n, h, w};
+    AFI_TRY(wgrad_std(ctx, prec, 1, &d, &Xv, cin, &DYv, cout, acc, st));
     AFI_TRY(unpack_wgrad(acc, cout, cin, prec_tc(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
     if (dxo) {
         AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, dt, st));
         ConvArgs a;
-        conv_args_init(a);
-        a.N = n; a.H = h; a.W = w; a.cin = cout; a.cout = cin; a.ntaps = 9; set_std_taps(a.taps, 0, 0);
-        a.in[0] = pview(DYb, h, w, ys); a.w = Wp; a.out = pview(DX, h, w, cin); a.out_dt = DT_F32;
+        conv_std(a, 1, &d, cout, cin, Wp);
+        a.out_dt = DT_F32;
+        a.p[0].in[0] = DYv; a.p[0].out = pview(DX, h, w, cin);
         AFI_TRY(run_conv(ctx, prec, a, st));
         afi_view4 none; memset(&none, 0, sizeof(none));
         AFI_TRY(nhwc_to_nchw<float>(pview(DX, h, w, cin), pview_null(), none, 0, 0, 1.f, n, cin, h, w, dxo, st));

@@ -63,36 +63,44 @@ static inline PView pview_ch(PView v, int coff, int elem_bytes) {
 struct Tap { int dy, dx, view, slab; };
 #define AFI_MAX_TAPS 36
 
-// One implicit-GEMM convolution:  out[n,y,x,co] = epi( sum_taps sum_ci in[view][n,y+dy,x+dx,ci] * W[slab][.][.] )
+// One GROUPED implicit-GEMM convolution over up to AFI_MAX_PROB independent problems that share weights, taps and the
+// epilogue recipe (the pyramid levels of one generator call, or the level x {real, fake} calls of the discriminator):
+//   out_p[n,y,x,co] = epi( sum_taps sum_ci in_p[view][n,y+dy,x+dx,ci] * W[slab][.][.] )        for every problem p
 // Epilogue order:  v = acc + bias;  v = act ? lrelu(v) : v;  v *= alpha;  v += beta1*r1 + beta2*r2 + accin;
 //                  v *= mask > 0 ? 1 : mask_slope;   store (bf16/f32 as out_dt says).
-struct ConvArgs {
-    int N, H, W;          // logical pixel grid (output pixels; every input view has the same grid)
-    int cin, cout;
-    int ntaps;
-    Tap taps[AFI_MAX_TAPS];
+#define AFI_MAX_PROB 10
+struct ConvProb {
+    int N, H, W, pad_;    // logical pixel grid (output pixels; every input view has the same grid)
     PView in[4];          // dtype = storage dtype T
+    PView out, r1, r2;
+    PView accin;          // f32
+    PView mask;           // dtype T
+};
+struct ConvArgs {
+    int cin, cout;
+    int ntaps, nprob;
+    Tap taps[AFI_MAX_TAPS];
     const void* w;        // packed slabs, dtype T.  SIMT engine: [slab][cin][cout]; tensor-core engine: [slab][cout][cin]
-    PView out; int out_dt;
     const float* bias;
     int act; float slope;
-    float alpha;
-    PView r1; int r1_dt; float beta1;
-    PView r2; int r2_dt; float beta2;
-    PView accin;          // f32
-    PView mask; float mask_slope;   // dtype T
+    float alpha, beta1, beta2, mask_slope;
+    int out_dt, r1_dt, r2_dt;
+    ConvProb p[AFI_MAX_PROB];
 };
 
-// dW[slab][..] += sum_p dY[p][co] * X[p + tap][ci]   (fp32 atomics into a pre-zeroed accumulator)
+// dW[slab][..] += sum over ALL problems' pixels of dY[p][co] * X[p + tap][ci]   (fp32 atomics into a pre-zeroed accumulator)
 // SIMT engine layout: [slab][cin][cout]; tensor-core engine: [slab][cout][cin].
-struct WgradArgs {
-    int N, H, W;
-    int cin, cout;
-    int ntaps;
-    Tap taps[9];          // .view unused, .slab = output slab
+struct WgradProb {
+    int N, H, W, pad_;
     PView x;              // T
     PView dy;             // T
+};
+struct WgradArgs {
+    int cin, cout;
+    int ntaps, nprob;
+    Tap taps[9];          // .view unused, .slab = output slab
     float* dw;
+    WgradProb p[AFI_MAX_PROB];
 };
 
 // optional per-launch CUDA-event profiling of the GEMM kernels (afi_profile_begin/_end; bench.py's roofline leg)

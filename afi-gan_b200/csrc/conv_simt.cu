@@ -89,16 +89,25 @@ __device__ __forceinline__ void tile_fma(const float (*As)[BM + LDS_PAD], const 
 // ---------------------------------------------------------------------------------------------------
 // convolution
 // ---------------------------------------------------------------------------------------------------
+struct SimtGroup {
+    int mt_begin[AFI_MAX_PROB + 1];          // conv: first M tile of each problem
+    long long px_begin[AFI_MAX_PROB + 1];    // wgrad: first global pixel of each problem
+};
+
 template <typename T, int BN>
-__global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvArgs a, const __grid_constant__ SimtGroup grp) {
     constexpr int RS = BN == 128 ? 2 : 1, CS = RS;
     constexpr int TXN = BN / (4 * CS);
     constexpr int EB = BN / 16;
     __shared__ __align__(16) float As[2][BK][BM + LDS_PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + LDS_PAD];
     const int tid = threadIdx.x;
-    const long long M = (long long)a.N * a.H * a.W;
-    const long long m0 = (long long)blockIdx.x * BM;
+    int pi = 0;
+    while (pi + 1 < a.nprob && (int)blockIdx.x >= grp.mt_begin[pi + 1]) pi++;
+    const ConvProb& pr = a.p[pi];
+    const int PH = pr.H, PW = pr.W;
+    const long long M = (long long)pr.N * PH * PW;
+    const long long m0 = (long long)((int)blockIdx.x - grp.mt_begin[pi]) * BM;
     const int n0 = blockIdx.y * BN;
 
     // A loader: one pixel row, 8 consecutive channels
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvA
     long long ap = m0 + arow;
     const bool arow_ok = ap < M;
     int ax = 0, ay = 0, an = 0;
-    if (arow_ok) { ax = (int)(ap % a.W); long long t = ap / a.W; ay = (int)(t % a.H); an = (int)(t / a.H); }
+    if (arow_ok) { ax = (int)(ap % PW); long long t = ap / PW; ay = (int)(t % PH); an = (int)(t / PH); }
     // B loader
     const int bk = tid >> 4, bnoff = (tid & 15) * EB;
     const bool bcol_ok = (n0 + bnoff) < a.cout;
@@ -120,8 +129,8 @@ __global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvA
         int tp = it / kc_per_tap, c0 = (it - tp * kc_per_tap) * BK;
         Tap t = a.taps[tp];
         int iy = ay + t.dy, ix = ax + t.dx;
-        if (arow_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
-            const PView& v = a.in[t.view];
+        if (arow_ok && iy >= 0 && iy < PH && ix >= 0 && ix < PW) {
+            const PView& v = pr.in[t.view];
             const T* p = reinterpret_cast<const T*>(v.ptr) + an * v.sn + iy * v.sy + ix * v.sx + c0 + akoff;
             VecLoad<T, 8>::load(p, ra);
         } else {
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvA
         for (int i = 0; i < 4; i++) {
             long long p = m0 + rs * 64 + ty * 4 + i;
             if (p >= M) continue;
-            int x = (int)(p % a.W); long long t = p / a.W; int y = (int)(t % a.H); int n = (int)(t / a.H);
+            int x = (int)(p % PW); long long t = p / PW; int y = (int)(t % PH); int n = (int)(t / PH);
 #pragma unroll
             for (int cs = 0; cs < CS; cs++) {
                 int col = n0 + cs * 64 + tx * 4;
@@ -183,24 +192,24 @@ __global__ void __launch_bounds__(256) k_conv_simt(const __grid_constant__ ConvA
                     v.z = v.z > 0.f ? v.z : v.z * a.slope; v.w = v.w > 0.f ? v.w : v.w * a.slope;
                 }
                 v.x *= a.alpha; v.y *= a.alpha; v.z *= a.alpha; v.w *= a.alpha;
-                if (a.r1.ptr) {
-                    float4 r = ld4g(a.r1.ptr, n * a.r1.sn + y * a.r1.sy + x * a.r1.sx + col, a.r1_dt);
+                if (pr.r1.ptr) {
+                    float4 r = ld4g(pr.r1.ptr, n * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx + col, a.r1_dt);
                     v.x += a.beta1 * r.x; v.y += a.beta1 * r.y; v.z += a.beta1 * r.z; v.w += a.beta1 * r.w;
                 }
-                if (a.r2.ptr) {
-                    float4 r = ld4g(a.r2.ptr, n * a.r2.sn + y * a.r2.sy + x * a.r2.sx + col, a.r2_dt);
+                if (pr.r2.ptr) {
+                    float4 r = ld4g(pr.r2.ptr, n * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx + col, a.r2_dt);
                     v.x += a.beta2 * r.x; v.y += a.beta2 * r.y; v.z += a.beta2 * r.z; v.w += a.beta2 * r.w;
                 }
-                if (a.accin.ptr) {
-                    float4 r = ld4g(a.accin.ptr, n * a.accin.sn + y * a.accin.sy + x * a.accin.sx + col, DT_F32);
+                if (pr.accin.ptr) {
+                    float4 r = ld4g(pr.accin.ptr, n * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx + col, DT_F32);
                     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
                 }
-                if (a.mask.ptr) {
-                    float4 m = ld4g(a.mask.ptr, n * a.mask.sn + y * a.mask.sy + x * a.mask.sx + col, dt_of<T>::v);
+                if (pr.mask.ptr) {
+                    float4 m = ld4g(pr.mask.ptr, n * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx + col, dt_of<T>::v);
                     v.x *= m.x > 0.f ? 1.f : a.mask_slope; v.y *= m.y > 0.f ? 1.f : a.mask_slope;
                     v.z *= m.z > 0.f ? 1.f : a.mask_slope; v.w *= m.w > 0.f ? 1.f : a.mask_slope;
                 }
-                st4g(a.out.ptr, n * a.out.sn + y * a.out.sy + x * a.out.sx + col, a.out_dt, v);
+                st4g(pr.out.ptr, n * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
             }
         }
     }
@@ -210,15 +219,25 @@ template <typename T>
 int conv_simt(const ConvArgs& a, cudaStream_t st) {
     AFI_REQUIRE(a.cin % BK == 0 && a.cout % 4 == 0 && a.cout % 32 == 0, "conv_simt: cin %d / cout %d unsupported", a.cin, a.cout);
     AFI_REQUIRE(a.ntaps >= 1 && a.ntaps <= AFI_MAX_TAPS, "conv_simt: bad tap count");
-    long long M = (long long)a.N * a.H * a.W;
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "conv_simt: bad problem count %d", a.nprob);
+    SimtGroup grp;
+    long long M = 0;
+    int mt = 0;
+    for (int i = 0; i < a.nprob; i++) {
+        long long Mi = (long long)a.p[i].N * a.p[i].H * a.p[i].W;
+        grp.mt_begin[i] = mt;
+        mt += (int)((Mi + BM - 1) / BM);
+        M += Mi;
+    }
+    grp.mt_begin[a.nprob] = mt;
     if (M == 0) return AFI_OK;
     ProfScope prof(PROF_CONV_SIMT, 2.0 * M * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, M, st);
     if (a.cout % 128 == 0 || a.cout > 128) {
-        dim3 grid((unsigned)((M + BM - 1) / BM), (a.cout + 127) / 128);
-        k_conv_simt<T, 128><<<grid, 256, 0, st>>>(a);
+        dim3 grid((unsigned)mt, (a.cout + 127) / 128);
+        k_conv_simt<T, 128><<<grid, 256, 0, st>>>(a, grp);
     } else {
-        dim3 grid((unsigned)((M + BM - 1) / BM), (a.cout + 31) / 32);
-        k_conv_simt<T, 32><<<grid, 256, 0, st>>>(a);
+        dim3 grid((unsigned)mt, (a.cout + 31) / 32);
+        k_conv_simt<T, 32><<<grid, 256, 0, st>>>(a, grp);
     }
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -230,14 +249,15 @@ template int conv_simt<bf16>(const ConvArgs&, cudaStream_t);
 // weight gradient
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int BN>
-__global__ void __launch_bounds__(256) k_wgrad_simt(const __grid_constant__ WgradArgs a, int ksplit, int chunk) {
+__global__ void __launch_bounds__(256) k_wgrad_simt(const __grid_constant__ WgradArgs a, const __grid_constant__ SimtGroup grp, int ksplit,
+                                                    int chunk) {
     constexpr int RS = BN == 128 ? 2 : 1, CS = RS;
     constexpr int TXN = BN / (4 * CS);
     constexpr int EB = BN / 16;
     __shared__ __align__(16) float As[2][BK][BM + LDS_PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + LDS_PAD];
     const int tid = threadIdx.x;
-    const long long P = (long long)a.N * a.H * a.W;
+    const long long P = grp.px_begin[a.nprob];
     const int ci0 = blockIdx.x * BM, co0 = blockIdx.y * BN;
     const int tp = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
     const Tap tap = a.taps[tp];
@@ -250,23 +270,23 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(const __grid_constant__ Wgra
     const int amoff = (tid & 15) * 8;             // 8 consecutive input channels
     const int bnoff = (tid & 15) * EB;
     const bool a_ok = (ci0 + amoff) < a.cin, b_ok = (co0 + bnoff) < a.cout;
-    const T* xp = reinterpret_cast<const T*>(a.x.ptr);
-    const T* gp = reinterpret_cast<const T*>(a.dy.ptr);
-
     float ra[8], rb[EB];
+    int pi = 0;      // the K range walks the concatenated pixels of all problems in order
     auto load_global = [&](int it) {
         long long p = pk0 + (long long)it * BK + lk;
         bool pok = p < pk1;
         int x = 0, y = 0, n = 0;
-        if (pok) { x = (int)(p % a.W); long long t = p / a.W; y = (int)(t % a.H); n = (int)(t / a.H); }
+        while (pi + 1 < a.nprob && p >= grp.px_begin[pi + 1]) pi++;
+        const WgradProb& pr = a.p[pi];
+        if (pok) { long long q = p - grp.px_begin[pi]; x = (int)(q % pr.W); long long t = q / pr.W; y = (int)(t % pr.H); n = (int)(t / pr.H); }
         int iy = y + tap.dy, ix = x + tap.dx;
-        if (pok && a_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-            VecLoad<T, 8>::load(xp + n * a.x.sn + iy * a.x.sy + ix * a.x.sx + ci0 + amoff, ra);
+        if (pok && a_ok && iy >= 0 && iy < pr.H && ix >= 0 && ix < pr.W)
+            VecLoad<T, 8>::load(reinterpret_cast<const T*>(pr.x.ptr) + n * pr.x.sn + iy * pr.x.sy + ix * pr.x.sx + ci0 + amoff, ra);
         else {
 #pragma unroll
             for (int i = 0; i < 8; i++) ra[i] = 0.f;
         }
-        if (pok && b_ok) VecLoad<T, EB>::load(gp + n * a.dy.sn + y * a.dy.sy + x * a.dy.sx + co0 + bnoff, rb);
+        if (pok && b_ok) VecLoad<T, EB>::load(reinterpret_cast<const T*>(pr.dy.ptr) + n * pr.dy.sn + y * pr.dy.sy + x * pr.dy.sx + co0 + bnoff, rb);
         else {
 #pragma unroll
             for (int i = 0; i < EB; i++) rb[i] = 0.f;
@@ -317,7 +337,11 @@ __global__ void __launch_bounds__(256) k_wgrad_simt(const __grid_constant__ Wgra
 template <typename T>
 int wgrad_simt(const WgradArgs& a, cudaStream_t st) {
     AFI_REQUIRE(a.cin % 8 == 0 && a.cout % 32 == 0, "wgrad_simt: cin %d / cout %d unsupported", a.cin, a.cout);
-    long long P = (long long)a.N * a.H * a.W;
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "wgrad_simt: bad problem count %d", a.nprob);
+    SimtGroup grp;
+    long long P = 0;
+    for (int i = 0; i < a.nprob; i++) { grp.px_begin[i] = P; P += (long long)a.p[i].N * a.p[i].H * a.p[i].W; }
+    grp.px_begin[a.nprob] = P;
     if (P == 0) return AFI_OK;
     int bn = (a.cout >= 128) ? 128 : 32;
     int tiles = ((a.cin + BM - 1) / BM) * ((a.cout + bn - 1) / bn) * a.ntaps;
@@ -330,8 +354,8 @@ int wgrad_simt(const WgradArgs& a, cudaStream_t st) {
     ksplit = (P + chunk - 1) / chunk;
     dim3 grid((a.cin + BM - 1) / BM, (a.cout + bn - 1) / bn, (unsigned)(a.ntaps * ksplit));
     ProfScope prof(PROF_WGRAD_SIMT, 2.0 * P * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, P, st);
-    if (bn == 128) k_wgrad_simt<T, 128><<<grid, 256, 0, st>>>(a, (int)ksplit, (int)chunk);
-    else k_wgrad_simt<T, 32><<<grid, 256, 0, st>>>(a, (int)ksplit, (int)chunk);
+    if (bn == 128) k_wgrad_simt<T, 128><<<grid, 256, 0, st>>>(a, grp, (int)ksplit, (int)chunk);
+    else k_wgrad_simt<T, 32><<<grid, 256, 0, st>>>(a, grp, (int)ksplit, (int)chunk);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

@@ -28,15 +28,21 @@ constexpr int NUM_THREADS = 192;
 constexpr int ACC_COLS = 256;
 
 struct alignas(64) Maps {
-    CUtensorMap a[4];
-    CUtensorMap b;
+    CUtensorMap a[AFI_MAX_PROB][4];   // conv: input views per problem;  wgrad: a[p][0] = dY, a[p][1] = X
+    CUtensorMap b;                    // conv: packed weights
+};
+struct TileP {                        // per problem
+    int TH, TW, tiles_x, tiles_y;     // spatial patch and patch grid per image
+    int begin;                        // conv: first work item (M tile x N tile) / wgrad: first K tile of this problem
+    int prob;                         // index into ConvArgs.p / WgradArgs.p (problems are scheduled largest first)
 };
 struct Tiling {
-    int TH, TW, tiles_x, tiles_y;   // spatial patch and patch grid per image
-    int bn, n_tiles;                // N tile (multiple of 16, <= 256)
-    int kchunks;                    // ceil(cin / 64)
-    int total;                      // work items
-    int m_tiles, ksplit, ktiles;    // wgrad only
+    int bn, n_tiles;                  // N tile (multiple of 16, <= 256)
+    int kchunks;                      // ceil(cin / 64)
+    int total;                        // work items
+    int nprob;
+    int m_tiles, ksplit, ktiles;      // wgrad only
+    TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -140,7 +146,7 @@ struct Smem {
 
 __device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int nmaps_a, int warp, int lane) {
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < nmaps_a; i++) prefetch_tmap(&maps.a[i]);
+        for (int i = 0; i < nmaps_a; i++) prefetch_tmap(&maps.a[0][i]);
         prefetch_tmap(&maps.b);
         for (int i = 0; i < STAGES; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), 4); }
@@ -209,27 +215,32 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     __shared__ Smem s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_base = setup(s, maps, 4, warp, lane);
+    const uint32_t tmem_base = setup(s, maps, 0, warp, lane);
     const int iters = a.ntaps * tl.kchunks;
-    const int tiles_per_img = tl.tiles_x * tl.tiles_y;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = A_BYTES + tl.bn * 128;
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
-                int nt = tile % tl.n_tiles, mt = tile / tl.n_tiles;
+                int ti = 0;
+                while (tile >= tl.p[ti + 1].begin) ti++;
+                const TileP& tp_ = tl.p[ti];
+                int local = tile - tp_.begin;
+                int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
+                int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
                 int img = mt / tiles_per_img, r = mt % tiles_per_img;
-                int y0 = (r / tl.tiles_x) * tl.TH, x0 = (r % tl.tiles_x) * tl.TW;
+                int y0 = (r / tp_.tiles_x) * tp_.TH, x0 = (r % tp_.tiles_x) * tp_.TW;
                 int n0 = nt * tl.bn;
                 for (int tp = 0; tp < a.ntaps; tp++) {
                     const Tap t = a.taps[tp];
+                    const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
                     for (int kc = 0; kc < tl.kchunks; kc++) {
                         mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 1);
                         uint32_t fb = smem_u32(&s.full[stage]);
                         uint32_t sa = tiles0 + stage * STAGE_BYTES;
                         mbar_expect_tx(fb, tx_bytes);
-                        tma_load_4d(&maps.a[t.view], fb, sa, kc * 64, x0 + t.dx, y0 + t.dy, img);
+                        tma_load_4d(amap, fb, sa, kc * 64, x0 + t.dx, y0 + t.dy, img);
                         tma_load_3d(&maps.b, fb, sa + A_BYTES, kc * 64, n0, t.slab);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -262,13 +273,19 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int ty = row / tl.TW, tx = row % tl.TW;
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
-            int nt = tile % tl.n_tiles, mt = tile / tl.n_tiles;
+            int ti = 0;
+            while (tile >= tl.p[ti + 1].begin) ti++;
+            const TileP& tp_ = tl.p[ti];
+            const ConvProb& pr = a.p[tp_.prob];
+            int local = tile - tp_.begin;
+            int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
+            int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
             int img = mt / tiles_per_img, r = mt % tiles_per_img;
-            int y = (r / tl.tiles_x) * tl.TH + ty, x = (r % tl.tiles_x) * tl.TW + tx;
-            const bool ok = (y < a.H) && (x < a.W);
+            const int ty = row / tp_.TW, tx = row % tp_.TW;
+            int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
+            const bool ok = (y < pr.H) && (x < pr.W);
             const int n0 = nt * tl.bn;
             mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
             tc_fence_after();
@@ -289,27 +306,27 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] *= a.alpha;
                     float t[16];
-                    if (a.r1.ptr) {
-                        ld16(a.r1.ptr, img * a.r1.sn + y * a.r1.sy + x * a.r1.sx + col, a.r1_dt, t);
+                    if (pr.r1.ptr) {
+                        ld16(pr.r1.ptr, img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx + col, a.r1_dt, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
                     }
-                    if (a.r2.ptr) {
-                        ld16(a.r2.ptr, img * a.r2.sn + y * a.r2.sy + x * a.r2.sx + col, a.r2_dt, t);
+                    if (pr.r2.ptr) {
+                        ld16(pr.r2.ptr, img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx + col, a.r2_dt, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
                     }
-                    if (a.accin.ptr) {
-                        ld16(a.accin.ptr, img * a.accin.sn + y * a.accin.sy + x * a.accin.sx + col, DT_F32, t);
+                    if (pr.accin.ptr) {
+                        ld16(pr.accin.ptr, img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx + col, DT_F32, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] += t[i];
                     }
-                    if (a.mask.ptr) {
-                        ld16(a.mask.ptr, img * a.mask.sn + y * a.mask.sy + x * a.mask.sx + col, DT_BF16, t);
+                    if (pr.mask.ptr) {
+                        ld16(pr.mask.ptr, img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx + col, DT_BF16, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
                     }
-                    st16(a.out.ptr, img * a.out.sn + y * a.out.sy + x * a.out.sx + col, a.out_dt, v);
+                    st16(pr.out.ptr, img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
                 }
             }
             tc_fence_before();
@@ -331,8 +348,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     __shared__ Smem s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_base = setup(s, maps, 1, warp, lane);
-    const int tiles_per_img = tl.tiles_x * tl.tiles_y;
+    const uint32_t tmem_base = setup(s, maps, 0, warp, lane);
     const int nb = tl.bn / 64;    // B boxes per stage
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
 
@@ -346,16 +362,21 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
                 const Tap t = a.taps[tp];
                 int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+                int ti = 0;
                 for (int kt = k0; kt < k1; kt++) {
-                    int img = kt / tiles_per_img, rr = kt % tiles_per_img;
-                    int y0 = (rr / tl.tiles_x) * tl.TH, x0 = (rr % tl.tiles_x) * tl.TW;
+                    while (kt >= tl.p[ti + 1].begin) ti++;      // K tiles walk the problems in schedule order
+                    const TileP& tp_ = tl.p[ti];
+                    int lk = kt - tp_.begin;
+                    int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
+                    int img = lk / tiles_per_img, rr = lk % tiles_per_img;
+                    int y0 = (rr / tp_.tiles_x) * tp_.TH, x0 = (rr % tp_.tiles_x) * tp_.TW;
                     mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
                     uint32_t fb = smem_u32(&s.full[stage]);
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
                     mbar_expect_tx(fb, tx_bytes);
                     // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
-                    tma_load_5d(&maps.a[0], fb, sa, 0, x0, y0, mt * 2, img);
-                    tma_load_5d(&maps.b, fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
+                    tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
+                    tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -480,27 +501,51 @@ int tc_init(afi_ctx* ctx) {
     return AFI_OK;
 }
 
+// problems are scheduled largest first (longest-processing-time order keeps the persistent CTAs' tail short)
+static void order_by_size(int n, const long long* size, int* order) {
+    for (int i = 0; i < n; i++) order[i] = i;
+    for (int i = 1; i < n; i++) {
+        int k = order[i], j = i - 1;
+        while (j >= 0 && size[order[j]] < size[k]) { order[j + 1] = order[j]; j--; }
+        order[j + 1] = k;
+    }
+}
+
 int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     using namespace tc;
     AFI_REQUIRE(ctx && ctx->encode_tiled, "conv_tc: context not initialised");
     AFI_REQUIRE(a.cin % 16 == 0 && a.cout % 16 == 0, "conv_tc: cin %d / cout %d must be multiples of 16", a.cin, a.cout);
-    if ((long long)a.N * a.H * a.W == 0) return AFI_OK;
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "conv_tc: bad problem count %d", a.nprob);
+    long long size[AFI_MAX_PROB], pixels = 0;
+    for (int i = 0; i < a.nprob; i++) { size[i] = (long long)a.p[i].N * a.p[i].H * a.p[i].W; pixels += size[i]; }
+    if (pixels == 0) return AFI_OK;
+    int order[AFI_MAX_PROB];
+    order_by_size(a.nprob, size, order);
     Tiling tl{};
-    pick_patch(a.H, a.W, 128, &tl.TH, &tl.TW);
-    tl.tiles_x = (a.W + tl.TW - 1) / tl.TW;
-    tl.tiles_y = (a.H + tl.TH - 1) / tl.TH;
     tl.n_tiles = (a.cout + 255) / 256;
     tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
     tl.kchunks = (a.cin + 63) / 64;
-    tl.total = a.N * tl.tiles_x * tl.tiles_y * tl.n_tiles;
-    Maps maps;
     int nviews = 0;
     for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
     AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc: bad view count");
-    for (int i = 0; i < 4; i++) {
-        const PView& v = a.in[i < nviews ? i : 0];
-        AFI_TRY(encode_view(ctx, &maps.a[i], v, a.cin, a.W, a.H, a.N, tl.TW, tl.TH));
+    Maps maps;
+    int begin = 0, np = 0;
+    for (int oi = 0; oi < a.nprob; oi++) {
+        const ConvProb& pr = a.p[order[oi]];
+        if (size[order[oi]] == 0) continue;
+        TileP& t = tl.p[np];
+        pick_patch(pr.H, pr.W, 128, &t.TH, &t.TW);
+        t.tiles_x = (pr.W + t.TW - 1) / t.TW;
+        t.tiles_y = (pr.H + t.TH - 1) / t.TH;
+        t.begin = begin;
+        t.prob = order[oi];
+        begin += pr.N * t.tiles_x * t.tiles_y * tl.n_tiles;
+        for (int v = 0; v < nviews; v++) AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.TW, t.TH));
+        np++;
     }
+    tl.nprob = np;
+    tl.p[np].begin = begin;
+    tl.total = begin;
     int nslab = 0;
     for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
     {
@@ -510,7 +555,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
     }
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
-    ProfScope prof(PROF_CONV_TC, 2.0 * a.N * a.H * a.W * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, (long long)a.N * a.H * a.W, st);
+    ProfScope prof(PROF_CONV_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
     k_conv_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -520,15 +565,36 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     using namespace tc;
     AFI_REQUIRE(ctx && ctx->encode_tiled, "wgrad_tc: context not initialised");
     AFI_REQUIRE(a.cin % 16 == 0 && a.cout % 16 == 0, "wgrad_tc: cin %d / cout %d must be multiples of 16", a.cin, a.cout);
-    if ((long long)a.N * a.H * a.W == 0) return AFI_OK;
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "wgrad_tc: bad problem count %d", a.nprob);
+    long long size[AFI_MAX_PROB], pixels = 0;
+    for (int i = 0; i < a.nprob; i++) { size[i] = (long long)a.p[i].N * a.p[i].H * a.p[i].W; pixels += size[i]; }
+    if (pixels == 0) return AFI_OK;
+    int order[AFI_MAX_PROB];
+    order_by_size(a.nprob, size, order);
     Tiling tl{};
-    pick_patch(a.H, a.W, 64, &tl.TH, &tl.TW);
-    tl.tiles_x = (a.W + tl.TW - 1) / tl.TW;
-    tl.tiles_y = (a.H + tl.TH - 1) / tl.TH;
-    tl.ktiles = a.N * tl.tiles_x * tl.tiles_y;
     tl.m_tiles = (a.cout + 127) / 128;
     tl.n_tiles = (a.cin + 255) / 256;
     tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
+    Maps maps;
+    int begin = 0, np = 0;
+    for (int oi = 0; oi < a.nprob; oi++) {
+        const WgradProb& pr = a.p[order[oi]];
+        if (size[order[oi]] == 0) continue;
+        TileP& t = tl.p[np];
+        pick_patch(pr.H, pr.W, 64, &t.TH, &t.TW);
+        t.tiles_x = (pr.W + t.TW - 1) / t.TW;
+        t.tiles_y = (pr.H + t.TH - 1) / t.TH;
+        t.begin = begin;
+        t.prob = order[oi];
+        begin += pr.N * t.tiles_x * t.tiles_y;
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][0], pr.dy, a.cout, pr.W, pr.H, pr.N, t.TW, t.TH, 2));
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N, t.TW, t.TH, tl.bn / 64));
+        np++;
+    }
+    tl.nprob = np;
+    tl.p[np].begin = begin;
+    tl.ktiles = begin;
+    maps.b = maps.a[tl.p[0].prob][0];
     int base = a.ntaps * tl.m_tiles * tl.n_tiles;
     int ks = (2 * ctx->sm_count + base - 1) / base;
     if (ks > tl.ktiles) ks = tl.ktiles;
@@ -536,12 +602,8 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     int kper = (tl.ktiles + ks - 1) / ks;
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
-    Maps maps;
-    AFI_TRY(encode_view_grouped(ctx, &maps.a[0], a.dy, a.cout, a.W, a.H, a.N, tl.TW, tl.TH, 2));
-    for (int i = 1; i < 4; i++) maps.a[i] = maps.a[0];
-    AFI_TRY(encode_view_grouped(ctx, &maps.b, a.x, a.cin, a.W, a.H, a.N, tl.TW, tl.TH, tl.bn / 64));
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
-    ProfScope prof(PROF_WGRAD_TC, 2.0 * a.N * a.H * a.W * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, (long long)a.N * a.H * a.W, st);
+    ProfScope prof(PROF_WGRAD_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
     k_wgrad_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;

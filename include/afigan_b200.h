@@ -39,6 +39,7 @@ extern "C" {
 #define AFI_PREC_BF16_SIMT 2 /* bf16 storage + CUDA-core GEMM: on-device cross-check of mode 1        */
 
 #define AFI_MAX_RDB 4
+#define AFI_MAX_CALLS 10 /* calls per grouped launch */
 #define AFI_CH 256 /* feature channels of the AF interpolator and of the discriminator input */
 
 typedef struct afi_ctx afi_ctx;
@@ -91,19 +92,25 @@ size_t afi_g_workspace_bytes(int prec, int n, int h, int w, int n_rdb, int lat_c
 /* Re-layout the parameters for the GEMM kernels.  Call again whenever the parameters change. */
 int afi_g_pack(afi_ctx*, int prec, const afi_g_params*, void* packed, void* stream);
 
-/* Generator.forward (generator_rdb.py:123-130): y[:, :, :oh, :ow] of Generators[0](x) + bilinear2x(x), x = [n,256,h,w],
- * oh <= 2h, ow <= 2w (the top-left crop of _reshape_stage1, stage1_trainer.py:437-443, folded in).
- * y is contiguous [n,256,oh,ow] fp32.  lateral may be NULL. */
-int afi_g_forward(afi_ctx*, int prec, const afi_g_params*, const void* packed, afi_view4 x, int n, int h, int w,
-                  float* y, int oh, int ow, const afi_lateral* lateral, void* ws, size_t ws_bytes,
+/* One Generator call.  Calls of a group (e.g. the five pyramid levels of a stage-1 step) share the weights and are
+ * evaluated by GROUPED kernel launches: one launch per layer covers every call of the group. */
+typedef struct {
+    afi_view4 x; int n, h, w;       /* input features [n,256,h,w]                                                     */
+    float* y; int oh, ow;           /* forward: contiguous [n,256,oh,ow] output, oh <= 2h, ow <= 2w (top-left crop)     */
+    afi_view4 dy; float* dx;        /* backward: dL/dy view of [n,256,oh,ow]; dx contiguous [n,256,h,w] or NULL         */
+    const afi_lateral* lateral;     /* optional fused FPN lateral (forward only for now), may be NULL                   */
+    void* ws; size_t ws_bytes;      /* workspace of afi_g_workspace_bytes(); keeps the activations between fwd and bwd  */
+} afi_g_call;
+
+/* Generator.forward (generator_rdb.py:123-130) for each call: y = (Generators[0](x) + bilinear2x(x))[:, :, :oh, :ow]
+ * (the top-left crop of _reshape_stage1, stage1_trainer.py:437-443, folded in). */
+int afi_g_forward(afi_ctx*, int prec, const afi_g_params*, const void* packed, const afi_g_call* calls, int ncalls,
                   int save_for_backward, void* stream);
 
-/* Backward of the call that filled `ws`.  dy = dL/dy, view of [n,256,oh,ow].  Weight/bias gradients are ADDED
- * into `gradacc` (packed, zero it with afi_zero first); dx (contiguous [n,256,h,w], may be NULL) is overwritten.
- * lat_dx / lat_gw / lat_gb (may be NULL) receive the lateral's input / weight / bias gradients (overwritten). */
-int afi_g_backward(afi_ctx*, int prec, const afi_g_params*, const void* packed, afi_view4 dy, int n, int h, int w,
-                   int oh, int ow, void* ws, size_t ws_bytes, float* gradacc, float* dx,
-                   const afi_lateral* lateral, float* lat_dx, float* lat_gw, float* lat_gb, void* stream);
+/* Backward of the calls that filled their `ws`.  Weight/bias gradients of ALL calls are ADDED into `gradacc` (packed,
+ * zero it with afi_zero first). */
+int afi_g_backward(afi_ctx*, int prec, const afi_g_params*, const void* packed, const afi_g_call* calls, int ncalls,
+                   float* gradacc, void* stream);
 
 /* grads (torch layouts) = [grads +] scale * unpack(gradacc) */
 int afi_g_unpack_grads(afi_ctx*, int prec, const float* gradacc, const afi_g_grads*, float scale, int accumulate, void* stream);
@@ -125,17 +132,24 @@ size_t afi_d_gradacc_bytes(void);
 size_t afi_d_workspace_bytes(int prec, int n, int h, int w, int save_for_backward);
 int afi_d_pack(afi_ctx*, int prec, const afi_d_params*, void* packed, void* stream);
 
-/* Discriminators[0](x) (feature_patch_discriminator.py:32-41 as called at stage1_trainer.py:349-353): x = [n,256,h,w],
- * logits = contiguous [n,1,h,w].  training != 0: BatchNorm uses this call's batch statistics (biased var, eps) and
- * updates the running buffers; training == 0: running statistics are used. */
-int afi_d_forward(afi_ctx*, int prec, const afi_d_params*, const void* packed, afi_view4 x, int n, int h, int w,
-                  float* logits, int training, float momentum, float eps, void* ws, size_t ws_bytes,
-                  int save_for_backward, void* stream);
+/* One discriminator call; a group (e.g. level x {real, fake} of a stage-1 phase) runs as grouped launches per layer. */
+typedef struct {
+    afi_view4 x; int n, h, w;       /* input [n,256,h,w]                               */
+    float* logits;                  /* forward: contiguous [n,1,h,w]                   */
+    const float* dlogits;           /* backward: contiguous [n,1,h,w]                  */
+    float* dx;                      /* backward: must be NULL (stage 1/2 detach the input) */
+    void* ws; size_t ws_bytes;
+} afi_d_call;
 
-/* Backward of the (training-mode) call that filled ws.  dlogits contiguous [n,1,h,w].  Gradients are ADDED into
- * gradacc (packed); dx (contiguous [n,256,h,w]) may be NULL -- stage 1/2 never need it (inputs are detached). */
-int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const float* dlogits, int n, int h, int w,
-                   void* ws, size_t ws_bytes, float* gradacc, float* dx, void* stream);
+/* Discriminators[0](x) (feature_patch_discriminator.py:32-41 as called at stage1_trainer.py:349-353) for each call, IN CALL
+ * ORDER as far as the BatchNorm running buffers are concerned.  training != 0: each call is normalised with ITS OWN batch
+ * statistics (biased var, eps) and updates the running buffers; training == 0: running statistics are used. */
+int afi_d_forward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls,
+                  int training, float momentum, float eps, int save_for_backward, void* stream);
+
+/* Backward of the (training-mode) calls that filled their ws.  Gradients of all calls are ADDED into gradacc (packed). */
+int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls,
+                   float* gradacc, void* stream);
 int afi_d_unpack_grads(afi_ctx*, int prec, const float* gradacc, const afi_d_grads*, float scale, int accumulate, void* stream);
 
 /* ---- losses of the stage-1/2 trainers ---------------------------------------------------------------- */
