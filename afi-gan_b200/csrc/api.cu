@@ -505,10 +505,12 @@ int afi_g_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_g
 namespace afi {
 static const int DC[4] = {256, 512, 1024, 1024};
 
-struct DPacked { size_t f[3], d[3], total; };
+struct DPacked { size_t f[3], d[3], hf, hb, total; };   // hf / hb: tensor-core head packs [16][1024] / [1024][16]
 static DPacked d_packed_layout() {
     DPacked L; size_t o = 0;
     for (int i = 0; i < 3; i++) { L.f[i] = o; o += (size_t)9 * DC[i] * DC[i + 1]; L.d[i] = o; o += (size_t)9 * DC[i] * DC[i + 1]; }
+    L.hf = o; o += 16 * DC[3];
+    L.hb = o; o += 16 * DC[3];
     L.total = o;
     return L;
 }
@@ -517,7 +519,7 @@ static DGradAcc d_gradacc_layout() {
     DGradAcc L; size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
     for (int i = 0; i < 3; i++) { L.w[i] = take((size_t)9 * DC[i] * DC[i + 1]); L.b[i] = take(DC[i + 1]); L.gamma[i] = take(DC[i + 1]); L.beta[i] = take(DC[i + 1]); }
-    L.w[3] = take(9 * DC[3]); L.b[3] = take(1);
+    L.w[3] = take(16 * DC[3]); L.b[3] = take(1);   // head: torch layout [1024][9] (CUDA-core engine) or [16][1024] (tensor-core engine)
     L.total = o;
     return L;
 }
@@ -525,7 +527,7 @@ struct DWs {
     void *A[4], *Z[3];
     float *mean[3], *rstd[3], *T9;
     double* sums;          // [2][1024]
-    void *DY[3], *DXb;
+    void *DY[3], *DXb, *G9;
     size_t total;
 };
 static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) {
@@ -535,11 +537,12 @@ static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) 
     W.A[0] = cv.take(P * DC[0] * es);
     for (int i = 0; i < 3; i++) { W.Z[i] = cv.take(P * DC[i + 1] * es); W.A[i + 1] = cv.take(P * DC[i + 1] * es); }
     for (int i = 0; i < 3; i++) { W.mean[i] = (float*)cv.take(1024 * 4); W.rstd[i] = (float*)cv.take(1024 * 4); }
-    W.T9 = (float*)cv.take(P * 9 * 4);
+    W.T9 = (float*)cv.take(P * 16 * 4);
     W.sums = (double*)cv.take(2 * 1024 * 8);
     if (backward) {
         for (int i = 0; i < 3; i++) W.DY[i] = cv.take(P * DC[i + 1] * es);
         W.DXb = cv.take(P * DC[0] * 4);
+        W.G9 = cv.take(P * 16 * 2);
     }
     W.total = cv.off;
     return W;
@@ -561,6 +564,7 @@ int afi_d_pack(afi_ctx* ctx, int prec, const afi_d_params* p, void* packed, void
         AFI_TRY(pack_weights(p->w[i], DC[i + 1], DC[i], pm(prec, 0), (char*)packed + L.f[i] * es, dt, st));
         AFI_TRY(pack_weights(p->w[i], DC[i + 1], DC[i], pm(prec, 1), (char*)packed + L.d[i] * es, dt, st));
     }
+    if (prec_tc(prec)) AFI_TRY(dhead_pack_tc(p->w[3], DC[3], (char*)packed + L.hf * es, (char*)packed + L.hb * es, st));
     return AFI_OK;
 }
 
@@ -589,6 +593,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         AFI_REQUIRE(calls[k].x.ptr && calls[k].logits, "afi_d_forward: call %d has a null pointer", k);
         AFI_TRY(to_nhwc(prec, calls[k].x, d[k].n, DC[0], d[k].h, d[k].w, pview(W[k].A[0], d[k].h, d[k].w, DC[0]), st));
     }
+    const bool tc = prec_tc(prec);
     for (int i = 0; i < 3; i++) {
         // Conv2d 3x3 + bias (all calls in one grouped launch) -> per call: BatchNorm with THIS call's batch statistics
         // -> LeakyReLU(0.2)                                                         feature_patch_discriminator.py:36-38
@@ -596,13 +601,16 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         conv_std(a, ncalls, d, DC[i], DC[i + 1], (const char*)packed + L.f[i] * es);
         a.bias = p->b[i]; a.out_dt = dt;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].A[i], d[k].h, d[k].w, DC[i]); a.p[k].out = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); }
+        if (training) for (int k = 0; k < ncalls; k++) AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+        const bool fuse_stats = training && tc && DC[i] >= 512;   // long-K layers hide the extra epilogue work behind the MMAs
+        if (fuse_stats) {   // tensor-core engine: the per-channel sum / sum of squares come out of the GEMM epilogue
+            a.stat_mode = 1;
+            for (int k = 0; k < ncalls; k++) { a.p[k].stat0 = W[k].sums; a.p[k].stat1 = W[k].sums + 1024; }
+        }
         AFI_TRY(run_conv(ctx, prec, a, st));
         for (int k = 0; k < ncalls; k++) {      // in call order: the running statistics see the calls sequentially
             PView Z = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]);
-            if (training) {
-                AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
-                AFI_TRY(col_stats(Z, dt, d[k].n, d[k].h, d[k].w, DC[i + 1], W[k].sums, W[k].sums + 1024, st));
-            }
+            if (training && !fuse_stats) AFI_TRY(col_stats(Z, dt, d[k].n, d[k].h, d[k].w, DC[i + 1], W[k].sums, W[k].sums + 1024, st));
             AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, (long long)d[k].n * d[k].h * d[k].w, DC[i + 1], eps, momentum, training, W[k].mean[i],
                                 W[k].rstd[i], p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
             AFI_TRY(bn_apply_lrelu(Z, pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]), dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], p->beta[i], 0.2f,
@@ -610,8 +618,20 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         }
     }
     // Conv2d 1024 -> 1                                                                   feature_patch_discriminator.py:40-41
-    for (int k = 0; k < ncalls; k++)
-        AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
+    if (tc) {
+        ConvArgs a;
+        conv_args_init(a);
+        a.cin = DC[3]; a.cout = 16; a.ntaps = 1; a.nprob = ncalls; a.w = (const char*)packed + L.hf * es; a.out_dt = DT_F32;
+        for (int k = 0; k < ncalls; k++) {
+            a.p[k].N = d[k].n; a.p[k].H = d[k].h; a.p[k].W = d[k].w;
+            a.p[k].in[0] = pview(W[k].A[3], d[k].h, d[k].w, DC[3]); a.p[k].out = pview(W[k].T9, d[k].h, d[k].w, 16);
+        }
+        AFI_TRY(run_conv(ctx, prec, a, st));
+        for (int k = 0; k < ncalls; k++) AFI_TRY(dhead_stencil16(W[k].T9, p->b[3], d[k].n, d[k].h, d[k].w, calls[k].logits, st));
+    } else {
+        for (int k = 0; k < ncalls; k++)
+            AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
+    }
     return AFI_OK;
 }
 
@@ -625,12 +645,32 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
     DPacked L = d_packed_layout();
     DGradAcc GL = d_gradacc_layout();
     PView X[AFI_MAX_PROB], DYv[AFI_MAX_PROB];
+    const bool tc = prec_tc(prec);
     for (int k = 0; k < ncalls; k++) {
         AFI_REQUIRE(calls[k].dlogits, "afi_d_backward: call %d has no dlogits", k);
         AFI_REQUIRE(!calls[k].dx, "afi_d_backward: input gradient is not implemented (stage 1/2 detach the discriminator input)");
-        // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
-        AFI_TRY(dhead_backward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], calls[k].dlogits, d[k].n, d[k].h, d[k].w, DC[3],
-                               gradacc + GL.w[3], gradacc + GL.b[3], pview(W[k].DY[2], d[k].h, d[k].w, DC[3]), st));
+    }
+    if (tc) {
+        // head: dy3 = (sum_t g[q - tap_t] w4[:, t]) * lrelu'(a3) is 9 FMAs per element -> one dense HBM-bound pass that also emits the
+        // two BatchNorm-backward reductions of layer 3; dW4 = g9^T a3 is a K = pixels GEMM on the tensor cores; db4 = sum g.
+        WgradArgs g;
+        memset(&g, 0, sizeof(g));
+        g.cin = DC[3]; g.cout = 16; g.ntaps = 1; g.nprob = ncalls; g.dw = gradacc + GL.w[3];
+        for (int k = 0; k < ncalls; k++) {
+            const int n = d[k].n, h = d[k].h, w = d[k].w;
+            AFI_TRY(dhead_build_g9(calls[k].dlogits, n, h, w, W[k].G9, st));
+            AFI_TRY(sum_f32(calls[k].dlogits, (long long)n * h * w, gradacc + GL.b[3], st));
+            AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+            PView G9 = pview(W[k].G9, h, w, 16), A3 = pview(W[k].A[3], h, w, DC[3]);
+            AFI_TRY(dhead_backward_dense(A3, pview(W[k].Z[2], h, w, DC[3]), pview(W[k].DY[2], h, w, DC[3]), dt, p->w[3], calls[k].dlogits,
+                                         W[k].mean[2], W[k].rstd[2], n, h, w, DC[3], W[k].sums, W[k].sums + 1024, st));
+            g.p[k].N = n; g.p[k].H = h; g.p[k].W = w; g.p[k].x = A3; g.p[k].dy = G9;
+        }
+        AFI_TRY(run_wgrad(ctx, prec, g, st));
+    } else {
+        for (int k = 0; k < ncalls; k++)   // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
+            AFI_TRY(dhead_backward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], calls[k].dlogits, d[k].n, d[k].h, d[k].w, DC[3],
+                                   gradacc + GL.w[3], gradacc + GL.b[3], pview(W[k].DY[2], d[k].h, d[k].w, DC[3]), st));
     }
     for (int i = 2; i >= 0; i--) {
         const int co = DC[i + 1], ci = DC[i];
@@ -639,8 +679,10 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             DYv[k] = pview(W[k].DY[i], d[k].h, d[k].w, co);
             X[k] = pview(W[k].A[i], d[k].h, d[k].w, ci);
             // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ)
-            AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
-            AFI_TRY(bn_bwd_reduce(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], d[k].n, d[k].h, d[k].w, co, W[k].sums, W[k].sums + 1024, st));
+            if (!(tc && i == 2)) {      // (the tensor-core path got layer 3's reductions from the fused head pass above)
+                AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+                AFI_TRY(bn_bwd_reduce(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], d[k].n, d[k].h, d[k].w, co, W[k].sums, W[k].sums + 1024, st));
+            }
             AFI_TRY(bn_bwd_apply(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], W[k].sums, W[k].sums + 1024, gradacc + GL.gamma[i],
                                  gradacc + GL.beta[i], d[k].n, d[k].h, d[k].w, co, st));
         }
@@ -669,7 +711,10 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
         if (g->gamma[i]) AFI_TRY(axpby_f32(gradacc + GL.gamma[i], g->gamma[i], DC[i + 1], scale, accumulate, st));
         if (g->beta[i]) AFI_TRY(axpby_f32(gradacc + GL.beta[i], g->beta[i], DC[i + 1], scale, accumulate, st));
     }
-    if (g->w[3]) AFI_TRY(axpby_f32(gradacc + GL.w[3], g->w[3], 9 * DC[3], scale, accumulate, st));
+    if (g->w[3]) {
+        if (nk) AFI_TRY(dhead_unpack_tc(gradacc + GL.w[3], DC[3], g->w[3], scale, accumulate, st));
+        else AFI_TRY(axpby_f32(gradacc + GL.w[3], g->w[3], 9 * DC[3], scale, accumulate, st));
+    }
     if (g->b[3]) AFI_TRY(axpby_f32(gradacc + GL.b[3], g->b[3], 1, scale, accumulate, st));
     return AFI_OK;
 }

@@ -75,6 +75,9 @@ struct ConvProb {
     PView out, r1, r2;
     PView accin;          // f32
     PView mask;           // dtype T
+    // fused per-channel reductions of the stored output v (tensor-core engine only; see ConvArgs.stat_mode)
+    double* stat0; double* stat1;
+    PView bnz; const float* bn_mean; const float* bn_rstd;
 };
 struct ConvArgs {
     int cin, cout;
@@ -85,6 +88,9 @@ struct ConvArgs {
     int act; float slope;
     float alpha, beta1, beta2, mask_slope;
     int out_dt, r1_dt, r2_dt;
+    // 0: none.  1: stat0[c] += sum_p v, stat1[c] += sum_p v^2 (BatchNorm batch statistics of a conv output).
+    // 2: stat0[c] += sum_p v, stat1[c] += sum_p v * (bnz - bn_mean[c]) * bn_rstd[c]  (the two reductions of BatchNorm backward).
+    int stat_mode;
     ConvProb p[AFI_MAX_PROB];
 };
 
@@ -164,6 +170,15 @@ int dhead_forward(PView a3, int dt, const float* w4 /*[c][9] torch layout*/, con
 // dW4 += , db4 += , dy3 = (sum_tap g[q-tap] w4[tap]) * lrelu'(a3)
 int dhead_backward(PView a3, int dt, const float* w4, const float* g, int n, int h, int w, int c, float* dw4_acc, float* db4_acc,
                    PView dy3, cudaStream_t st);
+
+// tensor-core formulation of the discriminator head (bf16 mode)
+int dhead_pack_tc(const float* w4, int c, void* fwd, void* bwd, cudaStream_t st);
+int dhead_build_g9(const float* g, int n, int h, int w, void* g9, cudaStream_t st);
+int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float* logits, cudaStream_t st);
+int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumulate, cudaStream_t st);
+int sum_f32(const float* x, long long n, float* out, cudaStream_t st);
+int dhead_backward_dense(PView a3, PView z3, PView dy3, int dt, const float* w4, const float* g, const float* mean, const float* rstd, int n,
+                         int h, int w, int c, double* s_dy, double* s_dyx, cudaStream_t st);
 
 template <typename T> struct dt_of;
 template <> struct dt_of<float> { static const int v = DT_F32; };

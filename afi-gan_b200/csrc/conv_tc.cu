@@ -24,7 +24,8 @@ constexpr int A_BYTES = 16384;          // 128 rows x 128 B
 constexpr int B_BYTES_MAX = 32768;      // 256 rows x 128 B
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;        // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter)
+constexpr int EPI_THREADS = 256;
 constexpr int ACC_COLS = 256;
 
 struct alignas(64) Maps {
@@ -136,6 +137,8 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+struct Aux { uint4 a, b, c, d; };   // one 16-column chunk of auxiliary epilogue operands (64 B per thread)
+
 struct Smem {
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
@@ -149,7 +152,7 @@ __device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int nmaps_a
         for (int i = 0; i < nmaps_a; i++) prefetch_tmap(&maps.a[0][i]);
         prefetch_tmap(&maps.b);
         for (int i = 0; i < STAGES; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -206,6 +209,28 @@ __device__ __forceinline__ void st16(void* base, long long off, int dt, const fl
     }
 }
 
+// Column sums of a [32 lanes x 16 columns] register tile in 16 shuffles (instead of 80): each step halves the number of
+// columns a lane is responsible for while doubling the rows it has summed.  On return lane l holds in s[0] the sum over
+// the whole warp of column butterfly_col(l) (both lanes of a pair hold the same value; even lanes publish it).
+template <int C, int O>
+__device__ __forceinline__ void butterfly_step(float (&s)[16], int lane) {
+    const bool up = (lane & O) != 0;
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+        float send = up ? s[i] : s[i + C];
+        float keep = up ? s[i + C] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+    }
+}
+__device__ __forceinline__ void butterfly16(float (&s)[16], int lane) {
+    butterfly_step<8, 16>(s, lane);     // fully static indexing: the arrays stay in registers
+    butterfly_step<4, 8>(s, lane);
+    butterfly_step<2, 4>(s, lane);
+    butterfly_step<1, 2>(s, lane);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+}
+__device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
 // ---------------------------------------------------------------------------------------------------
 // convolution kernel
 // ---------------------------------------------------------------------------------------------------
@@ -213,7 +238,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
+    __shared__ float sstat[EPI_THREADS / 32][2][ACC_COLS];   // per epilogue warp: no atomics (fp32 smem atomics are CAS loops)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (EPI_THREADS / 32) * 2 * ACC_COLS; i += NUM_THREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tmem_base = setup(s, maps, 0, warp, lane);
     const int iters = a.ntaps * tl.kchunks;
@@ -272,8 +299,32 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
         }
     } else {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         int as = 0; uint32_t aphase = 0;
+        // Column statistics stay in shared memory across the tiles of this CTA for as long as (problem, N tile) does not change
+        // (with gridDim a multiple of n_tiles that is the whole run of a problem) and are published with ONE fp64 atomic per
+        // column per run: same-address fp64 atomics from 148 CTAs on every tile were the bottleneck of the first version.
+        int cur_prob = -1, cur_nt = -1;
+        auto flush_stats = [&](int prob, int nt_) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const ConvProb& fp = a.p[prob];
+            const int fn0 = nt_ * tl.bn;
+            for (int c = row + half * 128; c < tl.bn; c += EPI_THREADS) {
+                const int w0 = ((c >> 4) & 1) * 4;      // the four warps (one per lane quarter) that own this column's chunk
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    t0 += sstat[w0 + j][0][c]; t1 += sstat[w0 + j][1][c];
+                    sstat[w0 + j][0][c] = 0.f; sstat[w0 + j][1][c] = 0.f;
+                }
+                if (fn0 + c < a.cout) {
+                    atomicAdd(fp.stat0 + fn0 + c, (double)t0);
+                    atomicAdd(fp.stat1 + fn0 + c, (double)t1);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        };
         for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
             int ti = 0;
             while (tile >= tl.p[ti + 1].begin) ti++;
@@ -281,23 +332,57 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             const ConvProb& pr = a.p[tp_.prob];
             int local = tile - tp_.begin;
             int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
+            if (a.stat_mode && (tp_.prob != cur_prob || nt != cur_nt)) {
+                if (cur_prob >= 0) flush_stats(cur_prob, cur_nt);
+                cur_prob = tp_.prob; cur_nt = nt;
+            }
             int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
             int img = mt / tiles_per_img, r = mt % tiles_per_img;
             const int ty = row / tp_.TW, tx = row % tp_.TW;
             int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
             const bool ok = (y < pr.H) && (x < pr.W);
             const int n0 = nt * tl.bn;
-            mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
-            tc_fence_after();
+            // Auxiliary epilogue operands (residuals / mask / BN input / fp32 accumulate-in) are prefetched one chunk ahead of their
+            // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
+            const long long offA = pr.mask.ptr ? img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx
+                                               : (pr.r1.ptr ? img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx : 0);
+            const long long offB = pr.bnz.ptr && a.stat_mode == 2 ? img * pr.bnz.sn + y * pr.bnz.sy + x * pr.bnz.sx
+                                                                  : (pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0);
+            const bf16* pA = pr.mask.ptr ? (const bf16*)pr.mask.ptr + offA : (pr.r1.ptr ? (const bf16*)pr.r1.ptr + offA : nullptr);
+            const bf16* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const bf16*)pr.bnz.ptr + offB : (pr.r2.ptr ? (const bf16*)pr.r2.ptr + offB : nullptr);
+            const float* pC = pr.accin.ptr ? (const float*)pr.accin.ptr + img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx : nullptr;
+            const int nchunks = tl.bn >> 4;
+            auto aux_load = [&](int ch, Aux& r) {
+                const int col = n0 + (ch << 4);
+                if (ch < nchunks && ok && col < a.cout) {
+                    if (pC) {
+                        const uint4* g = reinterpret_cast<const uint4*>(pC + col);
+                        r.a = g[0]; r.b = g[1]; r.c = g[2]; r.d = g[3];
+                    } else {
+                        if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + col); r.a = g[0]; r.b = g[1]; }
+                        if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + col); r.c = g[0]; r.d = g[1]; }
+                    }
+                }
+            };
+            auto unpack16 = [](const uint4& lo, const uint4& hi, float* t) {
+                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) { t[2 * j] = __uint_as_float(w[j] << 16); t[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+            };
+            // chunk ownership: the two warps of a TMEM lane quarter interleave the 16-column chunks (half = 0 / 1)
             const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < tl.bn; c0 += 16) {
+            auto process = [&](int ch, const Aux& ax) {
+                const int c0 = ch << 4;
                 float v[16];
                 tmem_ld16(taddr + c0, v);
                 const int col = n0 + c0;
-                if (ok && col < a.cout) {
+                const bool valid = ok && col < a.cout;
+                float zbn[16];
+                if (valid) {
                     if (a.bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] += __ldg(a.bias + col + i);
+                        for (int i = 0; i < 4; i++) { float4 b = __ldg(b4 + i); v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w; }
                     }
                     if (a.act) {
 #pragma unroll
@@ -306,34 +391,86 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] *= a.alpha;
                     float t[16];
-                    if (pr.r1.ptr) {
-                        ld16(pr.r1.ptr, img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx + col, a.r1_dt, t);
+                    if (pC) {
+                        const uint4 q4[4] = {ax.a, ax.b, ax.c, ax.d};
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
-                    }
-                    if (pr.r2.ptr) {
-                        ld16(pr.r2.ptr, img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx + col, a.r2_dt, t);
+                        for (int i = 0; i < 4; i++) {
+                            v[4 * i] += __uint_as_float(q4[i].x); v[4 * i + 1] += __uint_as_float(q4[i].y);
+                            v[4 * i + 2] += __uint_as_float(q4[i].z); v[4 * i + 3] += __uint_as_float(q4[i].w);
+                        }
+                    } else {
+                        if (pr.r1.ptr) {
+                            unpack16(ax.a, ax.b, t);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
-                    }
-                    if (pr.accin.ptr) {
-                        ld16(pr.accin.ptr, img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx + col, DT_F32, t);
+                            for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
+                        }
+                        if (pr.r2.ptr) {
+                            unpack16(ax.c, ax.d, t);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] += t[i];
-                    }
-                    if (pr.mask.ptr) {
-                        ld16(pr.mask.ptr, img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx + col, DT_BF16, t);
+                            for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
+                        }
+                        if (pr.mask.ptr) {
+                            unpack16(ax.a, ax.b, t);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
+                            for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
+                        }
+                        if (a.stat_mode == 2) unpack16(ax.c, ax.d, zbn);
                     }
                     st16(pr.out.ptr, img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
                 }
+                if (a.stat_mode) {      // warp-uniform: every lane takes part in the shuffles, invalid rows contribute zeros
+                    float s0[16], s1[16];
+                    if (a.stat_mode == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) { s0[i] = valid ? v[i] : 0.f; s1[i] = valid ? v[i] * v[i] : 0.f; }
+                    } else {
+                        float mu[16], rs[16];
+                        if (valid) {
+                            const float4* m4 = reinterpret_cast<const float4*>(pr.bn_mean + col);
+                            const float4* r4 = reinterpret_cast<const float4*>(pr.bn_rstd + col);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                float4 m = __ldg(m4 + i), r = __ldg(r4 + i);
+                                mu[4 * i] = m.x; mu[4 * i + 1] = m.y; mu[4 * i + 2] = m.z; mu[4 * i + 3] = m.w;
+                                rs[4 * i] = r.x; rs[4 * i + 1] = r.y; rs[4 * i + 2] = r.z; rs[4 * i + 3] = r.w;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            s0[i] = valid ? v[i] : 0.f;
+                            s1[i] = valid ? v[i] * (zbn[i] - mu[i]) * rs[i] : 0.f;
+                        }
+                    }
+                    butterfly16(s0, lane);
+                    butterfly16(s1, lane);
+                    if ((lane & 1) == 0) {      // 16 lanes own 16 distinct columns of this warp's private accumulator
+                        int cc = c0 + butterfly_col(lane);
+                        sstat[warp - 2][0][cc] += s0[0];
+                        sstat[warp - 2][1][cc] += s1[0];
+                    }
+                }
+            };
+            // two-deep ring of auxiliary-operand buffers per warp: chunk j of this warp lives in buffer j % 2 and is re-filled for
+            // chunk j + 2 right after it has been consumed (no register rotation, so no load is waited on early).  With eight
+            // epilogue warps that keeps 256 threads x 128 B = 32 KB of loads in flight per SM (~HBM latency x per-SM bandwidth).
+            Aux bA, bB;
+            bA.a = bA.b = bA.c = bA.d = make_uint4(0, 0, 0, 0);
+            bB = bA;
+            aux_load(half, bA);
+            aux_load(half + 2, bB);
+            mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
+            tc_fence_after();
+            for (int ch = half; ch < nchunks; ch += 4) {
+                process(ch, bA);
+                aux_load(ch + 4, bA);
+                if (ch + 2 < nchunks) { process(ch + 2, bB); aux_load(ch + 6, bB); }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[as]));
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
     }
     teardown(tmem_base, warp);
 }
@@ -410,6 +547,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
         }
     } else {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;       // the two warps of a lane quarter interleave the 16-column chunks
         const int row = q * 32 + lane;
         int as = 0; uint32_t aphase = 0;
         for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
@@ -422,7 +560,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             mbar_wait(smem_u32(&s.acc_full[as]), aphase, 14);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            for (int c0 = 0; c0 < tl.bn; c0 += 16) {
+            for (int c0 = half * 16; c0 < tl.bn; c0 += 32) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
                 const int ci = nt * tl.bn + c0;
@@ -517,7 +655,15 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     AFI_REQUIRE(a.cin % 16 == 0 && a.cout % 16 == 0, "conv_tc: cin %d / cout %d must be multiples of 16", a.cin, a.cout);
     AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "conv_tc: bad problem count %d", a.nprob);
     long long size[AFI_MAX_PROB], pixels = 0;
-    for (int i = 0; i < a.nprob; i++) { size[i] = (long long)a.p[i].N * a.p[i].H * a.p[i].W; pixels += size[i]; }
+    for (int i = 0; i < a.nprob; i++) {
+        const ConvProb& q = a.p[i];
+        size[i] = (long long)q.N * q.H * q.W; pixels += size[i];
+        // the epilogue prefetches its auxiliary operands through two bf16 slots (r1|mask, r2|bnz) or one fp32 slot (accin)
+        AFI_REQUIRE(!(q.mask.ptr && q.r1.ptr) && !(q.r2.ptr && a.stat_mode == 2), "conv_tc: unsupported epilogue operand combination");
+        AFI_REQUIRE(!q.accin.ptr || !(q.mask.ptr || q.r1.ptr || q.r2.ptr || a.stat_mode == 2), "conv_tc: accin excludes other epilogue operands");
+        AFI_REQUIRE((!q.r1.ptr || a.r1_dt == DT_BF16) && (!q.r2.ptr || a.r2_dt == DT_BF16), "conv_tc: residuals must be bf16");
+        if (a.stat_mode) AFI_REQUIRE(q.stat0 && q.stat1 && (a.stat_mode == 1 || (q.bnz.ptr && q.bn_mean && q.bn_rstd)), "conv_tc: missing statistics operands");
+    }
     if (pixels == 0) return AFI_OK;
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);

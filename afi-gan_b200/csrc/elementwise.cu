@@ -33,6 +33,18 @@ __device__ __forceinline__ float lmaskf(float a, float slope) { return a > 0.f ?
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+__device__ __forceinline__ double block_reduce_sum(double v) {
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    if (warp == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // decode a flat (pixel, channel-quad) index
 struct PixIdx { int n, y, x; };
 __device__ __forceinline__ PixIdx decode_pixel(long long p, int H, int W) {
@@ -250,7 +262,7 @@ static inline bool is_dense(const PView& v, int h, int w, int c) {
 }
 static inline bool dense_ok(int c) { return c % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0; }
 constexpr int DENSE_ROWS = 64;     // rows per block of the elementwise passes
-constexpr int REDUCE_ROWS = 256;   // rows per block of the column reductions
+constexpr int REDUCE_ROWS = 256;   // max rows per block of the column reductions (fewer for small tensors: keep >= ~600 blocks)
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bn_apply_dense(const T* __restrict__ z, T* __restrict__ a, long long P, int C,
@@ -312,7 +324,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_dense(T* __restrict__ dy, 
 template <int MODE, typename T>
 __global__ void __launch_bounds__(256) k_col_reduce_dense(const T* __restrict__ x, const T* __restrict__ z, long long P, int C,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                          double* o0, double* o1, float* of) {
+                                                          double* o0, double* o1, float* of, int rows_per_block) {
     __shared__ float sm0[256 * 8];
     __shared__ float sm1[MODE == 2 ? 8 : 256 * 8];
     const int tpr = C >> 3, rpb = 256 / tpr;
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(256) k_col_reduce_dense(const T* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; k++) { mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; }
     }
-    long long r0 = (long long)blockIdx.x * REDUCE_ROWS, r1 = r0 + REDUCE_ROWS;
+    long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
 #pragma unroll 4
     for (long long r = r0 + lane_r; r < r1; r += rpb) {
@@ -369,8 +381,11 @@ static int col_reduce_launch(int mode, PView x, PView z, int dt, const float* me
     long long npix = (long long)n * h * w;
     if (npix == 0) return AFI_OK;
     if (is_dense(x, h, w, c) && dense_ok(c) && (mode != 1 || is_dense(z, h, w, c))) {
-        int grid = cdiv(npix, REDUCE_ROWS);
-#define AFI_CR(M, T) k_col_reduce_dense<M, T><<<grid, 256, 0, st>>>((const T*)x.ptr, (const T*)z.ptr, npix, c, mean, rstd, o0, o1, of)
+        int rows = (int)(npix / 592);
+        if (rows > REDUCE_ROWS) rows = REDUCE_ROWS;
+        if (rows < 8) rows = 8;
+        int grid = cdiv(npix, rows);
+#define AFI_CR(M, T) k_col_reduce_dense<M, T><<<grid, 256, 0, st>>>((const T*)x.ptr, (const T*)z.ptr, npix, c, mean, rstd, o0, o1, of, rows)
         if (dt == DT_F32) { if (mode == 0) AFI_CR(0, float); else if (mode == 1) AFI_CR(1, float); else AFI_CR(2, float); }
         else { if (mode == 0) AFI_CR(0, bf16); else if (mode == 1) AFI_CR(1, bf16); else AFI_CR(2, bf16); }
 #undef AFI_CR
@@ -621,6 +636,157 @@ int dhead_backward(PView a3, int dt, const float* w4, const float* g, int n, int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// discriminator head on the tensor-core engine (bf16 mode): the 1024 -> 1 3x3 conv is evaluated as a 1x1 conv to 16
+// channels (t9[p][t] = <a3[p], w4[:, t]>, taps 9..15 zero) followed by a 3x3 shift-sum, and its backward as a 16 -> 1024
+// 1x1 conv of g9[q][t] = g[q - tap_t] plus a K = pixels weight-gradient GEMM.  Both stream a3 exactly once (HBM-bound).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_dhead_pack_tc(const float* __restrict__ w4, int c, bf16* __restrict__ fwd, bf16* __restrict__ bwd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 16 * c) return;
+    int t = i / c, cc = i % c;
+    float v = t < 9 ? w4[cc * 9 + t] : 0.f;
+    fwd[t * c + cc] = (bf16)v;       // [cout = 16][cin = c]
+    bwd[cc * 16 + t] = (bf16)v;      // [cout = c][cin = 16]
+}
+int dhead_pack_tc(const float* w4, int c, void* fwd, void* bwd, cudaStream_t st) {
+    k_dhead_pack_tc<<<cdiv(16 * c, 256), 256, 0, st>>>(w4, c, (bf16*)fwd, (bf16*)bwd);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+__global__ void k_dhead_build_g9(const float* __restrict__ g, int H, int W, long long npix, bf16* __restrict__ g9) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= npix * 16) return;
+    int t = (int)(i & 15);
+    PixIdx q = decode_pixel(i >> 4, H, W);
+    float v = 0.f;
+    if (t < 9) {
+        int yy = q.y - (t / 3 - 1), xx = q.x - (t % 3 - 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = g[((long long)q.n * H + yy) * W + xx];
+    }
+    g9[i] = (bf16)v;
+}
+int dhead_build_g9(const float* g, int n, int h, int w, void* g9, cudaStream_t st) {
+    long long npix = (long long)n * h * w;
+    k_dhead_build_g9<<<cdiv(npix * 16, 256), 256, 0, st>>>(g, h, w, npix, (bf16*)g9);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+__global__ void k_dhead_stencil16(const float* __restrict__ t9, const float* __restrict__ b4, int H, int W, long long npix, float* __restrict__ logits) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    PixIdx q = decode_pixel(p, H, W);
+    float v = b4 ? b4[0] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        int yy = q.y + t / 3 - 1, xx = q.x + t % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v += t9[(((long long)q.n * H + yy) * W + xx) * 16 + t];
+    }
+    logits[p] = v;
+}
+int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float* logits, cudaStream_t st) {
+    long long npix = (long long)n * h * w;
+    k_dhead_stencil16<<<cdiv(npix, 256), 256, 0, st>>>(t9, b4, h, w, npix, logits);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+// dy3[q][c] = (sum_t g[q - tap_t] w4[c][t]) * lrelu'(a3[q][c]) fused with the two BatchNorm-backward reductions of layer 3.
+// Dense [P][C] operands, a thread owns 8 channels (its 8x9 head weights live in registers) and walks rows.
+template <typename T>
+__global__ void __launch_bounds__(256) k_dhead_bwd_dense(const float* __restrict__ g, const T* __restrict__ a3, const T* __restrict__ z3,
+                                                         T* __restrict__ dy3, long long P, int C, int H, int W, const float* __restrict__ w4,
+                                                         const float* __restrict__ mean, const float* __restrict__ rstd, double* s_dy,
+                                                         double* s_dyx, int rows_per_block, float slope) {
+    __shared__ float sm0[256 * 8];
+    __shared__ float sm1[256 * 8];
+    const int tpr = C >> 3, rpb = 256 / tpr;
+    const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
+    const int c0 = cq * 8;
+    float wr[8][9], mu[8], rs[8], a0[8], a1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; a0[k] = 0.f; a1[k] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; t++) wr[k][t] = w4[(c0 + k) * 9 + t];
+    }
+    long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+    if (r1 > P) r1 = P;
+    for (long long r = r0 + lane_r; r < r1; r += rpb) {
+        PixIdx q = decode_pixel(r, H, W);
+        float g9[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            int yy = q.y - (t / 3 - 1), xx = q.x - (t % 3 - 1);
+            g9[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(g + ((long long)q.n * H + yy) * W + xx) : 0.f;
+        }
+        float av[8], zv[8], o[8];
+        V8<T>::ld(a3 + r * C + c0, av);
+        V8<T>::ld(z3 + r * C + c0, zv);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float d = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; t++) d = fmaf(g9[t], wr[k][t], d);
+            d *= av[k] > 0.f ? 1.f : slope;
+            o[k] = d;
+            a0[k] += d;
+            a1[k] = fmaf(d, (zv[k] - mu[k]) * rs[k], a1[k]);
+        }
+        V8<T>::st(dy3 + r * C + c0, o);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { sm0[(lane_r * 8 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 8 + k) * tpr + cq] = a1[k]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        int qd = c >> 3, k = c & 7;
+        float t0 = 0.f, t1 = 0.f;
+        for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 8 + k) * tpr + qd]; t1 += sm1[(l * 8 + k) * tpr + qd]; }
+        atomicAdd(s_dy + c, (double)t0);
+        atomicAdd(s_dyx + c, (double)t1);
+    }
+}
+int dhead_backward_dense(PView a3, PView z3, PView dy3, int dt, const float* w4, const float* g, const float* mean, const float* rstd, int n,
+                         int h, int w, int c, double* s_dy, double* s_dyx, cudaStream_t st) {
+    AFI_REQUIRE(is_dense(a3, h, w, c) && is_dense(z3, h, w, c) && is_dense(dy3, h, w, c) && dense_ok(c), "dhead_backward_dense: operands must be dense");
+    long long P = (long long)n * h * w;
+    if (P == 0) return AFI_OK;
+    int rows = (int)(P / 592);
+    if (rows > 128) rows = 128;
+    if (rows < 8) rows = 8;
+    int grid = cdiv(P, rows);
+    if (dt == DT_F32)
+        k_dhead_bwd_dense<float><<<grid, 256, 0, st>>>(g, (const float*)a3.ptr, (const float*)z3.ptr, (float*)dy3.ptr, P, c, h, w, w4, mean, rstd, s_dy, s_dyx, rows, 0.2f);
+    else
+        k_dhead_bwd_dense<bf16><<<grid, 256, 0, st>>>(g, (const bf16*)a3.ptr, (const bf16*)z3.ptr, (bf16*)dy3.ptr, P, c, h, w, w4, mean, rstd, s_dy, s_dyx, rows, 0.2f);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+__global__ void k_sum_f32(const float* __restrict__ x, long long n, float* out) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += (double)x[i];
+    acc = block_reduce_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(out, (float)acc);
+}
+int sum_f32(const float* x, long long n, float* out, cudaStream_t st) {
+    int grid = cdiv(n, 1024); if (grid > 296) grid = 296;
+    k_sum_f32<<<grid, 256, 0, st>>>(x, n, out);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+__global__ void k_dhead_unpack_tc(const float* __restrict__ acc, int c, float* __restrict__ dst, float scale, int accumulate) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * c) return;
+    int cc = i / 9, t = i % 9;
+    float v = scale * acc[t * c + cc];
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumulate, cudaStream_t st) {
+    k_dhead_unpack_tc<<<cdiv(9 * c, 256), 256, 0, st>>>(acc, c, dst, scale, accumulate);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // weight packing: torch layouts -> GEMM slabs
 //   KN: dst[slab][k = gemm-cin][n = gemm-cout]   (CUDA-core engine, N contiguous)
 //   NK: dst[slab][n = gemm-cout][k = gemm-cin]   (tensor-core engine, K contiguous = UMMA K-major B operand)
@@ -708,18 +874,6 @@ int axpby_f32(const float* src, float* dst, long long n, float scale, int accumu
 // ---------------------------------------------------------------------------------------------------
 // losses and the optimiser step
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_reduce_sum(double v) {
-    __shared__ double sh[32];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
-    if (warp == 0) for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 __global__ void k_bce(const float* __restrict__ x, long long count, float target, float* loss_out, float* loss_sum, float weight,
                       float* __restrict__ dlogits, float gscale) {
     double acc = 0.0;
