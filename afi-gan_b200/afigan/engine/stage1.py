@@ -21,6 +21,7 @@ import torch.distributed as dist
 
 from .. import native as N
 from ..functional import _u8, d_grad_struct, d_param_struct, g_param_struct
+from .sync import FlatGradSync
 
 CH = 256
 
@@ -34,9 +35,6 @@ class Stage1Step:
         self.precision = precision or G.precision or N.default_precision()
         self.prec = N.PRECISIONS[self.precision]
         self.pg = process_group
-        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1 \
-            if distributed is None else distributed
-        self.world = dist.get_world_size(process_group) if self.distributed else 1
         self.g_params: List[torch.nn.Parameter] = G._params()
         self.d_params: List[torch.nn.Parameter] = self.Dstack._params()
         dev = self.g_params[0].device
@@ -46,8 +44,11 @@ class Stage1Step:
         self.n_rdb = G.n_residual_dense_blocks
         self.lib, self.ctx = N.lib(), N.context(dev)
         # flat gradient buffers: param.grad are views, so one all-reduce per optimiser covers every parameter
-        self.g_flat, self.g_grads = self._flat_grads(self.g_params)
-        self.d_flat, self.d_grads = self._flat_grads(self.d_params)
+        self.g_sync = FlatGradSync(self.g_params, process_group, distributed)
+        self.d_sync = FlatGradSync(self.d_params, process_group, distributed)
+        self.g_flat, self.g_grads = self.g_sync.flat, self.g_sync.views
+        self.d_flat, self.d_grads = self.d_sync.flat, self.d_sync.views
+        self.distributed, self.world = self.g_sync.enabled, self.g_sync.world
         self.g_mom = [torch.zeros_like(p) for p in self.g_params]
         self.d_mom = [torch.zeros_like(p) for p in self.d_params]
         self.steps_done = 0
@@ -63,17 +64,6 @@ class Stage1Step:
         self._pack_d()
 
     # ---- helpers --------------------------------------------------------------------------------------
-    def _flat_grads(self, params):
-        total = sum(p.numel() for p in params)
-        flat = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        views, off = [], 0
-        for p in params:
-            v = flat[off:off + p.numel()].view_as(p)
-            p.grad = v
-            views.append(v)
-            off += p.numel()
-        return flat, views
-
     def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool, tag="") -> torch.Tensor:
         key = (kind, n, h, w, save, tag)
         if key not in self._ws:
@@ -188,8 +178,7 @@ class Stage1Step:
             p._version  # parameters are updated in place behind torch's back; packed copies are refreshed explicitly below
 
     def _allreduce(self, flat: torch.Tensor):
-        if self.distributed:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        (self.g_sync if flat is self.g_flat else self.d_sync).all_reduce()
 
     # ---- the step ---------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -73,10 +73,11 @@ class PackedWeights:
 
 
 class AFInterpolatorFn(torch.autograd.Function):
-    """Generator.forward (reference generator_rdb.py:123-130) with the stage-1 top-left crop folded in."""
+    """Generator.forward (reference generator_rdb.py:123-130) with the stage-1 top-left crop folded in and, optionally, the
+    FPN / PAFPN top-down merge fused: y = scale * (conv1x1(lat_x; lat_w, lat_b) + G(x))  (fpn_sr.py:151-157)."""
 
     @staticmethod
-    def forward(ctx, x: torch.Tensor, holder, prec: int, out_hw: Optional[Tuple[int, int]], grad_enabled: bool, *params: torch.Tensor):
+    def forward(ctx, x, lat_x, lat_w, lat_b, holder, prec: int, out_hw, scale: float, grad_enabled: bool, *params):
         if not x.is_cuda:
             raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
         if x.dim() != 4 or x.size(1) != CH:
@@ -88,36 +89,63 @@ class AFInterpolatorFn(torch.autograd.Function):
         dev = x.device
         ps = g_param_struct(params, n_rdb)
         packed = holder.packed.get("g", prec, params, ps, n_rdb)
-        need_bwd = grad_enabled and (any(ctx.needs_input_grad[5:]) or ctx.needs_input_grad[0])
+        need_bwd = grad_enabled and any(ctx.needs_input_grad)
         lib, actx = N.lib(), N.context(dev)
-        ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, n_rdb, 0, int(need_bwd)), dev)
+        lat_c, lat = 0, None
+        if lat_x is not None:
+            lat_x, lat_w = lat_x.float(), lat_w.float().contiguous()
+            lat_c = lat_x.size(1)
+            if tuple(lat_x.shape) != (n, lat_c, oh, ow) or tuple(lat_w.shape[:2]) != (CH, lat_c):
+                raise ValueError(f"lateral input {tuple(lat_x.shape)} / weight {tuple(lat_w.shape)} do not match the output [{n},{CH},{oh},{ow}]")
+            lat = N.Lateral(lat_x=N.view4(lat_x), lat_c=lat_c, lat_w=lat_w.data_ptr(), lat_b=N.ptr(lat_b), scale=scale)
+        ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, n_rdb, lat_c, int(need_bwd)), dev)
         y = torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev)
         call = N.GCall(x=N.view4(x), n=n, h=h, w=w, y=y.data_ptr(), oh=oh, ow=ow, ws=ws.data_ptr(), ws_bytes=ws.numel())
+        if lat is not None:
+            call.lateral = C.pointer(lat)
         N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, int(need_bwd), N.stream_ptr()))
-        ctx.holder, ctx.prec, ctx.shape, ctx.n_rdb = holder, prec, (n, h, w, oh, ow), n_rdb
+        ctx.prec, ctx.shape, ctx.n_rdb, ctx.scale, ctx.lat_c = prec, (n, h, w, oh, ow), n_rdb, scale, lat_c
         ctx.ws, ctx.packed = ws, packed
-        ctx.save_for_backward(*params)
+        ctx.has_lat_b = lat_b is not None
+        ctx.save_for_backward(lat_x if lat_x is not None else x.new_empty(0), lat_w if lat_w is not None else x.new_empty(0),
+                              lat_b if lat_b is not None else x.new_empty(0), *params)
         return y
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
-        params = ctx.saved_tensors
+        lat_x, lat_w, lat_b, *params = ctx.saved_tensors
         n, h, w, oh, ow = ctx.shape
         dev = dy.device
         lib, actx = N.lib(), N.context(dev)
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("AF interpolator: gradient w.r.t. the input feature is not implemented yet")
         dy = dy.float()
         acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
         N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
         ps = g_param_struct(params, ctx.n_rdb)
         call = N.GCall(n=n, h=h, w=w, oh=oh, ow=ow, dy=N.view4(dy), ws=ctx.ws.data_ptr(), ws_bytes=ctx.ws.numel())
+        dx = d_lat_x = d_lat_w = d_lat_b = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, CH, h, w), dtype=torch.float32, device=dev)
+            call.dx = dx.data_ptr()
+        lat = None
+        if ctx.lat_c:
+            lat = N.Lateral(lat_x=N.view4(lat_x), lat_c=ctx.lat_c, lat_w=lat_w.data_ptr(), lat_b=N.ptr(lat_b) if ctx.has_lat_b else None,
+                            scale=ctx.scale)
+            call.lateral = C.pointer(lat)
+            if ctx.needs_input_grad[1]:
+                d_lat_x = torch.empty((n, ctx.lat_c, oh, ow), dtype=torch.float32, device=dev)
+                call.lat_dx = d_lat_x.data_ptr()
+            if ctx.needs_input_grad[2]:
+                d_lat_w = torch.empty_like(lat_w)
+                call.lat_gw = d_lat_w.data_ptr()
+            if ctx.has_lat_b and ctx.needs_input_grad[3]:
+                d_lat_b = torch.empty_like(lat_b)
+                call.lat_gb = d_lat_b.data_ptr()
         N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, acc.data_ptr(), N.stream_ptr()))
-        grads = [torch.empty_like(p) if ctx.needs_input_grad[5 + i] else None for i, p in enumerate(params)]
+        grads = [torch.empty_like(p) if ctx.needs_input_grad[9 + i] else None for i, p in enumerate(params)]
         gs = g_param_struct(grads, ctx.n_rdb)
         N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
         ctx.ws = None
-        return (None, None, None, None, None, *grads)
+        return (dx, d_lat_x, d_lat_w, d_lat_b, None, None, None, None, None, *grads)
 
 
 class PatchDiscriminatorFn(torch.autograd.Function):

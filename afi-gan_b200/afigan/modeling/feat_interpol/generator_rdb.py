@@ -94,4 +94,15 @@ class Generator(nn.Module):
     def forward(self, features: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """features [N,256,H,W] -> [N,256,2H,2W] (or its top-left out_hw crop: the _reshape_stage1 of the trainers)."""
         prec = native.PRECISIONS[self.precision or native.default_precision()]
-        return AFInterpolatorFn.apply(features, self._native, prec, out_hw, torch.is_grad_enabled(), *self._params())
+        return AFInterpolatorFn.apply(features, None, None, None, self._native, prec, out_hw, 1.0, torch.is_grad_enabled(), *self._params())
+
+    def merge(self, prev_features: torch.Tensor, bottom_up: torch.Tensor, lateral_weight: torch.Tensor,
+              lateral_bias: Optional[torch.Tensor] = None, fuse_type: str = "sum") -> torch.Tensor:
+        """The top-down merge of the AFI necks in ONE library call (reference fpn_sr.py:151-157, pafpn_sr.py:175-181):
+        lateral_conv1x1(bottom_up) + self(prev_features), divided by 2 for fuse_type "avg".  The interpolated map is cropped to
+        the lateral's size when 2H x 2W overshoots it (odd pyramid sizes)."""
+        prec = native.PRECISIONS[self.precision or native.default_precision()]
+        oh, ow = bottom_up.shape[2:]
+        w2 = lateral_weight.reshape(lateral_weight.shape[0], lateral_weight.shape[1])
+        return AFInterpolatorFn.apply(prev_features, bottom_up, w2, lateral_bias, self._native, prec, (oh, ow),
+                                      0.5 if fuse_type == "avg" else 1.0, torch.is_grad_enabled(), *self._params())

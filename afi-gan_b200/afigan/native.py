@@ -46,7 +46,8 @@ class Lateral(C.Structure):
 
 class GCall(C.Structure):
     _fields_ = [("x", View4), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("y", C.c_void_p), ("oh", C.c_int), ("ow", C.c_int),
-                ("dy", View4), ("dx", C.c_void_p), ("lateral", C.POINTER(Lateral)), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("dy", View4), ("dx", C.c_void_p), ("lateral", C.POINTER(Lateral)), ("lat_dx", C.c_void_p), ("lat_gw", C.c_void_p),
+                ("lat_gb", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
 
 
 class DCall(C.Structure):

@@ -142,6 +142,7 @@ static GGradAcc g_gradacc_layout(int n_rdb) {
 struct GWs {
     void *X0, *B[AFI_MAX_RDB], *H1, *H2, *H3, *Yb, *LX, *LAT;           // forward (X0..H3 saved for backward)
     void *G0, *G1, *G2, *dH1, *GA[2], *DC5, *GC, *GH, *DXb, *LW;        // backward scratch
+    void *LWD, *LWG, *LDX;                                              // lateral backward: dgrad pack, wgrad accumulator, d(lat_x) NHWC
     size_t total;
 };
 static GWs g_ws_layout(void* base, int prec, int n, int h, int w, int n_rdb, int lat_c, int backward) {
@@ -159,6 +160,7 @@ static GWs g_ws_layout(void* base, int prec, int n, int h, int w, int n_rdb, int
         W.dH1 = cv.take(P * C * 4); W.GA[0] = cv.take(P * CB * 4); W.GA[1] = cv.take(P * CB * 4);
         W.DC5 = cv.take(P * C * es); W.GC = cv.take(P * GR * es); W.GH = cv.take(P * C * es);
         W.DXb = cv.take(P * C * 4);
+        if (lat_c > 0) { W.LWD = cv.take((size_t)C * lat_c * es); W.LWG = cv.take((size_t)C * lat_c * 4); W.LDX = cv.take(P4 * lat_c * 4); }
     }
     W.total = cv.off;
     return W;
@@ -373,10 +375,9 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     for (int k = 0; k < ncalls; k++) {
         const afi_g_call& c = calls[k];
         AFI_REQUIRE(c.dy.ptr && c.ws, "afi_g_backward: call %d has a null pointer", k);
-        AFI_REQUIRE(!c.lateral, "afi_g_backward: lateral backward is not implemented yet (wrap the lateral conv in torch autograd)");
-        AFI_REQUIRE(!c.dx, "afi_g_backward: input gradient is not implemented yet");
+        AFI_REQUIRE((c.dx != nullptr) == (calls[0].dx != nullptr), "afi_g_backward: either every call of a group or none asks for dx");
         AFI_TRY(g_check(prec, c.n, c.h, c.w, nr));
-        W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, 0, 1);
+        W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, c.lateral ? c.lateral->lat_c : 0, 1);
         if (W[k].total > c.ws_bytes) { set_error("afi_g_backward: workspace %zu B < required %zu B", c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
         const int h = c.h, w = c.w, H2x = 2 * h, W2x = 2 * w;
         d1[k] = {c.n, h, w};
@@ -395,6 +396,39 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         const afi_g_call& c = calls[k];
         AFI_CUDA(cudaMemsetAsync(W[k].G0, 0, (size_t)4 * c.n * c.h * c.w * C * es, st));
         AFI_TRY(to_nhwc(prec, c.dy, c.n, C, c.oh, c.ow, G0[k], st));
+        if (c.lateral) {
+            // y = scale * (lateral_conv(lat_x) + G(x)): both branches see scale * dy                       fpn_sr.py:152-157
+            const afi_lateral* lat = c.lateral;
+            const int lat_c = lat->lat_c;
+            if (lat->scale != 1.f)
+                AFI_TRY(ew_combine(G0[k], dt, G0[k], dt, pview_null(), 0, pview_null(), 0, 0.2f, lat->scale, c.n, 2 * c.h, 2 * c.w, C, st));
+            PView G0c = G0[k];                                   // the oh x ow crop of the 2h x 2w gradient buffer (same strides)
+            PView LX = pview(W[k].LX, c.oh, c.ow, lat_c);        // lateral input kept by the forward pass
+            Dim3 dc = {c.n, c.oh, c.ow};
+            if (c.lat_gw) {
+                AFI_CUDA(cudaMemsetAsync(W[k].LWG, 0, (size_t)C * lat_c * 4, st));
+                WgradArgs g;
+                memset(&g, 0, sizeof(g));
+                g.cin = lat_c; g.cout = C; g.ntaps = 1; g.nprob = 1; g.dw = (float*)W[k].LWG;
+                g.p[0].N = dc.n; g.p[0].H = dc.h; g.p[0].W = dc.w; g.p[0].x = LX; g.p[0].dy = G0c;
+                AFI_TRY(run_wgrad(ctx, prec, g, st));
+                AFI_TRY(unpack_1x1((const float*)W[k].LWG, C, lat_c, prec_tc(prec) ? 1 : 0, c.lat_gw, 1.f, 0, st));
+            }
+            if (c.lat_gb) {
+                AFI_CUDA(cudaMemsetAsync(c.lat_gb, 0, C * sizeof(float), st));
+                AFI_TRY(col_sum_f32(G0c, dt, dc.n, dc.h, dc.w, C, c.lat_gb, st));
+            }
+            if (c.lat_dx) {
+                AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 5), W[k].LWD, dt, st));
+                conv_args_init(a);
+                a.cin = C; a.cout = lat_c; a.ntaps = 1; a.nprob = 1; a.w = W[k].LWD; a.out_dt = DT_F32;
+                a.p[0].N = dc.n; a.p[0].H = dc.h; a.p[0].W = dc.w;
+                a.p[0].in[0] = G0c; a.p[0].out = pview(W[k].LDX, dc.h, dc.w, lat_c);
+                AFI_TRY(run_conv(ctx, prec, a, st));
+                afi_view4 none; memset(&none, 0, sizeof(none));
+                AFI_TRY(nhwc_to_nchw<float>(pview(W[k].LDX, dc.h, dc.w, lat_c), pview_null(), none, 0, 0, 1.f, dc.n, lat_c, dc.h, dc.w, c.lat_dx, st));
+            }
+        }
     }
     // output conv
     AFI_TRY(wgrad_std(ctx, prec, ncalls, d2, H3, C, G0, C, gradacc + GL.out_w, st));
@@ -473,6 +507,17 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
                            d1[k].w, C, st));
     AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, X0, C, GH, C, gradacc + GL.head_w, st));
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(GH[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.head_b, st));
+    if (calls[0].dx) {
+        // dx = dgrad(head conv)(g_head) + scale * bilinear2x^T(dy)   (needed when the interpolator sits inside a detector: stage 2/3)
+        conv_std(a, ncalls, d1, C, C, pk + L.head_d * es);
+        a.out_dt = DT_F32;
+        for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GH[k]; a.p[k].out = pview(W[k].DXb, d1[k].h, d1[k].w, C); }
+        AFI_TRY(run_conv(ctx, prec, a, st));
+        for (int k = 0; k < ncalls; k++) {
+            const afi_g_call& c = calls[k];
+            AFI_TRY(g_input_grad(pview(W[k].DXb, c.h, c.w, C), c.dy, c.lateral ? c.lateral->scale : 1.f, c.n, C, c.h, c.w, c.oh, c.ow, c.dx, st));
+        }
+    }
     (void)tmpx;
     return AFI_OK;
 }

@@ -147,11 +147,14 @@ int col_sum_f32(PView x, int dt, int n, int h, int w, int c, float* out, cudaStr
 // weight re-layout: dst[slab][r][c] from torch [co][ci][k][k] (see pack modes in elementwise.cu)
 enum PackMode { PACK_FWD_KN = 0, PACK_FWD_NK = 1, PACK_DGRAD_KN = 2, PACK_DGRAD_NK = 3,
                 PACK_DECONV_FWD_KN = 4, PACK_DECONV_FWD_NK = 5, PACK_DECONV_DGRAD_KN = 6, PACK_DECONV_DGRAD_NK = 7,
-                PACK_1X1_KN = 8, PACK_1X1_NK = 9 };
+                PACK_1X1_KN = 8, PACK_1X1_NK = 9, PACK_1X1_DGRAD_KN = 10, PACK_1X1_DGRAD_NK = 11 };
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st);
 // gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);
 int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st);
+int unpack_1x1(const float* packed, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st);
+// dx (contiguous NCHW) = dxb (NHWC fp32) + dy_scale * bilinear2x^T(dy)
+int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, int w, int oh, int ow, float* dst, cudaStream_t st);
 
 // BatchNorm helpers (stats buffers: double sum[C], sumsq[C])
 int bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum, int training,

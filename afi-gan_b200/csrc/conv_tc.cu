@@ -147,12 +147,11 @@ struct Smem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int nmaps_a, int warp, int lane) {
+__device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int epi_warps, int warp, int lane) {
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < nmaps_a; i++) prefetch_tmap(&maps.a[0][i]);
         prefetch_tmap(&maps.b);
         for (int i = 0; i < STAGES; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), EPI_THREADS / 32); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), epi_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -234,15 +233,21 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 // ---------------------------------------------------------------------------------------------------
 // convolution kernel
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EPI_WARPS = 4: one epilogue warp per TMEM lane quarter (long-K layers: the MMA main loop hides the epilogue; 192 threads leave
+// 255 registers per thread).  EPI_WARPS = 8: two warps per quarter interleave the 16-column chunks (short-K layers whose
+// epilogue -- residual / mask loads, statistics -- would otherwise be the critical path).
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
+    constexpr int HALVES = EPI_WARPS / 4;
+    constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
-    __shared__ float sstat[EPI_THREADS / 32][2][ACC_COLS];   // per epilogue warp: no atomics (fp32 smem atomics are CAS loops)
+    __shared__ float sstat[EPI_WARPS][2][ACC_COLS];   // per epilogue warp: no atomics (fp32 smem atomics are CAS loops)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < (EPI_THREADS / 32) * 2 * ACC_COLS; i += NUM_THREADS) (&sstat[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_base = setup(s, maps, 0, warp, lane);
+    const uint32_t tmem_base = setup(s, maps, EPI_WARPS, warp, lane);
     const int iters = a.ntaps * tl.kchunks;
 
     if (warp == 0) {
@@ -299,7 +304,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
         }
     } else {
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;       // 0 .. HALVES-1
         const int row = q * 32 + lane;
         int as = 0; uint32_t aphase = 0;
         // Column statistics stay in shared memory across the tiles of this CTA for as long as (problem, N tile) does not change
@@ -307,11 +312,11 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
         // column per run: same-address fp64 atomics from 148 CTAs on every tile were the bottleneck of the first version.
         int cur_prob = -1, cur_nt = -1;
         auto flush_stats = [&](int prob, int nt_) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             const ConvProb& fp = a.p[prob];
             const int fn0 = nt_ * tl.bn;
-            for (int c = row + half * 128; c < tl.bn; c += EPI_THREADS) {
-                const int w0 = ((c >> 4) & 1) * 4;      // the four warps (one per lane quarter) that own this column's chunk
+            for (int c = row + half * 128; c < tl.bn; c += 32 * EPI_WARPS) {
+                const int w0 = ((c >> 4) % HALVES) * 4;      // the four warps (one per lane quarter) that own this column's chunk
                 float t0 = 0.f, t1 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -323,7 +328,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                     atomicAdd(fp.stat1 + fn0 + c, (double)t1);
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         };
         for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
             int ti = 0;
@@ -457,13 +462,13 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             bA.a = bA.b = bA.c = bA.d = make_uint4(0, 0, 0, 0);
             bB = bA;
             aux_load(half, bA);
-            aux_load(half + 2, bB);
+            aux_load(half + HALVES, bB);
             mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
             tc_fence_after();
-            for (int ch = half; ch < nchunks; ch += 4) {
+            for (int ch = half; ch < nchunks; ch += 2 * HALVES) {
                 process(ch, bA);
-                aux_load(ch + 4, bA);
-                if (ch + 2 < nchunks) { process(ch + 2, bB); aux_load(ch + 6, bB); }
+                aux_load(ch + 2 * HALVES, bA);
+                if (ch + HALVES < nchunks) { process(ch + HALVES, bB); aux_load(ch + 3 * HALVES, bB); }
             }
             tc_fence_before();
             __syncwarp();
@@ -485,7 +490,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     __shared__ Smem s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_base = setup(s, maps, 0, warp, lane);
+    const uint32_t tmem_base = setup(s, maps, EPI_THREADS / 32, warp, lane);
     const int nb = tl.bn / 64;    // B boxes per stage
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
 
@@ -634,7 +639,8 @@ int tc_init(afi_ctx* ctx) {
         return AFI_ERR_CUDA;
     }
     ctx->encode_tiled = fn;
-    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     return AFI_OK;
 }
@@ -702,7 +708,9 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     }
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
     ProfScope prof(PROF_CONV_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
-    k_conv_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
+    // short-K layers (K = taps x cin < 4096) cannot hide their epilogue behind the MMAs: give them eight epilogue warps
+    if (a.ntaps * tl.kchunks * 64 < 4096) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
+    else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

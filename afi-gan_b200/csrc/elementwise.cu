@@ -150,6 +150,57 @@ template int nhwc_to_nchw<float>(PView, PView, afi_view4, int, int, float, int, 
 template int nhwc_to_nchw<bf16>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
+// Input gradient of the interpolator: dx[n,c,i,j] = dXb[n,i,j,c] (head-conv dgrad, NHWC fp32) + bilinear2x^T(dy)[n,c,i,j].
+// Adjoint of the x2 bilinear upsample (align_corners=False): x[i] feeds out[2i-1] (1/4), out[2i], out[2i+1] (3/4), out[2i+2] (1/4);
+// the edge clamps fold the missing neighbour's 1/4 onto out[0] / out[2H-1] (weight 1).  dy is only defined on the oh x ow crop.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bilin_adj_w(int i, int o, int size) {
+    if ((i == 0 && o == 0) || (i == size - 1 && o == 2 * size - 1)) return 1.f;
+    return (o == 2 * i || o == 2 * i + 1) ? 0.75f : 0.25f;
+}
+__global__ void k_g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int c, int h, int w, int oh, int ow, float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    int n = blockIdx.z / h, y = blockIdx.z % h;
+    int tx = threadIdx.x, ty = threadIdx.y;
+    const float* ap = reinterpret_cast<const float*>(dxb.ptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int xx = x0 + ty + 8 * i, cc = c0 + tx;
+        tile[ty + 8 * i][tx] = (cc < c && xx < w) ? ap[n * dxb.sn + y * dxb.sy + xx * dxb.sx + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int cc = c0 + ty + 8 * i, xx = x0 + tx;
+        if (cc < c && xx < w) {
+            float v = tile[tx][ty + 8 * i];
+            const float* g = dy.ptr + n * dy.sn + cc * dy.sc;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = -1; a <= 2; a++) {
+                int oy = 2 * y + a;
+                if (oy < 0 || oy >= oh || oy >= 2 * h) continue;
+                float wy = bilin_adj_w(y, oy, h);
+#pragma unroll
+                for (int b = -1; b <= 2; b++) {
+                    int ox = 2 * xx + b;
+                    if (ox < 0 || ox >= ow || ox >= 2 * w) continue;
+                    acc += wy * bilin_adj_w(xx, ox, w) * g[oy * dy.sh + ox * dy.sw];
+                }
+            }
+            dst[(((long long)n * c + cc) * h + y) * w + xx] = v + dy_scale * acc;
+        }
+    }
+}
+int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, int w, int oh, int ow, float* dst, cudaStream_t st) {
+    dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
+    k_g_input_grad<<<grid, block, 0, st>>>(dxb, dy, dy_scale, c, h, w, oh, ow, dst);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // dst = scale * (a + b) * lrelu'(mask)
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt,
@@ -802,7 +853,7 @@ __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T*
     if (i >= total) return;
     int nk = mode & 1, kind = mode >> 1;
     int gk = (kind == 0 || kind == 2 || kind == 4) ? ci : co;   // gemm-cin
-    int gn = (kind == 0 || kind == 2 || kind == 4) ? co : ci;   // gemm-cout
+    int gn = (kind == 0 || kind == 2 || kind == 4) ? co : ci;   // gemm-cout   (kinds 1, 3, 5 are dgrads: roles swapped)
     int inner = (int)(i % (nk ? gk : gn));
     long long t2 = i / (nk ? gk : gn);
     int outer = (int)(t2 % (nk ? gn : gk));
@@ -815,6 +866,8 @@ __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T*
         v = w[((long long)k * ci + n) * 9 + (8 - slab)];
     } else if (kind == 4) {     // 1x1 forward: w[co][ci], k = ci, n = co
         v = w[(long long)n * ci + k];
+    } else if (kind == 5) {     // 1x1 dgrad: k = co, n = ci
+        v = w[(long long)k * ci + n];
     } else {
         int ph = slab / 9, t = slab % 9, a = ph >> 1, b = ph & 1, d0 = t / 3 - 1, d1 = t % 3 - 1;
         if (kind == 2) {        // deconv fwd: k = ci, n = co
@@ -829,7 +882,7 @@ __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T*
 }
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st) {
     int kind = mode >> 1;
-    int slabs = kind == 4 ? 1 : (kind >= 2 ? 36 : 9);
+    int slabs = (kind == 4 || kind == 5) ? 1 : (kind >= 2 ? 36 : 9);
     long long total = (long long)slabs * co * ci;
     if (dst_dt == DT_F32) k_pack<float><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (float*)dst, total);
     else k_pack<bf16><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (bf16*)dst, total);
@@ -857,6 +910,19 @@ __global__ void k_unpack_wgrad(const float* __restrict__ packed, int co, int ci,
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st) {
     long long total = (long long)co * ci * (deconv ? 36 : 9);
     k_unpack_wgrad<<<cdiv(total, 256), 256, 0, st>>>(packed, co, ci, layout_nk, deconv, dst, scale, accumulate, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+// 1x1 weight gradient: packed [ci][co] (KN) or [co][ci] (NK) -> torch [co][ci]
+__global__ void k_unpack_1x1(const float* __restrict__ packed, int co, int ci, int nk, float* __restrict__ dst, float scale, int accumulate) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)co * ci) return;
+    int c_i = (int)(i % ci), c_o = (int)(i / ci);
+    float v = scale * (nk ? packed[i] : packed[(long long)c_i * co + c_o]);
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+int unpack_1x1(const float* packed, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st) {
+    k_unpack_1x1<<<cdiv((long long)co * ci, 256), 256, 0, st>>>(packed, co, ci, layout_nk, dst, scale, accumulate);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

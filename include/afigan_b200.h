@@ -98,7 +98,8 @@ typedef struct {
     afi_view4 x; int n, h, w;       /* input features [n,256,h,w]                                                     */
     float* y; int oh, ow;           /* forward: contiguous [n,256,oh,ow] output, oh <= 2h, ow <= 2w (top-left crop)     */
     afi_view4 dy; float* dx;        /* backward: dL/dy view of [n,256,oh,ow]; dx contiguous [n,256,h,w] or NULL         */
-    const afi_lateral* lateral;     /* optional fused FPN lateral (forward only for now), may be NULL                   */
+    const afi_lateral* lateral;     /* optional fused FPN lateral, may be NULL                                          */
+    float* lat_dx; float* lat_gw; float* lat_gb; /* backward: d lat_x [n,lat_c,oh,ow], d lat_w [256,lat_c], d lat_b [256] (overwritten; may be NULL) */
     void* ws; size_t ws_bytes;      /* workspace of afi_g_workspace_bytes(); keeps the activations between fwd and bwd  */
 } afi_g_call;
 

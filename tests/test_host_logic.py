@@ -1,0 +1,92 @@
+"""CPU-side host logic: config keys, registries, and the N > 1 gradient-synchronisation logic with world_size-2 gloo processes."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_keys_match_reference_names():
+    from afigan.config import get_cfg
+    cfg = get_cfg()
+    for k in ("GUIDE_ARCHITECTURE", "GUIDE_WEIGHTS", "AFI_GEN_WEIGHTS", "AFI_DIS_WEIGHTS", "AF_EXTRACTOR_WEIGHTS", "AFI_FREEZE"):
+        assert k in cfg.MODEL, k                                   # reference afigan/config/defaults.py:5-11
+    assert cfg.MODEL.GUIDE_BACKBONE.NAME == "build_resnet_fpn_backbone" and cfg.MODEL.GUIDE_BACKBONE.FREEZE_AT == 2
+    assert cfg.MODEL.BIFPN.FPN_REPEAT == 3 and cfg.MODEL.BIFPN.NORM == "SyncBN"
+    assert cfg.MODEL.SWINT.DEPTHS == [2, 2, 6, 2]
+    assert cfg.MODEL.RESNETS.RADIX == 1 and cfg.SOLVER.OPTIMIZER == "SGD" and cfg.SOLVER.AMP.ENABLED is False
+    cfg.merge_from_list(["MODEL.AFI_FREEZE", True, "MODEL.AFI_GEN_WEIGHTS", "/tmp/g.pth"])
+    assert cfg.MODEL.AFI_FREEZE is True
+    with pytest.raises(KeyError):
+        cfg.merge_from_list(["MODEL.SRF_FREEZE", True])            # the key one shipped yaml uses by mistake stays an error
+
+
+def test_backbone_registry_names():
+    from afigan._compat import BACKBONE_REGISTRY
+    import afigan.modeling  # noqa: F401
+    for name in ("build_resnet_fpn_sr_backbone", "build_resnest_fpn_sr_backbone", "build_resnet_pafpn_sr_backbone",
+                 "build_resnest_pafpn_sr_backbone"):
+        assert callable(BACKBONE_REGISTRY.get(name))
+
+
+def test_neck_parameter_names_on_cpu():
+    from afigan._compat import ShapeSpec
+    from afigan.modeling import FPN_AFIGAN, PAFPN_AFIGAN
+
+    class BU(torch.nn.Module):
+        def output_shape(self):
+            return {f"res{i + 2}": ShapeSpec(channels=c, stride=2 ** (i + 2)) for i, c in enumerate((256, 512, 1024, 2048))}
+
+    feats = ["res2", "res3", "res4", "res5"]
+    f = FPN_AFIGAN(BU(), feats, 256)
+    p = PAFPN_AFIGAN(BU(), feats, 256)
+    fn, pn = set(dict(f.named_parameters())), set(dict(p.named_parameters()))
+    assert {"fpn_lateral2.weight", "fpn_output5.bias", "srf_module.Generators.0.3.0.weight"} <= fn
+    assert {"fpn_lateral3.weight", "pafpn_output2.weight", "pafpn_downsample5.weight", "srf_module.Generators.0.1.RDBs.2.conv5.weight"} <= pn
+    assert "pafpn_downsample2.weight" not in pn
+    assert f.fpn_lateral5.weight.shape == (256, 2048, 1, 1)
+    assert sum(q.numel() for q in f.srf_module.parameters()) == 7_834_624
+
+
+def _ddp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "afi-gan_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from afigan.engine.sync import FlatGradSync
+    from oracle import afigan_oracle as O
+    torch.set_num_threads(2)
+    g_sd, d_sd = O.init_states(0)
+    lr_shapes, hr_shapes = ((4, 6),), ((7, 11),)
+    lr_f, hr_f = O.synthetic_features(1, rank, lr_shapes, hr_shapes)             # each rank its own shard (seed 1234 + rank)
+    res = O.stage1_step(dict(g_sd), {k: v.clone() for k, v in d_sd.items()}, lr_f, hr_f, lr=None)
+    keys = O.generator_param_keys()
+    params = [torch.nn.Parameter(g_sd[k].clone()) for k in keys]
+    sync = FlatGradSync(params)
+    for p, k in zip(params, keys):
+        assert p.grad.data_ptr() == sync.views[keys.index(k)].data_ptr()          # .grad are views into ONE flat buffer
+        p.grad.copy_(res["g_grads"][k])
+    sync.all_reduce()
+    assert sync.grad_scale == 1.0 / world
+    avg = {k: (p.grad * sync.grad_scale).clone() for p, k in zip(params, keys)}
+    if rank == 0:
+        torch.save({"avg": avg, "own": res["g_grads"]}, out)
+    else:
+        torch.save({"own": res["g_grads"]}, out + ".1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo(tmp_path):
+    """Intended DDP semantics: after the flat all-reduce every rank holds the mean of the per-shard oracle gradients."""
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_ddp_worker, args=(2, 29631, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out), torch.load(out + ".1")
+    for k, v in r0["avg"].items():
+        ref = 0.5 * (r0["own"][k] + r1["own"][k])
+        assert float((v - ref).norm()) <= 1e-6 * float(ref.norm()), k
+        assert float((r0["own"][k] - r1["own"][k]).norm()) > 1e-2 * float(ref.norm())     # the shards really differ
