@@ -91,6 +91,8 @@ def test_neck_matches_torch_composition(neck):
     from afigan.modeling import FPN_AFIGAN, PAFPN_AFIGAN
     from afigan.modeling.backbone import LastLevelMaxPool
     torch.manual_seed(1)
+    torch.backends.cudnn.allow_tf32 = False        # the neck's torch-side convs (out of the hot path) would otherwise run in TF32
+    torch.backends.cuda.matmul.allow_tf32 = False
     cfg = get_cfg()
     cls = FPN_AFIGAN if neck == "fpn" else PAFPN_AFIGAN
     m = cls(_ToyBottomUp(), ["res2", "res3", "res4", "res5"], 256, norm="", top_block=LastLevelMaxPool(), fuse_type="sum", cfg=cfg).cuda()
