@@ -243,7 +243,9 @@ def run_ours(args):
     roof = None
     if rank == 0:
         native.check(lib.afi_profile_begin(4096))
-        hbm_step()
+    hbm_step()                      # every rank runs the step (it contains the gradient all-reduces); only rank 0 records events
+    barrier()
+    if rank == 0:
         n = C.c_int()
         native.check(lib.afi_profile_end(C.byref(n)))
         agg = {}
