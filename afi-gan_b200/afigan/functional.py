@@ -163,9 +163,8 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         dev = x.device
         ps = d_param_struct(params, buffers)
         packed = holder.packed.get("d", prec, params, ps)
-        need_bwd = grad_enabled and (any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[0])
-        if need_bwd and not training:
-            raise NotImplementedError("discriminator backward in eval mode is not implemented")
+        need_bwd = grad_enabled and training and (any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[0])
+        ctx.eval_mode = not training     # forward in eval mode is fine; only a backward through it is unsupported
         lib, actx = N.lib(), N.context(dev)
         ws = _u8(lib.afi_d_workspace_bytes(prec, n, h, w, int(need_bwd)), dev)
         logits = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
@@ -182,6 +181,8 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         n, h, w = ctx.shape
         dev = dlogits.device
         lib, actx = N.lib(), N.context(dev)
+        if ctx.eval_mode:
+            raise NotImplementedError("discriminator backward in eval mode is not implemented (the trainers keep D in train mode)")
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("discriminator: gradient w.r.t. the input feature is not implemented "
                                       "(the stage-1/2 trainers detach it: stage1_trainer.py:339,399)")
