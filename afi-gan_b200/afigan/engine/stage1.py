@@ -28,7 +28,7 @@ CH = 256
 
 class Stage1Step:
     def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
-                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None):
+                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True):
         self.G, self.D = G, D
         self.Dstack = D.Discriminators[0]
         self.lr, self.momentum, self.wd, self.wd_norm = lr, momentum, weight_decay, weight_decay_norm
@@ -59,7 +59,12 @@ class Stage1Step:
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self.losses = torch.zeros(4, 8, dtype=torch.float32, device=dev)   # rows: d_loss, g_loss, adv, content ; cols: levels
-        self._tmp = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._tmp = torch.zeros(64, dtype=torch.float32, device=dev)
+        # Two side streams: the discriminator calls of a phase are issued as two groups (real / fake) whose HBM-bound passes (BatchNorm
+        # apply / backward, reductions, head) overlap the other group's tensor-bound GEMMs -- the persistent GEMM CTAs leave enough
+        # registers / shared memory per SM for the small elementwise CTAs to co-reside.
+        self.overlap = overlap
+        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap else []
         self._pack_g()
         self._pack_d()
 
@@ -144,31 +149,56 @@ class Stage1Step:
             logits.append(lg)
         return calls, logits
 
-    def _d_forward(self, xs, tags, save: bool):
+    def _sub(self, calls, idxs):
+        sub = (N.DCall * len(idxs))()
+        for j, i in enumerate(idxs):
+            sub[j] = calls[i]
+        return sub
+
+    def _d_phase(self, xs, tags, targets, loss_rows, save: bool, backward: bool):
+        """Discriminator calls `xs` (reference order), BCE against `targets[i]` accumulated into losses[loss_rows[i], level]; with
+        backward=True also d(BCE)/d(params) into the packed accumulator.  Calls with even / odd index (real / fake) form the two groups."""
+        lib = self.lib
         calls, logits = self._d_calls(xs, tags, save)
         ps = self._ds()
         bn = self.Dstack[0][0].norm
         mom = 0.1 if bn.momentum is None else bn.momentum
-        for i in range(0, len(calls), N.MAX_CALLS):
-            k = min(N.MAX_CALLS, len(calls) - i)
-            N.check(self.lib.afi_d_forward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(),
-                                           C.cast(C.byref(calls, i * C.sizeof(N.DCall)), C.POINTER(N.DCall)), k, 1, mom, bn.eps, int(save),
-                                           N.stream_ptr()))
+        dls = [self._buf(f"dlogit{i}", tuple(lg.shape)) if backward else None for i, lg in enumerate(logits)]
+        lp = self.losses.data_ptr()
+        groups = [list(range(0, len(xs), 2)), list(range(1, len(xs), 2))] if self.overlap else [list(range(len(xs)))]
+        cur = torch.cuda.current_stream()
+        keep = []
+        for gi, idxs in enumerate(groups):
+            st = self.streams[gi] if self.overlap else cur
+            if self.overlap:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                sp = C.c_void_p(st.cuda_stream)
+                for o in range(0, len(idxs), N.MAX_CALLS):
+                    part = idxs[o:o + N.MAX_CALLS]
+                    sub = self._sub(calls, part)
+                    keep.append(sub)
+                    N.check(lib.afi_d_forward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), sub, len(part), 2, mom, bn.eps,
+                                              int(save), sp))
+                    for j, i in enumerate(part):
+                        row = loss_rows[i]
+                        if row is not None:
+                            N.check(lib.afi_bce_with_logits(logits[i].data_ptr(), logits[i].numel(), targets[i], self._tmp[i:].data_ptr(),
+                                                            lp + 4 * (row * 8 + i // 2), 1.0, N.ptr(dls[i]), 1.0, sp))
+                        if backward:
+                            sub[j].dlogits = dls[i].data_ptr()
+                    if backward:
+                        N.check(lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), sub, len(part),
+                                                   self.d_acc.data_ptr(), sp))
+        if self.overlap:
+            for st in self.streams:
+                cur.wait_stream(st)
+        # BatchNorm running buffers: momentum updates in the reference's call order, after both groups are done
+        for o in range(0, len(xs), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(xs) - o)
+            N.check(lib.afi_d_update_running(self.ctx, self.prec, C.byref(ps), C.cast(C.byref(calls, o * C.sizeof(N.DCall)), C.POINTER(N.DCall)),
+                                             k, mom, N.stream_ptr()))
         return logits
-
-    def _d_backward(self, xs, tags, dlogits):
-        calls, _ = self._d_calls(xs, tags, True, dlogits)
-        ps = self._ds()
-        for i in range(0, len(calls), N.MAX_CALLS):
-            k = min(N.MAX_CALLS, len(calls) - i)
-            N.check(self.lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(),
-                                            C.cast(C.byref(calls, i * C.sizeof(N.DCall)), C.POINTER(N.DCall)), k, self.d_acc.data_ptr(),
-                                            N.stream_ptr()))
-
-    def _bce(self, logits: torch.Tensor, target: float, out_slot: int, sum_ptr: Optional[int], weight: float,
-             dlogits: Optional[torch.Tensor]):
-        N.check(self.lib.afi_bce_with_logits(logits.data_ptr(), logits.numel(), target, self._tmp[out_slot:].data_ptr(), sum_ptr, weight,
-                                             N.ptr(dlogits), 1.0, N.stream_ptr()))
 
     def _sgd(self, params, grads, moms, is_norm):
         first = int(self.steps_done == 0)
@@ -200,13 +230,8 @@ class Stage1Step:
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             xs += [hi[:, :, :tr.size(2), :tr.size(3)], tr]                          # D0(hr) BEFORE D0(tr)  (:349-350)
             tags += [f"r{l}", f"f{l}"]
-        logits = self._d_forward(xs, tags, True)
-        dls = []
-        for i, lg in enumerate(logits):
-            dl = self._buf(f"dlogit{i}", tuple(lg.shape))
-            self._bce(lg, 1.0 if i % 2 == 0 else 0.0, i % 2, slot(0, i // 2), 1.0, dl)   # d_loss_l = BCE(real,1) + BCE(fake,0)
-            dls.append(dl)
-        self._d_backward(xs, tags, dls)
+        # d_loss_l = BCE(D0(hr), 1) + BCE(D0(tr), 0); backward into D only
+        self._d_phase(xs, tags, [1.0 if i % 2 == 0 else 0.0 for i in range(len(xs))], [0] * len(xs), True, True)
         gs = d_grad_struct(self.d_grads)
         N.check(lib.afi_d_unpack_grads(self.ctx, self.prec, self.d_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
         self._allreduce(self.d_flat)
@@ -221,13 +246,13 @@ class Stage1Step:
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             xs += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                          # D0(tr) BEFORE D0(hr) here (:399-400)
             tags += [f"f{l}", f"r{l}"]
-        logits = self._d_forward(xs, tags, False)      # D0(hr) is dead compute kept for its BN running-stat side effect (:400)
+        # adv = BCE(D0(tr).detach(), 1): no gradient (:399); D0(hr) is dead compute kept for its BN running-stat side effect (:400)
+        self._d_phase(xs, tags, [1.0] * len(xs), [2 if i % 2 == 0 else None for i in range(len(xs))], False, False)
         dtrs = []
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
-            self._bce(logits[2 * l], 1.0, 2, slot(2, l), 1.0, None)                 # adv: no gradient (logit is .detach()-ed, :399)
             dtr = self._buf(f"dtr{l}", tuple(tr.shape))
             hi_c = hi[:, :, :tr.size(2), :tr.size(3)]
-            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), tr.size(0), CH, tr.size(2), tr.size(3), self._tmp[3:].data_ptr(),
+            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), tr.size(0), CH, tr.size(2), tr.size(3), self._tmp[40 + l:].data_ptr(),
                                     slot(3, l), 1.0, dtr.data_ptr(), 1.0, st()))
             dtrs.append(dtr)
         self._g_backward(lr_feats, hr_feats, dtrs, "g")

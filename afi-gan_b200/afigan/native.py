@@ -85,6 +85,7 @@ _SIGNATURES = {
     "afi_d_pack": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.c_void_p]),
     "afi_d_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_int, C.c_float,
                                 C.c_float, C.c_int, C.c_void_p]),
+    "afi_d_update_running": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.POINTER(DCall), C.c_int, C.c_float, C.c_void_p]),
     "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_void_p, C.c_void_p]),
     "afi_d_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(DGrads), C.c_float, C.c_int, C.c_void_p]),
     "afi_bce_with_logits": (C.c_int, [C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,

@@ -570,7 +570,7 @@ static DGradAcc d_gradacc_layout() {
 }
 struct DWs {
     void *A[4], *Z[3];
-    float *mean[3], *rstd[3], *T9;
+    float *mean[3], *rstd[3], *var[3], *T9;   // per-layer batch mean / 1/sqrt(var+eps) / unbiased var of THIS call
     double* sums;          // [2][1024]
     void *DY[3], *DXb, *G9;
     size_t total;
@@ -581,7 +581,7 @@ static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) 
     size_t es = dt_size(prec_dt(prec)), P = (size_t)n * h * w;
     W.A[0] = cv.take(P * DC[0] * es);
     for (int i = 0; i < 3; i++) { W.Z[i] = cv.take(P * DC[i + 1] * es); W.A[i + 1] = cv.take(P * DC[i + 1] * es); }
-    for (int i = 0; i < 3; i++) { W.mean[i] = (float*)cv.take(1024 * 4); W.rstd[i] = (float*)cv.take(1024 * 4); }
+    for (int i = 0; i < 3; i++) { W.mean[i] = (float*)cv.take(1024 * 4); W.rstd[i] = (float*)cv.take(1024 * 4); W.var[i] = (float*)cv.take(1024 * 4); }
     W.T9 = (float*)cv.take(P * 16 * 4);
     W.sums = (double*)cv.take(2 * 1024 * 8);
     if (backward) {
@@ -656,8 +656,11 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         for (int k = 0; k < ncalls; k++) {      // in call order: the running statistics see the calls sequentially
             PView Z = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]);
             if (training && !fuse_stats) AFI_TRY(col_stats(Z, dt, d[k].n, d[k].h, d[k].w, DC[i + 1], W[k].sums, W[k].sums + 1024, st));
+            // training == 2: the running-buffer update is deferred to afi_d_update_running (calls may then run on concurrent streams)
+            const bool inl = training != 2;
             AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, (long long)d[k].n * d[k].h * d[k].w, DC[i + 1], eps, momentum, training, W[k].mean[i],
-                                W[k].rstd[i], p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
+                                W[k].rstd[i], W[k].var[i], inl ? p->running_mean[i] : nullptr, inl ? p->running_var[i] : nullptr,
+                                inl ? p->num_batches_tracked[i] : nullptr, st));
             AFI_TRY(bn_apply_lrelu(Z, pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]), dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], p->beta[i], 0.2f,
                                    d[k].n, d[k].h, d[k].w, DC[i + 1], st));
         }
@@ -676,6 +679,19 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
     } else {
         for (int k = 0; k < ncalls; k++)
             AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
+    }
+    return AFI_OK;
+}
+
+int afi_d_update_running(afi_ctx* ctx, int prec, const afi_d_params* p, const afi_d_call* calls, int ncalls, float momentum, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_REQUIRE(ctx && p, "afi_d_update_running: null argument");
+    DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
+    AFI_TRY(d_calls_check("afi_d_update_running", prec, calls, ncalls, 0, W, d));
+    for (int i = 0; i < 3; i++) {
+        const float* mean[AFI_MAX_PROB]; const float* var[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) { mean[k] = W[k].mean[i]; var[k] = W[k].var[i]; }
+        AFI_TRY(bn_update_running(ncalls, mean, var, DC[i + 1], momentum, p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
     }
     return AFI_OK;
 }

@@ -158,7 +158,9 @@ int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, i
 
 // BatchNorm helpers (stats buffers: double sum[C], sumsq[C])
 int bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum, int training,
-                float* mean, float* rstd, float* running_mean, float* running_var, long long* nbt, cudaStream_t st);
+                float* mean, float* rstd, float* var_unb, float* running_mean, float* running_var, long long* nbt, cudaStream_t st);
+int bn_update_running(int ncalls, const float* const* mean, const float* const* var, int c, float momentum, float* rmean, float* rvar,
+                      long long* nbt, cudaStream_t st);
 // a = lrelu(gamma * (z - mean) * rstd + beta)
 int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
                    float slope, int n, int h, int w, int c, cudaStream_t st);

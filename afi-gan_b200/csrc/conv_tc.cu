@@ -504,14 +504,17 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
                 const Tap t = a.taps[tp];
                 int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+                // position of K tile k0: (problem, image, patch row, patch column); advanced incrementally below -- integer divisions
+                // per stage in this single producer thread were eating the 512-cycle stage budget
                 int ti = 0;
+                while (k0 >= tl.p[ti + 1].begin) ti++;
+                int lk0 = k0 - tl.p[ti].begin;
+                int tpi = tl.p[ti].tiles_x * tl.p[ti].tiles_y;
+                int img = lk0 / tpi, rr0 = lk0 % tpi;
+                int ty_ = rr0 / tl.p[ti].tiles_x, tx_ = rr0 % tl.p[ti].tiles_x;
                 for (int kt = k0; kt < k1; kt++) {
-                    while (kt >= tl.p[ti + 1].begin) ti++;      // K tiles walk the problems in schedule order
                     const TileP& tp_ = tl.p[ti];
-                    int lk = kt - tp_.begin;
-                    int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
-                    int img = lk / tiles_per_img, rr = lk % tiles_per_img;
-                    int y0 = (rr / tp_.tiles_x) * tp_.TH, x0 = (rr % tp_.tiles_x) * tp_.TW;
+                    const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
                     mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
                     uint32_t fb = smem_u32(&s.full[stage]);
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
@@ -520,6 +523,13 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
                     tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++tx_ == tp_.tiles_x) {
+                        tx_ = 0;
+                        if (++ty_ == tp_.tiles_y) {
+                            ty_ = 0;
+                            if (kt + 1 >= tl.p[ti + 1].begin) { ti++; img = 0; } else img++;
+                        }
+                    }
                 }
             }
         }

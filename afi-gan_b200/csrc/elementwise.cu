@@ -466,20 +466,19 @@ int bn_bwd_reduce(PView dy, PView z, int dt, const float* mean, const float* rst
 // BatchNorm finalize / apply / backward-apply
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum,
-                              int training, float* mean, float* rstd, float* rmean, float* rvar, long long* nbt) {
+                              int training, float* mean, float* rstd, float* var_unb, float* rmean, float* rvar, long long* nbt) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     if (training) {
         double m = sum[i] / (double)count;
         double var = sumsq[i] / (double)count - m * m;
         if (var < 0) var = 0;
+        double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
         mean[i] = (float)m;
         rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+        if (var_unb) var_unb[i] = (float)unb;
         if (rmean) rmean[i] = (1.f - momentum) * rmean[i] + momentum * (float)m;
-        if (rvar) {
-            double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
-            rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unb;
-        }
+        if (rvar) rvar[i] = (1.f - momentum) * rvar[i] + momentum * (float)unb;
         if (i == 0 && nbt) *nbt += 1;
     } else {
         mean[i] = rmean[i];
@@ -487,9 +486,33 @@ __global__ void k_bn_finalize(const double* sum, const double* sumsq, long long 
     }
 }
 int bn_finalize(const double* sum, const double* sumsq, long long count, int c, float eps, float momentum, int training,
-                float* mean, float* rstd, float* running_mean, float* running_var, long long* nbt, cudaStream_t st) {
+                float* mean, float* rstd, float* var_unb, float* running_mean, float* running_var, long long* nbt, cudaStream_t st) {
     if (!training) AFI_REQUIRE(running_mean && running_var, "bn_finalize: eval mode needs running statistics");
-    k_bn_finalize<<<cdiv(c, 256), 256, 0, st>>>(sum, sumsq, count, c, eps, momentum, training, mean, rstd, running_mean, running_var, nbt);
+    k_bn_finalize<<<cdiv(c, 256), 256, 0, st>>>(sum, sumsq, count, c, eps, momentum, training, mean, rstd, var_unb, running_mean, running_var, nbt);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+// Deferred running-statistics update: applies the momentum EMA of up to AFI_MAX_PROB calls IN CALL ORDER (so concurrent streams
+// may evaluate the calls themselves in any order): running = (1 - m) * running + m * batch_stat, num_batches_tracked += ncalls.
+struct BnRunArgs { int ncalls; const float* mean[AFI_MAX_PROB]; const float* var[AFI_MAX_PROB]; };
+__global__ void k_bn_update_running(BnRunArgs a, int c, float momentum, float* rmean, float* rvar, long long* nbt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    float m = rmean ? rmean[i] : 0.f, v = rvar ? rvar[i] : 0.f;
+    for (int k = 0; k < a.ncalls; k++) {
+        m = (1.f - momentum) * m + momentum * a.mean[k][i];
+        v = (1.f - momentum) * v + momentum * a.var[k][i];
+    }
+    if (rmean) rmean[i] = m;
+    if (rvar) rvar[i] = v;
+    if (i == 0 && nbt) *nbt += a.ncalls;
+}
+int bn_update_running(int ncalls, const float* const* mean, const float* const* var, int c, float momentum, float* rmean, float* rvar,
+                      long long* nbt, cudaStream_t st) {
+    BnRunArgs a;
+    a.ncalls = ncalls;
+    for (int k = 0; k < ncalls; k++) { a.mean[k] = mean[k]; a.var[k] = var[k]; }
+    k_bn_update_running<<<cdiv(c, 256), 256, 0, st>>>(a, c, momentum, rmean, rvar, nbt);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

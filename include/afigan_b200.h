@@ -144,9 +144,15 @@ typedef struct {
 
 /* Discriminators[0](x) (feature_patch_discriminator.py:32-41 as called at stage1_trainer.py:349-353) for each call, IN CALL
  * ORDER as far as the BatchNorm running buffers are concerned.  training != 0: each call is normalised with ITS OWN batch
- * statistics (biased var, eps) and updates the running buffers; training == 0: running statistics are used. */
+ * statistics (biased var, eps) and updates the running buffers; training == 0: running statistics are used; training == 2: see
+ * afi_d_update_running. */
 int afi_d_forward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls,
                   int training, float momentum, float eps, int save_for_backward, void* stream);
+
+/* training == 2 in afi_d_forward defers the running-buffer update: the calls (possibly issued as several groups on concurrent
+ * streams) only record their batch statistics in ws; afi_d_update_running then applies the momentum update of `calls` IN THE GIVEN
+ * ORDER (= the reference's call order) and bumps num_batches_tracked by ncalls. */
+int afi_d_update_running(afi_ctx*, int prec, const afi_d_params*, const afi_d_call* calls, int ncalls, float momentum, void* stream);
 
 /* Backward of the (training-mode) calls that filled their ws.  Gradients of all calls are ADDED into gradacc (packed). */
 int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls,

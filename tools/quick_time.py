@@ -18,7 +18,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 torch.manual_seed(0)
 G = Generator(n_residual_dense_blocks=3, precision=precision).cuda()
 D = Discriminator(precision=precision).cuda()
-step = Stage1Step(G, D, precision=precision)
+step = Stage1Step(G, D, precision=precision, overlap=os.environ.get('AFIGAN_OVERLAP', '1') == '1')
 lr_f, hr_f = O.synthetic_features(2, 0)
 lr_f, hr_f = [t.cuda() for t in lr_f], [t.cuda() for t in hr_f]
 step.run_step(lr_f, hr_f)

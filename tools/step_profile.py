@@ -18,7 +18,7 @@ precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 torch.manual_seed(0)
 G = Generator(n_residual_dense_blocks=3, precision=precision).cuda()
 D = Discriminator(precision=precision).cuda()
-step = Stage1Step(G, D, precision=precision)
+step = Stage1Step(G, D, precision=precision, overlap=False)   # single stream: per-launch event times do not overlap
 lr_f, hr_f = O.synthetic_features(2, 0)
 lr_f, hr_f = [t.cuda() for t in lr_f], [t.cuda() for t in hr_f]
 for _ in range(2):
