@@ -759,8 +759,9 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     tl.p[np].begin = begin;
     tl.ktiles = begin;
     maps.b = maps.a[tl.p[0].prob][0];
+    // split-K so that the work items fill (at most) two full waves of the persistent grid: base * ks <= 2 * SMs
     int base = a.ntaps * tl.m_tiles * tl.n_tiles;
-    int ks = (2 * ctx->sm_count + base - 1) / base;
+    int ks = (2 * ctx->sm_count) / base;
     if (ks > tl.ktiles) ks = tl.ktiles;
     if (ks < 1) ks = 1;
     int kper = (tl.ktiles + ks - 1) / ks;

@@ -784,28 +784,39 @@ __global__ void __launch_bounds__(256) k_dhead_bwd_dense(const float* __restrict
     }
     long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
-    for (long long r = r0 + lane_r; r < r1; r += rpb) {
-        PixIdx q = decode_pixel(r, H, W);
-        float g9[9];
+    // two rows per iteration, all global loads issued before any use: doubles the bytes in flight per thread (the 72 weight
+    // registers cap the occupancy at one 256-thread block per SM, so memory-level parallelism has to come from within the thread)
+    for (long long r = r0 + lane_r; r < r1; r += 2 * rpb) {
+        const long long rb = r + rpb;
+        const bool has_b = rb < r1;
+        float avA[8], zvA[8], avB[8], zvB[8];
+        V8<T>::ld(a3 + r * C + c0, avA);
+        V8<T>::ld(z3 + r * C + c0, zvA);
+        if (has_b) { V8<T>::ld(a3 + rb * C + c0, avB); V8<T>::ld(z3 + rb * C + c0, zvB); }
+        PixIdx qa = decode_pixel(r, H, W), qb = decode_pixel(has_b ? rb : r, H, W);
+        float gA[9], gB[9];
 #pragma unroll
         for (int t = 0; t < 9; t++) {
-            int yy = q.y - (t / 3 - 1), xx = q.x - (t % 3 - 1);
-            g9[t] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(g + ((long long)q.n * H + yy) * W + xx) : 0.f;
+            int ya = qa.y - (t / 3 - 1), xa = qa.x - (t % 3 - 1);
+            gA[t] = (ya >= 0 && ya < H && xa >= 0 && xa < W) ? __ldg(g + ((long long)qa.n * H + ya) * W + xa) : 0.f;
+            int yb = qb.y - (t / 3 - 1), xb = qb.x - (t % 3 - 1);
+            gB[t] = (has_b && yb >= 0 && yb < H && xb >= 0 && xb < W) ? __ldg(g + ((long long)qb.n * H + yb) * W + xb) : 0.f;
         }
-        float av[8], zv[8], o[8];
-        V8<T>::ld(a3 + r * C + c0, av);
-        V8<T>::ld(z3 + r * C + c0, zv);
+        float oA[8], oB[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            float d = 0.f;
+            float dA = 0.f, dB = 0.f;
 #pragma unroll
-            for (int t = 0; t < 9; t++) d = fmaf(g9[t], wr[k][t], d);
-            d *= av[k] > 0.f ? 1.f : slope;
-            o[k] = d;
-            a0[k] += d;
-            a1[k] = fmaf(d, (zv[k] - mu[k]) * rs[k], a1[k]);
+            for (int t = 0; t < 9; t++) { dA = fmaf(gA[t], wr[k][t], dA); dB = fmaf(gB[t], wr[k][t], dB); }
+            dA *= avA[k] > 0.f ? 1.f : slope;
+            oA[k] = dA; a0[k] += dA; a1[k] = fmaf(dA, (zvA[k] - mu[k]) * rs[k], a1[k]);
+            if (has_b) {
+                dB *= avB[k] > 0.f ? 1.f : slope;
+                oB[k] = dB; a0[k] += dB; a1[k] = fmaf(dB, (zvB[k] - mu[k]) * rs[k], a1[k]);
+            }
         }
-        V8<T>::st(dy3 + r * C + c0, o);
+        V8<T>::st(dy3 + r * C + c0, oA);
+        if (has_b) V8<T>::st(dy3 + rb * C + c0, oB);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) { sm0[(lane_r * 8 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 8 + k) * tpr + cq] = a1[k]; }

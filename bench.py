@@ -243,7 +243,9 @@ def run_ours(args):
     roof = None
     if rank == 0:
         native.check(lib.afi_profile_begin(4096))
+    step.overlap = False            # single stream for this step only: per-launch event times must not overlap another stream's kernels
     hbm_step()                      # every rank runs the step (it contains the gradient all-reduces); only rank 0 records events
+    step.overlap = True
     barrier()
     if rank == 0:
         n = C.c_int()
@@ -263,9 +265,15 @@ def run_ours(args):
         dom = max(agg, key=lambda k: agg[k][2])
         cnt, flops, tms = agg[dom]
         achieved = flops / (tms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # DRAM bytes of the dominant kernel's largest launch (ncu --set full)
+        traffic_detail = None
+        if os.path.exists(tpath) and dom == 0:
+            traffic_detail = json.load(open(tpath))
+            traffic = traffic_detail["bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16_burst"], "peak_source": pk["source"] +
-                " sustained bf16 (kernel timed inside a long step)", "traffic": None, "launches_per_step": cnt,
+                " sustained bf16 (kernel timed inside a long step)", "traffic": traffic, "traffic_detail": traffic_detail, "launches_per_step": cnt,
                 "flops_per_launch_avg": flops / cnt, "ms_per_launch_avg": tms / cnt, "share_of_step": tms / ms_step,
                 "per_kernel": {names[k]: {"launches": v[0], "ms": v[2], "tflops": v[1] / max(v[2], 1e-9) / 1e9} for k, v in agg.items()},
                 "largest_launch": None if top is None else {"ms": top[0], "tflops": top[1] / top[0] / 1e9, "cin": top[2], "cout": top[3],
