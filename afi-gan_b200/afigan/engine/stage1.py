@@ -276,3 +276,33 @@ class Stage1Step:
             out[f"adv_loss_p{l + 2}"] = float(v[2, l])
             out[f"content_loss_p{l + 2}"] = float(v[3, l])
         return out
+
+
+class FeaturePrefetcher:
+    """Host -> device staging of the step's feature pyramids (pinned host tensors) on a dedicated copy stream, double-buffered, so the H2D
+    copy of batch i+1 overlaps the compute of batch i (what a DataLoader with pin_memory + non_blocking copies gives the reference trainer,
+    rcnn_only.py:37).  `next()` returns device tensors that are safe to use on the current stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+
+    def submit(self, host_tensors):
+        """Start copying a batch (list of pinned CPU tensors) into the free slot."""
+        k = self.i & 1
+        self.stream.wait_stream(torch.cuda.current_stream())          # the slot's previous contents must have been consumed
+        with torch.cuda.stream(self.stream):
+            if self.slots[k] is None:
+                self.slots[k] = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_tensors]
+            for d, h in zip(self.slots[k], host_tensors):
+                d.copy_(h, non_blocking=True)
+            self.events[k].record(self.stream)
+        self.i += 1
+        return k
+
+    def get(self, k):
+        torch.cuda.current_stream().wait_event(self.events[k])
+        return self.slots[k]

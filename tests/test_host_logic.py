@@ -90,3 +90,40 @@ def test_gradient_allreduce_world2_gloo(tmp_path):
         ref = 0.5 * (r0["own"][k] + r1["own"][k])
         assert float((v - ref).norm()) <= 1e-6 * float(ref.norm()), k
         assert float((r0["own"][k] - r1["own"][k]).norm()) > 1e-2 * float(ref.norm())     # the shards really differ
+
+
+def test_checkpoint_key_remap_and_lr_schedule():
+    from afigan._compat import ShapeSpec
+    from afigan.engine import (convert_afi_names, load_extractor_into_detector, load_generator_into_extractor, remain_only_afi_names,
+                               warmup_multistep_lr)
+    from afigan.modeling import FPN_AFIGAN, Generator
+
+    class BU(torch.nn.Module):
+        def output_shape(self):
+            return {f"res{i + 2}": ShapeSpec(channels=c, stride=2 ** (i + 2)) for i, c in enumerate((256, 512, 1024, 2048))}
+
+    class Detector(torch.nn.Module):          # stands for GeneralizedRCNN_AFExtractor: the neck lives under `backbone.`
+        def __init__(self):
+            super().__init__()
+            self.backbone = FPN_AFIGAN(BU(), ["res2", "res3", "res4", "res5"], 256)
+
+    torch.manual_seed(7)
+    G = Generator(n_residual_dense_blocks=3)
+    ckpt = {"module." + k: v.clone() for k, v in G.state_dict().items()}          # saved from a DDP-wrapped stage-1 model
+    renamed, back = convert_afi_names({k[7:]: v for k, v in ckpt.items()})
+    assert "backbone.srf_module.Generators.0.3.0.weight" in renamed and back["backbone.srf_module.Generators.0.0.0.bias"] == "Generators.0.0.0.bias"
+    det = Detector()
+    assert not torch.equal(det.backbone.srf_module.Generators[0][0][0].weight, G.Generators[0][0][0].weight)
+    assert load_generator_into_extractor(det, ckpt) == len(G.state_dict())          # stage 1 -> stage 2
+    for k, v in G.state_dict().items():
+        assert torch.equal(det.state_dict()["backbone.srf_module." + k], v), k
+    kept, _ = remain_only_afi_names(det.state_dict())
+    assert len(kept) == len(G.state_dict()) and all("srf_module" in k for k in kept)
+    det3 = Detector()
+    lateral_before = det3.backbone.fpn_lateral2.weight.clone()
+    assert load_extractor_into_detector(det3, det.state_dict()) == len(G.state_dict())   # stage 2 -> stage 3: only the interpolator moves
+    assert torch.equal(det3.backbone.fpn_lateral2.weight, lateral_before)
+    assert torch.equal(det3.backbone.srf_module.Generators[0][4][0].weight, G.Generators[0][4][0].weight)
+    # WarmupMultiStepLR of the stage-1 recipe
+    assert abs(warmup_multistep_lr(0) - 1e-6) < 1e-12 and abs(warmup_multistep_lr(500) - 1e-3 * (0.001 * 0.5 + 0.5)) < 1e-12
+    assert warmup_multistep_lr(1000) == 1e-3 and warmup_multistep_lr(269999) == 1e-3 and abs(warmup_multistep_lr(270000) - 1e-4) < 1e-12
