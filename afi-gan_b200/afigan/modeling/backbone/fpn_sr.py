@@ -38,64 +38,76 @@ def topdown_merge(srf_module, prev_features, features, lateral_conv, fuse_type):
     return out / 2 if fuse_type == "avg" else out
 
 
-class FPN_AFIGAN(Backbone):
+class _AFINeck(Backbone):
+    """Shared construction of the AFI necks: the interpolator (`srf_module`), one 1x1 lateral + one 3x3 output conv per input level,
+    registered under the reference's attribute names so state dicts interchange."""
+
+    output_prefix = "fpn_output"
+
     def __init__(self, bottom_up, in_features, out_channels, norm="", top_block=None, fuse_type="sum", cfg=None):
         super().__init__()
-        self.cfg = cfg
-        input_shapes = bottom_up.output_shape()
-        in_strides = [input_shapes[f].stride for f in in_features]
-        in_channels = [input_shapes[f].channels for f in in_features]
-        _assert_strides_are_log2_contiguous(in_strides)
         if out_channels != 256:
             raise ValueError("the AF interpolator kernels are specialised for 256-channel pyramids (MODEL.FPN.OUT_CHANNELS = 256)")
-
-        self.srf_module = G_rdb.Generator(n_residual_dense_blocks=3)        # fpn_sr.py:65
+        assert fuse_type in {"avg", "sum"}
+        self.cfg = cfg
+        shapes = bottom_up.output_shape()
+        strides = [shapes[f].stride for f in in_features]
+        _assert_strides_are_log2_contiguous(strides)
+        self.srf_module = G_rdb.Generator(n_residual_dense_blocks=3)        # fpn_sr.py:65 / pafpn_sr.py:67
         if _afi_freeze(cfg):                                                # fpn_sr.py:67-69
             for p in self.srf_module.parameters():
                 p.requires_grad = False
-
-        lateral_convs, output_convs = [], []
-        use_bias = norm == ""
-        stage = 0
-        for idx, ch in enumerate(in_channels):
-            lateral_conv = Conv2d(ch, out_channels, kernel_size=1, bias=use_bias, norm=get_norm(norm, out_channels))
-            output_conv = Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=use_bias,
-                                 norm=get_norm(norm, out_channels))
-            c2_xavier_fill(lateral_conv)
-            c2_xavier_fill(output_conv)
-            stage = int(math.log2(in_strides[idx]))
-            self.add_module(f"fpn_lateral{stage}", lateral_conv)
-            self.add_module(f"fpn_output{stage}", output_conv)
-            lateral_convs.append(lateral_conv)
-            output_convs.append(output_conv)
-        self.lateral_convs = lateral_convs[::-1]     # top-down order
-        self.output_convs = output_convs[::-1]
-        self.top_block = top_block
-        self.in_features = in_features
-        self.bottom_up = bottom_up
-        self._out_feature_strides = {f"p{int(math.log2(s))}": s for s in in_strides}
-        if self.top_block is not None:
-            for s in range(stage, stage + self.top_block.num_levels):
-                self._out_feature_strides[f"p{s + 1}"] = 2 ** (s + 1)
-        self._out_features = list(self._out_feature_strides.keys())
+        self._norm, self._use_bias = norm, norm == ""
+        laterals, outputs = [], []
+        for f, stride in zip(in_features, strides):
+            stage = int(math.log2(stride))
+            lateral = self._conv(shapes[f].channels, out_channels, 1)
+            output = self._conv(out_channels, out_channels, 3)
+            self.add_module(f"fpn_lateral{stage}", lateral)
+            self.add_module(f"{self.output_prefix}{stage}", output)
+            laterals.append(lateral)
+            outputs.append(output)
+            self._extra_level_modules(stage, first=not laterals[:-1], out_channels=out_channels)
+        self._laterals_bottom_up, self._outputs_bottom_up = laterals, outputs
+        self.top_block, self.in_features, self.bottom_up = top_block, in_features, bottom_up
+        self._out_feature_strides = {f"p{int(math.log2(s))}": s for s in strides}
+        last = int(math.log2(strides[-1]))
+        if top_block is not None:
+            for s_ in range(last, last + top_block.num_levels):
+                self._out_feature_strides[f"p{s_ + 1}"] = 2 ** (s_ + 1)
+        self._out_features = list(self._out_feature_strides)
         self._out_feature_channels = {k: out_channels for k in self._out_features}
-        self._size_divisibility = in_strides[-1]
-        assert fuse_type in {"avg", "sum"}
+        self._size_divisibility = strides[-1]
         self._fuse_type = fuse_type
+
+    def _conv(self, cin, cout, k, stride=1):
+        conv = Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=self._use_bias, norm=get_norm(self._norm, cout))
+        c2_xavier_fill(conv)
+        return conv
+
+    def _extra_level_modules(self, stage, first, out_channels):
+        pass
 
     @property
     def size_divisibility(self):
         return self._size_divisibility
 
-    def forward(self, x):
-        bottom_up_features = self.bottom_up(x)
+    def output_shape(self):
+        return {name: ShapeSpec(channels=self._out_feature_channels[name], stride=self._out_feature_strides[name])
+                for name in self._out_features}
+
+    def _top_down(self, bottom_up_features):
+        """Merged maps, finest first: prev = lateral(C_l) + srf_module(prev) [/2]   (fpn_sr.py:147-157, pafpn_sr.py:172-181)."""
         feats = [bottom_up_features[f] for f in self.in_features[::-1]]
-        results = []
-        prev_features = self.lateral_convs[0](feats[0])
-        results.append(self.output_convs[0](prev_features))
-        for features, lateral_conv, output_conv in zip(feats[1:], self.lateral_convs[1:], self.output_convs[1:]):
-            prev_features = topdown_merge(self.srf_module, prev_features, features, lateral_conv, self._fuse_type)
-            results.insert(0, output_conv(prev_features))
+        laterals = self._laterals_bottom_up[::-1]
+        prev = laterals[0](feats[0])
+        merged = [prev]
+        for features, lateral_conv in zip(feats[1:], laterals[1:]):
+            prev = topdown_merge(self.srf_module, prev, features, lateral_conv, self._fuse_type)
+            merged.insert(0, prev)
+        return merged
+
+    def _finish(self, bottom_up_features, results):
         if self.top_block is not None:
             top_in = bottom_up_features.get(self.top_block.in_feature, None)
             if top_in is None:
@@ -104,9 +116,23 @@ class FPN_AFIGAN(Backbone):
         assert len(self._out_features) == len(results)
         return dict(zip(self._out_features, results))
 
-    def output_shape(self):
-        return {name: ShapeSpec(channels=self._out_feature_channels[name], stride=self._out_feature_strides[name])
-                for name in self._out_features}
+
+class FPN_AFIGAN(_AFINeck):
+    """FPN whose top-down path up-samples with the AF interpolator (reference FPN_AFIGAN, fpn_sr.py:18-166)."""
+
+    @property
+    def lateral_convs(self):      # top-down order, like the reference attribute
+        return self._laterals_bottom_up[::-1]
+
+    @property
+    def output_convs(self):
+        return self._outputs_bottom_up[::-1]
+
+    def forward(self, x):
+        bottom_up_features = self.bottom_up(x)
+        merged = self._top_down(bottom_up_features)
+        results = [conv(m) for conv, m in zip(self._outputs_bottom_up, merged)]
+        return self._finish(bottom_up_features, results)
 
 
 class LastLevelMaxPool(nn.Module):

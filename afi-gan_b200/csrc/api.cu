@@ -646,24 +646,36 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         conv_std(a, ncalls, d, DC[i], DC[i + 1], (const char*)packed + L.f[i] * es);
         a.bias = p->b[i]; a.out_dt = dt;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].A[i], d[k].h, d[k].w, DC[i]); a.p[k].out = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); }
-        if (training) for (int k = 0; k < ncalls; k++) AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
+        void* sums_p[AFI_MAX_PROB]; const double* sum_c[AFI_MAX_PROB]; const double* sq_c[AFI_MAX_PROB]; double* sum_m[AFI_MAX_PROB]; double* sq_m[AFI_MAX_PROB];
+        float* mean_p[AFI_MAX_PROB]; float* rstd_p[AFI_MAX_PROB]; float* var_p[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
+        const float* var_c[AFI_MAX_PROB]; long long cnt[AFI_MAX_PROB]; PView Zv[AFI_MAX_PROB], Av[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) {
+            sums_p[k] = W[k].sums; sum_c[k] = sum_m[k] = W[k].sums; sq_c[k] = sq_m[k] = W[k].sums + 1024;
+            mean_p[k] = W[k].mean[i]; rstd_p[k] = W[k].rstd[i]; var_p[k] = W[k].var[i];
+            mean_c[k] = W[k].mean[i]; rstd_c[k] = W[k].rstd[i]; var_c[k] = W[k].var[i];
+            cnt[k] = (long long)d[k].n * d[k].h * d[k].w;
+            Zv[k] = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); Av[k] = pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]);
+        }
+        if (training) AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
         const bool fuse_stats = training && tc && DC[i] >= 512;   // long-K layers hide the extra epilogue work behind the MMAs
         if (fuse_stats) {   // tensor-core engine: the per-channel sum / sum of squares come out of the GEMM epilogue
             a.stat_mode = 1;
             for (int k = 0; k < ncalls; k++) { a.p[k].stat0 = W[k].sums; a.p[k].stat1 = W[k].sums + 1024; }
         }
         AFI_TRY(run_conv(ctx, prec, a, st));
-        for (int k = 0; k < ncalls; k++) {      // in call order: the running statistics see the calls sequentially
-            PView Z = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]);
-            if (training && !fuse_stats) AFI_TRY(col_stats(Z, dt, d[k].n, d[k].h, d[k].w, DC[i + 1], W[k].sums, W[k].sums + 1024, st));
-            // training == 2: the running-buffer update is deferred to afi_d_update_running (calls may then run on concurrent streams)
-            const bool inl = training != 2;
-            AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, (long long)d[k].n * d[k].h * d[k].w, DC[i + 1], eps, momentum, training, W[k].mean[i],
-                                W[k].rstd[i], W[k].var[i], inl ? p->running_mean[i] : nullptr, inl ? p->running_var[i] : nullptr,
-                                inl ? p->num_batches_tracked[i] : nullptr, st));
-            AFI_TRY(bn_apply_lrelu(Z, pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]), dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], p->beta[i], 0.2f,
-                                   d[k].n, d[k].h, d[k].w, DC[i + 1], st));
+        if (training) {
+            // per call: BatchNorm with THIS call's batch statistics (one grouped launch per pass covers all calls)
+            if (!fuse_stats) AFI_TRY(col_reduce_group(0, ncalls, Zv, nullptr, dt, nullptr, nullptr, sum_m, sq_m, cnt, DC[i + 1], st));
+            AFI_TRY(bn_finalize_group(ncalls, sum_c, sq_c, cnt, DC[i + 1], eps, mean_p, rstd_p, var_p, st));
+            // training == 1: running buffers updated here, in call order; training == 2: deferred to afi_d_update_running
+            if (training != 2)
+                AFI_TRY(bn_update_running(ncalls, mean_c, var_c, DC[i + 1], momentum, p->running_mean[i], p->running_var[i], p->num_batches_tracked[i], st));
+        } else {
+            for (int k = 0; k < ncalls; k++)
+                AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, cnt[k], DC[i + 1], eps, momentum, 0, W[k].mean[i], W[k].rstd[i], W[k].var[i],
+                                    p->running_mean[i], p->running_var[i], nullptr, st));
         }
+        AFI_TRY(bn_apply_lrelu_group(ncalls, Zv, Av, dt, mean_c, rstd_c, p->gamma[i], p->beta[i], 0.2f, cnt, DC[i + 1], st));
     }
     // Conv2d 1024 -> 1                                                                   feature_patch_discriminator.py:40-41
     if (tc) {
@@ -717,11 +729,15 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         WgradArgs g;
         memset(&g, 0, sizeof(g));
         g.cin = DC[3]; g.cout = 16; g.ntaps = 1; g.nprob = ncalls; g.dw = gradacc + GL.w[3];
+        {
+            void* sums_p[AFI_MAX_PROB];
+            for (int k = 0; k < ncalls; k++) sums_p[k] = W[k].sums;
+            AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+        }
         for (int k = 0; k < ncalls; k++) {
             const int n = d[k].n, h = d[k].h, w = d[k].w;
             AFI_TRY(dhead_build_g9(calls[k].dlogits, n, h, w, W[k].G9, st));
             AFI_TRY(sum_f32(calls[k].dlogits, (long long)n * h * w, gradacc + GL.b[3], st));
-            AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
             PView G9 = pview(W[k].G9, h, w, 16), A3 = pview(W[k].A[3], h, w, DC[3]);
             AFI_TRY(dhead_backward_dense(A3, pview(W[k].Z[2], h, w, DC[3]), pview(W[k].DY[2], h, w, DC[3]), dt, p->w[3], calls[k].dlogits,
                                          W[k].mean[2], W[k].rstd[2], n, h, w, DC[3], W[k].sums, W[k].sums + 1024, st));
@@ -735,18 +751,22 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
     }
     for (int i = 2; i >= 0; i--) {
         const int co = DC[i + 1], ci = DC[i];
+        void* sums_p[AFI_MAX_PROB]; double* s0[AFI_MAX_PROB]; double* s1[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
+        long long cnt[AFI_MAX_PROB]; PView Zv[AFI_MAX_PROB];
         for (int k = 0; k < ncalls; k++) {
-            PView Z = pview(W[k].Z[i], d[k].h, d[k].w, co);
+            Zv[k] = pview(W[k].Z[i], d[k].h, d[k].w, co);
             DYv[k] = pview(W[k].DY[i], d[k].h, d[k].w, co);
             X[k] = pview(W[k].A[i], d[k].h, d[k].w, ci);
-            // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ)
-            if (!(tc && i == 2)) {      // (the tensor-core path got layer 3's reductions from the fused head pass above)
-                AFI_CUDA(cudaMemsetAsync(W[k].sums, 0, 2 * 1024 * sizeof(double), st));
-                AFI_TRY(bn_bwd_reduce(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], d[k].n, d[k].h, d[k].w, co, W[k].sums, W[k].sums + 1024, st));
-            }
-            AFI_TRY(bn_bwd_apply(DYv[k], Z, dt, W[k].mean[i], W[k].rstd[i], p->gamma[i], W[k].sums, W[k].sums + 1024, gradacc + GL.gamma[i],
-                                 gradacc + GL.beta[i], d[k].n, d[k].h, d[k].w, co, st));
+            sums_p[k] = W[k].sums; s0[k] = W[k].sums; s1[k] = W[k].sums + 1024; mean_c[k] = W[k].mean[i]; rstd_c[k] = W[k].rstd[i];
+            cnt[k] = (long long)d[k].n * d[k].h * d[k].w;
         }
+        // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ);
+        // each pass is one grouped launch over all calls
+        if (!(tc && i == 2)) {      // (the tensor-core path got layer 3's reductions from the fused head pass above)
+            AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+            AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
+        }
+        AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co, st));
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d, X, ci, DYv, co, gradacc + GL.w[i], st));
         // bias gradient: this bias feeds a train-mode BatchNorm, so dL/db = sum_p dz = 0 identically (the reference gets
         // ~1e-9 rounding noise there); the accumulator slot stays at its zero-initialised value.

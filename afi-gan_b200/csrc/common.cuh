@@ -176,6 +176,18 @@ int dhead_forward(PView a3, int dt, const float* w4 /*[c][9] torch layout*/, con
 int dhead_backward(PView a3, int dt, const float* w4, const float* g, int n, int h, int w, int c, float* dw4_acc, float* db4_acc,
                    PView dy3, cudaStream_t st);
 
+// grouped dense BatchNorm passes over several discriminator calls (dense [P][C] operands, C/8 dividing 256)
+int dense_group_ok(int c);
+int bn_apply_lrelu_group(int nprob, const PView* z, const PView* a, int dt, const float* const* mean, const float* const* rstd,
+                         const float* gamma, const float* beta, float slope, const long long* P, int c, cudaStream_t st);
+int bn_bwd_apply_group(int nprob, const PView* dy, const PView* z, int dt, const float* const* mean, const float* const* rstd, const float* gamma,
+                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, cudaStream_t st);
+int col_reduce_group(int mode, int nprob, const PView* x, const PView* z, int dt, const float* const* mean, const float* const* rstd,
+                     double* const* o0, double* const* o1, const long long* P, int c, cudaStream_t st);
+int bn_finalize_group(int ncalls, const double* const* sum, const double* const* sumsq, const long long* count, int c, float eps,
+                      float* const* mean, float* const* rstd, float* const* var, cudaStream_t st);
+int zero_group(int n, void* const* ptrs, size_t bytes, cudaStream_t st);
+
 // tensor-core formulation of the discriminator head (bf16 mode)
 int dhead_pack_tc(const float* w4, int c, void* fwd, void* bwd, cudaStream_t st);
 int dhead_build_g9(const float* g, int n, int h, int w, void* g9, cudaStream_t st);

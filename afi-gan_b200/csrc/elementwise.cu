@@ -2,6 +2,7 @@
 // apply / backward, the 1024->1 discriminator head, the BCE / L1 losses and the SGD update.
 // All kernels are coalesced along the channel (innermost NHWC) dimension, 4 channels per thread,
 // reductions are warp/block-reduced before one atomic per channel per block.
+#include <string.h>
 #include "common.cuh"
 
 namespace afi {
@@ -426,6 +427,239 @@ __global__ void __launch_bounds__(256) k_col_reduce_dense(const T* __restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Grouped dense passes: ONE launch covers the same BatchNorm pass of up to AFI_MAX_PROB discriminator calls (each call keeps its own
+// statistics).  The small pyramid levels are latency-bound as separate launches (10-17 us each for a few MB); grouped they ride along
+// with the large ones.  blockIdx.x -> (problem, row block) through a prefix table.
+// ---------------------------------------------------------------------------------------------------
+struct DenseProbD {
+    const void* a; const void* b; void* out;
+    long long P;
+    const float* mean; const float* rstd;
+    double* o0; double* o1;
+    int block_begin, rows_per_block;
+};
+struct DenseGroupD { int nprob, C; DenseProbD p[AFI_MAX_PROB + 1]; };
+
+__device__ __forceinline__ int find_prob(const DenseGroupD& G, int b) {
+    int k = 0;
+    while (k + 1 < G.nprob && b >= G.p[k + 1].block_begin) k++;
+    return k;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_apply_group(const __grid_constant__ DenseGroupD G, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float slope) {
+    const int k = find_prob(G, blockIdx.x);
+    const DenseProbD& q = G.p[k];
+    const int C = G.C, tpr = C >> 3, rpb = 256 / tpr;
+    const int c0 = (threadIdx.x % tpr) * 8;
+    const T* __restrict__ z = reinterpret_cast<const T*>(q.a);
+    T* __restrict__ a = reinterpret_cast<T*>(q.out);
+    float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { mu[i] = q.mean[c0 + i]; rs[i] = q.rstd[c0 + i]; ga[i] = gamma[c0 + i]; be[i] = beta[c0 + i]; }
+    long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
+    if (r1 > q.P) r1 = q.P;
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
+        float v[8];
+        V8<T>::ld(z + r * C + c0, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float t = (v[i] - mu[i]) * rs[i] * ga[i] + be[i];
+            v[i] = t > 0.f ? t : t * slope;
+        }
+        V8<T>::st(a + r * C + c0, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_group(const __grid_constant__ DenseGroupD G, const float* __restrict__ gamma,
+                                                            float* dgamma_acc, float* dbeta_acc) {
+    const int k = find_prob(G, blockIdx.x);
+    const DenseProbD& q = G.p[k];
+    const int C = G.C, tpr = C >> 3, rpb = 256 / tpr;
+    if ((int)blockIdx.x == q.block_begin) {     // d gamma = sum dy*xhat, d beta = sum dy: once per call
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)q.o1[c]);
+            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)q.o0[c]);
+        }
+    }
+    const int c0 = (threadIdx.x % tpr) * 8;
+    T* __restrict__ dy = reinterpret_cast<T*>(q.out);
+    const T* __restrict__ z = reinterpret_cast<const T*>(q.b);
+    const float inv_m = 1.f / (float)q.P;
+    float mu[8], rs[8], gr[8], m1[8], m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        mu[i] = q.mean[c0 + i]; rs[i] = q.rstd[c0 + i]; gr[i] = gamma[c0 + i] * rs[i];
+        m1[i] = (float)q.o0[c0 + i] * inv_m; m2[i] = (float)q.o1[c0 + i] * inv_m;
+    }
+    long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
+    if (r1 > q.P) r1 = q.P;
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
+        float g[8], zz[8];
+        V8<T>::ld(dy + r * C + c0, g);
+        V8<T>::ld(z + r * C + c0, zz);
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = gr[i] * (g[i] - m1[i] - (zz[i] - mu[i]) * rs[i] * m2[i]);
+        V8<T>::st(dy + r * C + c0, g);
+    }
+}
+
+// MODE 0: o0 += sum x, o1 += sum x^2.  MODE 1: o0 += sum dy, o1 += sum dy*xhat.
+template <int MODE, typename T>
+__global__ void __launch_bounds__(256) k_col_reduce_group(const __grid_constant__ DenseGroupD G) {
+    __shared__ float sm0[256 * 8];
+    __shared__ float sm1[256 * 8];
+    const int k = find_prob(G, blockIdx.x);
+    const DenseProbD& q = G.p[k];
+    const int C = G.C, tpr = C >> 3, rpb = 256 / tpr;
+    const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
+    const int c0 = cq * 8;
+    const T* __restrict__ x = reinterpret_cast<const T*>(q.a);
+    const T* __restrict__ z = reinterpret_cast<const T*>(q.b);
+    float a0[8], a1[8], mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a0[i] = 0.f; a1[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { mu[i] = q.mean[c0 + i]; rs[i] = q.rstd[c0 + i]; }
+    }
+    long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
+    if (r1 > q.P) r1 = q.P;
+#pragma unroll 4
+    for (long long r = r0 + lane_r; r < r1; r += rpb) {
+        float v[8];
+        V8<T>::ld(x + r * C + c0, v);
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a0[i] += v[i]; a1[i] = fmaf(v[i], v[i], a1[i]); }
+        } else {
+            float zz[8];
+            V8<T>::ld(z + r * C + c0, zz);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { a0[i] += v[i]; a1[i] = fmaf(v[i], (zz[i] - mu[i]) * rs[i], a1[i]); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sm0[(lane_r * 8 + i) * tpr + cq] = a0[i]; sm1[(lane_r * 8 + i) * tpr + cq] = a1[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        int qd = c >> 3, i = c & 7;
+        float t0 = 0.f, t1 = 0.f;
+        for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 8 + i) * tpr + qd]; t1 += sm1[(l * 8 + i) * tpr + qd]; }
+        atomicAdd(q.o0 + c, (double)t0);
+        atomicAdd(q.o1 + c, (double)t1);
+    }
+}
+
+// per call: mean / rstd / unbiased var from the sums (training) -- grid (C/256, ncalls)
+struct FinalizeGroup { int ncalls; const double* sum[AFI_MAX_PROB]; const double* sumsq[AFI_MAX_PROB]; long long count[AFI_MAX_PROB];
+                       float* mean[AFI_MAX_PROB]; float* rstd[AFI_MAX_PROB]; float* var[AFI_MAX_PROB]; };
+__global__ void k_bn_finalize_group(const __grid_constant__ FinalizeGroup F, int c, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i >= c) return;
+    double cnt = (double)F.count[k];
+    double m = F.sum[k][i] / cnt;
+    double var = F.sumsq[k][i] / cnt - m * m;
+    if (var < 0) var = 0;
+    F.mean[k][i] = (float)m;
+    F.rstd[k][i] = (float)(1.0 / sqrt(var + (double)eps));
+    F.var[k][i] = (float)(cnt > 1 ? var * cnt / (cnt - 1) : var);
+}
+struct ZeroGroup { int n; void* p[AFI_MAX_PROB]; };
+__global__ void k_zero_group(const __grid_constant__ ZeroGroup Z, int words) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) reinterpret_cast<uint32_t*>(Z.p[blockIdx.y])[i] = 0u;
+}
+
+static void dense_group_blocks(DenseGroupD& G, int max_rows, int target_blocks) {
+    long long total = 0;
+    for (int k = 0; k < G.nprob; k++) total += G.p[k].P;
+    long long rows = total / target_blocks;
+    if (rows > max_rows) rows = max_rows;
+    if (rows < 8) rows = 8;
+    int b = 0;
+    for (int k = 0; k < G.nprob; k++) {
+        G.p[k].block_begin = b;
+        G.p[k].rows_per_block = (int)rows;
+        b += (int)((G.p[k].P + rows - 1) / rows);
+    }
+    G.p[G.nprob].block_begin = b;
+}
+
+int dense_group_ok(int c) { return dense_ok(c) ? 1 : 0; }
+
+int bn_apply_lrelu_group(int nprob, const PView* z, const PView* a, int dt, const float* const* mean, const float* const* rstd,
+                         const float* gamma, const float* beta, float slope, const long long* P, int c, cudaStream_t st) {
+    DenseGroupD G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob; G.C = c;
+    for (int k = 0; k < nprob; k++) { G.p[k].a = z[k].ptr; G.p[k].out = a[k].ptr; G.p[k].P = P[k]; G.p[k].mean = mean[k]; G.p[k].rstd = rstd[k]; }
+    dense_group_blocks(G, DENSE_ROWS, 2368);
+    int grid = G.p[nprob].block_begin;
+    if (grid == 0) return AFI_OK;
+    if (dt == DT_F32) k_bn_apply_group<float><<<grid, 256, 0, st>>>(G, gamma, beta, slope);
+    else k_bn_apply_group<bf16><<<grid, 256, 0, st>>>(G, gamma, beta, slope);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+int bn_bwd_apply_group(int nprob, const PView* dy, const PView* z, int dt, const float* const* mean, const float* const* rstd, const float* gamma,
+                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, cudaStream_t st) {
+    DenseGroupD G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob; G.C = c;
+    for (int k = 0; k < nprob; k++) {
+        G.p[k].out = dy[k].ptr; G.p[k].b = z[k].ptr; G.p[k].P = P[k]; G.p[k].mean = mean[k]; G.p[k].rstd = rstd[k];
+        G.p[k].o0 = s_dy[k]; G.p[k].o1 = s_dyx[k];
+    }
+    dense_group_blocks(G, DENSE_ROWS, 2368);
+    int grid = G.p[nprob].block_begin;
+    if (grid == 0) return AFI_OK;
+    if (dt == DT_F32) k_bn_bwd_apply_group<float><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc);
+    else k_bn_bwd_apply_group<bf16><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+int col_reduce_group(int mode, int nprob, const PView* x, const PView* z, int dt, const float* const* mean, const float* const* rstd,
+                     double* const* o0, double* const* o1, const long long* P, int c, cudaStream_t st) {
+    DenseGroupD G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob; G.C = c;
+    for (int k = 0; k < nprob; k++) {
+        G.p[k].a = x[k].ptr; G.p[k].b = z ? z[k].ptr : nullptr; G.p[k].P = P[k];
+        G.p[k].mean = mean ? mean[k] : nullptr; G.p[k].rstd = rstd ? rstd[k] : nullptr; G.p[k].o0 = o0[k]; G.p[k].o1 = o1[k];
+    }
+    dense_group_blocks(G, REDUCE_ROWS, 1184);
+    int grid = G.p[nprob].block_begin;
+    if (grid == 0) return AFI_OK;
+    if (mode == 0) { if (dt == DT_F32) k_col_reduce_group<0, float><<<grid, 256, 0, st>>>(G); else k_col_reduce_group<0, bf16><<<grid, 256, 0, st>>>(G); }
+    else { if (dt == DT_F32) k_col_reduce_group<1, float><<<grid, 256, 0, st>>>(G); else k_col_reduce_group<1, bf16><<<grid, 256, 0, st>>>(G); }
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+int bn_finalize_group(int ncalls, const double* const* sum, const double* const* sumsq, const long long* count, int c, float eps,
+                      float* const* mean, float* const* rstd, float* const* var, cudaStream_t st) {
+    FinalizeGroup F; memset(&F, 0, sizeof(F));
+    F.ncalls = ncalls;
+    for (int k = 0; k < ncalls; k++) { F.sum[k] = sum[k]; F.sumsq[k] = sumsq[k]; F.count[k] = count[k]; F.mean[k] = mean[k]; F.rstd[k] = rstd[k]; F.var[k] = var[k]; }
+    dim3 grid(cdiv(c, 256), ncalls);
+    k_bn_finalize_group<<<grid, 256, 0, st>>>(F, c, eps);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+int zero_group(int n, void* const* ptrs, size_t bytes, cudaStream_t st) {
+    ZeroGroup Z; memset(&Z, 0, sizeof(Z));
+    Z.n = n;
+    for (int k = 0; k < n; k++) Z.p[k] = ptrs[k];
+    int words = (int)(bytes / 4);
+    dim3 grid(cdiv(words, 256), n);
+    k_zero_group<<<grid, 256, 0, st>>>(Z, words);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
 static int col_reduce_launch(int mode, PView x, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
                              double* o0, double* o1, float* of, cudaStream_t st) {
     AFI_REQUIRE(c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0, "col_reduce: unsupported channel count %d", c);
@@ -764,35 +998,49 @@ int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float
     return AFI_OK;
 }
 // dy3[q][c] = (sum_t g[q - tap_t] w4[c][t]) * lrelu'(a3[q][c]) fused with the two BatchNorm-backward reductions of layer 3.
-// Dense [P][C] operands, a thread owns 8 channels (its 8x9 head weights live in registers) and walks rows.
+// Dense [P][C] operands.  A thread owns 4 channels (its 4x9 head weights live in registers: ~90 registers -> two 256-thread blocks per
+// SM) and walks rows two at a time with all global loads issued up front.
+template <typename T> struct V4;
+template <> struct V4<float> {
+    __device__ static __forceinline__ void ld(const float* p, float* v) { float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
+    __device__ static __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct V4<bf16> {
+    __device__ static __forceinline__ void ld(const bf16* p, float* v) {
+        uint2 u = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u); v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+    __device__ static __forceinline__ void st(bf16* p, const float* v) {
+        uint2 u; u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
 template <typename T>
-__global__ void __launch_bounds__(256) k_dhead_bwd_dense(const float* __restrict__ g, const T* __restrict__ a3, const T* __restrict__ z3,
-                                                         T* __restrict__ dy3, long long P, int C, int H, int W, const float* __restrict__ w4,
-                                                         const float* __restrict__ mean, const float* __restrict__ rstd, double* s_dy,
-                                                         double* s_dyx, int rows_per_block, float slope) {
-    __shared__ float sm0[256 * 8];
-    __shared__ float sm1[256 * 8];
-    const int tpr = C >> 3, rpb = 256 / tpr;
+__global__ void __launch_bounds__(256, 2) k_dhead_bwd_dense(const float* __restrict__ g, const T* __restrict__ a3, const T* __restrict__ z3,
+                                                            T* __restrict__ dy3, long long P, int C, int H, int W, const float* __restrict__ w4,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd, double* s_dy,
+                                                            double* s_dyx, int rows_per_block, float slope) {
+    __shared__ float sm0[256 * 4];
+    __shared__ float sm1[256 * 4];
+    const int tpr = C >> 2, rpb = 256 / tpr;
     const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
-    const int c0 = cq * 8;
-    float wr[8][9], mu[8], rs[8], a0[8], a1[8];
+    const int c0 = cq * 4;
+    float wr[4][9], mu[4], rs[4], a0[4], a1[4];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 4; k++) {
         mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; a0[k] = 0.f; a1[k] = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; t++) wr[k][t] = w4[(c0 + k) * 9 + t];
     }
     long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
     if (r1 > P) r1 = P;
-    // two rows per iteration, all global loads issued before any use: doubles the bytes in flight per thread (the 72 weight
-    // registers cap the occupancy at one 256-thread block per SM, so memory-level parallelism has to come from within the thread)
     for (long long r = r0 + lane_r; r < r1; r += 2 * rpb) {
         const long long rb = r + rpb;
         const bool has_b = rb < r1;
-        float avA[8], zvA[8], avB[8], zvB[8];
-        V8<T>::ld(a3 + r * C + c0, avA);
-        V8<T>::ld(z3 + r * C + c0, zvA);
-        if (has_b) { V8<T>::ld(a3 + rb * C + c0, avB); V8<T>::ld(z3 + rb * C + c0, zvB); }
+        float avA[4], zvA[4], avB[4], zvB[4];
+        V4<T>::ld(a3 + r * C + c0, avA);
+        V4<T>::ld(z3 + r * C + c0, zvA);
+        if (has_b) { V4<T>::ld(a3 + rb * C + c0, avB); V4<T>::ld(z3 + rb * C + c0, zvB); }
         PixIdx qa = decode_pixel(r, H, W), qb = decode_pixel(has_b ? rb : r, H, W);
         float gA[9], gB[9];
 #pragma unroll
@@ -802,9 +1050,9 @@ __global__ void __launch_bounds__(256) k_dhead_bwd_dense(const float* __restrict
             int yb = qb.y - (t / 3 - 1), xb = qb.x - (t % 3 - 1);
             gB[t] = (has_b && yb >= 0 && yb < H && xb >= 0 && xb < W) ? __ldg(g + ((long long)qb.n * H + yb) * W + xb) : 0.f;
         }
-        float oA[8], oB[8];
+        float oA[4], oB[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 4; k++) {
             float dA = 0.f, dB = 0.f;
 #pragma unroll
             for (int t = 0; t < 9; t++) { dA = fmaf(gA[t], wr[k][t], dA); dB = fmaf(gB[t], wr[k][t], dB); }
@@ -815,28 +1063,29 @@ __global__ void __launch_bounds__(256) k_dhead_bwd_dense(const float* __restrict
                 oB[k] = dB; a0[k] += dB; a1[k] = fmaf(dB, (zvB[k] - mu[k]) * rs[k], a1[k]);
             }
         }
-        V8<T>::st(dy3 + r * C + c0, oA);
-        if (has_b) V8<T>::st(dy3 + rb * C + c0, oB);
+        V4<T>::st(dy3 + r * C + c0, oA);
+        if (has_b) V4<T>::st(dy3 + rb * C + c0, oB);
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) { sm0[(lane_r * 8 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 8 + k) * tpr + cq] = a1[k]; }
+    for (int k = 0; k < 4; k++) { sm0[(lane_r * 4 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 4 + k) * tpr + cq] = a1[k]; }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
-        int qd = c >> 3, k = c & 7;
+        int qd = c >> 2, k = c & 3;
         float t0 = 0.f, t1 = 0.f;
-        for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 8 + k) * tpr + qd]; t1 += sm1[(l * 8 + k) * tpr + qd]; }
+        for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 4 + k) * tpr + qd]; t1 += sm1[(l * 4 + k) * tpr + qd]; }
         atomicAdd(s_dy + c, (double)t0);
         atomicAdd(s_dyx + c, (double)t1);
     }
 }
 int dhead_backward_dense(PView a3, PView z3, PView dy3, int dt, const float* w4, const float* g, const float* mean, const float* rstd, int n,
                          int h, int w, int c, double* s_dy, double* s_dyx, cudaStream_t st) {
-    AFI_REQUIRE(is_dense(a3, h, w, c) && is_dense(z3, h, w, c) && is_dense(dy3, h, w, c) && dense_ok(c), "dhead_backward_dense: operands must be dense");
+    AFI_REQUIRE(is_dense(a3, h, w, c) && is_dense(z3, h, w, c) && is_dense(dy3, h, w, c) && c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0,
+                "dhead_backward_dense: operands must be dense with C/4 dividing 256");
     long long P = (long long)n * h * w;
     if (P == 0) return AFI_OK;
-    int rows = (int)(P / 592);
-    if (rows > 128) rows = 128;
-    if (rows < 8) rows = 8;
+    int rows = (int)(P / 1184);
+    if (rows > 64) rows = 64;
+    if (rows < 4) rows = 4;
     int grid = cdiv(P, rows);
     if (dt == DT_F32)
         k_dhead_bwd_dense<float><<<grid, 256, 0, st>>>(g, (const float*)a3.ptr, (const float*)z3.ptr, (float*)dy3.ptr, P, c, h, w, w4, mean, rstd, s_dy, s_dyx, rows, 0.2f);
