@@ -201,11 +201,11 @@ class Stage1Step:
         return logits
 
     def _sgd(self, params, grads, moms, is_norm):
+        # parameters are updated in place behind torch's back; the packed GEMM-layout copies are refreshed explicitly by the caller
         first = int(self.steps_done == 0)
         for p, g, m, nrm in zip(params, grads, moms, is_norm):
             N.check(self.lib.afi_sgd_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel(), self.lr, self.momentum,
                                           self.wd_norm if nrm else self.wd, 1.0 / self.world, first, N.stream_ptr()))
-            p._version  # parameters are updated in place behind torch's back; packed copies are refreshed explicitly below
 
     def _allreduce(self, flat: torch.Tensor):
         (self.g_sync if flat is self.g_flat else self.d_sync).all_reduce()

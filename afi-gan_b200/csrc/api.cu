@@ -218,7 +218,7 @@ int afi_create(afi_ctx** out) {
         return AFI_ERR_ARCH;
     }
     afi_ctx* c = new afi_ctx();
-    c->device = dev; c->sm_count = prop.multiProcessorCount; c->encode_tiled = nullptr; c->tile_counter = nullptr;
+    c->device = dev; c->sm_count = prop.multiProcessorCount; c->encode_tiled = nullptr;
     int r = tc_init(c);
     if (r != AFI_OK) { delete c; return r; }
     *out = c;

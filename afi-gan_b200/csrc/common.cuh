@@ -206,6 +206,5 @@ template <> struct dt_of<bf16> { static const int v = DT_BF16; };
 struct afi_ctx {
     int device;
     int sm_count;
-    void* encode_tiled;   // cuTensorMapEncodeTiled entry point
-    int* tile_counter;    // reserved
+    void* encode_tiled;   // cuTensorMapEncodeTiled entry point (resolved through cudaGetDriverEntryPoint: no libcuda link dependency)
 };
