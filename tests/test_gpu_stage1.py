@@ -100,3 +100,28 @@ def test_stage1_two_steps_with_sgd_fp32():
             continue      # zero-gradient biases: only rounding noise moves them
         # BN beta starts at 0, so after two steps it IS lr * gradient: it carries the gradient's 5e-3 noise floor
         assert rel(p, d_sd[k]) < (5e-3 if k.endswith("norm.bias") else 1e-4), k
+
+
+def test_bf16_and_fp32_modes_train_alike():
+    """Mode-independent check suggested by SURVEY.md App. F (3): with per-element gradient errors of 4-7e-2 in bf16 mode, what matters is that
+    the optimiser trajectory is the same -- six SGD steps on a fixed batch in both operand modes: the loss curves must agree and the L1
+    content loss must fall (G learns) while d_loss falls (D learns)."""
+    lr_shapes, hr_shapes = ((26, 42), (13, 21), (7, 11)), ((50, 84), (25, 42), (13, 21))
+    lr_f, hr_f = O.synthetic_features(2, 0, lr_shapes, hr_shapes, seed=123)
+    lr_c, hr_c = [t.cuda() for t in lr_f], [t.cuda() for t in hr_f]
+    curves = {}
+    for precision in ("fp32", "bf16"):
+        G, D, step = _build(precision)
+        step.lr = 1e-3
+        hist = []
+        for _ in range(6):
+            step.run_step(lr_c, hr_c)
+            m = step.metrics(3)
+            hist.append((sum(m[f"d_loss_p{l}"] for l in (2, 3, 4)), sum(m[f"content_loss_p{l}"] for l in (2, 3, 4))))
+        curves[precision] = hist
+    for (d32, c32), (d16, c16) in zip(curves["fp32"], curves["bf16"]):
+        assert abs(d16 - d32) <= 2e-2 * abs(d32) + 1e-3, (curves["fp32"], curves["bf16"])
+        assert abs(c16 - c32) <= 1e-3 * abs(c32) + 1e-5
+    for mode in ("fp32", "bf16"):
+        assert curves[mode][-1][0] < curves[mode][0][0]          # the discriminator loss falls
+        assert curves[mode][-1][1] < curves[mode][0][1]          # the L1 content loss falls
