@@ -36,6 +36,28 @@ WORKLOAD = ("stage-1 AFI-GAN step (G fwd x2 + bwd, D fwd x4 + bwd x2, BCE/L1, 2 
             "features of an 800x1333 image and its 0.5x copy, p2-p6, batch 2 per GPU")
 
 
+# ---- workload definition (config 1/2 of BASELINE.json).  Kept here so that the measured arm never touches oracle/.
+C1_LR_SHAPES = ((104, 168), (52, 84), (26, 42), (13, 21), (7, 11))       # p2..p6 of the 0.5x image (400x666 -> padded 416x672)
+C1_HR_SHAPES = ((200, 336), (100, 168), (50, 84), (25, 42), (13, 21))    # p2..p6 of the 800x1333 image (padded 800x1344)
+G_FWD_FLOP_PER_INPUT_PX = 19_206_144
+D_FWD_FLOP_PER_PX = 30_689_280
+
+
+def synthetic_features(batch, rank, lr_shapes=C1_LR_SHAPES, hr_shapes=C1_HR_SHAPES, channels=256, seed=1234):
+    """N(0,1) fp32 features, torch.Generator seeded with 1234 + rank; all HR levels are drawn first, then all LR levels."""
+    import torch
+    gen = torch.Generator().manual_seed(seed + rank)
+    hr = [torch.randn(batch, channels, h, w, generator=gen) for h, w in hr_shapes]
+    lr = [torch.randn(batch, channels, h, w, generator=gen) for h, w in lr_shapes]
+    return lr, hr
+
+
+def stage1_step_flops(lr_px, hr_px):
+    """2 G fwd + 1 G bwd (no input grad) + 4 D fwd + 2 D bwd (no input grad): SURVEY.md §8d."""
+    g, d = G_FWD_FLOP_PER_INPUT_PX, D_FWD_FLOP_PER_PX
+    return 2 * g * lr_px + (2 * g - 1_179_648) * lr_px + 4 * d * hr_px + 2 * (2 * d - 2_359_296) * hr_px
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -93,7 +115,8 @@ class ClockSampler:
 
 
 def cpu_reference_step_time(sample_levels, steps, warmup, batch=PER_GPU_BATCH):
-    """Times the CPU port of the reference step (oracle) on the given pyramid levels; returns (seconds per step, cores)."""
+    """Times the CPU port of the reference step (oracle) on the given pyramid levels; returns (seconds per step, cores).
+    This function (the cpu_baseline / --impl reference legs) is the ONLY place bench.py touches oracle/."""
     import torch
     from oracle import afigan_oracle as O
     torch.set_num_threads(os.cpu_count())
@@ -112,10 +135,9 @@ def cpu_reference_step_time(sample_levels, steps, warmup, batch=PER_GPU_BATCH):
 
 
 def sample_flop_fraction(sample_levels):
-    from oracle import afigan_oracle as O
-    full = O.stage1_step_flops(sum(h * w for h, w in O.C1_LR_SHAPES), sum(h * w for h, w in O.C1_HR_SHAPES))
-    part = O.stage1_step_flops(sum(O.C1_LR_SHAPES[i][0] * O.C1_LR_SHAPES[i][1] for i in sample_levels),
-                               sum(O.C1_HR_SHAPES[i][0] * O.C1_HR_SHAPES[i][1] for i in sample_levels))
+    full = stage1_step_flops(sum(h * w for h, w in C1_LR_SHAPES), sum(h * w for h, w in C1_HR_SHAPES))
+    part = stage1_step_flops(sum(C1_LR_SHAPES[i][0] * C1_LR_SHAPES[i][1] for i in sample_levels),
+                             sum(C1_HR_SHAPES[i][0] * C1_HR_SHAPES[i][1] for i in sample_levels))
     return part / full
 
 
@@ -166,7 +188,6 @@ def run_ours(args):
     from afigan import native
     from afigan.engine import Stage1Step
     from afigan.modeling import Discriminator, Generator
-    from oracle import afigan_oracle as O
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,7 +207,7 @@ def run_ours(args):
         for p in list(G.parameters()) + list(D.parameters()):
             dist.broadcast(p.data, 0)
     step = Stage1Step(G, D, lr=1e-3, momentum=0.9, weight_decay=1e-4, precision=precision)
-    lr_h, hr_h = O.synthetic_features(PER_GPU_BATCH, rank)   # N(0,1) fp32, seed 1234 + rank
+    lr_h, hr_h = synthetic_features(PER_GPU_BATCH, rank)     # N(0,1) fp32, seed 1234 + rank
     lr_h, hr_h = [t.pin_memory() for t in lr_h], [t.pin_memory() for t in hr_h]
     lr_d, hr_d = [t.to(dev) for t in lr_h], [t.to(dev) for t in hr_h]
     h2d_bytes = sum(t.numel() * 4 for t in lr_h + hr_h)
@@ -289,7 +310,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    flops_step = O.stage1_step_flops(PER_GPU_BATCH * sum(h * w for h, w in O.C1_LR_SHAPES), PER_GPU_BATCH * sum(h * w for h, w in O.C1_HR_SHAPES))
+    flops_step = stage1_step_flops(PER_GPU_BATCH * sum(h * w for h, w in C1_LR_SHAPES), PER_GPU_BATCH * sum(h * w for h, w in C1_HR_SHAPES))
     cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
