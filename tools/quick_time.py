@@ -11,7 +11,7 @@ import torch  # noqa: E402
 from afigan import native  # noqa: E402
 from afigan.engine import Stage1Step  # noqa: E402
 from afigan.modeling import Discriminator, Generator  # noqa: E402
-from oracle import afigan_oracle as O  # noqa: E402
+import bench as O  # noqa: E402  (workload definition: shapes, synthetic features, FLOP count)
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2

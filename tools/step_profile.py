@@ -12,7 +12,7 @@ import torch  # noqa: E402
 from afigan import native  # noqa: E402
 from afigan.engine import Stage1Step  # noqa: E402
 from afigan.modeling import Discriminator, Generator  # noqa: E402
-from oracle import afigan_oracle as O  # noqa: E402
+import bench as O  # noqa: E402  (workload definition: shapes, synthetic features, FLOP count)
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 torch.manual_seed(0)
