@@ -188,7 +188,7 @@ class Stage1Step:
                         if backward:
                             sub[j].dlogits = dls[i].data_ptr()
                     if backward:
-                        N.check(lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), sub, len(part),
+                        N.check(lib.afi_d_backward(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), sub, len(part), 1,
                                                    self.d_acc.data_ptr(), sp))
         if self.overlap:
             for st in self.streams:

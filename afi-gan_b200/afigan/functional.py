@@ -163,15 +163,14 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         dev = x.device
         ps = d_param_struct(params, buffers)
         packed = holder.packed.get("d", prec, params, ps)
-        need_bwd = grad_enabled and training and (any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[0])
-        ctx.eval_mode = not training     # forward in eval mode is fine; only a backward through it is unsupported
+        need_bwd = grad_enabled and (any(ctx.needs_input_grad[8:]) or ctx.needs_input_grad[0])
         lib, actx = N.lib(), N.context(dev)
         ws = _u8(lib.afi_d_workspace_bytes(prec, n, h, w, int(need_bwd)), dev)
         logits = torch.empty((n, 1, h, w), dtype=torch.float32, device=dev)
         call = N.DCall(x=N.view4(x), n=n, h=h, w=w, logits=logits.data_ptr(), ws=ws.data_ptr(), ws_bytes=ws.numel())
         N.check(lib.afi_d_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, int(training), momentum, eps, int(need_bwd),
                                   N.stream_ptr()))
-        ctx.prec, ctx.shape, ctx.ws, ctx.packed, ctx.buffers = prec, (n, h, w), ws, packed, buffers
+        ctx.prec, ctx.shape, ctx.ws, ctx.packed, ctx.buffers, ctx.training = prec, (n, h, w), ws, packed, buffers, bool(training)
         ctx.save_for_backward(*params)
         return logits
 
@@ -181,22 +180,22 @@ class PatchDiscriminatorFn(torch.autograd.Function):
         n, h, w = ctx.shape
         dev = dlogits.device
         lib, actx = N.lib(), N.context(dev)
-        if ctx.eval_mode:
-            raise NotImplementedError("discriminator backward in eval mode is not implemented (the trainers keep D in train mode)")
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("discriminator: gradient w.r.t. the input feature is not implemented "
-                                      "(the stage-1/2 trainers detach it: stage1_trainer.py:339,399)")
         dl = dlogits.float().contiguous()
         acc = _u8(lib.afi_d_gradacc_bytes(), dev)
         N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
         ps = d_param_struct(params, ctx.buffers)
         call = N.DCall(n=n, h=h, w=w, dlogits=dl.data_ptr(), ws=ctx.ws.data_ptr(), ws_bytes=ctx.ws.numel())
-        N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, acc.data_ptr(), N.stream_ptr()))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((n, CH, h, w), dtype=torch.float32, device=dev)
+            call.dx = dx.data_ptr()
+        N.check(lib.afi_d_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, int(ctx.training), acc.data_ptr(),
+                                   N.stream_ptr()))
         grads = [torch.empty_like(p) if ctx.needs_input_grad[8 + i] else None for i, p in enumerate(params)]
         gs = d_grad_struct(grads)
         N.check(lib.afi_d_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
         ctx.ws = None
-        return (None, None, None, None, None, None, None, None, *grads)
+        return (dx, None, None, None, None, None, None, None, *grads)
 
 
 def bce_with_logits(logits: torch.Tensor, target: float) -> torch.Tensor:
@@ -228,6 +227,46 @@ def conv3x3_backward(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, pr
     ws = _u8(lib.afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout), x.device)
     dw = torch.empty_like(weight)
     dx = torch.empty_like(x) if need_dx else None
-    N.check(lib.afi_conv3x3_backward(actx, prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(dx),
+    N.check(lib.afi_conv3x3_backward(actx, prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), None, N.ptr(dx),
                                      ws.data_ptr(), ws.numel(), N.stream_ptr()))
     return dw, dx
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 convolution (+bias) through the library's implicit-GEMM engine with autograd: the necks' output convs
+    (reference fpn_sr.py:144-158, pafpn_sr.py:184-193) when they carry no norm."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec: int):
+        if not x.is_cuda:
+            raise RuntimeError("conv3x3: input must live on an sm_100a CUDA device (no CPU fallback)")
+        x, weight = x.float(), weight.float().contiguous()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout), x.device)
+        y = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+        N.check(lib.afi_conv3x3(actx, prec, N.view4(x), n, cin, h, w, weight.data_ptr(), N.ptr(bias), cout, 0, y.data_ptr(), ws.data_ptr(),
+                                ws.numel(), N.stream_ptr()))
+        ctx.prec, ctx.has_bias = prec, bias is not None
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.float()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv3x3_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
+        dw = torch.empty_like(weight)
+        db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        N.check(lib.afi_conv3x3_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(db),
+                                         N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
+        return dx, dw, db, None
+
+
+def conv3x3_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
+    return Conv3x3Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])

@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..._compat import BACKBONE_REGISTRY, Backbone, Conv2d, ShapeSpec, c2_xavier_fill, get_norm
+from ...functional import conv3x3_autograd
 from ..feat_interpol import generator_rdb as G_rdb
 
 __all__ = ["build_resnet_fpn_sr_backbone", "build_resnest_fpn_sr_backbone", "FPN_AFIGAN", "LastLevelMaxPool"]
@@ -26,6 +27,16 @@ def _afi_freeze(cfg) -> bool:
 def _assert_strides_are_log2_contiguous(strides):
     for i, stride in enumerate(strides[1:], 1):
         assert stride == 2 * strides[i - 1], f"Strides {stride} {strides[i - 1]} are not log2 contiguous"
+
+
+def output_conv3x3(conv, x, precision=None):
+    """The necks' 3x3 output convs (fpn_sr.py:144-158): through the library's implicit-GEMM engine when the conv is bare (NORM == "",
+    stride 1, 256 channels a multiple of 32), plain torch otherwise."""
+    bare = (getattr(conv, "norm", None) is None and getattr(conv, "activation", None) is None and conv.stride == (1, 1)
+            and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.in_channels % 32 == 0 and conv.out_channels % 32 == 0)
+    if bare and x.is_cuda:
+        return conv3x3_autograd(x, conv.weight, conv.bias, precision)
+    return conv(x)
 
 
 def topdown_merge(srf_module, prev_features, features, lateral_conv, fuse_type):
@@ -131,7 +142,7 @@ class FPN_AFIGAN(_AFINeck):
     def forward(self, x):
         bottom_up_features = self.bottom_up(x)
         merged = self._top_down(bottom_up_features)
-        results = [conv(m) for conv, m in zip(self._outputs_bottom_up, merged)]
+        results = [output_conv3x3(conv, m, self.srf_module.precision) for conv, m in zip(self._outputs_bottom_up, merged)]
         return self._finish(bottom_up_features, results)
 
 

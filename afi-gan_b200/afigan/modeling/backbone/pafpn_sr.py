@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch.nn.functional as F
 
 from ..._compat import BACKBONE_REGISTRY, ShapeSpec
-from .fpn_sr import _AFINeck, _build, _resnest_builder, _resnet_builder
+from .fpn_sr import _AFINeck, _build, _resnest_builder, _resnet_builder, output_conv3x3
 
 __all__ = ["build_resnet_pafpn_sr_backbone", "build_resnest_pafpn_sr_backbone", "PAFPN_AFIGAN"]
 
@@ -29,12 +29,12 @@ class PAFPN_AFIGAN(_AFINeck):
         bottom_up_features = self.bottom_up(x)
         merged = self._top_down(bottom_up_features)                    # finest first
         pa_prev = merged[0]
-        results = [self._outputs_bottom_up[0](pa_prev)]
+        results = [output_conv3x3(self._outputs_bottom_up[0], pa_prev, self.srf_module.precision)]
         for inter, down, out_conv in zip(merged[1:], self.downsample_convs, self._outputs_bottom_up[1:]):   # :186-193
             pa_prev = inter + F.relu_(down(pa_prev))
             if self._fuse_type == "avg":
                 pa_prev = pa_prev / 2
-            results.append(out_conv(pa_prev))
+            results.append(output_conv3x3(out_conv, pa_prev, self.srf_module.precision))
         return self._finish(bottom_up_features, results)
 
 

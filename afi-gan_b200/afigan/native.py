@@ -86,7 +86,8 @@ _SIGNATURES = {
     "afi_d_forward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_int, C.c_float,
                                 C.c_float, C.c_int, C.c_void_p]),
     "afi_d_update_running": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.POINTER(DCall), C.c_int, C.c_float, C.c_void_p]),
-    "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_void_p, C.c_void_p]),
+    "afi_d_backward": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DParams), C.c_void_p, C.POINTER(DCall), C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p]),
     "afi_d_unpack_grads": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(DGrads), C.c_float, C.c_int, C.c_void_p]),
     "afi_bce_with_logits": (C.c_int, [C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float,
                                       C.c_void_p]),
@@ -98,7 +99,7 @@ _SIGNATURES = {
     "afi_conv3x3": (C.c_int, [C.c_void_p, C.c_int, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "afi_conv3x3_backward": (C.c_int, [C.c_void_p, C.c_int, View4, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "afi_conv3x3_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "afi_launch_count": (C.c_longlong, [C.c_int]),
     "afi_profile_begin": (C.c_int, [C.c_int]),

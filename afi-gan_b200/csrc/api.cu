@@ -708,8 +708,8 @@ int afi_d_update_running(afi_ctx* ctx, int prec, const afi_d_params* p, const af
     return AFI_OK;
 }
 
-int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, const afi_d_call* calls, int ncalls, float* gradacc,
-                   void* stream) {
+int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* packed, const afi_d_call* calls, int ncalls, int training,
+                   float* gradacc, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     AFI_REQUIRE(ctx && p && packed && gradacc, "afi_d_backward: null argument");
     DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
@@ -721,7 +721,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
     const bool tc = prec_tc(prec);
     for (int k = 0; k < ncalls; k++) {
         AFI_REQUIRE(calls[k].dlogits, "afi_d_backward: call %d has no dlogits", k);
-        AFI_REQUIRE(!calls[k].dx, "afi_d_backward: input gradient is not implemented (stage 1/2 detach the discriminator input)");
+        AFI_REQUIRE((calls[k].dx != nullptr) == (calls[0].dx != nullptr), "afi_d_backward: either every call of a group or none asks for dx");
     }
     if (tc) {
         // head: dy3 = (sum_t g[q - tap_t] w4[:, t]) * lrelu'(a3) is 9 FMAs per element -> one dense HBM-bound pass that also emits the
@@ -766,10 +766,23 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
             AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
         }
-        AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co, st));
+        AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co,
+                                   training ? 0 : 1, st));
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d, X, ci, DYv, co, gradacc + GL.w[i], st));
-        // bias gradient: this bias feeds a train-mode BatchNorm, so dL/db = sum_p dz = 0 identically (the reference gets
-        // ~1e-9 rounding noise there); the accumulator slot stays at its zero-initialised value.
+        // bias gradient: in training mode this bias feeds a batch-statistics BatchNorm, so dL/db = sum_p dz = 0 identically (the reference
+        // gets ~1e-9 rounding noise there) and the accumulator slot stays at its zero-initialised value; in eval mode the
+        // statistics are constants and db = sum_p dz.
+        if (!training) for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(DYv[k], dt, d[k].n, d[k].h, d[k].w, co, gradacc + GL.b[i], st));
+        if (i == 0 && calls[0].dx) {   // input gradient (never needed by the stage-1/2 trainers, which detach D's input; kept for autograd completeness)
+            ConvArgs a;
+            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[0] * es);
+            a.out_dt = DT_F32;
+            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].out = pview(W[k].DXb, d[k].h, d[k].w, ci); }
+            AFI_TRY(run_conv(ctx, prec, a, st));
+            afi_view4 none; memset(&none, 0, sizeof(none));
+            for (int k = 0; k < ncalls; k++)
+                AFI_TRY(nhwc_to_nchw<float>(pview(W[k].DXb, d[k].h, d[k].w, ci), pview_null(), none, 0, 0, 1.f, d[k].n, ci, d[k].h, d[k].w, calls[k].dx, st));
+        }
         if (i > 0) {   // dA_i * lrelu'(a_i) -> DY[i-1]
             ConvArgs a;
             conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * es);
@@ -832,7 +845,7 @@ int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int 
     return AFI_OK;
 }
 int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
-                         float* dw, float* dxo, void* ws, size_t ws_bytes, void* stream) {
+                         float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     AFI_REQUIRE(ctx && x.ptr && dy.ptr && weight && dw && ws && prec_ok(prec), "afi_conv3x3_backward: bad argument");
     AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv3x3_backward: channels must be multiples of 32");
@@ -854,6 +867,10 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     Dim3 d = {n, h, w};
     AFI_TRY(wgrad_std(ctx, prec, 1, &d, &Xv, cin, &DYv, cout, acc, st));
     AFI_TRY(unpack_wgrad(acc, cout, cin, prec_tc(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
+    if (db) {
+        AFI_CUDA(cudaMemsetAsync(db, 0, cout * sizeof(float), st));
+        AFI_TRY(col_sum_f32(DYv, dt, n, h, w, cout, db, st));
+    }
     if (dxo) {
         AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, dt, st));
         ConvArgs a;

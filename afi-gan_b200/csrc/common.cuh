@@ -181,7 +181,8 @@ int dense_group_ok(int c);
 int bn_apply_lrelu_group(int nprob, const PView* z, const PView* a, int dt, const float* const* mean, const float* const* rstd,
                          const float* gamma, const float* beta, float slope, const long long* P, int c, cudaStream_t st);
 int bn_bwd_apply_group(int nprob, const PView* dy, const PView* z, int dt, const float* const* mean, const float* const* rstd, const float* gamma,
-                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, cudaStream_t st);
+                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode,
+                       cudaStream_t st);
 int col_reduce_group(int mode, int nprob, const PView* x, const PView* z, int dt, const float* const* mean, const float* const* rstd,
                      double* const* o0, double* const* o1, const long long* P, int c, cudaStream_t st);
 int bn_finalize_group(int ncalls, const double* const* sum, const double* const* sumsq, const long long* count, int c, float eps,

@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_group(const __grid_constant__ 
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply_group(const __grid_constant__ DenseGroupD G, const float* __restrict__ gamma,
-                                                            float* dgamma_acc, float* dbeta_acc) {
+                                                            float* dgamma_acc, float* dbeta_acc, int eval_mode) {
     const int k = find_prob(G, blockIdx.x);
     const DenseProbD& q = G.p[k];
     const int C = G.C, tpr = C >> 3, rpb = 256 / tpr;
@@ -495,7 +495,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_group(const __grid_constan
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         mu[i] = q.mean[c0 + i]; rs[i] = q.rstd[c0 + i]; gr[i] = gamma[c0 + i] * rs[i];
-        m1[i] = (float)q.o0[c0 + i] * inv_m; m2[i] = (float)q.o1[c0 + i] * inv_m;
+        // eval mode: the statistics are constants (running buffers), so dz = gamma * rstd * dy without the two mean terms
+        m1[i] = eval_mode ? 0.f : (float)q.o0[c0 + i] * inv_m; m2[i] = eval_mode ? 0.f : (float)q.o1[c0 + i] * inv_m;
     }
     long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
     if (r1 > q.P) r1 = q.P;
@@ -608,7 +609,8 @@ int bn_apply_lrelu_group(int nprob, const PView* z, const PView* a, int dt, cons
     return AFI_OK;
 }
 int bn_bwd_apply_group(int nprob, const PView* dy, const PView* z, int dt, const float* const* mean, const float* const* rstd, const float* gamma,
-                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, cudaStream_t st) {
+                       double* const* s_dy, double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode,
+                       cudaStream_t st) {
     DenseGroupD G; memset(&G, 0, sizeof(G));
     G.nprob = nprob; G.C = c;
     for (int k = 0; k < nprob; k++) {
@@ -618,8 +620,8 @@ int bn_bwd_apply_group(int nprob, const PView* dy, const PView* z, int dt, const
     dense_group_blocks(G, DENSE_ROWS, 2368);
     int grid = G.p[nprob].block_begin;
     if (grid == 0) return AFI_OK;
-    if (dt == DT_F32) k_bn_bwd_apply_group<float><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc);
-    else k_bn_bwd_apply_group<bf16><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc);
+    if (dt == DT_F32) k_bn_bwd_apply_group<float><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc, eval_mode);
+    else k_bn_bwd_apply_group<bf16><<<grid, 256, 0, st>>>(G, gamma, dgamma_acc, dbeta_acc, eval_mode);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

@@ -138,7 +138,7 @@ typedef struct {
     afi_view4 x; int n, h, w;       /* input [n,256,h,w]                               */
     float* logits;                  /* forward: contiguous [n,1,h,w]                   */
     const float* dlogits;           /* backward: contiguous [n,1,h,w]                  */
-    float* dx;                      /* backward: must be NULL (stage 1/2 detach the input) */
+    float* dx;                      /* backward: contiguous [n,256,h,w] or NULL           */
     void* ws; size_t ws_bytes;
 } afi_d_call;
 
@@ -154,8 +154,10 @@ int afi_d_forward(afi_ctx*, int prec, const afi_d_params*, const void* packed, c
  * ORDER (= the reference's call order) and bumps num_batches_tracked by ncalls. */
 int afi_d_update_running(afi_ctx*, int prec, const afi_d_params*, const afi_d_call* calls, int ncalls, float momentum, void* stream);
 
-/* Backward of the (training-mode) calls that filled their ws.  Gradients of all calls are ADDED into gradacc (packed). */
-int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls,
+/* Backward of the calls that filled their ws with save_for_backward; `training` must repeat the forward's mode (non-zero: batch
+ * statistics; 0: running statistics, where the BatchNorm backward has no mean terms and the conv biases get a gradient).
+ * Gradients of all calls are ADDED into gradacc (packed); dx (optional, all calls or none) is overwritten. */
+int afi_d_backward(afi_ctx*, int prec, const afi_d_params*, const void* packed, const afi_d_call* calls, int ncalls, int training,
                    float* gradacc, void* stream);
 int afi_d_unpack_grads(afi_ctx*, int prec, const float* gradacc, const afi_d_grads*, float scale, int accumulate, void* stream);
 
@@ -181,9 +183,10 @@ int afi_zero(void* ptr, size_t bytes, void* stream);
 /* y = [lrelu](conv3x3(x, w) + b) with stride 1, pad 1; x [n,cin,h,w] view, w [cout,cin,3,3], y contiguous [n,cout,h,w]. */
 int afi_conv3x3(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, const float* weight, const float* bias,
                 int cout, int lrelu, float* y, void* ws, size_t ws_bytes, void* stream);
-/* dw [cout,cin,3,3] = wgrad of the same conv for upstream gradient dy [n,cout,h,w] (contiguous), dxo = dgrad (may be NULL) */
+/* dw [cout,cin,3,3] = wgrad of the same conv for upstream gradient dy [n,cout,h,w]; db [cout] = bias gradient (may be NULL);
+ * dxo = dgrad, contiguous [n,cin,h,w] (may be NULL).  Also backs the necks' 3x3 output convs (fpn_sr.py:144-158). */
 int afi_conv3x3_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
-                         int cout, float* dw, float* dxo, void* ws, size_t ws_bytes, void* stream);
+                         int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to

@@ -110,3 +110,64 @@ def test_cpu_tensor_is_a_hard_error():
     G = Generator(n_residual_dense_blocks=3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         G(torch.zeros(1, 256, 4, 4))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_discriminator_input_gradient(precision):
+    """Gradient w.r.t. the discriminator's input (the trainers detach it, but the module must be a well-behaved autograd citizen)."""
+    _, D, _, d_sd = _modules(precision)
+    stack = D.Discriminators[0]
+    stack.train()
+    x = torch.randn(2, 256, 9, 12, generator=torch.Generator().manual_seed(41))
+    xr = x.clone().requires_grad_(True)
+    O.bce_logits_mean(O.discriminator_forward({k: v.clone() for k, v in d_sd.items()}, xr, True), 1.0).backward()
+    xc = x.cuda().requires_grad_(True)
+    logit = stack(xc)
+    torch.nn.functional.binary_cross_entropy_with_logits(logit, torch.ones_like(logit)).backward()
+    r = rel(xc.grad, xr.grad)
+    assert r < (5e-3 if precision == "fp32" else 0.15) and cosine(xc.grad, xr.grad) > (0.9999 if precision == "fp32" else 0.985), r
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_discriminator_eval_mode_backward(precision):
+    """Backward through an eval-mode discriminator (running statistics are constants: no mean terms, conv biases DO get a gradient)."""
+    _, D, _, d_sd = _modules(precision)
+    tol = TOL[precision]
+    stack = D.Discriminators[0]
+    gen = torch.Generator().manual_seed(42)
+    sd = {k: v.clone() for k, v in d_sd.items()}
+    for n in range(3):      # non-trivial running statistics
+        sd[f"Discriminators.0.{n}.0.norm.running_mean"] = 0.1 * torch.randn(sd[f"Discriminators.0.{n}.0.norm.running_mean"].shape, generator=gen)
+        sd[f"Discriminators.0.{n}.0.norm.running_var"] = 1 + 50 * torch.rand(sd[f"Discriminators.0.{n}.0.norm.running_var"].shape, generator=gen)
+    D.load_state_dict(sd)
+    stack.eval()
+    x = torch.randn(2, 256, 8, 10, generator=gen)
+    keys = O.discriminator_param_keys()
+    params = dict(sd)
+    for k in keys:
+        params[k] = sd[k].clone().requires_grad_(True)
+    O.bce_logits_mean(O.discriminator_forward(params, x, False), 0.0).backward()
+    logit = stack(x.cuda())
+    torch.nn.functional.binary_cross_entropy_with_logits(logit, torch.zeros_like(logit)).backward()
+    for k, p in zip(keys, stack._params()):
+        r = rel(p.grad, params[k].grad)
+        assert r < tol["dgrad"], f"{precision} {k}: {r:.3e}"
+    assert int(D.state_dict()["Discriminators.0.0.0.norm.num_batches_tracked"]) == 0          # eval mode leaves the buffers alone
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv3x3_autograd_function(precision):
+    from afigan.functional import conv3x3_autograd
+    gen = torch.Generator().manual_seed(43)
+    x = torch.randn(2, 256, 12, 17, generator=gen)
+    w = torch.randn(256, 256, 3, 3, generator=gen) * 0.03
+    b = torch.randn(256, generator=gen)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.conv2d(xr, wr, br, padding=1)
+    dy = torch.randn(ref.shape, generator=gen)
+    (ref * dy).sum().backward()
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    out = conv3x3_autograd(xc, wc, bc, precision)
+    (out * dy.cuda()).sum().backward()
+    t = 1e-5 if precision == "fp32" else 1e-2
+    assert rel(out, ref) < t and rel(xc.grad, xr.grad) < t and rel(wc.grad, wr.grad) < t and rel(bc.grad, br.grad) < t
