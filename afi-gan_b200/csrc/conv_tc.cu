@@ -14,6 +14,7 @@
 //   warp 2-5: epilogue                    -- tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x 256 cols)
 //                                            so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace afi {
@@ -685,6 +686,8 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     order_by_size(a.nprob, size, order);
     Tiling tl{};
     tl.n_tiles = (a.cout + 255) / 256;
+    // (halving the N tile to get more waves on the generator's small levels was measured SLOWER: 806 -> 605 TFLOP/s on 256->256;
+    //  those layers are bound by L2 -> SM operand traffic, which a narrower tile increases)
     tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
     tl.kchunks = (a.cin + 63) / 64;
     int nviews = 0;
