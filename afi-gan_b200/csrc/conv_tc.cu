@@ -6,13 +6,19 @@
 //           zero-filled by the TMA unit, which IS the conv padding (and handles ragged 13x21 / 7x11 levels).
 //           Box rows land as 128-byte, 128B-swizzled rows = the UMMA K-major SWIZZLE_128B canonical layout.
 //   wgrad : D[128 couts x bn cins] += dY[64 px x 128 co]^T * X_shift[64 px x bn ci]: both operands MN-major
-//           (channels contiguous), K = pixels; same TMA boxes, split-K over spatial patches, fp32 RED into dW.
+//           (channels contiguous), K = pixels; ONE 5-D grouped TMA box per operand per stage, split-K over the concatenated
+//           spatial patches of all problems of the group, fp32 RED into dW.
+//   Both kernels are GROUPED: one launch covers up to AFI_MAX_PROB problems (pyramid levels / discriminator calls) that share the
+//   weights; the persistent CTAs walk a largest-first work list spanning all of them.
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over a static tile list):
-//   warp 0 : TMA producer (one lane)      -- 4-stage smem ring, mbarrier full/empty
-//   warp 1 : TMEM allocator + MMA issuer  -- tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128, N=bn
-//   warp 2-5: epilogue                    -- tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x 256 cols)
-//                                            so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (1 CTA/SM, persistent over a static work list):
+//   warp 0   : TMA producer (one lane)      -- 4-stage smem ring, mbarrier full/empty
+//   warp 1   : TMEM allocator + MMA issuer  -- tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128, N=bn (runtime)
+//   warps 2+ : epilogue, 4 warps (long-K convs: 192 threads) or 8 warps (short-K convs and wgrad: 320 threads)
+//                                            -- tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x 256 columns)
+//                                               so the epilogue of tile i overlaps the MMAs of tile i+1; optional fused per-channel
+//                                               statistics (BatchNorm sum / sum of squares) via a 16-shuffle butterfly per chunk.
+// Every mbarrier wait has a 4 s watchdog that traps instead of hanging the GPU.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
