@@ -238,6 +238,7 @@ class Stage1Step:
         if apply_updates:
             self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
             self._pack_d()
+            self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
 
         # ------------------------------ G phase (stage1_trainer.py:384-433)
         N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
@@ -263,6 +264,7 @@ class Stage1Step:
         if apply_updates:
             self._sgd(self.g_params, self.g_grads, self.g_mom, [False] * len(self.g_params))
             self._pack_g()
+            self.G._native.packed.key = None
             self.steps_done += 1
         return self.losses
 

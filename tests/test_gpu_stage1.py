@@ -125,3 +125,19 @@ def test_bf16_and_fp32_modes_train_alike():
     for mode in ("fp32", "bf16"):
         assert curves[mode][-1][0] < curves[mode][0][0]          # the discriminator loss falls
         assert curves[mode][-1][1] < curves[mode][0][1]          # the L1 content loss falls
+
+
+def test_module_forward_sees_weights_updated_by_the_fused_step():
+    """Stage1Step updates the parameters in place inside the library; the nn.Module path must not keep using a stale packed copy."""
+    G, D, step = _build("fp32")
+    lr_f, hr_f = O.synthetic_features(1, 0, ((5, 7),), ((9, 13),), seed=9)
+    x = lr_f[0].cuda()
+    with torch.no_grad():
+        y0 = G(x).clone()                                   # populates the module's packed-weight cache
+    step.lr = 0.5                                           # large step so the change is visible
+    step.run_step([x], [hr_f[0].cuda()])
+    with torch.no_grad():
+        y1 = G(x)
+    sd = {k: v.detach().cpu() for k, v in G.state_dict().items()}
+    assert rel(y1, O.generator_forward(sd, lr_f[0])) < 1e-5         # consistent with the CURRENT parameters
+    assert rel(y1 - y0, y0) > 1e-6                                   # and they did change
