@@ -10,6 +10,8 @@ from typing import Optional
 
 import torch
 
+from ..._compat import BACKBONE_REGISTRY, ShapeSpec
+
 
 def bifpn_feature_fusion(srf_module, cur_feature: torch.Tensor, top_feature: torch.Tensor,
                          weight: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -18,3 +20,11 @@ def bifpn_feature_fusion(srf_module, cur_feature: torch.Tensor, top_feature: tor
     if weight is None:
         return cur_feature + up
     return cur_feature * weight[0] + up * weight[1]
+
+
+@BACKBONE_REGISTRY.register()
+def build_swint_bifpn_sr_backbone(cfg, input_shape: ShapeSpec):
+    """bifpn_sr.py:791-816.  The Swin bottom-up and the seven hand-unrolled BiFPN layers are not re-implemented (SURVEY.md §2 rows 7, 8, 11);
+    only their interpolator fusion site is native (`bifpn_feature_fusion`)."""
+    raise ImportError("build_swint_bifpn_sr_backbone needs the reference's Swin backbone and BiFPN layer stack (out of the hot path's scope); "
+                      "patch the reference BiFPN_AFIGAN._feature_funsion to call afigan.modeling.backbone.bifpn_sr.bifpn_feature_fusion")

@@ -29,8 +29,15 @@ def test_backbone_registry_names():
     from afigan._compat import BACKBONE_REGISTRY
     import afigan.modeling  # noqa: F401
     for name in ("build_resnet_fpn_sr_backbone", "build_resnest_fpn_sr_backbone", "build_resnet_pafpn_sr_backbone",
-                 "build_resnest_pafpn_sr_backbone"):
+                 "build_resnest_pafpn_sr_backbone", "build_swint_bifpn_sr_backbone"):
         assert callable(BACKBONE_REGISTRY.get(name))
+    from afigan.config import get_cfg
+    from afigan.modeling import GUIDE_ARCH_REGISTRY, build_guide_model
+    cfg = get_cfg()
+    cfg.MODEL.GUIDE_ARCHITECTURE = "RCNN_FPN_only"                 # configs/step1_*.yaml:5
+    assert callable(GUIDE_ARCH_REGISTRY.get("RCNN_FPN_only"))
+    with pytest.raises(ImportError, match="out of scope"):          # the guide model itself is a producer of the path's inputs
+        build_guide_model(cfg)
 
 
 def test_neck_parameter_names_on_cpu():
