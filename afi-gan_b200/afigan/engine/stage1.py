@@ -58,6 +58,7 @@ class Stage1Step:
         self.d_packed = _u8(self.lib.afi_d_packed_bytes(self.prec), dev)
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._bufs: Dict[tuple, torch.Tensor] = {}
+        self._sgd_tabs: Dict[int, tuple] = {}
         self.losses = torch.zeros(4, 8, dtype=torch.float32, device=dev)   # rows: d_loss, g_loss, adv, content ; cols: levels
         self._tmp = torch.zeros(64, dtype=torch.float32, device=dev)
         # Two side streams: the discriminator calls of a phase are issued as two groups (real / fake) whose HBM-bound passes (BatchNorm
@@ -201,11 +202,22 @@ class Stage1Step:
         return logits
 
     def _sgd(self, params, grads, moms, is_norm):
-        # parameters are updated in place behind torch's back; the packed GEMM-layout copies are refreshed explicitly by the caller
+        # parameters are updated in place behind torch's back; the packed GEMM-layout copies are refreshed explicitly by the caller.
+        # ONE multi-tensor launch per optimiser; the host-side pointer tables are rebuilt only when a tensor moved.
         first = int(self.steps_done == 0)
-        for p, g, m, nrm in zip(params, grads, moms, is_norm):
-            N.check(self.lib.afi_sgd_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel(), self.lr, self.momentum,
-                                          self.wd_norm if nrm else self.wd, 1.0 / self.world, first, N.stream_ptr()))
+        n = len(params)
+        key = tuple(t.data_ptr() for ts in (params, grads, moms) for t in ts) + (self.wd, self.wd_norm)
+        tab = self._sgd_tabs.get(id(params))
+        if tab is None or tab[0] != key:
+            P = (C.c_void_p * n)(*[p.data_ptr() for p in params])
+            G = (C.c_void_p * n)(*[g.data_ptr() for g in grads])
+            M = (C.c_void_p * n)(*[m.data_ptr() for m in moms])
+            cnt = (C.c_longlong * n)(*[p.numel() for p in params])
+            wd = (C.c_float * n)(*[self.wd_norm if nrm else self.wd for nrm in is_norm])
+            tab = (key, P, G, M, cnt, wd)
+            self._sgd_tabs[id(params)] = tab
+        _, P, G, M, cnt, wd = tab
+        N.check(self.lib.afi_sgd_step_multi(n, P, G, M, cnt, wd, self.lr, self.momentum, 1.0 / self.world, first, N.stream_ptr()))
 
     def _allreduce(self, flat: torch.Tensor):
         (self.g_sync if flat is self.g_flat else self.d_sync).all_reduce()

@@ -239,21 +239,20 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     GPacked L = g_packed_layout(p->n_rdb);
     int dt = prec_dt(prec); size_t es = dt_size(dt);
     char* b = (char*)packed;
-    AFI_TRY(pack_weights(p->head_w, C, C, pm(prec, 0), b + L.head_f * es, dt, st));
-    AFI_TRY(pack_weights(p->head_w, C, C, pm(prec, 1), b + L.head_d * es, dt, st));
+    PackJob jobs[AFI_MAX_PACK]; int nj = 0;     // forward + dgrad layouts of every conv: one grouped launch
+    auto add = [&](const float* w, int co, int ci, int kind, size_t off) {
+        PackJob& j = jobs[nj++]; j.w = w; j.dst = b + off * es; j.co = co; j.ci = ci; j.mode = pm(prec, kind); j.pad_ = 0;
+    };
+    add(p->head_w, C, C, 0, L.head_f); add(p->head_w, C, C, 1, L.head_d);
     for (int r = 0; r < p->n_rdb; r++)
         for (int i = 0; i < 5; i++) {
             int co = i < 4 ? GR : C, ci = C + GR * i;
-            AFI_TRY(pack_weights(p->rdb_w[r][i], co, ci, pm(prec, 0), b + L.rdb_f[r][i] * es, dt, st));
-            AFI_TRY(pack_weights(p->rdb_w[r][i], co, ci, pm(prec, 1), b + L.rdb_d[r][i] * es, dt, st));
+            add(p->rdb_w[r][i], co, ci, 0, L.rdb_f[r][i]); add(p->rdb_w[r][i], co, ci, 1, L.rdb_d[r][i]);
         }
-    AFI_TRY(pack_weights(p->post_w, C, C, pm(prec, 0), b + L.post_f * es, dt, st));
-    AFI_TRY(pack_weights(p->post_w, C, C, pm(prec, 1), b + L.post_d * es, dt, st));
-    AFI_TRY(pack_weights(p->up_w, C, C, pm(prec, 2), b + L.up_f * es, dt, st));
-    AFI_TRY(pack_weights(p->up_w, C, C, pm(prec, 3), b + L.up_d * es, dt, st));
-    AFI_TRY(pack_weights(p->out_w, C, C, pm(prec, 0), b + L.out_f * es, dt, st));
-    AFI_TRY(pack_weights(p->out_w, C, C, pm(prec, 1), b + L.out_d * es, dt, st));
-    return AFI_OK;
+    add(p->post_w, C, C, 0, L.post_f); add(p->post_w, C, C, 1, L.post_d);
+    add(p->up_w, C, C, 2, L.up_f); add(p->up_w, C, C, 3, L.up_d);
+    add(p->out_w, C, C, 0, L.out_f); add(p->out_w, C, C, 1, L.out_d);
+    return pack_weights_group(nj, jobs, dt, st);
 }
 
 int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* packed, const afi_g_call* calls, int ncalls, int save,
@@ -573,6 +572,7 @@ struct DWs {
     float *mean[3], *rstd[3], *var[3], *T9;   // per-layer batch mean / 1/sqrt(var+eps) / unbiased var of THIS call
     double* sums;          // [2][1024]
     void *DY[3], *DXb, *G9;
+    float* G9F;            // fp32 copy [P][12] of the shifted head gradients
     size_t total;
 };
 static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) {
@@ -588,6 +588,7 @@ static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) 
         for (int i = 0; i < 3; i++) W.DY[i] = cv.take(P * DC[i + 1] * es);
         W.DXb = cv.take(P * DC[0] * 4);
         W.G9 = cv.take(P * 16 * 2);
+        W.G9F = (float*)cv.take(P * 12 * 4);
     }
     W.total = cv.off;
     return W;
@@ -605,10 +606,12 @@ int afi_d_pack(afi_ctx* ctx, int prec, const afi_d_params* p, void* packed, void
     AFI_REQUIRE(ctx && p && packed && prec_ok(prec), "afi_d_pack: bad argument");
     DPacked L = d_packed_layout();
     int dt = prec_dt(prec); size_t es = dt_size(dt);
+    PackJob jobs[6];
     for (int i = 0; i < 3; i++) {
-        AFI_TRY(pack_weights(p->w[i], DC[i + 1], DC[i], pm(prec, 0), (char*)packed + L.f[i] * es, dt, st));
-        AFI_TRY(pack_weights(p->w[i], DC[i + 1], DC[i], pm(prec, 1), (char*)packed + L.d[i] * es, dt, st));
+        jobs[2 * i] = {p->w[i], (char*)packed + L.f[i] * es, DC[i + 1], DC[i], pm(prec, 0), 0};
+        jobs[2 * i + 1] = {p->w[i], (char*)packed + L.d[i] * es, DC[i + 1], DC[i], pm(prec, 1), 0};
     }
+    AFI_TRY(pack_weights_group(6, jobs, dt, st));
     if (prec_tc(prec)) AFI_TRY(dhead_pack_tc(p->w[3], DC[3], (char*)packed + L.hf * es, (char*)packed + L.hb * es, st));
     return AFI_OK;
 }
@@ -724,25 +727,29 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         AFI_REQUIRE((calls[k].dx != nullptr) == (calls[0].dx != nullptr), "afi_d_backward: either every call of a group or none asks for dx");
     }
     if (tc) {
-        // head: dy3 = (sum_t g[q - tap_t] w4[:, t]) * lrelu'(a3) is 9 FMAs per element -> one dense HBM-bound pass that also emits the
-        // two BatchNorm-backward reductions of layer 3; dW4 = g9^T a3 is a K = pixels GEMM on the tensor cores; db4 = sum g.
+        // head: dy3 = (sum_t g[q - tap_t] w4[:, t]) * lrelu'(a3) is 9 FMAs per element, so it is never stored: two grouped HBM-bound passes
+        // over z3 recompute it, the first for the two BatchNorm-backward reductions of layer 3, the second for dz3 itself;
+        // dW4 = g9^T a3 is a K = pixels GEMM on the tensor cores; db4 = sum g.
         WgradArgs g;
         memset(&g, 0, sizeof(g));
         g.cin = DC[3]; g.cout = 16; g.ntaps = 1; g.nprob = ncalls; g.dw = gradacc + GL.w[3];
-        {
-            void* sums_p[AFI_MAX_PROB];
-            for (int k = 0; k < ncalls; k++) sums_p[k] = W[k].sums;
-            AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+        void* sums_p[AFI_MAX_PROB]; double* s0[AFI_MAX_PROB]; double* s1[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
+        const float* g9f[AFI_MAX_PROB]; long long cnt[AFI_MAX_PROB]; PView Z3[AFI_MAX_PROB], DZ3[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) {
+            sums_p[k] = W[k].sums; s0[k] = W[k].sums; s1[k] = W[k].sums + 1024; mean_c[k] = W[k].mean[2]; rstd_c[k] = W[k].rstd[2];
+            g9f[k] = W[k].G9F; cnt[k] = (long long)d[k].n * d[k].h * d[k].w;
+            Z3[k] = pview(W[k].Z[2], d[k].h, d[k].w, DC[3]); DZ3[k] = pview(W[k].DY[2], d[k].h, d[k].w, DC[3]);
         }
+        AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
         for (int k = 0; k < ncalls; k++) {
             const int n = d[k].n, h = d[k].h, w = d[k].w;
-            AFI_TRY(dhead_build_g9(calls[k].dlogits, n, h, w, W[k].G9, st));
+            AFI_TRY(dhead_build_g9(calls[k].dlogits, n, h, w, W[k].G9, W[k].G9F, st));
             AFI_TRY(sum_f32(calls[k].dlogits, (long long)n * h * w, gradacc + GL.b[3], st));
-            PView G9 = pview(W[k].G9, h, w, 16), A3 = pview(W[k].A[3], h, w, DC[3]);
-            AFI_TRY(dhead_backward_dense(A3, pview(W[k].Z[2], h, w, DC[3]), pview(W[k].DY[2], h, w, DC[3]), dt, p->w[3], calls[k].dlogits,
-                                         W[k].mean[2], W[k].rstd[2], n, h, w, DC[3], W[k].sums, W[k].sums + 1024, st));
-            g.p[k].N = n; g.p[k].H = h; g.p[k].W = w; g.p[k].x = A3; g.p[k].dy = G9;
+            g.p[k].N = n; g.p[k].H = h; g.p[k].W = w; g.p[k].x = pview(W[k].A[3], h, w, DC[3]); g.p[k].dy = pview(W[k].G9, h, w, 16);
         }
+        for (int pass = 1; pass <= 2; pass++)
+            AFI_TRY(dhead_backward_group(pass, ncalls, g9f, Z3, DZ3, dt, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
+                                         gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
         AFI_TRY(run_wgrad(ctx, prec, g, st));
     } else {
         for (int k = 0; k < ncalls; k++)   // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
@@ -762,12 +769,12 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         }
         // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ);
         // each pass is one grouped launch over all calls
-        if (!(tc && i == 2)) {      // (the tensor-core path got layer 3's reductions from the fused head pass above)
+        if (!(tc && i == 2)) {      // (the tensor-core path did layer 3's BatchNorm backward in the fused head passes above)
             AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
             AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
+            AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co,
+                                       training ? 0 : 1, st));
         }
-        AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co,
-                                   training ? 0 : 1, st));
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d, X, ci, DYv, co, gradacc + GL.w[i], st));
         // bias gradient: in training mode this bias feeds a batch-statistics BatchNorm, so dL/db = sum_p dz = 0 identically (the reference
         // gets ~1e-9 rounding noise there) and the accumulator slot stays at its zero-initialised value; in eval mode the

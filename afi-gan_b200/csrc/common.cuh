@@ -149,6 +149,10 @@ enum PackMode { PACK_FWD_KN = 0, PACK_FWD_NK = 1, PACK_DGRAD_KN = 2, PACK_DGRAD_
                 PACK_DECONV_FWD_KN = 4, PACK_DECONV_FWD_NK = 5, PACK_DECONV_DGRAD_KN = 6, PACK_DECONV_DGRAD_NK = 7,
                 PACK_1X1_KN = 8, PACK_1X1_NK = 9, PACK_1X1_DGRAD_KN = 10, PACK_1X1_DGRAD_NK = 11 };
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st);
+#define AFI_MAX_PACK 48
+#define AFI_MAX_SGD 48
+struct PackJob { const float* w; void* dst; int co, ci, mode, pad_; };
+int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st);
 // gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);
 int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st);
@@ -191,12 +195,14 @@ int zero_group(int n, void* const* ptrs, size_t bytes, cudaStream_t st);
 
 // tensor-core formulation of the discriminator head (bf16 mode)
 int dhead_pack_tc(const float* w4, int c, void* fwd, void* bwd, cudaStream_t st);
-int dhead_build_g9(const float* g, int n, int h, int w, void* g9, cudaStream_t st);
+int dhead_build_g9(const float* g, int n, int h, int w, void* g9, float* g9f, cudaStream_t st);
 int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float* logits, cudaStream_t st);
 int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumulate, cudaStream_t st);
 int sum_f32(const float* x, long long n, float* out, cudaStream_t st);
-int dhead_backward_dense(PView a3, PView z3, PView dy3, int dt, const float* w4, const float* g, const float* mean, const float* rstd, int n,
-                         int h, int w, int c, double* s_dy, double* s_dyx, cudaStream_t st);
+// head backward fused with layer 3's BatchNorm backward (pass 1: the two reductions; pass 2: dz3), grouped over calls
+int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PView* z3, const PView* dz3, int dt, const float* w4,
+                         const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
+                         double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st);
 
 template <typename T> struct dt_of;
 template <> struct dt_of<float> { static const int v = DT_F32; };

@@ -21,6 +21,7 @@
 // Every mbarrier wait has a 4 s watchdog that traps instead of hanging the GPU.
 #include <cuda.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include "common.cuh"
 
 namespace afi {
@@ -50,6 +51,12 @@ struct Tiling {
     int total;                        // work items
     int nprob;
     int m_tiles, ksplit, ktiles;      // wgrad only
+    // halo-tile convolution only: A ring of `sa` slots (one (view, 64-channel chunk) halo each), B ring of `sb` slots (one (tap, chunk)
+    // weight tile each); planes = 1: ONE {64 ch, TW+2, TH+2} box, taps address it through shifted descriptors; planes = 3: three
+    // {64 ch, TW, TH+2} boxes (dx = -1, 0, +1), taps shift by whole 1024-byte swizzle atoms only
+    int planes, sa, sb, a_slot, b_slot, a_bytes, nviews;
+    int view_tap0[5];                 // taps of view v: [view_tap0[v], view_tap0[v+1])
+    long long* dbg;                   // optional [grid][8] stall-cycle counters (AFIGAN_HALO_DBG)
     TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
 };
 
@@ -237,6 +244,187 @@ __device__ __forceinline__ void butterfly16(float (&s)[16], int lane) {
 }
 __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
+// Epilogue warps of the convolution kernels (shared by the per-tap and the halo-tile main loops): TMEM -> registers -> bias / activation /
+// residuals / mask / statistics -> global memory, for every work item of this CTA.
+template <int EPI_WARPS>
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& tl, uint64_t* acc_full, uint64_t* acc_empty,
+                                              float (*sstat)[2][ACC_COLS], const uint32_t tmem_base, const int warp, const int lane) {
+    constexpr int HALVES = EPI_WARPS / 4;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;       // 0 .. HALVES-1
+    const int row = q * 32 + lane;
+    int as = 0; uint32_t aphase = 0;
+    // Column statistics stay in shared memory across the tiles of this CTA for as long as (problem, N tile) does not change
+    // (with gridDim a multiple of n_tiles that is the whole run of a problem) and are published with ONE fp64 atomic per
+    // column per run: same-address fp64 atomics from 148 CTAs on every tile were the bottleneck of the first version.
+    int cur_prob = -1, cur_nt = -1;
+    auto flush_stats = [&](int prob, int nt_) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        const ConvProb& fp = a.p[prob];
+        const int fn0 = nt_ * tl.bn;
+        for (int c = row + half * 128; c < tl.bn; c += 32 * EPI_WARPS) {
+            const int w0 = ((c >> 4) % HALVES) * 4;      // the four warps (one per lane quarter) that own this column's chunk
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                t0 += sstat[w0 + j][0][c]; t1 += sstat[w0 + j][1][c];
+                sstat[w0 + j][0][c] = 0.f; sstat[w0 + j][1][c] = 0.f;
+            }
+            if (fn0 + c < a.cout) {
+                atomicAdd(fp.stat0 + fn0 + c, (double)t0);
+                atomicAdd(fp.stat1 + fn0 + c, (double)t1);
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    };
+    for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+        int ti = 0;
+        while (tile >= tl.p[ti + 1].begin) ti++;
+        const TileP& tp_ = tl.p[ti];
+        const ConvProb& pr = a.p[tp_.prob];
+        int local = tile - tp_.begin;
+        int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
+        if (a.stat_mode && (tp_.prob != cur_prob || nt != cur_nt)) {
+            if (cur_prob >= 0) flush_stats(cur_prob, cur_nt);
+            cur_prob = tp_.prob; cur_nt = nt;
+        }
+        int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
+        int img = mt / tiles_per_img, r = mt % tiles_per_img;
+        const int ty = row / tp_.TW, tx = row % tp_.TW;
+        int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
+        const bool ok = (y < pr.H) && (x < pr.W);
+        const int n0 = nt * tl.bn;
+        // Auxiliary epilogue operands (residuals / mask / BN input / fp32 accumulate-in) are prefetched one chunk ahead of their
+        // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
+        const long long offA = pr.mask.ptr ? img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx
+                                           : (pr.r1.ptr ? img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx : 0);
+        const long long offB = pr.bnz.ptr && a.stat_mode == 2 ? img * pr.bnz.sn + y * pr.bnz.sy + x * pr.bnz.sx
+                                                              : (pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0);
+        const bf16* pA = pr.mask.ptr ? (const bf16*)pr.mask.ptr + offA : (pr.r1.ptr ? (const bf16*)pr.r1.ptr + offA : nullptr);
+        const bf16* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const bf16*)pr.bnz.ptr + offB : (pr.r2.ptr ? (const bf16*)pr.r2.ptr + offB : nullptr);
+        const float* pC = pr.accin.ptr ? (const float*)pr.accin.ptr + img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx : nullptr;
+        const int nchunks = tl.bn >> 4;
+        auto aux_load = [&](int ch, Aux& r) {
+            const int col = n0 + (ch << 4);
+            if (ch < nchunks && ok && col < a.cout) {
+                if (pC) {
+                    const uint4* g = reinterpret_cast<const uint4*>(pC + col);
+                    r.a = g[0]; r.b = g[1]; r.c = g[2]; r.d = g[3];
+                } else {
+                    if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + col); r.a = g[0]; r.b = g[1]; }
+                    if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + col); r.c = g[0]; r.d = g[1]; }
+                }
+            }
+        };
+        auto unpack16 = [](const uint4& lo, const uint4& hi, float* t) {
+            const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) { t[2 * j] = __uint_as_float(w[j] << 16); t[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
+        };
+        // chunk ownership: the two warps of a TMEM lane quarter interleave the 16-column chunks (half = 0 / 1)
+        const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+        auto process = [&](int ch, const Aux& ax) {
+            const int c0 = ch << 4;
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            const int col = n0 + c0;
+            const bool valid = ok && col < a.cout;
+            float zbn[16];
+            if (valid) {
+                if (a.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { float4 b = __ldg(b4 + i); v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w; }
+                }
+                if (a.act) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * a.slope;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] *= a.alpha;
+                float t[16];
+                if (pC) {
+                    const uint4 q4[4] = {ax.a, ax.b, ax.c, ax.d};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v[4 * i] += __uint_as_float(q4[i].x); v[4 * i + 1] += __uint_as_float(q4[i].y);
+                        v[4 * i + 2] += __uint_as_float(q4[i].z); v[4 * i + 3] += __uint_as_float(q4[i].w);
+                    }
+                } else {
+                    if (pr.r1.ptr) {
+                        unpack16(ax.a, ax.b, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
+                    }
+                    if (pr.r2.ptr) {
+                        unpack16(ax.c, ax.d, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
+                    }
+                    if (pr.mask.ptr) {
+                        unpack16(ax.a, ax.b, t);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
+                    }
+                    if (a.stat_mode == 2) unpack16(ax.c, ax.d, zbn);
+                }
+                st16(pr.out.ptr, img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
+            }
+            if (a.stat_mode) {      // warp-uniform: every lane takes part in the shuffles, invalid rows contribute zeros
+                float s0[16], s1[16];
+                if (a.stat_mode == 1) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { s0[i] = valid ? v[i] : 0.f; s1[i] = valid ? v[i] * v[i] : 0.f; }
+                } else {
+                    float mu[16], rs[16];
+                    if (valid) {
+                        const float4* m4 = reinterpret_cast<const float4*>(pr.bn_mean + col);
+                        const float4* r4 = reinterpret_cast<const float4*>(pr.bn_rstd + col);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            float4 m = __ldg(m4 + i), r = __ldg(r4 + i);
+                            mu[4 * i] = m.x; mu[4 * i + 1] = m.y; mu[4 * i + 2] = m.z; mu[4 * i + 3] = m.w;
+                            rs[4 * i] = r.x; rs[4 * i + 1] = r.y; rs[4 * i + 2] = r.z; rs[4 * i + 3] = r.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        s0[i] = valid ? v[i] : 0.f;
+                        s1[i] = valid ? v[i] * (zbn[i] - mu[i]) * rs[i] : 0.f;
+                    }
+                }
+                butterfly16(s0, lane);
+                butterfly16(s1, lane);
+                if ((lane & 1) == 0) {      // 16 lanes own 16 distinct columns of this warp's private accumulator
+                    int cc = c0 + butterfly_col(lane);
+                    sstat[warp - 2][0][cc] += s0[0];
+                    sstat[warp - 2][1][cc] += s1[0];
+                }
+            }
+        };
+        // two-deep ring of auxiliary-operand buffers per warp: chunk j of this warp lives in buffer j % 2 and is re-filled for
+        // chunk j + 2 right after it has been consumed (no register rotation, so no load is waited on early).  With eight
+        // epilogue warps that keeps 256 threads x 128 B = 32 KB of loads in flight per SM (~HBM latency x per-SM bandwidth).
+        Aux bA, bB;
+        bA.a = bA.b = bA.c = bA.d = make_uint4(0, 0, 0, 0);
+        bB = bA;
+        aux_load(half, bA);
+        aux_load(half + HALVES, bB);
+        mbar_wait(smem_u32(&acc_full[as]), aphase, 4);
+        tc_fence_after();
+        for (int ch = half; ch < nchunks; ch += 2 * HALVES) {
+            process(ch, bA);
+            aux_load(ch + 2 * HALVES, bA);
+            if (ch + HALVES < nchunks) { process(ch + HALVES, bB); aux_load(ch + 3 * HALVES, bB); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // convolution kernel
 // ---------------------------------------------------------------------------------------------------
@@ -246,7 +434,6 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 template <int EPI_WARPS>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
-    constexpr int HALVES = EPI_WARPS / 4;
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
@@ -310,179 +497,167 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             }
         }
     } else {
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;       // 0 .. HALVES-1
-        const int row = q * 32 + lane;
-        int as = 0; uint32_t aphase = 0;
-        // Column statistics stay in shared memory across the tiles of this CTA for as long as (problem, N tile) does not change
-        // (with gridDim a multiple of n_tiles that is the whole run of a problem) and are published with ONE fp64 atomic per
-        // column per run: same-address fp64 atomics from 148 CTAs on every tile were the bottleneck of the first version.
-        int cur_prob = -1, cur_nt = -1;
-        auto flush_stats = [&](int prob, int nt_) {
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-            const ConvProb& fp = a.p[prob];
-            const int fn0 = nt_ * tl.bn;
-            for (int c = row + half * 128; c < tl.bn; c += 32 * EPI_WARPS) {
-                const int w0 = ((c >> 4) % HALVES) * 4;      // the four warps (one per lane quarter) that own this column's chunk
-                float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    t0 += sstat[w0 + j][0][c]; t1 += sstat[w0 + j][1][c];
-                    sstat[w0 + j][0][c] = 0.f; sstat[w0 + j][1][c] = 0.f;
-                }
-                if (fn0 + c < a.cout) {
-                    atomicAdd(fp.stat0 + fn0 + c, (double)t0);
-                    atomicAdd(fp.stat1 + fn0 + c, (double)t1);
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-        };
-        for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
-            int ti = 0;
-            while (tile >= tl.p[ti + 1].begin) ti++;
-            const TileP& tp_ = tl.p[ti];
-            const ConvProb& pr = a.p[tp_.prob];
-            int local = tile - tp_.begin;
-            int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
-            if (a.stat_mode && (tp_.prob != cur_prob || nt != cur_nt)) {
-                if (cur_prob >= 0) flush_stats(cur_prob, cur_nt);
-                cur_prob = tp_.prob; cur_nt = nt;
-            }
-            int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
-            int img = mt / tiles_per_img, r = mt % tiles_per_img;
-            const int ty = row / tp_.TW, tx = row % tp_.TW;
-            int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
-            const bool ok = (y < pr.H) && (x < pr.W);
-            const int n0 = nt * tl.bn;
-            // Auxiliary epilogue operands (residuals / mask / BN input / fp32 accumulate-in) are prefetched one chunk ahead of their
-            // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
-            const long long offA = pr.mask.ptr ? img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx
-                                               : (pr.r1.ptr ? img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx : 0);
-            const long long offB = pr.bnz.ptr && a.stat_mode == 2 ? img * pr.bnz.sn + y * pr.bnz.sy + x * pr.bnz.sx
-                                                                  : (pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0);
-            const bf16* pA = pr.mask.ptr ? (const bf16*)pr.mask.ptr + offA : (pr.r1.ptr ? (const bf16*)pr.r1.ptr + offA : nullptr);
-            const bf16* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const bf16*)pr.bnz.ptr + offB : (pr.r2.ptr ? (const bf16*)pr.r2.ptr + offB : nullptr);
-            const float* pC = pr.accin.ptr ? (const float*)pr.accin.ptr + img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx : nullptr;
-            const int nchunks = tl.bn >> 4;
-            auto aux_load = [&](int ch, Aux& r) {
-                const int col = n0 + (ch << 4);
-                if (ch < nchunks && ok && col < a.cout) {
-                    if (pC) {
-                        const uint4* g = reinterpret_cast<const uint4*>(pC + col);
-                        r.a = g[0]; r.b = g[1]; r.c = g[2]; r.d = g[3];
-                    } else {
-                        if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + col); r.a = g[0]; r.b = g[1]; }
-                        if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + col); r.c = g[0]; r.d = g[1]; }
-                    }
-                }
+        conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
+    }
+    teardown(tmem_base, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo-tile convolution kernel (3x3-footprint taps): the M tile is a 16 x 8 patch (8 pixels wide, so one 8-row swizzle atom of the A
+// operand = one patch row).  Per (view, 64-channel chunk) the producer fetches the 18 x 10 HALO of the patch ONCE and all taps of the
+// view read it in place: tap (dy, dx) is the SAME shared-memory tile addressed through a UMMA descriptor whose start address is
+// shifted by ((dy+1)*10 + (dx+1)) pixel rows of 128 B and whose 8-row-group stride (SBO) is 10 rows = 1280 B.  TMA and UMMA both
+// apply the 128-byte swizzle to absolute shared-memory address bits, so the shifted views stay consistent.  That divides the
+// L2 -> SM traffic of the A operand by ~6.4 (180 instead of 9 x 128 pixel rows per chunk); the weight tiles keep their own ring.
+//   planes == 3 is the conservative variant: three 18 x 8 boxes (dx = -1, 0, 1) whose rows are whole swizzle atoms, taps shift by
+//   multiples of 1024 B only (2.7x less A traffic).
+// ---------------------------------------------------------------------------------------------------
+constexpr int HALO_SA_MAX = 4, HALO_SB_MAX = 8;
+constexpr int HALO_TH = 16, HALO_TW = 8;
+constexpr int HALO_PLANE3_BYTES = (HALO_TH + 2) * HALO_TW * 128;               // 18432
+constexpr int HALO_BOX1_BYTES = (HALO_TH + 2) * (HALO_TW + 2) * 128;           // 23040
+struct SmemH {
+    uint64_t a_full[HALO_SA_MAX], a_empty[HALO_SA_MAX];
+    uint64_t b_full[HALO_SB_MAX], b_empty[HALO_SB_MAX];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+struct HaloTile { int prob, img, x0, y0, n0; };
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long& acc, bool on) {
+    if (on) { long long t0 = clock64(); mbar_wait(bar, parity, who); acc += clock64() - t0; }
+    else mbar_wait(bar, parity, who);
+}
+
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
+    constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ SmemH s;
+    __shared__ float sstat[EPI_WARPS][2][ACC_COLS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
+    const uint32_t a0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b0 = a0 + tl.sa * tl.a_slot;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.b);
+        for (int i = 0; i < tl.sa; i++) { mbar_init(smem_u32(&s.a_full[i]), 1); mbar_init(smem_u32(&s.a_empty[i]), 1); }
+        for (int i = 0; i < tl.sb; i++) { mbar_init(smem_u32(&s.b_full[i]), 1); mbar_init(smem_u32(&s.b_empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int nchunks = tl.nviews * tl.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
+            long long w_ae = 0, w_be = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
+            const uint32_t b_tx = tl.bn * 128;
+            // with three A slots the next halo is requested before the current chunk's weight tiles; with two, half-way through them
+            // (its slot is released by the previous chunk's last MMA)
+            const int pref = tl.sa >= 3 ? 0 : 4;
+            auto decode = [&](int tile, HaloTile& h) {
+                int ti = 0;
+                while (tile >= tl.p[ti + 1].begin) ti++;
+                const TileP& tp_ = tl.p[ti];
+                int local = tile - tp_.begin;
+                int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
+                int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
+                int r = mt % tiles_per_img;
+                h.prob = tp_.prob; h.img = mt / tiles_per_img;
+                h.y0 = (r / tp_.tiles_x) * HALO_TH; h.x0 = (r % tp_.tiles_x) * HALO_TW; h.n0 = nt * tl.bn;
             };
-            auto unpack16 = [](const uint4& lo, const uint4& hi, float* t) {
-                const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            auto issue_a = [&](const HaloTile& h, int chunk) {
+                const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
+                mbar_wait_t(smem_u32(&s.a_empty[ai]), aph ^ 1, 21, w_ae, dbg_on);
+                const uint32_t fb = smem_u32(&s.a_full[ai]);
+                const uint32_t dst = a0 + ai * tl.a_slot;
+                const CUtensorMap* amap = &maps.a[h.prob][view];
+                mbar_expect_tx(fb, tl.a_bytes);
+                if (tl.planes == 1) {
+                    tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; j++) { t[2 * j] = __uint_as_float(w[j] << 16); t[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
-            };
-            // chunk ownership: the two warps of a TMEM lane quarter interleave the 16-column chunks (half = 0 / 1)
-            const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            auto process = [&](int ch, const Aux& ax) {
-                const int c0 = ch << 4;
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                const int col = n0 + c0;
-                const bool valid = ok && col < a.cout;
-                float zbn[16];
-                if (valid) {
-                    if (a.bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) { float4 b = __ldg(b4 + i); v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w; }
-                    }
-                    if (a.act) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * a.slope;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] *= a.alpha;
-                    float t[16];
-                    if (pC) {
-                        const uint4 q4[4] = {ax.a, ax.b, ax.c, ax.d};
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            v[4 * i] += __uint_as_float(q4[i].x); v[4 * i + 1] += __uint_as_float(q4[i].y);
-                            v[4 * i + 2] += __uint_as_float(q4[i].z); v[4 * i + 3] += __uint_as_float(q4[i].w);
-                        }
-                    } else {
-                        if (pr.r1.ptr) {
-                            unpack16(ax.a, ax.b, t);
-#pragma unroll
-                            for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
-                        }
-                        if (pr.r2.ptr) {
-                            unpack16(ax.c, ax.d, t);
-#pragma unroll
-                            for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
-                        }
-                        if (pr.mask.ptr) {
-                            unpack16(ax.a, ax.b, t);
-#pragma unroll
-                            for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
-                        }
-                        if (a.stat_mode == 2) unpack16(ax.c, ax.d, zbn);
-                    }
-                    st16(pr.out.ptr, img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
+                    for (int p = 0; p < 3; p++) tma_load_4d(amap, fb, dst + p * HALO_PLANE3_BYTES, kc * 64, h.x0 + p - 1, h.y0 - 1, h.img);
                 }
-                if (a.stat_mode) {      // warp-uniform: every lane takes part in the shuffles, invalid rows contribute zeros
-                    float s0[16], s1[16];
-                    if (a.stat_mode == 1) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) { s0[i] = valid ? v[i] : 0.f; s1[i] = valid ? v[i] * v[i] : 0.f; }
-                    } else {
-                        float mu[16], rs[16];
-                        if (valid) {
-                            const float4* m4 = reinterpret_cast<const float4*>(pr.bn_mean + col);
-                            const float4* r4 = reinterpret_cast<const float4*>(pr.bn_rstd + col);
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                float4 m = __ldg(m4 + i), r = __ldg(r4 + i);
-                                mu[4 * i] = m.x; mu[4 * i + 1] = m.y; mu[4 * i + 2] = m.z; mu[4 * i + 3] = m.w;
-                                rs[4 * i] = r.x; rs[4 * i + 1] = r.y; rs[4 * i + 2] = r.z; rs[4 * i + 3] = r.w;
-                            }
+                if (++ai == tl.sa) { ai = 0; aph ^= 1; }
+            };
+            HaloTile cur, nxt;
+            int tile = blockIdx.x;
+            if (tile < tl.total) { decode(tile, cur); issue_a(cur, 0); }
+            while (tile < tl.total) {
+                const int ntile = tile + gridDim.x;
+                const bool has_next = ntile < tl.total;
+                if (has_next) decode(ntile, nxt);
+                for (int chunk = 0; chunk < nchunks; chunk++) {
+                    const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
+                    const int t0 = tl.view_tap0[view], t1 = tl.view_tap0[view + 1];
+                    const bool last = chunk + 1 == nchunks;
+                    const int pf = (t1 - t0 - 1) < pref ? (t1 - t0 - 1) : pref;
+                    for (int t = t0; t < t1; t++) {
+                        if (t - t0 == pf) {
+                            if (!last) issue_a(cur, chunk + 1);
+                            else if (has_next) issue_a(nxt, 0);
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            s0[i] = valid ? v[i] : 0.f;
-                            s1[i] = valid ? v[i] * (zbn[i] - mu[i]) * rs[i] : 0.f;
-                        }
-                    }
-                    butterfly16(s0, lane);
-                    butterfly16(s1, lane);
-                    if ((lane & 1) == 0) {      // 16 lanes own 16 distinct columns of this warp's private accumulator
-                        int cc = c0 + butterfly_col(lane);
-                        sstat[warp - 2][0][cc] += s0[0];
-                        sstat[warp - 2][1][cc] += s1[0];
+                        mbar_wait_t(smem_u32(&s.b_empty[bi]), bph ^ 1, 22, w_be, dbg_on);
+                        const uint32_t fb = smem_u32(&s.b_full[bi]);
+                        mbar_expect_tx(fb, b_tx);
+                        tma_load_3d(&maps.b, fb, b0 + bi * tl.b_slot, kc * 64, cur.n0, a.taps[t].slab);
+                        if (++bi == tl.sb) { bi = 0; bph ^= 1; }
                     }
                 }
-            };
-            // two-deep ring of auxiliary-operand buffers per warp: chunk j of this warp lives in buffer j % 2 and is re-filled for
-            // chunk j + 2 right after it has been consumed (no register rotation, so no load is waited on early).  With eight
-            // epilogue warps that keeps 256 threads x 128 B = 32 KB of loads in flight per SM (~HBM latency x per-SM bandwidth).
-            Aux bA, bB;
-            bA.a = bA.b = bA.c = bA.d = make_uint4(0, 0, 0, 0);
-            bB = bA;
-            aux_load(half, bA);
-            aux_load(half + HALVES, bB);
-            mbar_wait(smem_u32(&s.acc_full[as]), aphase, 4);
-            tc_fence_after();
-            for (int ch = half; ch < nchunks; ch += 2 * HALVES) {
-                process(ch, bA);
-                aux_load(ch + 2 * HALVES, bA);
-                if (ch + HALVES < nchunks) { process(ch + HALVES, bB); aux_load(ch + 3 * HALVES, bB); }
+                cur = nxt; tile = ntile;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[as]));
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_ae; d[1] = w_be; d[2] = clock64() - t_start; }
         }
-        if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
+            int as = 0; uint32_t aphase = 0;
+            long long w_af = 0, w_bf = 0, w_acc = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
+            const uint32_t idesc = make_idesc(tl.bn, 0, 0);
+            const uint32_t sbo = tl.planes == 1 ? (HALO_TW + 2) * 128 : HALO_TW * 128;
+            for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+                mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 23, w_acc, dbg_on);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                uint32_t accum = 0;
+                for (int chunk = 0; chunk < nchunks; chunk++) {
+                    const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
+                    const int t0 = tl.view_tap0[view], t1 = tl.view_tap0[view + 1];
+                    int nk = (a.cin - kc * 64 + 15) >> 4;           // 16-channel MMA steps with data in this chunk
+                    if (nk > 4) nk = 4;
+                    mbar_wait_t(smem_u32(&s.a_full[ai]), aph, 24, w_af, dbg_on);
+                    const uint32_t abase = a0 + ai * tl.a_slot;
+                    for (int t = t0; t < t1; t++) {
+                        const int dy = a.taps[t].dy, dx = a.taps[t].dx;
+                        const uint32_t aoff = tl.planes == 1 ? (uint32_t)((dy + 1) * (HALO_TW + 2) + (dx + 1)) * 128u
+                                                             : (uint32_t)(dx + 1) * HALO_PLANE3_BYTES + (uint32_t)(dy + 1) * (HALO_TW * 128);
+                        mbar_wait_t(smem_u32(&s.b_full[bi]), bph, 25, w_bf, dbg_on);
+                        tc_fence_after();
+                        const uint64_t ad = make_desc(abase + aoff, 16, sbo), bd = make_desc(b0 + bi * tl.b_slot, 16, 1024);
+                        for (int k = 0; k < nk; k++) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum); accum = 1; }
+                        umma_commit(smem_u32(&s.b_empty[bi]));
+                        if (++bi == tl.sb) { bi = 0; bph ^= 1; }
+                    }
+                    umma_commit(smem_u32(&s.a_empty[ai]));
+                    if (++ai == tl.sa) { ai = 0; aph ^= 1; }
+                }
+                umma_commit(smem_u32(&s.acc_full[as]));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
+        }
+    } else {
+        conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
     }
     teardown(tmem_base, warp);
 }
@@ -645,6 +820,28 @@ static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
     *TH = bh; *TW = bw;
 }
 
+static int g_halo_dyn_max[2] = {0, 0};
+// AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tile with shifted descriptors; 3: three-plane halo
+static int halo_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("AFIGAN_CONV_HALO");
+        mode = e ? atoi(e) : 0;
+        if (mode != 0 && mode != 1 && mode != 3) mode = 0;
+    }
+    return mode;
+}
+// taps must be grouped by view (non-decreasing) and stay inside the 3x3 footprint
+static bool halo_eligible(const ConvArgs& a) {
+    if (a.ntaps < 2) return false;
+    for (int i = 0; i < a.ntaps; i++) {
+        const Tap& t = a.taps[i];
+        if (t.dy < -1 || t.dy > 1 || t.dx < -1 || t.dx > 1) return false;
+        if (i > 0 && t.view < a.taps[i - 1].view) return false;
+    }
+    return true;
+}
+
 }  // namespace tc
 
 int tc_init(afi_ctx* ctx) {
@@ -659,6 +856,14 @@ int tc_init(afi_ctx* ctx) {
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    // halo-tile kernels: everything the SM has beyond their static shared memory (statistics scratch + barriers)
+    cudaFuncAttributes fa;
+    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<4>));
+    tc::g_halo_dyn_max[0] = 232448 - (int)fa.sharedSizeBytes;
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
+    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<8>));
+    tc::g_halo_dyn_max[1] = 232448 - (int)fa.sharedSizeBytes;
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
     return AFI_OK;
 }
 
@@ -700,18 +905,44 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
     AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc: bad view count");
     Maps maps;
+    const int hmode = halo_eligible(a) ? halo_mode() : 0;
+    const int epi8 = a.ntaps * tl.kchunks * 64 < 4096 ? 1 : 0;   // short-K layers cannot hide their epilogue behind the MMAs
+    if (hmode) {
+        tl.planes = hmode; tl.nviews = nviews;
+        tl.a_bytes = hmode == 1 ? HALO_BOX1_BYTES : 3 * HALO_PLANE3_BYTES;
+        tl.a_slot = (tl.a_bytes + 1023) / 1024 * 1024;
+        tl.b_slot = (tl.bn * 128 + 1023) / 1024 * 1024;
+        tl.sa = hmode == 1 ? 3 : 2;
+        if (const char* e = getenv("AFIGAN_HALO_SA")) { int v = atoi(e); if (v >= 2 && v <= HALO_SA_MAX) tl.sa = v; }
+        int room = g_halo_dyn_max[epi8] - 1024 - tl.sa * tl.a_slot;
+        tl.sb = room / tl.b_slot;
+        if (tl.sb > HALO_SB_MAX) tl.sb = HALO_SB_MAX;
+        AFI_REQUIRE(tl.sb >= 2, "conv_tc: shared memory budget leaves %d weight stages", tl.sb);
+        if (tl.sb >= 6 && hmode == 3 && room - tl.sb * tl.b_slot >= tl.a_slot) tl.sa = 3;   // narrow N tiles: room for a third halo slot
+        if (getenv("AFIGAN_HALO_DBG")) {
+            static long long* dbg = nullptr;
+            if (!dbg) cudaMalloc(&dbg, 256 * 8 * sizeof(long long));
+            cudaMemsetAsync(dbg, 0, 256 * 8 * sizeof(long long), st);
+            tl.dbg = dbg;
+        }
+        int v = 0;
+        for (int i = 0; i < a.ntaps; i++) { while (v <= a.taps[i].view) tl.view_tap0[v++] = i; }
+        while (v <= 4) tl.view_tap0[v++] = a.ntaps;
+    }
     int begin = 0, np = 0;
     for (int oi = 0; oi < a.nprob; oi++) {
         const ConvProb& pr = a.p[order[oi]];
         if (size[order[oi]] == 0) continue;
         TileP& t = tl.p[np];
-        pick_patch(pr.H, pr.W, 128, &t.TH, &t.TW);
+        if (hmode) { t.TH = HALO_TH; t.TW = HALO_TW; }
+        else pick_patch(pr.H, pr.W, 128, &t.TH, &t.TW);
         t.tiles_x = (pr.W + t.TW - 1) / t.TW;
         t.tiles_y = (pr.H + t.TH - 1) / t.TH;
         t.begin = begin;
         t.prob = order[oi];
         begin += pr.N * t.tiles_x * t.tiles_y * tl.n_tiles;
-        for (int v = 0; v < nviews; v++) AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.TW, t.TH));
+        const int bw = hmode == 1 ? t.TW + 2 : t.TW, bh = hmode ? t.TH + 2 : t.TH;
+        for (int v = 0; v < nviews; v++) AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, bw, bh));
         np++;
     }
     tl.nprob = np;
@@ -727,8 +958,21 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     }
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
     ProfScope prof(PROF_CONV_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
-    // short-K layers (K = taps x cin < 4096) cannot hide their epilogue behind the MMAs: give them eight epilogue warps
-    if (a.ntaps * tl.kchunks * 64 < 4096) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
+    // short-K layers (K = taps x cin < 4096) get eight epilogue warps
+    if (hmode) {
+        const int dyn = 1024 + tl.sa * tl.a_slot + tl.sb * tl.b_slot;
+        if (epi8) k_conv_halo<8><<<grid, 64 + 32 * 8, dyn, st>>>(maps, a, tl);
+        else k_conv_halo<4><<<grid, 64 + 32 * 4, dyn, st>>>(maps, a, tl);
+        if (tl.dbg) {      // experiment aid: per-CTA stall cycles of the producer / MMA threads
+            long long h[256 * 8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, tl.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            double sum[8] = {0};
+            for (int b = 0; b < grid; b++) for (int i = 0; i < 8; i++) sum[i] += (double)h[b * 8 + i];
+            fprintf(stderr, "[halo dbg] cin %d cout %d sa %d sb %d tiles %d: producer wait a_empty %.0f b_empty %.0f of %.0f | mma wait a_full %.0f b_full %.0f acc_empty %.0f of %.0f (avg cycles per CTA)\n",
+                    a.cin, a.cout, tl.sa, tl.sb, tl.total, sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, sum[4] / grid, sum[5] / grid, sum[6] / grid);
+        }
+    } else if (epi8) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
     else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;

@@ -963,7 +963,7 @@ int dhead_pack_tc(const float* w4, int c, void* fwd, void* bwd, cudaStream_t st)
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
-__global__ void k_dhead_build_g9(const float* __restrict__ g, int H, int W, long long npix, bf16* __restrict__ g9) {
+__global__ void k_dhead_build_g9(const float* __restrict__ g, int H, int W, long long npix, bf16* __restrict__ g9, float* __restrict__ g9f) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= npix * 16) return;
     int t = (int)(i & 15);
@@ -974,10 +974,11 @@ __global__ void k_dhead_build_g9(const float* __restrict__ g, int H, int W, long
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = g[((long long)q.n * H + yy) * W + xx];
     }
     g9[i] = (bf16)v;
+    if (g9f && t < 12) g9f[(i >> 4) * 12 + t] = v;     // fp32 copy [P][12] for the fused head-backward passes
 }
-int dhead_build_g9(const float* g, int n, int h, int w, void* g9, cudaStream_t st) {
+int dhead_build_g9(const float* g, int n, int h, int w, void* g9, float* g9f, cudaStream_t st) {
     long long npix = (long long)n * h * w;
-    k_dhead_build_g9<<<cdiv(npix * 16, 256), 256, 0, st>>>(g, h, w, npix, (bf16*)g9);
+    k_dhead_build_g9<<<cdiv(npix * 16, 256), 256, 0, st>>>(g, h, w, npix, (bf16*)g9, g9f);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
@@ -999,9 +1000,6 @@ int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
-// dy3[q][c] = (sum_t g[q - tap_t] w4[c][t]) * lrelu'(a3[q][c]) fused with the two BatchNorm-backward reductions of layer 3.
-// Dense [P][C] operands.  A thread owns 4 channels (its 4x9 head weights live in registers: ~90 registers -> two 256-thread blocks per
-// SM) and walks rows two at a time with all global loads issued up front.
 template <typename T> struct V4;
 template <> struct V4<float> {
     __device__ static __forceinline__ void ld(const float* p, float* v) { float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
@@ -1017,82 +1015,113 @@ template <> struct V4<bf16> {
         *reinterpret_cast<uint2*>(p) = u;
     }
 };
-template <typename T>
-__global__ void __launch_bounds__(256, 2) k_dhead_bwd_dense(const float* __restrict__ g, const T* __restrict__ a3, const T* __restrict__ z3,
-                                                            T* __restrict__ dy3, long long P, int C, int H, int W, const float* __restrict__ w4,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd, double* s_dy,
-                                                            double* s_dyx, int rows_per_block, float slope) {
-    __shared__ float sm0[256 * 4];
-    __shared__ float sm1[256 * 4];
-    const int tpr = C >> 2, rpb = 256 / tpr;
+// ---------------------------------------------------------------------------------------------------
+// Discriminator head backward fused with layer 3's train-mode BatchNorm backward, grouped over calls, in TWO passes that never
+// materialise dy3:   dy3[q][c] = (sum_t g9[q][t] * w4[c][t]) * lrelu'(bn3(z3[q][c]))      (9 FMAs per element, recomputed in both)
+//   PASS 1: s_dy[c] += dy3, s_dyx[c] += dy3 * xhat                      reads z3 only          (2 B / element in bf16)
+//   PASS 2: dz3 = gamma * rstd * (dy3 - s_dy/M - xhat * s_dyx/M)        reads z3, writes dz3   (4 B / element)
+// versus 12 B / element for "write dy3 (reading a3 and z3), then a BatchNorm-backward pass over dy3 and z3".  The LeakyReLU mask is
+// re-derived from z3 with the SAME fp32 expression bn_apply uses, so it equals the sign of the stored activation.
+// A thread owns 4 channels (its 4 x 9 head weights stay in registers) and keeps ROWS independent 8-byte loads in flight.
+// ---------------------------------------------------------------------------------------------------
+template <int PASS, typename T>
+__global__ void __launch_bounds__(256, 2) k_dhead_bwd_group(const __grid_constant__ DenseGroupD G, const float* __restrict__ w4,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* dgamma_acc, float* dbeta_acc, float slope, int eval_mode) {
+    constexpr int ROWS = PASS == 1 ? 8 : 4;
+    __shared__ float sm0[PASS == 1 ? 256 * 4 : 1];
+    __shared__ float sm1[PASS == 1 ? 256 * 4 : 1];
+    const int kp = find_prob(G, blockIdx.x);
+    const DenseProbD& q = G.p[kp];
+    const int C = G.C, tpr = C >> 2, rpb = 256 / tpr;
     const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
     const int c0 = cq * 4;
-    float wr[4][9], mu[4], rs[4], a0[4], a1[4];
+    const float* __restrict__ g9 = reinterpret_cast<const float*>(q.a);
+    const T* __restrict__ z = reinterpret_cast<const T*>(q.b);
+    T* __restrict__ dz = reinterpret_cast<T*>(q.out);
+    if (PASS == 2 && (int)blockIdx.x == q.block_begin) {     // d gamma = sum dy*xhat, d beta = sum dy: once per call
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)q.o1[c]);
+            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)q.o0[c]);
+        }
+    }
+    float wr[4][9], mu[4], rs[4], ga[4], be[4], a0[4], a1[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; a0[k] = 0.f; a1[k] = 0.f;
+        mu[k] = q.mean[c0 + k]; rs[k] = q.rstd[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k];
+        if (PASS == 1) { a0[k] = 0.f; a1[k] = 0.f; }
+        else {
+            const float inv_m = 1.f / (float)q.P;
+            a0[k] = eval_mode ? 0.f : (float)q.o0[c0 + k] * inv_m; a1[k] = eval_mode ? 0.f : (float)q.o1[c0 + k] * inv_m;
+        }
 #pragma unroll
         for (int t = 0; t < 9; t++) wr[k][t] = w4[(c0 + k) * 9 + t];
     }
-    long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
-    if (r1 > P) r1 = P;
-    for (long long r = r0 + lane_r; r < r1; r += 2 * rpb) {
-        const long long rb = r + rpb;
-        const bool has_b = rb < r1;
-        float avA[4], zvA[4], avB[4], zvB[4];
-        V4<T>::ld(a3 + r * C + c0, avA);
-        V4<T>::ld(z3 + r * C + c0, zvA);
-        if (has_b) { V4<T>::ld(a3 + rb * C + c0, avB); V4<T>::ld(z3 + rb * C + c0, zvB); }
-        PixIdx qa = decode_pixel(r, H, W), qb = decode_pixel(has_b ? rb : r, H, W);
-        float gA[9], gB[9];
+    long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
+    if (r1 > q.P) r1 = q.P;
+    for (long long rb = r0 + lane_r; rb < r1; rb += (long long)ROWS * rpb) {
+        float zv[ROWS][4];
 #pragma unroll
-        for (int t = 0; t < 9; t++) {
-            int ya = qa.y - (t / 3 - 1), xa = qa.x - (t % 3 - 1);
-            gA[t] = (ya >= 0 && ya < H && xa >= 0 && xa < W) ? __ldg(g + ((long long)qa.n * H + ya) * W + xa) : 0.f;
-            int yb = qb.y - (t / 3 - 1), xb = qb.x - (t % 3 - 1);
-            gB[t] = (has_b && yb >= 0 && yb < H && xb >= 0 && xb < W) ? __ldg(g + ((long long)qb.n * H + yb) * W + xb) : 0.f;
+        for (int j = 0; j < ROWS; j++) {
+            const long long r = rb + (long long)j * rpb;
+            if (r < r1) V4<T>::ld(z + r * C + c0, zv[j]);
         }
-        float oA[4], oB[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float dA = 0.f, dB = 0.f;
+        for (int j = 0; j < ROWS; j++) {
+            const long long r = rb + (long long)j * rpb;
+            if (r < r1) {
+                const float4* gp = reinterpret_cast<const float4*>(g9 + r * 12);
+                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+                const float gt[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
+                float o[4];
 #pragma unroll
-            for (int t = 0; t < 9; t++) { dA = fmaf(gA[t], wr[k][t], dA); dB = fmaf(gB[t], wr[k][t], dB); }
-            dA *= avA[k] > 0.f ? 1.f : slope;
-            oA[k] = dA; a0[k] += dA; a1[k] = fmaf(dA, (zvA[k] - mu[k]) * rs[k], a1[k]);
-            if (has_b) {
-                dB *= avB[k] > 0.f ? 1.f : slope;
-                oB[k] = dB; a0[k] += dB; a1[k] = fmaf(dB, (zvB[k] - mu[k]) * rs[k], a1[k]);
+                for (int k = 0; k < 4; k++) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; t++) d = fmaf(gt[t], wr[k][t], d);
+                    const float xh = (zv[j][k] - mu[k]) * rs[k];
+                    const float y = (zv[j][k] - mu[k]) * rs[k] * ga[k] + be[k];      // == bn_apply's expression: sign(y) is the stored activation's sign
+                    d *= y > 0.f ? 1.f : slope;
+                    if (PASS == 1) { a0[k] += d; a1[k] = fmaf(d, xh, a1[k]); }
+                    else o[k] = ga[k] * rs[k] * (d - a0[k] - xh * a1[k]);
+                }
+                if (PASS == 2) V4<T>::st(dz + r * C + c0, o);
             }
         }
-        V4<T>::st(dy3 + r * C + c0, oA);
-        if (has_b) V4<T>::st(dy3 + rb * C + c0, oB);
     }
+    if (PASS == 1) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { sm0[(lane_r * 4 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 4 + k) * tpr + cq] = a1[k]; }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += 256) {
-        int qd = c >> 2, k = c & 3;
-        float t0 = 0.f, t1 = 0.f;
-        for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 4 + k) * tpr + qd]; t1 += sm1[(l * 4 + k) * tpr + qd]; }
-        atomicAdd(s_dy + c, (double)t0);
-        atomicAdd(s_dyx + c, (double)t1);
+        for (int k = 0; k < 4; k++) { sm0[(lane_r * 4 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 4 + k) * tpr + cq] = a1[k]; }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            int qd = c >> 2, k = c & 3;
+            float t0 = 0.f, t1 = 0.f;
+            for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 4 + k) * tpr + qd]; t1 += sm1[(l * 4 + k) * tpr + qd]; }
+            atomicAdd(q.o0 + c, (double)t0);
+            atomicAdd(q.o1 + c, (double)t1);
+        }
     }
 }
-int dhead_backward_dense(PView a3, PView z3, PView dy3, int dt, const float* w4, const float* g, const float* mean, const float* rstd, int n,
-                         int h, int w, int c, double* s_dy, double* s_dyx, cudaStream_t st) {
-    AFI_REQUIRE(is_dense(a3, h, w, c) && is_dense(z3, h, w, c) && is_dense(dy3, h, w, c) && c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0,
-                "dhead_backward_dense: operands must be dense with C/4 dividing 256");
-    long long P = (long long)n * h * w;
-    if (P == 0) return AFI_OK;
-    int rows = (int)(P / 1184);
-    if (rows > 64) rows = 64;
-    if (rows < 4) rows = 4;
-    int grid = cdiv(P, rows);
-    if (dt == DT_F32)
-        k_dhead_bwd_dense<float><<<grid, 256, 0, st>>>(g, (const float*)a3.ptr, (const float*)z3.ptr, (float*)dy3.ptr, P, c, h, w, w4, mean, rstd, s_dy, s_dyx, rows, 0.2f);
-    else
-        k_dhead_bwd_dense<bf16><<<grid, 256, 0, st>>>(g, (const bf16*)a3.ptr, (const bf16*)z3.ptr, (bf16*)dy3.ptr, P, c, h, w, w4, mean, rstd, s_dy, s_dyx, rows, 0.2f);
+int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PView* z3, const PView* dz3, int dt, const float* w4,
+                         const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
+                         double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st) {
+    AFI_REQUIRE(c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0, "dhead_backward_group: C/4 must divide 256");
+    DenseGroupD G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob; G.C = c;
+    for (int k = 0; k < nprob; k++) {
+        G.p[k].a = g9f[k]; G.p[k].b = z3[k].ptr; G.p[k].out = dz3[k].ptr; G.p[k].P = P[k]; G.p[k].mean = mean[k]; G.p[k].rstd = rstd[k];
+        G.p[k].o0 = s_dy[k]; G.p[k].o1 = s_dyx[k];
+    }
+    dense_group_blocks(G, pass == 1 ? 128 : 64, pass == 1 ? 1184 : 2368);
+    int grid = G.p[nprob].block_begin;
+    if (grid == 0) return AFI_OK;
+    if (pass == 1) {
+        if (dt == DT_F32) k_dhead_bwd_group<1, float><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+        else k_dhead_bwd_group<1, bf16><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+    } else {
+        if (dt == DT_F32) k_dhead_bwd_group<2, float><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+        else k_dhead_bwd_group<2, bf16><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+    }
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
@@ -1132,10 +1161,13 @@ int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumu
 // deconv dgrad : slab = phase*9 + t, t=(e+1)*3+(f+1) <- w[ci][co][2(1+e)+a][2(1+f)+b], gemm-cin = co, gemm-cout = ci
 // 1x1 forward  : w[co][ci] (lateral conv of the FPN merge), one slab (mode kind 4)
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long pack_total_dev(int co, int ci, int mode) {
+    int kind = mode >> 1;
+    int slabs = (kind == 4 || kind == 5) ? 1 : (kind >= 2 ? 36 : 9);
+    return (long long)slabs * co * ci;
+}
 template <typename T>
-__global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
+__device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long i) {
     int nk = mode & 1, kind = mode >> 1;
     int gk = (kind == 0 || kind == 2 || kind == 4) ? ci : co;   // gemm-cin
     int gn = (kind == 0 || kind == 2 || kind == 4) ? co : ci;   // gemm-cout   (kinds 1, 3, 5 are dgrads: roles swapped)
@@ -1165,12 +1197,46 @@ __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T*
     }
     dst[i] = (T)v;
 }
-int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st) {
+template <typename T>
+__global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < total) pack_one<T>(w, co, ci, mode, dst, i);
+}
+static inline long long pack_total(int co, int ci, int mode) {
     int kind = mode >> 1;
     int slabs = (kind == 4 || kind == 5) ? 1 : (kind >= 2 ? 36 : 9);
-    long long total = (long long)slabs * co * ci;
+    return (long long)slabs * co * ci;
+}
+int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st) {
+    long long total = pack_total(co, ci, mode);
     if (dst_dt == DT_F32) k_pack<float><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (float*)dst, total);
     else k_pack<bf16><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (bf16*)dst, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+// all the re-layouts of one module in ONE launch (the generator has 38 of them, most far too small to fill a launch of their own)
+struct PackGroup { int njobs; int block_begin[AFI_MAX_PACK + 1]; PackJob j[AFI_MAX_PACK]; };
+template <typename T>
+__global__ void k_pack_group(const __grid_constant__ PackGroup G) {
+    int k = 0;
+    while (k + 1 < G.njobs && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
+    const PackJob& q = G.j[k];
+    long long i = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x;
+    const long long total = pack_total_dev(q.co, q.ci, q.mode);
+#pragma unroll
+    for (int u = 0; u < 4; u++, i += 256)
+        if (i < total) pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
+}
+int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st) {
+    AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_PACK, "pack_weights_group: %d jobs (max %d)", njobs, AFI_MAX_PACK);
+    if (njobs == 0) return AFI_OK;
+    PackGroup G; memset(&G, 0, sizeof(G));
+    G.njobs = njobs;
+    int b = 0;
+    for (int k = 0; k < njobs; k++) { G.j[k] = jobs[k]; G.block_begin[k] = b; b += cdiv(pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode), 1024); }
+    G.block_begin[njobs] = b;
+    if (dst_dt == DT_F32) k_pack_group<float><<<b, 256, 0, st>>>(G);
+    else k_pack_group<bf16><<<b, 256, 0, st>>>(G);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
@@ -1270,12 +1336,51 @@ __global__ void k_l1(afi_view4 a, afi_view4 b, int c, int h, int w, long long to
         if (loss_sum) atomicAdd(loss_sum, weight * m);
     }
 }
+// both operands contiguous NCHW: a flat float4 stream, four independent 16-byte loads per operand in flight per thread
+__global__ void __launch_bounds__(256) k_l1_dense(const float4* __restrict__ a, const float4* __restrict__ b, long long n4, long long total,
+                                                  float* loss_out, float* loss_sum, float weight, float4* __restrict__ da, float gscale) {
+    double acc = 0.0;
+    const float ginv = gscale / (float)total;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { long long i = i0 + u * stride; if (i < n4) { va[u] = a[i]; vb[u] = b[i]; } }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            long long i = i0 + u * stride;
+            if (i < n4) {
+                float d0 = va[u].x - vb[u].x, d1 = va[u].y - vb[u].y, d2 = va[u].z - vb[u].z, d3 = va[u].w - vb[u].w;
+                acc += (double)((fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3)));
+                if (da) da[i] = make_float4(d0 > 0.f ? ginv : (d0 < 0.f ? -ginv : 0.f), d1 > 0.f ? ginv : (d1 < 0.f ? -ginv : 0.f),
+                                            d2 > 0.f ? ginv : (d2 < 0.f ? -ginv : 0.f), d3 > 0.f ? ginv : (d3 < 0.f ? -ginv : 0.f));
+            }
+        }
+    }
+    double accd = block_reduce_sum(acc);
+    if (threadIdx.x == 0) {
+        float m = (float)(accd / (double)total);
+        if (loss_out) atomicAdd(loss_out, m);
+        if (loss_sum) atomicAdd(loss_sum, weight * m);
+    }
+}
+static inline bool view4_contiguous(const afi_view4& v, int c, int h, int w) {
+    return v.sw == 1 && v.sh == w && v.sc == (long long)h * w && v.sn == (long long)c * h * w;
+}
 extern "C" int afi_l1_loss(afi_view4 a, afi_view4 b, int n, int c, int h, int w, float* loss_out, float* loss_sum, float weight,
                            float* da, float grad_scale, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     long long total = (long long)n * c * h * w;
     AFI_REQUIRE(total > 0, "l1: empty tensors");
     if (loss_out) AFI_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    if (total % 4 == 0 && view4_contiguous(a, c, h, w) && view4_contiguous(b, c, h, w) && ((uintptr_t)a.ptr & 15) == 0 &&
+        ((uintptr_t)b.ptr & 15) == 0 && (!da || ((uintptr_t)da & 15) == 0)) {
+        long long n4 = total / 4;
+        int grid = cdiv(n4, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
+        k_l1_dense<<<grid, 256, 0, st>>>((const float4*)a.ptr, (const float4*)b.ptr, n4, total, loss_out, loss_sum, weight, (float4*)da, grad_scale);
+        AFI_LAUNCH_CHECK();
+        return AFI_OK;
+    }
     int grid = cdiv(total, 256 * 8); if (grid > 148 * 8) grid = 148 * 8;
     k_l1<<<grid, 256, 0, st>>>(a, b, c, h, w, total, loss_out, loss_sum, weight, da, grad_scale);
     AFI_LAUNCH_CHECK();
@@ -1296,6 +1401,42 @@ extern "C" int afi_sgd_step(float* p, const float* g, float* m, long long count,
     if (count == 0) return AFI_OK;
     k_sgd<<<cdiv(count, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, count, lr, momentum, wd, grad_scale, first);
     AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+// every parameter of one optimiser in ONE launch: blockIdx.x -> (tensor, 1024-element chunk) through a prefix table
+struct SgdGroup { int n; int block_begin[AFI_MAX_SGD + 1]; float* p[AFI_MAX_SGD]; const float* g[AFI_MAX_SGD]; float* m[AFI_MAX_SGD];
+                  long long count[AFI_MAX_SGD]; float wd[AFI_MAX_SGD]; };
+__global__ void k_sgd_group(const __grid_constant__ SgdGroup G, float lr, float mom, float gscale, int first) {
+    int k = 0;
+    while (k + 1 < G.n && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
+    float* __restrict__ p = G.p[k]; const float* __restrict__ g = G.g[k]; float* __restrict__ m = G.m[k];
+    const long long n = G.count[k]; const float wd = G.wd[k];
+    long long i = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 4; u++, i += 256) {
+        if (i < n) {
+            float d = gscale * g[i] + wd * p[i];
+            float b = first ? d : mom * m[i] + d;
+            m[i] = b;
+            p[i] = p[i] - lr * b;
+        }
+    }
+}
+extern "C" int afi_sgd_step_multi(int n, float* const* p, const float* const* g, float* const* m, const long long* count, const float* wd,
+                                  float lr, float momentum, float grad_scale, int first, void* stream) {
+    AFI_REQUIRE(n >= 0 && (n == 0 || (p && g && m && count && wd)), "afi_sgd_step_multi: null argument");
+    for (int o = 0; o < n; o += AFI_MAX_SGD) {
+        SgdGroup G; memset(&G, 0, sizeof(G));
+        int b = 0, k = 0;
+        for (; k < AFI_MAX_SGD && o + k < n; k++) {
+            G.p[k] = p[o + k]; G.g[k] = g[o + k]; G.m[k] = m[o + k]; G.count[k] = count[o + k]; G.wd[k] = wd[o + k];
+            G.block_begin[k] = b; b += cdiv(count[o + k], 1024);
+        }
+        G.n = k; G.block_begin[k] = b;
+        if (b == 0) continue;
+        k_sgd_group<<<b, 256, 0, (cudaStream_t)stream>>>(G, lr, momentum, grad_scale, first);
+        AFI_LAUNCH_CHECK();
+    }
     return AFI_OK;
 }
 extern "C" int afi_zero(void* ptr, size_t bytes, void* stream) {

@@ -177,6 +177,10 @@ int afi_l1_loss(afi_view4 a, afi_view4 b, int n, int c, int h, int w, float* los
  * m = first ? d : momentum*m + d;  p -= lr*m.  grad_scale folds the 1/world_size of the gradient all-reduce. */
 int afi_sgd_step(float* p, const float* g, float* m, long long count, float lr, float momentum, float wd,
                  float grad_scale, int first, void* stream);
+/* The same update for n tensors in ONE launch (a detectron2 optimiser step over all parameters of a module, one param group each:
+ * weight decay per tensor).  p, g, m, count, wd are HOST arrays of length n. */
+int afi_sgd_step_multi(int n, float* const* p, const float* const* g, float* const* m, const long long* count, const float* wd,
+                       float lr, float momentum, float grad_scale, int first, void* stream);
 int afi_zero(void* ptr, size_t bytes, void* stream);
 
 /* ---- single-layer entry points (unit tests and kernel benchmarks call the GEMM kernels through these) ---- */
