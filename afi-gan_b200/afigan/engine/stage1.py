@@ -135,7 +135,7 @@ class Stage1Step:
                                             C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, self.g_acc.data_ptr(),
                                             N.stream_ptr()))
 
-    def _d_calls(self, xs, tags, save: bool, dlogits=None):
+    def _d_calls(self, xs, tags, save: bool, dlogits=None, stats_only=None):
         calls = (N.DCall * len(xs))()
         logits = []
         for i, (x, tag) in enumerate(zip(xs, tags)):
@@ -143,7 +143,8 @@ class Stage1Step:
             ws = self._ws_for("d", n, h, w, save, tag)
             lg = self._buf("logit" + tag, (n, 1, h, w))
             c = calls[i]
-            c.x, c.n, c.h, c.w, c.logits = N.view4(x), n, h, w, lg.data_ptr()
+            # a call whose output nobody reads (the reference's dead D0(hr) of the G phase) runs for its BatchNorm statistics only
+            c.x, c.n, c.h, c.w, c.logits = N.view4(x), n, h, w, (None if stats_only and stats_only[i] else lg.data_ptr())
             c.ws, c.ws_bytes = ws.data_ptr(), ws.numel()
             if dlogits is not None:
                 c.dlogits = dlogits[i].data_ptr()
@@ -160,7 +161,7 @@ class Stage1Step:
         """Discriminator calls `xs` (reference order), BCE against `targets[i]` accumulated into losses[loss_rows[i], level]; with
         backward=True also d(BCE)/d(params) into the packed accumulator.  Calls with even / odd index (real / fake) form the two groups."""
         lib = self.lib
-        calls, logits = self._d_calls(xs, tags, save)
+        calls, logits = self._d_calls(xs, tags, save, stats_only=[r is None and not backward for r in loss_rows])
         ps = self._ds()
         bn = self.Dstack[0][0].norm
         mom = 0.1 if bn.momentum is None else bn.momentum

@@ -638,7 +638,10 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
     const int dt = prec_dt(prec); const size_t es = dt_size(dt);
     DPacked L = d_packed_layout();
     for (int k = 0; k < ncalls; k++) {
-        AFI_REQUIRE(calls[k].x.ptr && calls[k].logits, "afi_d_forward: call %d has a null pointer", k);
+        AFI_REQUIRE(calls[k].x.ptr, "afi_d_forward: call %d has a null input", k);
+        // logits == NULL: the call is evaluated for its BatchNorm statistics only (stage1_trainer.py:400 computes D(hr) in the G phase and
+        // drops the result: what survives is the running-buffer update), so layer 3's normalise pass and the head are skipped
+        AFI_REQUIRE(calls[k].logits || (training && !save), "afi_d_forward: call %d: a statistics-only call (logits == NULL) needs training mode and no backward", k);
         AFI_TRY(to_nhwc(prec, calls[k].x, d[k].n, DC[0], d[k].h, d[k].w, pview(W[k].A[0], d[k].h, d[k].w, DC[0]), st));
     }
     const bool tc = prec_tc(prec);
@@ -678,7 +681,9 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
                 AFI_TRY(bn_finalize(W[k].sums, W[k].sums + 1024, cnt[k], DC[i + 1], eps, momentum, 0, W[k].mean[i], W[k].rstd[i], W[k].var[i],
                                     p->running_mean[i], p->running_var[i], nullptr, st));
         }
-        AFI_TRY(bn_apply_lrelu_group(ncalls, Zv, Av, dt, mean_c, rstd_c, p->gamma[i], p->beta[i], 0.2f, cnt, DC[i + 1], st));
+        long long cnt_apply[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) cnt_apply[k] = (i == 2 && !calls[k].logits) ? 0 : cnt[k];
+        AFI_TRY(bn_apply_lrelu_group(ncalls, Zv, Av, dt, mean_c, rstd_c, p->gamma[i], p->beta[i], 0.2f, cnt_apply, DC[i + 1], st));
     }
     // Conv2d 1024 -> 1                                                                   feature_patch_discriminator.py:40-41
     if (tc) {
@@ -686,14 +691,15 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         conv_args_init(a);
         a.cin = DC[3]; a.cout = 16; a.ntaps = 1; a.nprob = ncalls; a.w = (const char*)packed + L.hf * es; a.out_dt = DT_F32;
         for (int k = 0; k < ncalls; k++) {
-            a.p[k].N = d[k].n; a.p[k].H = d[k].h; a.p[k].W = d[k].w;
+            a.p[k].N = calls[k].logits ? d[k].n : 0; a.p[k].H = d[k].h; a.p[k].W = d[k].w;
             a.p[k].in[0] = pview(W[k].A[3], d[k].h, d[k].w, DC[3]); a.p[k].out = pview(W[k].T9, d[k].h, d[k].w, 16);
         }
         AFI_TRY(run_conv(ctx, prec, a, st));
-        for (int k = 0; k < ncalls; k++) AFI_TRY(dhead_stencil16(W[k].T9, p->b[3], d[k].n, d[k].h, d[k].w, calls[k].logits, st));
+        for (int k = 0; k < ncalls; k++)
+            if (calls[k].logits) AFI_TRY(dhead_stencil16(W[k].T9, p->b[3], d[k].n, d[k].h, d[k].w, calls[k].logits, st));
     } else {
         for (int k = 0; k < ncalls; k++)
-            AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
+            if (calls[k].logits) AFI_TRY(dhead_forward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], p->b[3], d[k].n, d[k].h, d[k].w, DC[3], W[k].T9, calls[k].logits, st));
     }
     return AFI_OK;
 }

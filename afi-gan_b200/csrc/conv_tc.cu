@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <stdio.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace afi {
@@ -51,11 +52,9 @@ struct Tiling {
     int total;                        // work items
     int nprob;
     int m_tiles, ksplit, ktiles;      // wgrad only
-    // halo-tile convolution only: A ring of `sa` slots (one (view, 64-channel chunk) halo each), B ring of `sb` slots (one (tap, chunk)
-    // weight tile each); planes = 1: ONE {64 ch, TW+2, TH+2} box, taps address it through shifted descriptors; planes = 3: three
-    // {64 ch, TW, TH+2} boxes (dx = -1, 0, +1), taps shift by whole 1024-byte swizzle atoms only
-    int planes, sa, sb, a_slot, b_slot, a_bytes, nviews;
-    int view_tap0[5];                 // taps of view v: [view_tap0[v], view_tap0[v+1])
+    // halo-tile convolution only: B ring of `sb` slots of b_slot bytes (one (tap, chunk) weight tile, or half of it in pair mode)
+    int sb, b_slot, nviews, rot;
+    int view_slab0[4];                // first weight slab of view v (its nine taps use slab0 .. slab0 + 8 in standard order)
     long long* dbg;                   // optional [grid][8] stall-cycle counters (AFIGAN_HALO_DBG)
     TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
 };
@@ -94,6 +93,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
         }
     }
 }
+// AFI_STALL_COUNTERS (build-time): per-thread stall-cycle counters of the producer / MMA threads, printed by conv_tc() when the
+// environment has AFIGAN_HALO_DBG -- the instrument behind the pipeline notes in DESIGN.md.  Off in the shipped library: every
+// instruction in those single-thread loops is on the critical path.
+#ifdef AFI_STALL_COUNTERS
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long& acc, bool on) {
+    if (on) { long long t0 = clock64(); mbar_wait(bar, parity, who); acc += clock64() - t0; }
+    else mbar_wait(bar, parity, who);
+}
+#else
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long&, bool) { mbar_wait(bar, parity, who); }
+#endif
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -108,6 +118,40 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// ---- cta_group::2 (CTA pair) variants ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA 0 of the cluster (the pair's leader)
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// TMA loads issued by either CTA of the pair into ITS OWN shared memory, completing bytes on the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -146,9 +190,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
     return d;
 }
 // instruction descriptor kind::f16: D=f32, A=B=bf16, M=128
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major, int m = 128) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct Aux { uint4 a, b, c, d; };   // one 16-column chunk of auxiliary epilogue operands (64 B per thread)
@@ -246,10 +290,15 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 
 // Epilogue warps of the convolution kernels (shared by the per-tap and the halo-tile main loops): TMEM -> registers -> bias / activation /
 // residuals / mask / statistics -> global memory, for every work item of this CTA.
-template <int EPI_WARPS>
+// PAIR: the CTA is one half of a cta_group::2 pair.  Work items are (pair of M tiles, N tile); this CTA owns M tile 2 * pair + rank
+// (a duplicate of the last tile, with stores and statistics masked, when the problem has an odd tile count) and releases the
+// accumulator stage on the LEADER's barrier, which counts the epilogue warps of both CTAs.
+template <int EPI_WARPS, bool PAIR = false>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& tl, uint64_t* acc_full, uint64_t* acc_empty,
-                                              float (*sstat)[2][ACC_COLS], const uint32_t tmem_base, const int warp, const int lane) {
+                                              float (*sstat)[2][ACC_COLS], const uint32_t tmem_base, const int warp, const int lane,
+                                              const int rank = 0) {
     constexpr int HALVES = EPI_WARPS / 4;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;       // 0 .. HALVES-1
     const int row = q * 32 + lane;
@@ -277,7 +326,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
     };
-    for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+    for (int tile = item0; tile < tl.total; tile += item_stride) {
         int ti = 0;
         while (tile >= tl.p[ti + 1].begin) ti++;
         const TileP& tp_ = tl.p[ti];
@@ -289,10 +338,16 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             cur_prob = tp_.prob; cur_nt = nt;
         }
         int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
+        bool tile_valid = true;
+        if (PAIR) {
+            mt = 2 * mt + rank;
+            const int m_tiles = pr.N * tiles_per_img;
+            if (mt >= m_tiles) { mt = m_tiles - 1; tile_valid = false; }
+        }
         int img = mt / tiles_per_img, r = mt % tiles_per_img;
         const int ty = row / tp_.TW, tx = row % tp_.TW;
         int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
-        const bool ok = (y < pr.H) && (x < pr.W);
+        const bool ok = tile_valid && (y < pr.H) && (x < pr.W);
         const int n0 = nt * tl.bn;
         // Auxiliary epilogue operands (residuals / mask / BN input / fp32 accumulate-in) are prefetched one chunk ahead of their
         // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
@@ -419,7 +474,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        if (lane == 0) {
+            if (PAIR) mbar_arrive_cta0(smem_u32(&acc_empty[as]));
+            else mbar_arrive(smem_u32(&acc_empty[as]));
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
@@ -447,7 +505,11 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            long long w_e = 0, w_l = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
             const uint32_t tx_bytes = A_BYTES + tl.bn * 128;
+            // every CTA walks the (tap, channel chunk) reduction in its own rotation, so that at any moment the CTAs read DIFFERENT weight
+            // tiles: in lock-step all of them hit the same L2 lines at once
+            const int rot_k = tl.rot ? (int)(blockIdx.x % tl.kchunks) : 0, rot_t = tl.rot ? (int)((blockIdx.x / tl.kchunks) % a.ntaps) : 0;
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
                 int ti = 0;
                 while (tile >= tl.p[ti + 1].begin) ti++;
@@ -458,32 +520,39 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 int img = mt / tiles_per_img, r = mt % tiles_per_img;
                 int y0 = (r / tp_.tiles_x) * tp_.TH, x0 = (r % tp_.tiles_x) * tp_.TW;
                 int n0 = nt * tl.bn;
+                int tpr = rot_t;
                 for (int tp = 0; tp < a.ntaps; tp++) {
-                    const Tap t = a.taps[tp];
+                    const Tap t = a.taps[tpr];
+                    if (++tpr == a.ntaps) tpr = 0;
                     const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
-                    for (int kc = 0; kc < tl.kchunks; kc++) {
-                        mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 1);
+                    int kc = rot_k;
+                    for (int kci = 0; kci < tl.kchunks; kci++) {
+                        const int kc_ = kc;
+                        if (++kc == tl.kchunks) kc = 0;
+                        mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
                         uint32_t fb = smem_u32(&s.full[stage]);
                         uint32_t sa = tiles0 + stage * STAGE_BYTES;
                         mbar_expect_tx(fb, tx_bytes);
-                        tma_load_4d(amap, fb, sa, kc * 64, x0 + t.dx, y0 + t.dy, img);
-                        tma_load_3d(&maps.b, fb, sa + A_BYTES, kc * 64, n0, t.slab);
+                        tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
+                        tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, t.slab);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_l; d[1] = w_e; d[2] = clock64() - t_start; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
+            long long w_f = 0, w_acc = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
             const uint32_t idesc = make_idesc(tl.bn, 0, 0);
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
-                mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 2);
+                mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 2, w_acc, dbg_on);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * ACC_COLS;
                 for (int it = 0; it < iters; it++) {
-                    mbar_wait(smem_u32(&s.full[stage]), phase, 3);
+                    mbar_wait_t(smem_u32(&s.full[stage]), phase, 3, w_f, dbg_on);
                     tc_fence_after();
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
                     uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
@@ -495,6 +564,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 umma_commit(smem_u32(&s.acc_full[as]));
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
+            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
         conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
@@ -503,32 +573,39 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// halo-tile convolution kernel (3x3-footprint taps): the M tile is a 16 x 8 patch (8 pixels wide, so one 8-row swizzle atom of the A
-// operand = one patch row).  Per (view, 64-channel chunk) the producer fetches the 18 x 10 HALO of the patch ONCE and all taps of the
-// view read it in place: tap (dy, dx) is the SAME shared-memory tile addressed through a UMMA descriptor whose start address is
+// halo-tile convolution kernel for standard 3x3 tap sets: the M tile is a 16 x 8 patch (8 pixels wide, so one 8-row swizzle atom of
+// the A operand = one patch row).  Per (view, 64-channel chunk) the producer fetches the 18 x 10 HALO of the patch ONCE and all nine
+// taps read it in place: tap (dy, dx) is the SAME shared-memory tile addressed through a UMMA descriptor whose start address is
 // shifted by ((dy+1)*10 + (dx+1)) pixel rows of 128 B and whose 8-row-group stride (SBO) is 10 rows = 1280 B.  TMA and UMMA both
-// apply the 128-byte swizzle to absolute shared-memory address bits, so the shifted views stay consistent.  That divides the
-// L2 -> SM traffic of the A operand by ~6.4 (180 instead of 9 x 128 pixel rows per chunk); the weight tiles keep their own ring.
-//   planes == 3 is the conservative variant: three 18 x 8 boxes (dx = -1, 0, 1) whose rows are whole swizzle atoms, taps shift by
-//   multiples of 1024 B only (2.7x less A traffic).
+// apply the 128-byte swizzle to absolute shared-memory address bits, so the shifted views stay consistent (checked against the
+// CUDA-core engine by tests/test_gpu_conv.py).  L2 -> SM traffic of the A operand drops ~6.4x (180 instead of 9 x 128 pixel rows per
+// chunk); the weight tiles stream through their own, deeper ring.
+//
+// PAIR = true: the two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 stream, M = 256 = two patches (one
+// per CTA), N = bn.  Each CTA stages its own halo and only HALF of the weight tile (bn/2 rows); the tensor cores read the other half
+// from the peer's shared memory.  Per SM that halves the weight bytes read from L2 and the shared-memory fill, cuts the operand reads
+// per MMA from 12 KB to 8 KB, and gives the B ring 8 stages of 16 KB.  Protocol (as CUTLASS' 2-SM pipelines): both producers wait on
+// their OWN empty barriers and issue cta_group::2 TMA loads that complete bytes on the LEADER's full barrier (the leader's producer
+// posts the expected bytes of both CTAs); the leader's MMA thread issues the MMAs and multicasts its commits to the empty /
+// accumulator-full barriers of both CTAs; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+//
+// The single producer / MMA threads are the serial resources of the design: their per-tap loops are fully unrolled over the nine taps
+// with compile-time operand offsets and touch no dynamically indexed kernel parameter (a dependent LDC per tap cost ~300 cycles per
+// tap in the first version, measured with per-thread stall counters).
 // ---------------------------------------------------------------------------------------------------
-constexpr int HALO_SA_MAX = 4, HALO_SB_MAX = 8;
+constexpr int HALO_SA = 3, HALO_SB_MAX = 8;
 constexpr int HALO_TH = 16, HALO_TW = 8;
-constexpr int HALO_PLANE3_BYTES = (HALO_TH + 2) * HALO_TW * 128;               // 18432
-constexpr int HALO_BOX1_BYTES = (HALO_TH + 2) * (HALO_TW + 2) * 128;           // 23040
+constexpr int HALO_BYTES = (HALO_TH + 2) * (HALO_TW + 2) * 128;           // 23040
+constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;              // 23552
 struct SmemH {
-    uint64_t a_full[HALO_SA_MAX], a_empty[HALO_SA_MAX];
+    uint64_t a_full[HALO_SA], a_empty[HALO_SA];
     uint64_t b_full[HALO_SB_MAX], b_empty[HALO_SB_MAX];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 struct HaloTile { int prob, img, x0, y0, n0; };
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long& acc, bool on) {
-    if (on) { long long t0 = clock64(); mbar_wait(bar, parity, who); acc += clock64() - t0; }
-    else mbar_wait(bar, parity, who);
-}
 
-template <int EPI_WARPS>
+template <int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
@@ -536,130 +613,190 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     __shared__ SmemH s;
     __shared__ float sstat[EPI_WARPS][2][ACC_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t a0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b0 = a0 + tl.sa * tl.a_slot;
+    const uint32_t b0 = a0 + HALO_SA * HALO_SLOT;
+    const int sb = tl.sb;
+    const uint32_t b_slot = tl.b_slot;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.b);
-        for (int i = 0; i < tl.sa; i++) { mbar_init(smem_u32(&s.a_full[i]), 1); mbar_init(smem_u32(&s.a_empty[i]), 1); }
-        for (int i = 0; i < tl.sb; i++) { mbar_init(smem_u32(&s.b_full[i]), 1); mbar_init(smem_u32(&s.b_empty[i]), 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), EPI_WARPS); }
+        for (int i = 0; i < HALO_SA; i++) { mbar_init(smem_u32(&s.a_full[i]), 1); mbar_init(smem_u32(&s.a_empty[i]), 1); }
+        for (int i = 0; i < sb; i++) { mbar_init(smem_u32(&s.b_full[i]), 1); mbar_init(smem_u32(&s.b_empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), (PAIR ? 2 : 1) * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const int nchunks = tl.nviews * tl.kchunks;
+    const int kchunks = tl.kchunks;
+    const int nchunks = tl.nviews * kchunks;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total = tl.total;
+    const bool dbg_on = tl.dbg != nullptr;
+    // every CTA (pair) walks the channel chunks in its own rotation: in lock-step all CTAs would read the same weight tile, i.e. hit
+    // the same L2 lines, at the same moment
+    const int rot = tl.rot ? item0 % nchunks : 0;
+    const int rot_v = rot / kchunks, rot_k = rot % kchunks;
 
     if (warp == 0) {
         if (lane == 0) {
+            long long w_ae = 0, w_be = 0; const long long t_start = clock64();
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
-            long long w_ae = 0, w_be = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
-            const uint32_t b_tx = tl.bn * 128;
-            // with three A slots the next halo is requested before the current chunk's weight tiles; with two, half-way through them
-            // (its slot is released by the previous chunk's last MMA)
-            const int pref = tl.sa >= 3 ? 0 : 4;
-            auto decode = [&](int tile, HaloTile& h) {
+            const uint32_t b_tx = (uint32_t)tl.bn * 128u;               // bytes of a whole weight tile (both halves in pair mode)
+            const int brow = PAIR ? rank * (tl.bn >> 1) : 0;
+            const uint32_t bar_af = smem_u32(&s.a_full[0]), bar_ae = smem_u32(&s.a_empty[0]);
+            const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
+            auto decode = [&](int item, HaloTile& h) {
                 int ti = 0;
-                while (tile >= tl.p[ti + 1].begin) ti++;
+                while (item >= tl.p[ti + 1].begin) ti++;
                 const TileP& tp_ = tl.p[ti];
-                int local = tile - tp_.begin;
-                int nt = local % tl.n_tiles, mt = local / tl.n_tiles;
-                int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
-                int r = mt % tiles_per_img;
+                const int local = item - tp_.begin;
+                const int nt = local % tl.n_tiles;
+                const int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
+                int mt = local / tl.n_tiles;
+                if (PAIR) {
+                    const int m_tiles = a.p[tp_.prob].N * tiles_per_img;
+                    mt = 2 * mt + rank;
+                    if (mt >= m_tiles) mt = m_tiles - 1;     // odd tile count: this CTA recomputes the last tile (its epilogue is masked)
+                }
+                const int r = mt % tiles_per_img;
                 h.prob = tp_.prob; h.img = mt / tiles_per_img;
                 h.y0 = (r / tp_.tiles_x) * HALO_TH; h.x0 = (r % tp_.tiles_x) * HALO_TW; h.n0 = nt * tl.bn;
             };
-            auto issue_a = [&](const HaloTile& h, int chunk) {
-                const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
-                mbar_wait_t(smem_u32(&s.a_empty[ai]), aph ^ 1, 21, w_ae, dbg_on);
-                const uint32_t fb = smem_u32(&s.a_full[ai]);
-                const uint32_t dst = a0 + ai * tl.a_slot;
+            auto issue_a = [&](const HaloTile& h, int view, int kc) {
+                mbar_wait_t(bar_ae + 8 * ai, aph ^ 1, 21, w_ae, dbg_on);
+                const uint32_t fb = bar_af + 8 * ai;
+                const uint32_t dst = a0 + ai * HALO_SLOT;
                 const CUtensorMap* amap = &maps.a[h.prob][view];
-                mbar_expect_tx(fb, tl.a_bytes);
-                if (tl.planes == 1) {
-                    tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                if (PAIR) {
+                    if (leader) mbar_expect_tx(fb, 2 * HALO_BYTES);
+                    tma_load_4d_pair(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
                 } else {
-#pragma unroll
-                    for (int p = 0; p < 3; p++) tma_load_4d(amap, fb, dst + p * HALO_PLANE3_BYTES, kc * 64, h.x0 + p - 1, h.y0 - 1, h.img);
+                    mbar_expect_tx(fb, HALO_BYTES);
+                    tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
                 }
-                if (++ai == tl.sa) { ai = 0; aph ^= 1; }
+                if (++ai == HALO_SA) { ai = 0; aph ^= 1; }
             };
             HaloTile cur, nxt;
-            int tile = blockIdx.x;
-            if (tile < tl.total) { decode(tile, cur); issue_a(cur, 0); }
-            while (tile < tl.total) {
-                const int ntile = tile + gridDim.x;
-                const bool has_next = ntile < tl.total;
-                if (has_next) decode(ntile, nxt);
+            int item = item0;
+            if (item < total) { decode(item, cur); issue_a(cur, rot_v, rot_k); }
+            while (item < total) {
+                const int nitem = item + item_stride;
+                const bool has_next = nitem < total;
+                if (has_next) decode(nitem, nxt);
+                int view = rot_v, kc = rot_k;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
-                    const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
-                    const int t0 = tl.view_tap0[view], t1 = tl.view_tap0[view + 1];
-                    const bool last = chunk + 1 == nchunks;
-                    const int pf = (t1 - t0 - 1) < pref ? (t1 - t0 - 1) : pref;
-                    for (int t = t0; t < t1; t++) {
-                        if (t - t0 == pf) {
-                            if (!last) issue_a(cur, chunk + 1);
-                            else if (has_next) issue_a(nxt, 0);
+                    const int slab0 = tl.view_slab0[view];
+                    const int kcol = kc * 64, nrow = cur.n0 + brow;
+                    int nview = view, nkc = kc + 1;
+                    if (nkc == kchunks) { nkc = 0; if (++nview == tl.nviews) nview = 0; }
+                    // the halo of the NEXT chunk is requested before this chunk's weight tiles (three A slots: its slot was released long ago)
+                    if (chunk + 1 < nchunks) issue_a(cur, nview, nkc);
+                    else if (has_next) issue_a(nxt, rot_v, rot_k);
+#pragma unroll
+                    for (int j = 0; j < 9; j++) {
+                        mbar_wait_t(bar_be + 8 * bi, bph ^ 1, 22, w_be, dbg_on);
+                        const uint32_t fb = bar_bf + 8 * bi;
+                        const uint32_t dst = b0 + bi * b_slot;
+                        const int bk = kcol, bs = slab0 + j;
+                        if (PAIR) {
+                            if (leader) mbar_expect_tx(fb, b_tx);
+                            tma_load_3d_pair(&maps.b, fb, dst, bk, nrow, bs);
+                        } else {
+                            mbar_expect_tx(fb, b_tx);
+                            tma_load_3d(&maps.b, fb, dst, bk, nrow, bs);
                         }
-                        mbar_wait_t(smem_u32(&s.b_empty[bi]), bph ^ 1, 22, w_be, dbg_on);
-                        const uint32_t fb = smem_u32(&s.b_full[bi]);
-                        mbar_expect_tx(fb, b_tx);
-                        tma_load_3d(&maps.b, fb, b0 + bi * tl.b_slot, kc * 64, cur.n0, a.taps[t].slab);
-                        if (++bi == tl.sb) { bi = 0; bph ^= 1; }
+                        if (++bi == sb) { bi = 0; bph ^= 1; }
                     }
+                    view = nview; kc = nkc;
                 }
-                cur = nxt; tile = ntile;
+                cur = nxt; item = nitem;
             }
             if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_ae; d[1] = w_be; d[2] = clock64() - t_start; }
+            if (PAIR) {
+                // producer tail: every release the leader multicast to this CTA has landed before the CTA may exit
+                for (int i = 0; i < HALO_SA; i++) { mbar_wait(bar_ae + 8 * ai, aph ^ 1, 33); if (++ai == HALO_SA) { ai = 0; aph ^= 1; } }
+                for (int i = 0; i < sb; i++) { mbar_wait(bar_be + 8 * bi, bph ^ 1, 34); if (++bi == sb) { bi = 0; bph ^= 1; } }
+            }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && leader) {
+            long long w_af = 0, w_bf = 0, w_acc = 0; const long long t_start = clock64();
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
             int as = 0; uint32_t aphase = 0;
-            long long w_af = 0, w_bf = 0, w_acc = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
-            const uint32_t idesc = make_idesc(tl.bn, 0, 0);
-            const uint32_t sbo = tl.planes == 1 ? (HALO_TW + 2) * 128 : HALO_TW * 128;
-            for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+            const uint32_t idesc = make_idesc(tl.bn, 0, 0, PAIR ? 256 : 128);
+            const uint64_t adesc0 = make_desc(0, 16, (HALO_TW + 2) * 128), bdesc0 = make_desc(0, 16, 1024);
+            const uint32_t bar_af = smem_u32(&s.a_full[0]), bar_ae = smem_u32(&s.a_empty[0]);
+            const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
+            const int cin = a.cin;
+            auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            for (int item = item0; item < total; item += item_stride) {
                 mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 23, w_acc, dbg_on);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * ACC_COLS;
                 uint32_t accum = 0;
+                int kc = rot_k;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
-                    const int view = chunk / tl.kchunks, kc = chunk - view * tl.kchunks;
-                    const int t0 = tl.view_tap0[view], t1 = tl.view_tap0[view + 1];
-                    int nk = (a.cin - kc * 64 + 15) >> 4;           // 16-channel MMA steps with data in this chunk
-                    if (nk > 4) nk = 4;
-                    mbar_wait_t(smem_u32(&s.a_full[ai]), aph, 24, w_af, dbg_on);
-                    const uint32_t abase = a0 + ai * tl.a_slot;
-                    for (int t = t0; t < t1; t++) {
-                        const int dy = a.taps[t].dy, dx = a.taps[t].dx;
-                        const uint32_t aoff = tl.planes == 1 ? (uint32_t)((dy + 1) * (HALO_TW + 2) + (dx + 1)) * 128u
-                                                             : (uint32_t)(dx + 1) * HALO_PLANE3_BYTES + (uint32_t)(dy + 1) * (HALO_TW * 128);
-                        mbar_wait_t(smem_u32(&s.b_full[bi]), bph, 25, w_bf, dbg_on);
+                    int nk = (cin - kc * 64 + 15) >> 4;              // 16-channel MMA steps with data in this chunk
+                    if (++kc == kchunks) kc = 0;
+                    mbar_wait_t(bar_af + 8 * ai, aph, 24, w_af, dbg_on);
+                    const uint32_t abase = a0 + ai * HALO_SLOT;
+#pragma unroll
+                    for (int j = 0; j < 9; j++) {
+                        const uint32_t aaddr = abase + (uint32_t)(((j / 3) * (HALO_TW + 2) + (j % 3)) * 128);
+                        const uint32_t baddr = b0 + bi * b_slot;
+                        mbar_wait_t(bar_bf + 8 * bi, bph, 25, w_bf, dbg_on);
                         tc_fence_after();
-                        const uint64_t ad = make_desc(abase + aoff, 16, sbo), bd = make_desc(b0 + bi * tl.b_slot, 16, 1024);
-                        for (int k = 0; k < nk; k++) { umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum); accum = 1; }
-                        umma_commit(smem_u32(&s.b_empty[bi]));
-                        if (++bi == tl.sb) { bi = 0; bph ^= 1; }
+                        const uint64_t ad = adesc0 | (uint64_t)((aaddr >> 4) & 0x3FFFu), bd = bdesc0 | (uint64_t)((baddr >> 4) & 0x3FFFu);
+                        if (nk >= 4) {
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                if (PAIR) umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum | (uint32_t)(j | k));
+                                else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum | (uint32_t)(j | k));
+                            }
+                        } else {
+                            for (int k = 0; k < nk; k++) {
+                                if (PAIR) umma_bf16_pair(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum | (uint32_t)(j | k));
+                                else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum | (uint32_t)(j | k));
+                            }
+                        }
+                        commit(bar_be + 8 * bi);
+                        if (++bi == sb) { bi = 0; bph ^= 1; }
                     }
-                    umma_commit(smem_u32(&s.a_empty[ai]));
-                    if (++ai == tl.sa) { ai = 0; aph ^= 1; }
+                    accum = 1;
+                    commit(bar_ae + 8 * ai);
+                    if (++ai == HALO_SA) { ai = 0; aph ^= 1; }
                 }
-                umma_commit(smem_u32(&s.acc_full[as]));
+                commit(smem_u32(&s.acc_full[as]));
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
-        conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
+        conv_epilogue<EPI_WARPS, PAIR>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
     }
-    teardown(tmem_base, warp);
+    tc_fence_before();
+    __syncwarp();
+    if (PAIR) cluster_sync_all();      // neither CTA frees TMEM / exits while the other may still read its shared memory or signal it
+    else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -821,23 +958,23 @@ static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
 }
 
 static int g_halo_dyn_max[2] = {0, 0};
-// AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tile with shifted descriptors; 3: three-plane halo
+// AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tiles, one CTA per tile; 2: halo tiles on CTA pairs (cta_group::2)
 static int halo_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("AFIGAN_CONV_HALO");
         mode = e ? atoi(e) : 0;
-        if (mode != 0 && mode != 1 && mode != 3) mode = 0;
+        if (mode < 0 || mode > 2) mode = 0;
     }
     return mode;
 }
-// taps must be grouped by view (non-decreasing) and stay inside the 3x3 footprint
+// the halo kernels take standard tap sets only: per view the nine taps (dy, dx) = (-1,-1) .. (1,1) in row-major order on consecutive slabs
 static bool halo_eligible(const ConvArgs& a) {
-    if (a.ntaps < 2) return false;
+    if (a.ntaps < 9 || a.ntaps % 9 != 0) return false;
     for (int i = 0; i < a.ntaps; i++) {
         const Tap& t = a.taps[i];
-        if (t.dy < -1 || t.dy > 1 || t.dx < -1 || t.dx > 1) return false;
-        if (i > 0 && t.view < a.taps[i - 1].view) return false;
+        const int j = i % 9;
+        if (t.view != i / 9 || t.dy != j / 3 - 1 || t.dx != j % 3 - 1 || t.slab != a.taps[i - j].slab + j) return false;
     }
     return true;
 }
@@ -858,12 +995,14 @@ int tc_init(afi_ctx* ctx) {
     AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     // halo-tile kernels: everything the SM has beyond their static shared memory (statistics scratch + barriers)
     cudaFuncAttributes fa;
-    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<4>));
+    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<4, true>));
     tc::g_halo_dyn_max[0] = 232448 - (int)fa.sharedSizeBytes;
-    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
-    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<8>));
+    AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<8, true>));
     tc::g_halo_dyn_max[1] = 232448 - (int)fa.sharedSizeBytes;
-    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
     return AFI_OK;
 }
 
@@ -907,27 +1046,22 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     Maps maps;
     const int hmode = halo_eligible(a) ? halo_mode() : 0;
     const int epi8 = a.ntaps * tl.kchunks * 64 < 4096 ? 1 : 0;   // short-K layers cannot hide their epilogue behind the MMAs
+    const bool pair = hmode == 2;
+    tl.rot = getenv("AFIGAN_CONV_ROT") ? atoi(getenv("AFIGAN_CONV_ROT")) : 0;   // measured: no effect (the weight tiles are not an L2 hot spot)
+    if (getenv("AFIGAN_HALO_DBG")) {
+        static long long* dbg = nullptr;
+        if (!dbg) cudaMalloc(&dbg, 4096 * sizeof(long long));
+        cudaMemsetAsync(dbg, 0, 4096 * sizeof(long long), st);
+        tl.dbg = dbg;
+    }
     if (hmode) {
-        tl.planes = hmode; tl.nviews = nviews;
-        tl.a_bytes = hmode == 1 ? HALO_BOX1_BYTES : 3 * HALO_PLANE3_BYTES;
-        tl.a_slot = (tl.a_bytes + 1023) / 1024 * 1024;
-        tl.b_slot = (tl.bn * 128 + 1023) / 1024 * 1024;
-        tl.sa = hmode == 1 ? 3 : 2;
-        if (const char* e = getenv("AFIGAN_HALO_SA")) { int v = atoi(e); if (v >= 2 && v <= HALO_SA_MAX) tl.sa = v; }
-        int room = g_halo_dyn_max[epi8] - 1024 - tl.sa * tl.a_slot;
+        tl.nviews = nviews;
+        tl.b_slot = ((pair ? tl.bn * 64 : tl.bn * 128) + 1023) / 1024 * 1024;
+        const int room = g_halo_dyn_max[epi8] - 1024 - HALO_SA * HALO_SLOT;
         tl.sb = room / tl.b_slot;
         if (tl.sb > HALO_SB_MAX) tl.sb = HALO_SB_MAX;
         AFI_REQUIRE(tl.sb >= 2, "conv_tc: shared memory budget leaves %d weight stages", tl.sb);
-        if (tl.sb >= 6 && hmode == 3 && room - tl.sb * tl.b_slot >= tl.a_slot) tl.sa = 3;   // narrow N tiles: room for a third halo slot
-        if (getenv("AFIGAN_HALO_DBG")) {
-            static long long* dbg = nullptr;
-            if (!dbg) cudaMalloc(&dbg, 256 * 8 * sizeof(long long));
-            cudaMemsetAsync(dbg, 0, 256 * 8 * sizeof(long long), st);
-            tl.dbg = dbg;
-        }
-        int v = 0;
-        for (int i = 0; i < a.ntaps; i++) { while (v <= a.taps[i].view) tl.view_tap0[v++] = i; }
-        while (v <= 4) tl.view_tap0[v++] = a.ntaps;
+        for (int v = 0; v < nviews; v++) tl.view_slab0[v] = a.taps[9 * v].slab;
     }
     int begin = 0, np = 0;
     for (int oi = 0; oi < a.nprob; oi++) {
@@ -940,8 +1074,9 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         t.tiles_y = (pr.H + t.TH - 1) / t.TH;
         t.begin = begin;
         t.prob = order[oi];
-        begin += pr.N * t.tiles_x * t.tiles_y * tl.n_tiles;
-        const int bw = hmode == 1 ? t.TW + 2 : t.TW, bh = hmode ? t.TH + 2 : t.TH;
+        const int m_tiles = pr.N * t.tiles_x * t.tiles_y;
+        begin += (pair ? (m_tiles + 1) / 2 : m_tiles) * tl.n_tiles;
+        const int bw = hmode ? t.TW + 2 : t.TW, bh = hmode ? t.TH + 2 : t.TH;
         for (int v = 0; v < nviews; v++) AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, bw, bh));
         np++;
     }
@@ -953,27 +1088,41 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)tl.bn, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), 1};
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
     }
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    if (pair) { int ncl = ctx->sm_count / 2; grid = 2 * (tl.total < ncl ? tl.total : ncl); }
     ProfScope prof(PROF_CONV_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
     // short-K layers (K = taps x cin < 4096) get eight epilogue warps
-    if (hmode) {
-        const int dyn = 1024 + tl.sa * tl.a_slot + tl.sb * tl.b_slot;
-        if (epi8) k_conv_halo<8><<<grid, 64 + 32 * 8, dyn, st>>>(maps, a, tl);
-        else k_conv_halo<4><<<grid, 64 + 32 * 4, dyn, st>>>(maps, a, tl);
+    if (pair) {
+        const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * (epi8 ? 8 : 4)); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, true>, maps, a, tl));
+        else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, true>, maps, a, tl));
+    } else if (hmode) {
+        const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
+        if (epi8) k_conv_halo<8, false><<<grid, 64 + 32 * 8, dyn, st>>>(maps, a, tl);
+        else k_conv_halo<4, false><<<grid, 64 + 32 * 4, dyn, st>>>(maps, a, tl);
+    } else if (epi8) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
+    else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
+    {
         if (tl.dbg) {      // experiment aid: per-CTA stall cycles of the producer / MMA threads
             long long h[256 * 8];
             cudaStreamSynchronize(st);
             cudaMemcpy(h, tl.dbg, sizeof(h), cudaMemcpyDeviceToHost);
             double sum[8] = {0};
+            const int mg = pair ? grid / 2 : grid;
             for (int b = 0; b < grid; b++) for (int i = 0; i < 8; i++) sum[i] += (double)h[b * 8 + i];
             fprintf(stderr, "[halo dbg] cin %d cout %d sa %d sb %d tiles %d: producer wait a_empty %.0f b_empty %.0f of %.0f | mma wait a_full %.0f b_full %.0f acc_empty %.0f of %.0f (avg cycles per CTA)\n",
-                    a.cin, a.cout, tl.sa, tl.sb, tl.total, sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / grid, sum[4] / grid, sum[5] / grid, sum[6] / grid);
+                    a.cin, a.cout, hmode ? HALO_SA : 0, tl.sb, tl.total, sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / mg, sum[4] / mg, sum[5] / mg, sum[6] / mg);
         }
-    } else if (epi8) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
-    else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
+    }
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

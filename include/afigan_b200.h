@@ -136,7 +136,8 @@ int afi_d_pack(afi_ctx*, int prec, const afi_d_params*, void* packed, void* stre
 /* One discriminator call; a group (e.g. level x {real, fake} of a stage-1 phase) runs as grouped launches per layer. */
 typedef struct {
     afi_view4 x; int n, h, w;       /* input [n,256,h,w]                               */
-    float* logits;                  /* forward: contiguous [n,1,h,w]                   */
+    float* logits;                  /* forward: contiguous [n,1,h,w]; NULL (training, no backward) = the call only contributes
+                                     * its BatchNorm batch statistics -- the dead D(hr) of stage1_trainer.py:400          */
     const float* dlogits;           /* backward: contiguous [n,1,h,w]                  */
     float* dx;                      /* backward: contiguous [n,256,h,w] or NULL           */
     void* ws; size_t ws_bytes;
