@@ -153,6 +153,17 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a CONVERGED warp (the whole warp runs the role loop; only the instruction issue is elected -- the code the compiler emits
+// for tcgen05 / TMA instructions inside a divergent `if (lane == 0)` region wraps each of them in an ELECT / branch loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -503,7 +514,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     const int iters = a.ntaps * tl.kchunks;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             long long w_e = 0, w_l = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
             const uint32_t tx_bytes = A_BYTES + tl.bn * 128;
@@ -532,17 +543,20 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                         mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
                         uint32_t fb = smem_u32(&s.full[stage]);
                         uint32_t sa = tiles0 + stage * STAGE_BYTES;
-                        mbar_expect_tx(fb, tx_bytes);
-                        tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
-                        tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, t.slab);
+                        if (elect_one()) {
+                            mbar_expect_tx(fb, tx_bytes);
+                            tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
+                            tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, t.slab);
+                        }
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_l; d[1] = w_e; d[2] = clock64() - t_start; }
+            if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_l; d[1] = w_e; d[2] = clock64() - t_start; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             long long w_f = 0, w_acc = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
@@ -556,15 +570,19 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                     tc_fence_after();
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
                     uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
-                    umma_commit(smem_u32(&s.empty[stage]));
+                        for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+                        umma_commit(smem_u32(&s.empty[stage]));
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&s.acc_full[as]));
+                if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
+                __syncwarp();
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
+            if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
         conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
@@ -652,7 +670,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     const int rot_v = rot / kchunks, rot_k = rot % kchunks;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             long long w_ae = 0, w_be = 0; const long long t_start = clock64();
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
             const uint32_t b_tx = (uint32_t)tl.bn * 128u;               // bytes of a whole weight tile (both halves in pair mode)
@@ -681,13 +699,16 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 const uint32_t fb = bar_af + 8 * ai;
                 const uint32_t dst = a0 + ai * HALO_SLOT;
                 const CUtensorMap* amap = &maps.a[h.prob][view];
-                if (PAIR) {
-                    if (leader) mbar_expect_tx(fb, 2 * HALO_BYTES);
-                    tma_load_4d_pair(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
-                } else {
-                    mbar_expect_tx(fb, HALO_BYTES);
-                    tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                if (elect_one()) {
+                    if (PAIR) {
+                        if (leader) mbar_expect_tx(fb, 2 * HALO_BYTES);
+                        tma_load_4d_pair(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                    } else {
+                        mbar_expect_tx(fb, HALO_BYTES);
+                        tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                    }
                 }
+                __syncwarp();
                 if (++ai == HALO_SA) { ai = 0; aph ^= 1; }
             };
             HaloTile cur, nxt;
@@ -711,21 +732,23 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                         mbar_wait_t(bar_be + 8 * bi, bph ^ 1, 22, w_be, dbg_on);
                         const uint32_t fb = bar_bf + 8 * bi;
                         const uint32_t dst = b0 + bi * b_slot;
-                        const int bk = kcol, bs = slab0 + j;
-                        if (PAIR) {
-                            if (leader) mbar_expect_tx(fb, b_tx);
-                            tma_load_3d_pair(&maps.b, fb, dst, bk, nrow, bs);
-                        } else {
-                            mbar_expect_tx(fb, b_tx);
-                            tma_load_3d(&maps.b, fb, dst, bk, nrow, bs);
+                        if (elect_one()) {
+                            if (PAIR) {
+                                if (leader) mbar_expect_tx(fb, b_tx);
+                                tma_load_3d_pair(&maps.b, fb, dst, kcol, nrow, slab0 + j);
+                            } else {
+                                mbar_expect_tx(fb, b_tx);
+                                tma_load_3d(&maps.b, fb, dst, kcol, nrow, slab0 + j);
+                            }
                         }
+                        __syncwarp();
                         if (++bi == sb) { bi = 0; bph ^= 1; }
                     }
                     view = nview; kc = nkc;
                 }
                 cur = nxt; item = nitem;
             }
-            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_ae; d[1] = w_be; d[2] = clock64() - t_start; }
+            if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[0] = w_ae; d[1] = w_be; d[2] = clock64() - t_start; }
             if (PAIR) {
                 // producer tail: every release the leader multicast to this CTA has landed before the CTA may exit
                 for (int i = 0; i < HALO_SA; i++) { mbar_wait(bar_ae + 8 * ai, aph ^ 1, 33); if (++ai == HALO_SA) { ai = 0; aph ^= 1; } }
@@ -733,7 +756,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
+        if (leader) {
             long long w_af = 0, w_bf = 0, w_acc = 0; const long long t_start = clock64();
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
             int as = 0; uint32_t aphase = 0;
@@ -761,6 +784,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                         mbar_wait_t(bar_bf + 8 * bi, bph, 25, w_bf, dbg_on);
                         tc_fence_after();
                         const uint64_t ad = adesc0 | (uint64_t)((aaddr >> 4) & 0x3FFFu), bd = bdesc0 | (uint64_t)((baddr >> 4) & 0x3FFFu);
+                        if (elect_one()) {
                         if (nk >= 4) {
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
@@ -774,16 +798,20 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                             }
                         }
                         commit(bar_be + 8 * bi);
+                        }
+                        __syncwarp();
                         if (++bi == sb) { bi = 0; bph ^= 1; }
                     }
                     accum = 1;
-                    commit(bar_ae + 8 * ai);
+                    if (elect_one()) commit(bar_ae + 8 * ai);
+                    __syncwarp();
                     if (++ai == HALO_SA) { ai = 0; aph ^= 1; }
                 }
-                commit(smem_u32(&s.acc_full[as]));
+                if (elect_one()) commit(smem_u32(&s.acc_full[as]));
+                __syncwarp();
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
-            if (dbg_on) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
+            if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
         conv_epilogue<EPI_WARPS, PAIR>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
@@ -813,8 +841,9 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     const int nb = tl.bn / 64;    // B boxes per stage
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
 
+    // the producer and MMA warps run their loops CONVERGED; only the TMA / tcgen05 instruction issue is elected (see elect_one())
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             const uint32_t tx_bytes = A_BYTES + nb * 8192;
             for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
@@ -837,10 +866,13 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
                     uint32_t fb = smem_u32(&s.full[stage]);
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
-                    mbar_expect_tx(fb, tx_bytes);
-                    // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
-                    tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
-                    tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, tx_bytes);
+                        // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
+                        tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
+                        tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (++tx_ == tp_.tiles_x) {
                         tx_ = 0;
@@ -853,7 +885,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             const uint32_t idesc = make_idesc(tl.bn, 1, 1);
@@ -869,13 +901,17 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     uint32_t sa = tiles0 + stage * STAGE_BYTES;
                     // MN-major SW128: LBO = stride between 64-channel groups (8192 B), SBO = stride between 8-pixel groups (1024 B)
                     uint64_t ad = make_desc(sa, 8192, 1024), bd = make_desc(sa + A_BYTES, 8192, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)     // 16 pixels = 2048 B per MMA
-                        umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
-                    umma_commit(smem_u32(&s.empty[stage]));
+                        for (int k = 0; k < 4; k++)     // 16 pixels = 2048 B per MMA
+                            umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
+                        umma_commit(smem_u32(&s.empty[stage]));
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&s.acc_full[as]));
+                if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
+                __syncwarp();
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -963,8 +999,8 @@ static int halo_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("AFIGAN_CONV_HALO");
-        mode = e ? atoi(e) : 0;
-        if (mode < 0 || mode > 2) mode = 0;
+        mode = e ? atoi(e) : 2;
+        if (mode < 0 || mode > 2) mode = 2;
     }
     return mode;
 }
@@ -1044,8 +1080,14 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
     AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc: bad view count");
     Maps maps;
-    const int hmode = halo_eligible(a) ? halo_mode() : 0;
-    const int epi8 = a.ntaps * tl.kchunks * 64 < 4096 ? 1 : 0;   // short-K layers cannot hide their epilogue behind the MMAs
+    // short-K layers (K = taps x cin < 4096) cannot hide their epilogue behind the MMAs: eight epilogue warps; so do the layers with
+    // fused statistics below K = 8192 (measured: 512 -> 1024 with statistics on four warps is epilogue-bound in pair mode)
+    const int K = a.ntaps * tl.kchunks * 64;
+    const int epi8 = (K < 4096 || (a.stat_mode && K < 8192)) ? 1 : 0;
+    // halo tiles on CTA pairs pay off on the long-K layers (weight-tile traffic per FLOP halves); the short-K layers are bound by
+    // tile granularity and epilogue overlap, where the single-CTA per-tap kernel measured slightly faster
+    int hmode = halo_eligible(a) ? halo_mode() : 0;
+    if (hmode == 2 && K < 4096 && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
     const bool pair = hmode == 2;
     tl.rot = getenv("AFIGAN_CONV_ROT") ? atoi(getenv("AFIGAN_CONV_ROT")) : 0;   // measured: no effect (the weight tiles are not an L2 hot spot)
     if (getenv("AFIGAN_HALO_DBG")) {
