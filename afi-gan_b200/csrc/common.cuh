@@ -110,7 +110,7 @@ struct WgradArgs {
 };
 
 // optional per-launch CUDA-event profiling of the GEMM kernels (afi_profile_begin/_end; bench.py's roofline leg)
-enum ProfKind { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_CONV_SIMT = 2, PROF_WGRAD_SIMT = 3 };
+enum ProfKind { PROF_CONV_TC = 0, PROF_WGRAD_TC = 1, PROF_CONV_SIMT = 2, PROF_WGRAD_SIMT = 3, PROF_CONV_PAIR = 4, PROF_CONV_HALO = 5 };
 extern bool g_prof_on;
 void prof_begin(int kind, double flops, int cin, int cout, long long pixels, cudaStream_t st);
 void prof_end(cudaStream_t st);

@@ -28,7 +28,8 @@
 namespace afi {
 
 namespace tc {
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;             // stages of A_BYTES + B_BYTES_MAX that fit; narrower N tiles get more (Tiling.nstages)
+constexpr int STAGES_MAX = 10;
 constexpr int A_BYTES = 16384;          // 128 rows x 128 B
 constexpr int B_BYTES_MAX = 32768;      // 256 rows x 128 B
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
@@ -52,6 +53,7 @@ struct Tiling {
     int total;                        // work items
     int nprob;
     int m_tiles, ksplit, ktiles;      // wgrad only
+    int nstages, stage_bytes;         // per-tap conv and wgrad: operand ring (a narrow N tile leaves room for more, smaller stages)
     // halo-tile convolution only: B ring of `sb` slots of b_slot bytes (one (tap, chunk) weight tile, or half of it in pair mode)
     int sb, b_slot, nviews, rot;
     int view_slab0[4];                // first weight slab of view v (its nine taps use slab0 .. slab0 + 8 in standard order)
@@ -209,8 +211,8 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
 struct Aux { uint4 a, b, c, d; };   // one 16-column chunk of auxiliary epilogue operands (64 B per thread)
 
 struct Smem {
-    uint64_t full[STAGES];
-    uint64_t empty[STAGES];
+    uint64_t full[STAGES_MAX];
+    uint64_t empty[STAGES_MAX];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint32_t tmem_base;
@@ -219,7 +221,7 @@ struct Smem {
 __device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int epi_warps, int warp, int lane) {
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.b);
-        for (int i = 0; i < STAGES; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
+        for (int i = 0; i < STAGES_MAX; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), epi_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -512,6 +514,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tmem_base = setup(s, maps, EPI_WARPS, warp, lane);
     const int iters = a.ntaps * tl.kchunks;
+    const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
 
     if (warp == 0) {
         {
@@ -542,14 +545,14 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                         if (++kc == tl.kchunks) kc = 0;
                         mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
                         uint32_t fb = smem_u32(&s.full[stage]);
-                        uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                        uint32_t sa = tiles0 + stage * stage_bytes;
                         if (elect_one()) {
                             mbar_expect_tx(fb, tx_bytes);
                             tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
                             tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, t.slab);
                         }
                         __syncwarp();
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -568,7 +571,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 for (int it = 0; it < iters; it++) {
                     mbar_wait_t(smem_u32(&s.full[stage]), phase, 3, w_f, dbg_on);
                     tc_fence_after();
-                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    uint32_t sa = tiles0 + stage * stage_bytes;
                     uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
                     if (elect_one()) {
 #pragma unroll
@@ -576,7 +579,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                         umma_commit(smem_u32(&s.empty[stage]));
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
@@ -839,6 +842,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tmem_base = setup(s, maps, EPI_THREADS / 32, warp, lane);
     const int nb = tl.bn / 64;    // B boxes per stage
+    const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
 
     // the producer and MMA warps run their loops CONVERGED; only the TMA / tcgen05 instruction issue is elected (see elect_one())
@@ -865,7 +869,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
                     mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
                     uint32_t fb = smem_u32(&s.full[stage]);
-                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    uint32_t sa = tiles0 + stage * stage_bytes;
                     if (elect_one()) {
                         mbar_expect_tx(fb, tx_bytes);
                         // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
@@ -873,7 +877,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                         tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                     if (++tx_ == tp_.tiles_x) {
                         tx_ = 0;
                         if (++ty_ == tp_.tiles_y) {
@@ -898,7 +902,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 for (int kt = k0; kt < k1; kt++) {
                     mbar_wait(smem_u32(&s.full[stage]), phase, 13);
                     tc_fence_after();
-                    uint32_t sa = tiles0 + stage * STAGE_BYTES;
+                    uint32_t sa = tiles0 + stage * stage_bytes;
                     // MN-major SW128: LBO = stride between 64-channel groups (8192 B), SBO = stride between 8-pixel groups (1024 B)
                     uint64_t ad = make_desc(sa, 8192, 1024), bd = make_desc(sa + A_BYTES, 8192, 1024);
                     if (elect_one()) {
@@ -908,7 +912,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                         umma_commit(smem_u32(&s.empty[stage]));
                     }
                     __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
                 if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
@@ -1133,9 +1137,12 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), 1};
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
     }
+    tl.stage_bytes = A_BYTES + (tl.bn * 128 + 1023) / 1024 * 1024;
+    tl.nstages = (SMEM_BYTES - 1024) / tl.stage_bytes;
+    if (tl.nstages > STAGES_MAX) tl.nstages = STAGES_MAX;
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
     if (pair) { int ncl = ctx->sm_count / 2; grid = 2 * (tl.total < ncl ? tl.total : ncl); }
-    ProfScope prof(PROF_CONV_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
+    ProfScope prof(pair ? PROF_CONV_PAIR : (hmode ? PROF_CONV_HALO : PROF_CONV_TC), 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
     // short-K layers (K = taps x cin < 4096) get eight epilogue warps
     if (pair) {
         const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
@@ -1211,6 +1218,9 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     int kper = (tl.ktiles + ks - 1) / ks;
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
+    tl.stage_bytes = A_BYTES + (tl.bn / 64) * 8192;
+    tl.nstages = (SMEM_BYTES - 1024) / tl.stage_bytes;
+    if (tl.nstages > STAGES_MAX) tl.nstages = STAGES_MAX;
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
     ProfScope prof(PROF_WGRAD_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
     k_wgrad_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);

@@ -285,18 +285,20 @@ def run_ours(args):
             lib.afi_profile_get(i, C.byref(kind), C.byref(fl), C.byref(ms), C.byref(cin), C.byref(cout), C.byref(px))
             a = agg.setdefault(kind.value, [0, 0.0, 0.0])
             a[0] += 1; a[1] += fl.value; a[2] += ms.value
-            if kind.value in (0, 2) and (top is None or ms.value > top[0]):
+            if kind.value in (0, 2, 4, 5) and (top is None or ms.value > top[0]):
                 top = (ms.value, fl.value, cin.value, cout.value, px.value)
         pk = peaks()
-        names = {0: "k_conv_tc (tcgen05 implicit-GEMM conv/dgrad)", 1: "k_wgrad_tc (tcgen05 weight gradient)",
-                 2: "k_conv_simt (fp32 FFMA implicit GEMM)", 3: "k_wgrad_simt (fp32 FFMA weight gradient)"}
+        names = {0: "k_conv_tc (tcgen05 implicit-GEMM conv/dgrad, per-tap tiles: short-K and 1x1 layers)", 1: "k_wgrad_tc (tcgen05 weight gradient)",
+                 2: "k_conv_simt (fp32 FFMA implicit GEMM)", 3: "k_wgrad_simt (fp32 FFMA weight gradient)",
+                 4: "k_conv_halo<PAIR> (tcgen05 cta_group::2 implicit-GEMM conv/dgrad, halo tiles on CTA pairs: long-K layers)",
+                 5: "k_conv_halo (tcgen05 implicit-GEMM conv/dgrad, halo tiles on single CTAs)"}
         dom = max(agg, key=lambda k: agg[k][2])
         cnt, flops, tms = agg[dom]
         achieved = flops / (tms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # DRAM bytes of the dominant kernel's largest launch (ncu --set full)
         traffic_detail = None
-        if os.path.exists(tpath) and dom == 0:
+        if os.path.exists(tpath) and dom == 4:
             traffic_detail = json.load(open(tpath))
             traffic = traffic_detail["bytes_per_launch"]
         roof = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",

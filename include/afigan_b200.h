@@ -195,8 +195,9 @@ int afi_conv3x3_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, i
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
- * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05,
- * 1 wgrad tcgen05, 2 conv CUDA-core, 3 wgrad CUDA-core), algorithmic FLOPs (2*pixels*taps*cin*cout), milliseconds. */
+ * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05 per-tap
+ * kernel, 1 wgrad tcgen05, 2 conv CUDA-core, 3 wgrad CUDA-core, 4 conv tcgen05 halo tiles on CTA pairs, 5 conv tcgen05 halo tiles on
+ * single CTAs), algorithmic FLOPs (2*pixels*taps*cin*cout), milliseconds. */
 int afi_profile_begin(int max_launches);
 int afi_profile_end(int* n_launches);
 int afi_profile_get(int i, int* kind, double* flops, float* ms, int* cin, int* cout, long long* pixels);

@@ -1,4 +1,5 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_conv.py tests/test_gpu_stage1.py -x -q -m gpu 2>&1 | tail -3
-for m in 0 2; do AFIGAN_CONV_HALO=$m timeout 300 python tools/quick_time.py bf16 10 2>&1 | tail -1; done
-timeout 300 python tools/step_profile.py bf16 2>&1 | tail -34 | head -14
+mkdir -p gpurun_out
+python tools/profile_one.py 2 1024 1024 200 336 3 && \
+ncu --set full --clock-control none --import-source on -k regex:k_conv_halo -s 1 -c 1 -f -o gpurun_out/r2_conv3_pair python tools/profile_one.py 2 1024 1024 200 336 3 > gpurun_out/ncu_conv3_pair.log 2>&1
+echo "ncu exit $?"

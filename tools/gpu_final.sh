@@ -5,7 +5,7 @@ run all_gpu python -m pytest tests -q -m gpu
 run smoke python __graft_entry__.py smoke
 run bench python bench.py --steps 20 --warmup 3
 run bench_ref python bench.py --impl reference --steps 2 --warmup 1
-run stepprof python tools/step_profile.py bf16
-python tools/quick_time.py bf16 1 > gpurun_out/plain_qt.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_conv_tc -s 24 -c 1 -o gpurun_out/prof_final_conv3 python tools/quick_time.py bf16 1 > gpurun_out/ncu_final.log 2>&1
-echo "ncu exit $?"
+TAILN=34 run stepprof python tools/step_profile.py bf16
+AFIGAN_OVERLAP=0 python tools/quick_time.py bf16 1 > gpurun_out/plain_qt.log 2>&1 && \
+AFIGAN_OVERLAP=0 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_final.csv python tools/quick_time.py bf16 1 > gpurun_out/ncu_qt.log 2>&1
+echo "ncu launch list exit $?"

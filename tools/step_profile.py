@@ -36,7 +36,7 @@ for i in range(n.value):
     key = (kind.value, cin.value, cout.value, px.value, round(fl.value / (2.0 * px.value * cin.value * cout.value)))
     a = agg.setdefault(key, [0, 0.0, 0.0])
     a[0] += 1; a[1] += fl.value; a[2] += ms.value
-names = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_simt", 3: "wgrad_simt"}
+names = {0: "conv_tc", 1: "wgrad_tc", 2: "conv_simt", 3: "wgrad_simt", 4: "conv_pair", 5: "conv_halo"}
 tot = sum(v[2] for v in agg.values())
 print(f"GEMM launches {n.value}, total {tot:.2f} ms")
 print(f"{'kernel':10s} {'cin':>5s} {'cout':>5s} {'pixels':>8s} {'taps':>4s} {'n':>4s} {'ms':>8s} {'%':>6s} {'TFLOP/s':>8s}")
