@@ -28,7 +28,8 @@ CH = 256
 
 class Stage1Step:
     def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
-                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True):
+                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
+                 reuse_g_forward: Optional[bool] = None):
         self.G, self.D = G, D
         self.Dstack = D.Discriminators[0]
         self.lr, self.momentum, self.wd, self.wd_norm = lr, momentum, weight_decay, weight_decay_norm
@@ -65,6 +66,14 @@ class Stage1Step:
         # apply / backward, reductions, head) overlap the other group's tensor-bound GEMMs -- the persistent GEMM CTAs leave enough
         # registers / shared memory per SM for the small elementwise CTAs to co-reside.
         self.overlap = overlap
+        # The reference evaluates G(lr) twice per step -- detached for the D phase (:341-346), with a graph for the G phase (:390-395) --
+        # with the SAME generator weights (G's optimiser only steps at the end of the G phase) and the same input, and G has no
+        # normalisation, dropout or other state: the two evaluations are bit-identical.  One forward (kept for the backward) serves both.
+        # AFIGAN_REUSE_G_FORWARD=0 restores the literal second evaluation.
+        if reuse_g_forward is None:
+            import os
+            reuse_g_forward = os.environ.get("AFIGAN_REUSE_G_FORWARD", "1") != "0"
+        self.reuse_g_forward = reuse_g_forward
         self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap else []
         self._pack_g()
         self._pack_d()
@@ -238,7 +247,8 @@ class Stage1Step:
 
         # ------------------------------ D phase (stage1_trainer.py:334-381)
         N.check(lib.afi_zero(self.d_acc.data_ptr(), self.d_acc.numel(), st()))
-        trs = self._g_forward(lr_feats, hr_feats, False, "d")                       # G(lr).detach(), cropped
+        # G(lr).detach(), cropped
+        trs = self._g_forward(lr_feats, hr_feats, True, "g") if self.reuse_g_forward else self._g_forward(lr_feats, hr_feats, False, "d")
         xs, tags = [], []
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             xs += [hi[:, :, :tr.size(2), :tr.size(3)], tr]                          # D0(hr) BEFORE D0(tr)  (:349-350)
@@ -255,7 +265,8 @@ class Stage1Step:
 
         # ------------------------------ G phase (stage1_trainer.py:384-433)
         N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
-        trs = self._g_forward(lr_feats, hr_feats, True, "g")
+        if not self.reuse_g_forward:
+            trs = self._g_forward(lr_feats, hr_feats, True, "g")
         xs, tags = [], []
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             xs += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                          # D0(tr) BEFORE D0(hr) here (:399-400)

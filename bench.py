@@ -52,10 +52,11 @@ def synthetic_features(batch, rank, lr_shapes=C1_LR_SHAPES, hr_shapes=C1_HR_SHAP
     return lr, hr
 
 
-def stage1_step_flops(lr_px, hr_px):
-    """2 G fwd + 1 G bwd (no input grad) + 4 D fwd + 2 D bwd (no input grad): SURVEY.md §8d."""
+def stage1_step_flops(lr_px, hr_px, g_forwards=2):
+    """2 G fwd + 1 G bwd (no input grad) + 4 D fwd + 2 D bwd (no input grad): SURVEY.md §8d.  g_forwards=1: what the step EXECUTES when the
+    two bit-identical G(lr) evaluations of the reference (same weights, same input, no state in G) share one forward pass."""
     g, d = G_FWD_FLOP_PER_INPUT_PX, D_FWD_FLOP_PER_PX
-    return 2 * g * lr_px + (2 * g - 1_179_648) * lr_px + 4 * d * hr_px + 2 * (2 * d - 2_359_296) * hr_px
+    return g_forwards * g * lr_px + (2 * g - 1_179_648) * lr_px + 4 * d * hr_px + 2 * (2 * d - 2_359_296) * hr_px
 
 
 def peaks():
@@ -312,7 +313,9 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    flops_step = stage1_step_flops(PER_GPU_BATCH * sum(h * w for h, w in C1_LR_SHAPES), PER_GPU_BATCH * sum(h * w for h, w in C1_HR_SHAPES))
+    lr_px, hr_px = PER_GPU_BATCH * sum(h * w for h, w in C1_LR_SHAPES), PER_GPU_BATCH * sum(h * w for h, w in C1_HR_SHAPES)
+    flops_ref = stage1_step_flops(lr_px, hr_px)                                            # the reference's op count
+    flops_step = stage1_step_flops(lr_px, hr_px, 1 if step.reuse_g_forward else 2)        # what this step executes
     cpu = cpu_baseline() if (world == 1 and not args.no_cpu_baseline) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,6 +324,10 @@ def run_ours(args):
                        "parallelism": f"dp{world}", "operand_mode": precision,
                        "l2": "no flush needed: per-step inputs (231 MB fp32) and activations (several GB) exceed the 126 MB L2"},
             "step_tflops_per_gpu": flops_step / (ms_step * 1e-3) / 1e12,
+            "step_flops": {"executed": flops_step, "reference_op_count": flops_ref,
+                           "note": "the reference evaluates G(lr) twice per step with identical weights and inputs (detached for the D phase, with a graph "
+                                   "for the G phase); this step evaluates it once and uses the bit-identical result in both phases"
+                                   if step.reuse_g_forward else "literal: two G(lr) evaluations per step"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * 8 * 4},
             "gpu_launches": launches, "roofline": roof}

@@ -1,5 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-python tools/profile_one.py 2 1024 1024 200 336 3 && \
-ncu --set full --clock-control none --import-source on -k regex:k_conv_halo -s 1 -c 1 -f -o gpurun_out/r2_conv3_pair python tools/profile_one.py 2 1024 1024 200 336 3 > gpurun_out/ncu_conv3_pair.log 2>&1
-echo "ncu exit $?"
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for r in 0 1; do AFIGAN_REUSE_G_FORWARD=$r timeout 300 python tools/quick_time.py bf16 10 2>&1 | tail -1; done

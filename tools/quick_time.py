@@ -32,6 +32,6 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
-fl = O.stage1_step_flops(2 * 23282, 2 * 89523)
+fl = O.stage1_step_flops(2 * 23282, 2 * 89523, 1 if step.reuse_g_forward else 2)
 print(f"[{precision}] {ms:.2f} ms/step  {2000.0 / ms:.2f} img/s  {fl / ms / 1e9:.1f} TFLOP/s  launches/step {native.lib().afi_launch_count(0) / steps:.0f}"
       f"  mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
