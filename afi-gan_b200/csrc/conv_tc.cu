@@ -46,6 +46,7 @@ struct TileP {                        // per problem
     int TH, TW, tiles_x, tiles_y;     // spatial patch and patch grid per image
     int begin;                        // conv: first work item (M tile x N tile) / wgrad: first K tile of this problem
     int prob;                         // index into ConvArgs.p / WgradArgs.p (problems are scheduled largest first)
+    int orient;                       // halo kernels: 0 = 16 rows x 8 columns (8-pixel groups run along x), 1 = 8 rows x 16 columns (along y)
 };
 struct Tiling {
     int bn, n_tiles;                  // N tile (multiple of 16, <= 256)
@@ -358,7 +359,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             if (mt >= m_tiles) { mt = m_tiles - 1; tile_valid = false; }
         }
         int img = mt / tiles_per_img, r = mt % tiles_per_img;
-        const int ty = row / tp_.TW, tx = row % tp_.TW;
+        const int ty = tp_.orient ? (row & 7) : row / tp_.TW, tx = tp_.orient ? (row >> 3) : row % tp_.TW;
         int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
         const bool ok = tile_valid && (y < pr.H) && (x < pr.W);
         const int n0 = nt * tl.bn;
@@ -624,7 +625,7 @@ struct SmemH {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
-struct HaloTile { int prob, img, x0, y0, n0; };
+struct HaloTile { int prob, img, c1, c2, n0; };      // c1 / c2: TMA coordinates of the halo's first pixel along its fast / slow axis
 
 template <int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
@@ -695,7 +696,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 }
                 const int r = mt % tiles_per_img;
                 h.prob = tp_.prob; h.img = mt / tiles_per_img;
-                h.y0 = (r / tp_.tiles_x) * HALO_TH; h.x0 = (r % tp_.tiles_x) * HALO_TW; h.n0 = nt * tl.bn;
+                const int y0 = (r / tp_.tiles_x) * tp_.TH - 1, x0 = (r % tp_.tiles_x) * tp_.TW - 1;
+                h.c1 = tp_.orient ? y0 : x0; h.c2 = tp_.orient ? x0 : y0; h.n0 = nt * tl.bn;
             };
             auto issue_a = [&](const HaloTile& h, int view, int kc) {
                 mbar_wait_t(bar_ae + 8 * ai, aph ^ 1, 21, w_ae, dbg_on);
@@ -705,10 +707,10 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 if (elect_one()) {
                     if (PAIR) {
                         if (leader) mbar_expect_tx(fb, 2 * HALO_BYTES);
-                        tma_load_4d_pair(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                        tma_load_4d_pair(amap, fb, dst, kc * 64, h.c1, h.c2, h.img);
                     } else {
                         mbar_expect_tx(fb, HALO_BYTES);
-                        tma_load_4d(amap, fb, dst, kc * 64, h.x0 - 1, h.y0 - 1, h.img);
+                        tma_load_4d(amap, fb, dst, kc * 64, h.c1, h.c2, h.img);
                     }
                 }
                 __syncwarp();
@@ -764,12 +766,15 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
             int as = 0; uint32_t aphase = 0;
             const uint32_t idesc = make_idesc(tl.bn, 0, 0, PAIR ? 256 : 128);
-            const uint64_t adesc0 = make_desc(0, 16, (HALO_TW + 2) * 128), bdesc0 = make_desc(0, 16, 1024);
+            const uint64_t adesc0 = make_desc(0, 16, 10 * 128), bdesc0 = make_desc(0, 16, 1024);
             const uint32_t bar_af = smem_u32(&s.a_full[0]), bar_ae = smem_u32(&s.a_empty[0]);
             const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
             const int cin = a.cin;
             auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            int ti = 0;
             for (int item = item0; item < total; item += item_stride) {
+                while (item >= tl.p[ti + 1].begin) ti++;
+                const bool orient = tl.p[ti].orient != 0;
                 mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 23, w_acc, dbg_on);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * ACC_COLS;
@@ -782,7 +787,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                     const uint32_t abase = a0 + ai * HALO_SLOT;
 #pragma unroll
                     for (int j = 0; j < 9; j++) {
-                        const uint32_t aaddr = abase + (uint32_t)(((j / 3) * (HALO_TW + 2) + (j % 3)) * 128);
+                        // tap j = (dy, dx) = (j/3 - 1, j%3 - 1): shift of dy halo lines + dx pixels (orient 0) or dx lines + dy pixels (orient 1)
+                        const uint32_t aaddr = abase + (orient ? (uint32_t)(((j % 3) * 10 + (j / 3)) * 128) : (uint32_t)(((j / 3) * 10 + (j % 3)) * 128));
                         const uint32_t baddr = b0 + bi * b_slot;
                         mbar_wait_t(bar_bf + 8 * bi, bph, 25, w_bf, dbg_on);
                         tc_fence_after();
@@ -968,6 +974,13 @@ static int encode_map(afi_ctx* ctx, CUtensorMap* m, void* ptr, int rank, const c
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AFI_ERR_CUDA; }
     return AFI_OK;
 }
+// halo box {64 ch, 10, 18, 1}; orient 1 swaps the roles of x and y (the 10-pixel axis, along which the 8-pixel swizzle groups run, is y)
+static int encode_view_halo(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int W, int H, int N, int orient) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(orient ? H : W), (cuuint64_t)(orient ? W : H), (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)(orient ? v.sy : v.sx) * 2, (cuuint64_t)(orient ? v.sx : v.sy) * 2, (cuuint64_t)v.sn * 2};
+    cuuint32_t box[4] = {64, 10, 18, 1};
+    return encode_map(ctx, m, v.ptr, 4, dims, strides, box);
+}
 static int encode_view(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int W, int H, int N, int TW, int TH) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)v.sx * 2, (cuuint64_t)v.sy * 2, (cuuint64_t)v.sn * 2};
@@ -999,13 +1012,10 @@ static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
 
 static int g_halo_dyn_max[2] = {0, 0};
 // AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tiles, one CTA per tile; 2: halo tiles on CTA pairs (cta_group::2)
-static int halo_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("AFIGAN_CONV_HALO");
-        mode = e ? atoi(e) : 2;
-        if (mode < 0 || mode > 2) mode = 2;
-    }
+static int halo_mode() {      // read on every call (tests switch variants in-process)
+    const char* e = getenv("AFIGAN_CONV_HALO");
+    int mode = e ? atoi(e) : 2;
+    if (mode < 0 || mode > 2) mode = 2;
     return mode;
 }
 // the halo kernels take standard tap sets only: per view the nine taps (dy, dx) = (-1,-1) .. (1,1) in row-major order on consecutive slabs
@@ -1114,16 +1124,22 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         const ConvProb& pr = a.p[order[oi]];
         if (size[order[oi]] == 0) continue;
         TileP& t = tl.p[np];
-        if (hmode) { t.TH = HALO_TH; t.TW = HALO_TW; }
-        else pick_patch(pr.H, pr.W, 128, &t.TH, &t.TW);
+        t.orient = 0;
+        if (hmode) {     // 16 x 8 or 8 x 16 patches, whichever pads the level less
+            const long long n0 = (long long)((pr.H + 15) / 16) * ((pr.W + 7) / 8), n1 = (long long)((pr.H + 7) / 8) * ((pr.W + 15) / 16);
+            t.orient = n1 < n0 ? 1 : 0;
+            t.TH = t.orient ? 8 : 16; t.TW = t.orient ? 16 : 8;
+        } else pick_patch(pr.H, pr.W, 128, &t.TH, &t.TW);
         t.tiles_x = (pr.W + t.TW - 1) / t.TW;
         t.tiles_y = (pr.H + t.TH - 1) / t.TH;
         t.begin = begin;
         t.prob = order[oi];
         const int m_tiles = pr.N * t.tiles_x * t.tiles_y;
         begin += (pair ? (m_tiles + 1) / 2 : m_tiles) * tl.n_tiles;
-        const int bw = hmode ? t.TW + 2 : t.TW, bh = hmode ? t.TH + 2 : t.TH;
-        for (int v = 0; v < nviews; v++) AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, bw, bh));
+        for (int v = 0; v < nviews; v++) {
+            if (hmode) AFI_TRY(encode_view_halo(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.orient));
+            else AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.TW, t.TH));
+        }
         np++;
     }
     tl.nprob = np;

@@ -65,3 +65,40 @@ def test_strided_and_channels_last_inputs():
     assert rel(y, ref) < 2e-5
     y2 = conv3x3(crop.contiguous().cuda().to(memory_format=torch.channels_last), wt.cuda(), None, False, "fp32").cpu()
     assert rel(y2, ref) < 2e-5
+
+
+# The three tcgen05 convolution kernels must agree with the oracle op on every shape, whichever the library would pick by default:
+# per-tap tiles (AFIGAN_CONV_HALO=0), halo tiles on single CTAs (1), halo tiles on CTA pairs for every K (2 + AFIGAN_PAIR_ALL).
+VARIANTS = {
+    "per_tap": {"AFIGAN_CONV_HALO": "0"},
+    "halo": {"AFIGAN_CONV_HALO": "1"},
+    "pair": {"AFIGAN_CONV_HALO": "2", "AFIGAN_PAIR_ALL": "1"},
+}
+VARIANT_SHAPES = SHAPES + [
+    (1, 512, 512, 16, 8),       # exactly one 16 x 8 patch: a pair with a masked duplicate tile
+    (1, 512, 256, 8, 16),       # one 8 x 16 patch (the other orientation)
+    (3, 256, 256, 17, 9),       # odd tile counts, ragged in both directions
+    (1, 1024, 1024, 25, 42),    # long K, four N tiles, 8 x 16 orientation
+    (2, 64, 64, 5, 40),         # wide and flat
+]
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("shape", VARIANT_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_kernel_variants(shape, variant, monkeypatch):
+    from afigan.functional import conv3x3, conv3x3_backward
+    for k, v in VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    n, cin, cout, h, w = shape
+    g = torch.Generator().manual_seed(7 + hash(shape) % 1000)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g)).requires_grad_(True)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * 0.05).requires_grad_(True)
+    b = torch.randn(cout, generator=g)
+    dy = bf16_round(torch.randn(n, cout, h, w, generator=g))
+    ref = F.leaky_relu(F.conv2d(x, wt, b, padding=1), 0.2)
+    y = conv3x3(x.detach().cuda(), wt.detach().cuda(), b.cuda(), True, "bf16").cpu()
+    assert rel(y, bf16_round(ref)) < 2e-3, f"{variant} {shape}: forward rel err {rel(y, bf16_round(ref)):.3e}"
+    F.conv2d(x, wt, None, padding=1).backward(dy)
+    dw, dx = conv3x3_backward(x.detach().cuda(), dy.cuda(), wt.detach().cuda(), "bf16")
+    assert rel(dx, x.grad) < 3e-5, f"{variant} {shape}: dgrad rel err {rel(dx, x.grad):.3e}"
+    assert rel(dw, wt.grad) < 3e-5
