@@ -124,15 +124,19 @@ static GPacked g_packed_layout(int n_rdb) {
     L.total = o;
     return L;
 }
-struct GGradAcc {  // float offsets
-    size_t head_w, head_b, rdb_w[AFI_MAX_RDB][5], post_w, post_b, up_w, up_b, out_w, out_b, total;
+struct GGradAcc {  // float offsets.  rdb_g[r]: the four growth convs of dense block r share ONE [9][128][352] accumulator (row block i =
+                   // conv i+1; its columns >= 256 + 32 i are non-causal products nobody reads); rdb_w[r][4]: the fusion conv
+    size_t head_w, head_b, rdb_g[AFI_MAX_RDB], rdb_w[AFI_MAX_RDB][5], post_w, post_b, up_w, up_b, out_w, out_b, total;
 };
 static GGradAcc g_gradacc_layout(int n_rdb) {
     GGradAcc L; size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 63) / 64 * 64; return r; };
     L.head_w = take(9 * C * C); L.head_b = take(C);
-    for (int r = 0; r < n_rdb; r++)
-        for (int i = 0; i < 5; i++) L.rdb_w[r][i] = take((size_t)9 * (C + GR * i) * (i < 4 ? GR : C));
+    for (int r = 0; r < n_rdb; r++) {
+        L.rdb_g[r] = take((size_t)9 * (4 * GR) * (C + 3 * GR));
+        for (int i = 0; i < 4; i++) L.rdb_w[r][i] = L.rdb_g[r];
+        L.rdb_w[r][4] = take((size_t)9 * CB * C);
+    }
     L.post_w = take(9 * C * C); L.post_b = take(C);
     L.up_w = take(36 * C * C); L.up_b = take(C);
     L.out_w = take(9 * C * C); L.out_b = take(C);
@@ -158,7 +162,7 @@ static GWs g_ws_layout(void* base, int prec, int n, int h, int w, int n_rdb, int
     if (backward) {
         W.G0 = cv.take(P4 * C * es); W.G1 = cv.take(P4 * C * es); W.G2 = cv.take(P * C * es);
         W.dH1 = cv.take(P * C * 4); W.GA[0] = cv.take(P * CB * 4); W.GA[1] = cv.take(P * CB * 4);
-        W.DC5 = cv.take(P * C * es); W.GC = cv.take(P * GR * es); W.GH = cv.take(P * C * es);
+        W.DC5 = cv.take(P * C * es); W.GC = cv.take(P * 4 * GR * es); W.GH = cv.take(P * C * es);
         W.DXb = cv.take(P * C * 4);
         if (lat_c > 0) { W.LWD = cv.take((size_t)C * lat_c * es); W.LWG = cv.take((size_t)C * lat_c * 4); W.LDX = cv.take(P4 * lat_c * 4); }
     }
@@ -383,7 +387,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         d2[k] = {c.n, H2x, W2x};
         X0[k] = pview(W[k].X0, h, w, C); H1[k] = pview(W[k].H1, h, w, C); H2[k] = pview(W[k].H2, h, w, C); H3[k] = pview(W[k].H3, H2x, W2x, C);
         G0[k] = pview(W[k].G0, H2x, W2x, C); G1[k] = pview(W[k].G1, H2x, W2x, C); G2[k] = pview(W[k].G2, h, w, C);
-        dH1[k] = pview(W[k].dH1, h, w, C); DC5[k] = pview(W[k].DC5, h, w, C); GC[k] = pview(W[k].GC, h, w, GR); GH[k] = pview(W[k].GH, h, w, C);
+        dH1[k] = pview(W[k].dH1, h, w, C); DC5[k] = pview(W[k].DC5, h, w, C); GC[k] = pview(W[k].GC, h, w, 4 * GR); GH[k] = pview(W[k].GH, h, w, C);
     }
     GPacked L = g_packed_layout(nr);
     GGradAcc GL = g_gradacc_layout(nr);
@@ -488,15 +492,19 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         for (int i = 3; i >= 0; i--) {
             int cin_f = C + GR * i;
             // g = GA[:, slice_i] * lrelu'(c_{i+1})
+            // (the four masked growth gradients sit side by side in one 128-channel buffer: slice i feeds this dgrad, all four feed ONE
+            //  weight-gradient GEMM below)
             for (int k = 0; k < ncalls; k++)
-                AFI_TRY(ew_combine(GC[k], dt, pview_ch(GA[k], cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br[k], cin_f, es), dt, 0.2f, 1.f,
-                                   d1[k].n, d1[k].h, d1[k].w, GR, st));
-            AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, cin_f, GC, GR, gradacc + GL.rdb_w[r][i], st));
+                AFI_TRY(ew_combine(pview_ch(GC[k], GR * i, es), dt, pview_ch(GA[k], cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br[k], cin_f, es), dt,
+                                   0.2f, 1.f, d1[k].n, d1[k].h, d1[k].w, GR, st));
             conv_std(a, ncalls, d1, GR, cin_f, pk + L.rdb_d[r][i] * es);
             a.out_dt = DT_F32;
-            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GC[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
+            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview_ch(GC[k], GR * i, es); a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
+        // weight gradients of the four growth convs in one GEMM: dW[128 = 4 x 32 couts][352 cins] per tap fills a whole 128-row MMA tile
+        // (four separate 32-cout GEMMs use a quarter of it each); the non-causal blocks are computed and ignored
+        AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, C + 3 * GR, GC, 4 * GR, gradacc + GL.rdb_g[r], st));
         for (int k = 0; k < ncalls; k++) d_out[k] = GA[k];
         d_scale = 1.f; cur ^= 1;
     }
@@ -529,9 +537,11 @@ int afi_g_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_g
     int nk = prec_tc(prec) ? 1 : 0;
     if (g->head_w) AFI_TRY(unpack_wgrad(gradacc + GL.head_w, C, C, nk, 0, g->head_w, scale, accumulate, st));
     if (g->head_b) AFI_TRY(axpby_f32(gradacc + GL.head_b, g->head_b, C, scale, accumulate, st));
-    for (int r = 0; r < g->n_rdb; r++)
-        for (int i = 0; i < 5; i++)
-            if (g->rdb_w[r][i]) AFI_TRY(unpack_wgrad(gradacc + GL.rdb_w[r][i], i < 4 ? GR : C, C + GR * i, nk, 0, g->rdb_w[r][i], scale, accumulate, st));
+    for (int r = 0; r < g->n_rdb; r++) {
+        for (int i = 0; i < 4; i++)
+            if (g->rdb_w[r][i]) AFI_TRY(unpack_wgrad_sub(gradacc + GL.rdb_g[r], 4 * GR, C + 3 * GR, GR * i, GR, C + GR * i, nk, g->rdb_w[r][i], scale, accumulate, st));
+        if (g->rdb_w[r][4]) AFI_TRY(unpack_wgrad(gradacc + GL.rdb_w[r][4], C, CB, nk, 0, g->rdb_w[r][4], scale, accumulate, st));
+    }
     if (g->post_w) AFI_TRY(unpack_wgrad(gradacc + GL.post_w, C, C, nk, 0, g->post_w, scale, accumulate, st));
     if (g->post_b) AFI_TRY(axpby_f32(gradacc + GL.post_b, g->post_b, C, scale, accumulate, st));
     if (g->up_w) AFI_TRY(unpack_wgrad(gradacc + GL.up_w, C, C, nk, 1, g->up_w, scale, accumulate, st));

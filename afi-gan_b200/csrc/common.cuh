@@ -155,6 +155,8 @@ struct PackJob { const float* w; void* dst; int co, ci, mode, pad_; };
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st);
 // gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);
+// the [co][ci] sub-block starting at row co_off of a packed [slab][CO][CI] (nk) / [slab][CI][CO] gradient -> torch [co][ci][3][3]
+int unpack_wgrad_sub(const float* packed, int CO, int CI, int co_off, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st);
 int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st);
 int unpack_1x1(const float* packed, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st);
 // dx (contiguous NCHW) = dxb (NHWC fp32) + dy_scale * bilinear2x^T(dy)

@@ -1264,6 +1264,22 @@ int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv,
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
+__global__ void k_unpack_wgrad_sub(const float* __restrict__ packed, int CO, int CI, int co_off, int co, int ci, int nk, float* __restrict__ dst,
+                                   float scale, int accumulate, long long total) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int slab = (int)(i % 9); long long t = i / 9; int c_i = (int)(t % ci); int c_o = (int)(t / ci);
+    long long src = nk ? ((long long)slab * CO + co_off + c_o) * CI + c_i : ((long long)slab * CI + c_i) * CO + co_off + c_o;
+    float v = packed[src] * scale;
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+int unpack_wgrad_sub(const float* packed, int CO, int CI, int co_off, int co, int ci, int layout_nk, float* dst, float scale, int accumulate,
+                     cudaStream_t st) {
+    long long total = (long long)co * ci * 9;
+    k_unpack_wgrad_sub<<<cdiv(total, 256), 256, 0, st>>>(packed, CO, CI, co_off, co, ci, layout_nk, dst, scale, accumulate, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
 // 1x1 weight gradient: packed [ci][co] (KN) or [co][ci] (NK) -> torch [co][ci]
 __global__ void k_unpack_1x1(const float* __restrict__ packed, int co, int ci, int nk, float* __restrict__ dst, float scale, int accumulate) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
