@@ -773,6 +773,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             AFI_TRY(dhead_backward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], calls[k].dlogits, d[k].n, d[k].h, d[k].w, DC[3],
                                    gradacc + GL.w[3], gradacc + GL.b[3], pview(W[k].DY[2], d[k].h, d[k].w, DC[3]), st));
     }
+    bool stats_ready = false;     // layer i's two BatchNorm-backward reductions already came out of the dgrad GEMM that produced DY[i]
     for (int i = 2; i >= 0; i--) {
         const int co = DC[i + 1], ci = DC[i];
         void* sums_p[AFI_MAX_PROB]; double* s0[AFI_MAX_PROB]; double* s1[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
@@ -787,8 +788,10 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ);
         // each pass is one grouped launch over all calls
         if (!(tc && i == 2)) {      // (the tensor-core path did layer 3's BatchNorm backward in the fused head passes above)
-            AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
-            AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
+            if (!stats_ready) {
+                AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+                AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
+            }
             AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co,
                                        training ? 0 : 1, st));
         }
@@ -812,6 +815,19 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * es);
             a.out_dt = dt;
             for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].mask = X[k]; a.p[k].out = pview(W[k].DY[i - 1], d[k].h, d[k].w, ci); }
+            // opt-in (AFIGAN_FUSE_BWD_STATS=1): the long-K dgrads can also emit sum(dy) and sum(dy * xhat) of the layer below (its
+            // BatchNorm-backward reductions) from their epilogue.  Measured 0.4 ms/step SLOWER than the separate grouped reduction
+            // pass (42.7 vs 42.3 ms): the extra operand stream and shuffles cost the GEMM more than the 0.37 ms pass they replace.
+            static const int fuse_bwd = getenv("AFIGAN_FUSE_BWD_STATS") ? atoi(getenv("AFIGAN_FUSE_BWD_STATS")) : 0;
+            stats_ready = tc && fuse_bwd && 9 * co >= 4096;
+            if (stats_ready) {
+                AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+                a.stat_mode = 2;
+                for (int k = 0; k < ncalls; k++) {
+                    a.p[k].stat0 = W[k].sums; a.p[k].stat1 = W[k].sums + 1024;
+                    a.p[k].bnz = pview(W[k].Z[i - 1], d[k].h, d[k].w, ci); a.p[k].bn_mean = W[k].mean[i - 1]; a.p[k].bn_rstd = W[k].rstd[i - 1];
+                }
+            }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
     }
