@@ -764,9 +764,17 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             AFI_TRY(sum_f32(calls[k].dlogits, (long long)n * h * w, gradacc + GL.b[3], st));
             g.p[k].N = n; g.p[k].H = h; g.p[k].W = w; g.p[k].x = pview(W[k].A[3], h, w, DC[3]); g.p[k].dy = pview(W[k].G9, h, w, 16);
         }
-        for (int pass = 1; pass <= 2; pass++)
-            AFI_TRY(dhead_backward_group(pass, ncalls, g9f, Z3, DZ3, dt, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
-                                         gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
+        const void* g9b[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) g9b[k] = W[k].G9;
+        static const int head_mma = getenv("AFIGAN_DHEAD_MMA") ? atoi(getenv("AFIGAN_DHEAD_MMA")) : 1;
+        for (int pass = 1; pass <= 2; pass++) {
+            if (head_mma && dt == DT_BF16)
+                AFI_TRY(dhead_backward_group_mma(pass, ncalls, g9b, Z3, DZ3, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
+                                                 gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
+            else
+                AFI_TRY(dhead_backward_group(pass, ncalls, g9f, Z3, DZ3, dt, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
+                                             gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
+        }
         AFI_TRY(run_wgrad(ctx, prec, g, st));
     } else {
         for (int k = 0; k < ncalls; k++)   // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3

@@ -206,6 +206,11 @@ int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PVi
                          const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
                          double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st);
 
+// bf16 variant with the 9-tap product on warp-level tensor-core MMAs (g9: the bf16 [P][16] shifted head gradients)
+int dhead_backward_group_mma(int pass, int nprob, const void* const* g9, const PView* z3, const PView* dz3, const float* w4,
+                             const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
+                             double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st);
+
 template <typename T> struct dt_of;
 template <> struct dt_of<float> { static const int v = DT_F32; };
 template <> struct dt_of<bf16> { static const int v = DT_BF16; };

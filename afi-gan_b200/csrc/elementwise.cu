@@ -1126,6 +1126,143 @@ int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PVi
     return AFI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same two passes with the 9-tap product on the tensor cores (bf16 operand mode): dy[16 rows x 8 channels] = g9[16 x 16] * w4^T[16 x 8]
+// is one warp-level mma.sync.m16n8k16 (bf16 x bf16 -> fp32) instead of 9 x 128 FMAs, which turns the passes from FMA-bound into
+// HBM-bound.  The columns of the four MMAs a warp issues per 16-row block are PERMUTED (column j of MMA nb <-> channel
+// (j/2)*8 + nb*2 + j%2 of the warp's 32) so that the accumulator fragment of a thread is 8 CONSECUTIVE channels of two rows: z3 / dz3
+// move as 16-byte vectors.  Block = 8 warps = 256 channels (blockIdx.y) x a range of rows; g9 is the bf16 [P][16] tensor the dW4 GEMM uses.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int PASS>
+__global__ void __launch_bounds__(256, 2) k_dhead_bwd_mma(const __grid_constant__ DenseGroupD G, const float* __restrict__ w4,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* dgamma_acc, float* dbeta_acc, float slope, int eval_mode) {
+    constexpr int UNROLL = 2;            // 16-row blocks in flight per warp: 4 x 16 B of z3 per thread
+    const int kp = find_prob(G, blockIdx.x);
+    const DenseProbD& pr = G.p[kp];
+    const int C = G.C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane & 3, rl = lane >> 2;
+    const int cw = blockIdx.y * 256 + warp * 32;     // first channel of this warp
+    const int c0 = cw + q * 8;                       // this thread's 8 channels
+    const bf16* __restrict__ g9 = reinterpret_cast<const bf16*>(pr.a);
+    const bf16* __restrict__ z = reinterpret_cast<const bf16*>(pr.b);
+    bf16* __restrict__ dz = reinterpret_cast<bf16*>(pr.out);
+    if (PASS == 2 && (int)blockIdx.x == pr.block_begin) {     // d gamma = sum dy*xhat, d beta = sum dy: once per call and channel
+        const int c = blockIdx.y * 256 + threadIdx.x;
+        if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)pr.o1[c]);
+        if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)pr.o0[c]);
+    }
+    // B fragments: MMA nb, column n = rl  <->  channel cw + (rl/2)*8 + nb*2 + rl%2; rows k = 2q, 2q+1 (b0) and 2q+8, 2q+9 (b1) = taps
+    uint32_t bfr[4][2];
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {
+        const float* wc = w4 + (size_t)(cw + (rl >> 1) * 8 + nb * 2 + (rl & 1)) * 9;
+        const int k0 = 2 * q;
+        bfr[nb][0] = pack_bf16x2(wc[k0], wc[k0 + 1]);                    // taps 0..7
+        bfr[nb][1] = q == 0 ? pack_bf16x2(wc[8], 0.f) : 0u;              // tap 8; taps 9..15 do not exist
+    }
+    float mu[8], rs[8], ga[8], be[8], a0[8], a1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        mu[k] = pr.mean[c0 + k]; rs[k] = pr.rstd[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k];
+        if (PASS == 1) { a0[k] = 0.f; a1[k] = 0.f; }
+        else {
+            const float inv_m = 1.f / (float)pr.P;
+            a0[k] = eval_mode ? 0.f : (float)pr.o0[c0 + k] * inv_m; a1[k] = eval_mode ? 0.f : (float)pr.o1[c0 + k] * inv_m;
+        }
+    }
+    const long long r0 = (long long)(blockIdx.x - pr.block_begin) * pr.rows_per_block;
+    long long r1 = r0 + pr.rows_per_block;
+    if (r1 > pr.P) r1 = pr.P;
+    for (long long rb = r0; rb < r1; rb += 16 * UNROLL) {
+        uint4 zv[UNROLL][2];
+        uint32_t af[UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long r = rb + u * 16 + h * 8 + rl;
+                zv[u][h] = make_uint4(0, 0, 0, 0);
+                af[u][h] = 0; af[u][h + 2] = 0;
+                if (r < r1) {
+                    zv[u][h] = *reinterpret_cast<const uint4*>(z + r * C + c0);
+                    const uint32_t* gp = reinterpret_cast<const uint32_t*>(g9 + r * 16);
+                    af[u][h] = __ldg(gp + q); af[u][h + 2] = __ldg(gp + q + 4);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            float c[4][4];
+#pragma unroll
+            for (int nb = 0; nb < 4; nb++) { c[nb][0] = c[nb][1] = c[nb][2] = c[nb][3] = 0.f; mma_bf16_16816(c[nb], af[u], bfr[nb][0], bfr[nb][1]); }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long r = rb + u * 16 + h * 8 + rl;
+                const uint32_t zw[4] = {zv[u][h].x, zv[u][h].y, zv[u][h].z, zv[u][h].w};
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float zz = (k & 1) ? __uint_as_float(zw[k >> 1] & 0xffff0000u) : __uint_as_float(zw[k >> 1] << 16);
+                    float d = c[k >> 1][(k & 1) + 2 * h];
+                    const float xh = (zz - mu[k]) * rs[k];
+                    const float y = (zz - mu[k]) * rs[k] * ga[k] + be[k];      // == bn_apply's expression: sign(y) is the stored activation's sign
+                    d *= y > 0.f ? 1.f : slope;
+                    if (PASS == 1) { if (r < r1) { a0[k] += d; a1[k] = fmaf(d, xh, a1[k]); } }
+                    else o[k] = ga[k] * rs[k] * (d - a0[k] - xh * a1[k]);
+                }
+                if (PASS == 2 && r < r1) {
+                    uint4 ov;
+                    ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+                    *reinterpret_cast<uint4*>(dz + r * C + c0) = ov;
+                }
+            }
+        }
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) { a0[k] += __shfl_xor_sync(0xffffffffu, a0[k], o); a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o); }
+        }
+        if (rl == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { atomicAdd(pr.o0 + c0 + k, (double)a0[k]); atomicAdd(pr.o1 + c0 + k, (double)a1[k]); }
+        }
+    }
+}
+int dhead_backward_group_mma(int pass, int nprob, const void* const* g9, const PView* z3, const PView* dz3, const float* w4,
+                             const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
+                             double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st) {
+    AFI_REQUIRE(c % 256 == 0, "dhead_backward_group_mma: C must be a multiple of 256");
+    DenseGroupD G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob; G.C = c;
+    for (int k = 0; k < nprob; k++) {
+        G.p[k].a = g9[k]; G.p[k].b = z3[k].ptr; G.p[k].out = dz3[k].ptr; G.p[k].P = P[k]; G.p[k].mean = mean[k]; G.p[k].rstd = rstd[k];
+        G.p[k].o0 = s_dy[k]; G.p[k].o1 = s_dyx[k];
+    }
+    // rows per block: a multiple of 32 (two 16-row MMA blocks per iteration); ~600 row blocks x C/256 channel slabs
+    long long total = 0;
+    for (int k = 0; k < nprob; k++) total += P[k];
+    long long rows = (total / 600 + 31) / 32 * 32;
+    if (rows > 512) rows = 512;
+    if (rows < 32) rows = 32;
+    int b = 0;
+    for (int k = 0; k < nprob; k++) { G.p[k].block_begin = b; G.p[k].rows_per_block = (int)rows; b += (int)((P[k] + rows - 1) / rows); }
+    G.p[nprob].block_begin = b;
+    if (b == 0) return AFI_OK;
+    dim3 grid(b, c / 256);
+    if (pass == 1) k_dhead_bwd_mma<1><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+    else k_dhead_bwd_mma<2><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
 __global__ void k_sum_f32(const float* __restrict__ x, long long n, float* out) {
     double acc = 0.0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += (double)x[i];
