@@ -106,18 +106,27 @@ static void conv_std(ConvArgs& a, int nprob, const Dim3* d, int cin, int cout, c
 // =====================================================================================================
 static const int C = AFI_CH, GR = 32, CB = AFI_CH + 4 * 32;   // 256, growth 32, dense buffer width 384
 
-struct GPacked {   // element offsets into the packed weight buffer (dtype T)
-    size_t head_f, head_d, rdb_f[AFI_MAX_RDB][5], rdb_d[AFI_MAX_RDB][5], post_f, post_d, up_f, up_d, out_f, out_d, total;
+struct GPacked {   // element offsets into the packed weight buffer (dtype T).  Dgrad operands of a dense block: rdb_d[r][4] the fusion conv;
+                   // rdb_xd[r] = [9][256][128], the part of the four growth convs that reaches the block input x (gemm-cin = the four
+                   // 32-channel growth gradients side by side); rdb_cd[r][i], i = 1..3 = [9][32 i][32], the part of growth conv i+1 that
+                   // reaches the earlier growth channels
+    size_t head_f, head_d, rdb_f[AFI_MAX_RDB][5], rdb_d[AFI_MAX_RDB][5], rdb_xd[AFI_MAX_RDB], rdb_cd[AFI_MAX_RDB][4], post_f, post_d, up_f, up_d,
+        out_f, out_d, total;
 };
 static GPacked g_packed_layout(int n_rdb) {
     GPacked L; size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += (n + 127) / 128 * 128; return r; };
     L.head_f = take(9 * C * C); L.head_d = take(9 * C * C);
-    for (int r = 0; r < n_rdb; r++)
+    for (int r = 0; r < n_rdb; r++) {
         for (int i = 0; i < 5; i++) {
             size_t n = (size_t)9 * (C + GR * i) * (i < 4 ? GR : C);
-            L.rdb_f[r][i] = take(n); L.rdb_d[r][i] = take(n);
+            L.rdb_f[r][i] = take(n);
+            L.rdb_d[r][i] = i == 4 ? take(n) : 0;
         }
+        L.rdb_xd[r] = take((size_t)9 * C * 4 * GR);
+        L.rdb_cd[r][0] = 0;
+        for (int i = 1; i < 4; i++) L.rdb_cd[r][i] = take((size_t)9 * GR * i * GR);
+    }
     L.post_f = take(9 * C * C); L.post_d = take(9 * C * C);
     L.up_f = take(36 * C * C); L.up_d = take(36 * C * C);
     L.out_f = take(9 * C * C); L.out_d = take(9 * C * C);
@@ -245,13 +254,22 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     char* b = (char*)packed;
     PackJob jobs[AFI_MAX_PACK]; int nj = 0;     // forward + dgrad layouts of every conv: one grouped launch
     auto add = [&](const float* w, int co, int ci, int kind, size_t off) {
-        PackJob& j = jobs[nj++]; j.w = w; j.dst = b + off * es; j.co = co; j.ci = ci; j.mode = pm(prec, kind); j.pad_ = 0;
+        PackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j)); j.w = w; j.dst = b + off * es; j.co = co; j.ci = ci; j.mode = pm(prec, kind);
+    };
+    auto add_sub = [&](const float* w, int co, int ci, size_t off, int n0, int ncnt, int koff, int ktot) {
+        PackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j)); j.w = w; j.dst = b + off * es; j.co = co; j.ci = ci; j.mode = pm(prec, 1);
+        j.sub = 1; j.n0 = n0; j.ncnt = ncnt; j.koff = koff; j.ktot = ktot;
     };
     add(p->head_w, C, C, 0, L.head_f); add(p->head_w, C, C, 1, L.head_d);
     for (int r = 0; r < p->n_rdb; r++)
         for (int i = 0; i < 5; i++) {
             int co = i < 4 ? GR : C, ci = C + GR * i;
-            add(p->rdb_w[r][i], co, ci, 0, L.rdb_f[r][i]); add(p->rdb_w[r][i], co, ci, 1, L.rdb_d[r][i]);
+            add(p->rdb_w[r][i], co, ci, 0, L.rdb_f[r][i]);
+            if (i == 4) add(p->rdb_w[r][i], co, ci, 1, L.rdb_d[r][i]);
+            else {
+                add_sub(p->rdb_w[r][i], GR, ci, L.rdb_xd[r], 0, C, GR * i, 4 * GR);                  // x part: all four convs, one operand
+                if (i > 0) add_sub(p->rdb_w[r][i], GR, ci, L.rdb_cd[r][i], C, GR * i, 0, GR);       // growth part of conv i+1
+            }
         }
     add(p->post_w, C, C, 0, L.post_f); add(p->post_w, C, C, 1, L.post_d);
     add(p->up_w, C, C, 2, L.up_f); add(p->up_w, C, C, 3, L.up_d);
@@ -497,11 +515,20 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             for (int k = 0; k < ncalls; k++)
                 AFI_TRY(ew_combine(pview_ch(GC[k], GR * i, es), dt, pview_ch(GA[k], cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br[k], cin_f, es), dt,
                                    0.2f, 1.f, d1[k].n, d1[k].h, d1[k].w, GR, st));
-            conv_std(a, ncalls, d1, GR, cin_f, pk + L.rdb_d[r][i] * es);
-            a.out_dt = DT_F32;
-            for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview_ch(GC[k], GR * i, es); a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
-            AFI_TRY(run_conv(ctx, prec, a, st));
+            if (i > 0) {      // the part of this conv's dgrad that the remaining masks depend on: growth channels [256, 256 + 32 i)
+                conv_std(a, ncalls, d1, GR, GR * i, pk + L.rdb_cd[r][i] * es);
+                a.out_dt = DT_F32;
+                for (int k = 0; k < ncalls; k++) {
+                    a.p[k].in[0] = pview_ch(GC[k], GR * i, es); a.p[k].accin = pview_ch(GA[k], C, 4); a.p[k].out = pview_ch(GA[k], C, 4);
+                }
+                AFI_TRY(run_conv(ctx, prec, a, st));
+            }
         }
+        // ... and the part that reaches the block input x, for all four growth convs in ONE GEMM (K = 4 x 32 channels per tap, N = 256)
+        conv_std(a, ncalls, d1, 4 * GR, C, pk + L.rdb_xd[r] * es);
+        a.out_dt = DT_F32;
+        for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GC[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
+        AFI_TRY(run_conv(ctx, prec, a, st));
         // weight gradients of the four growth convs in one GEMM: dW[128 = 4 x 32 couts][352 cins] per tap fills a whole 128-row MMA tile
         // (four separate 32-cout GEMMs use a quarter of it each); the non-causal blocks are computed and ignored
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, C + 3 * GR, GC, 4 * GR, gradacc + GL.rdb_g[r], st));
@@ -618,8 +645,11 @@ int afi_d_pack(afi_ctx* ctx, int prec, const afi_d_params* p, void* packed, void
     int dt = prec_dt(prec); size_t es = dt_size(dt);
     PackJob jobs[6];
     for (int i = 0; i < 3; i++) {
-        jobs[2 * i] = {p->w[i], (char*)packed + L.f[i] * es, DC[i + 1], DC[i], pm(prec, 0), 0};
-        jobs[2 * i + 1] = {p->w[i], (char*)packed + L.d[i] * es, DC[i + 1], DC[i], pm(prec, 1), 0};
+        memset(&jobs[2 * i], 0, 2 * sizeof(PackJob));
+        jobs[2 * i].w = jobs[2 * i + 1].w = p->w[i];
+        jobs[2 * i].dst = (char*)packed + L.f[i] * es; jobs[2 * i + 1].dst = (char*)packed + L.d[i] * es;
+        jobs[2 * i].co = jobs[2 * i + 1].co = DC[i + 1]; jobs[2 * i].ci = jobs[2 * i + 1].ci = DC[i];
+        jobs[2 * i].mode = pm(prec, 0); jobs[2 * i + 1].mode = pm(prec, 1);
     }
     AFI_TRY(pack_weights_group(6, jobs, dt, st));
     if (prec_tc(prec)) AFI_TRY(dhead_pack_tc(p->w[3], DC[3], (char*)packed + L.hf * es, (char*)packed + L.hb * es, st));

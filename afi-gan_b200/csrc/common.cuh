@@ -149,9 +149,11 @@ enum PackMode { PACK_FWD_KN = 0, PACK_FWD_NK = 1, PACK_DGRAD_KN = 2, PACK_DGRAD_
                 PACK_DECONV_FWD_KN = 4, PACK_DECONV_FWD_NK = 5, PACK_DECONV_DGRAD_KN = 6, PACK_DECONV_DGRAD_NK = 7,
                 PACK_1X1_KN = 8, PACK_1X1_NK = 9, PACK_1X1_DGRAD_KN = 10, PACK_1X1_DGRAD_NK = 11 };
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st);
-#define AFI_MAX_PACK 48
+#define AFI_MAX_PACK 64
 #define AFI_MAX_SGD 48
-struct PackJob { const float* w; void* dst; int co, ci, mode, pad_; };
+// sub != 0 (dgrad modes only): pack the gemm-cout range [n0, n0 + ncnt) of this weight into the gemm-cin slice [koff, koff + co) of a
+// destination whose gemm-cin extent is ktot (several convs that read the same gradient buffer share one packed operand)
+struct PackJob { const float* w; void* dst; int co, ci, mode, sub; int n0, ncnt, koff, ktot; };
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st);
 // gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);

@@ -1334,6 +1334,19 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, in
     }
     dst[i] = (T)v;
 }
+// dgrad sub-block: dst[slab][n - n0][koff + k] (NK) or dst[slab][koff + k][n - n0] (KN) = w[k][n][8 - slab], k < co, n0 <= n < n0 + ncnt
+template <typename T>
+__device__ __forceinline__ void pack_sub(const PackJob& q, long long i) {
+    const int nk = q.mode & 1;
+    const int inner = (int)(i % (nk ? q.co : q.ncnt));
+    const long long t2 = i / (nk ? q.co : q.ncnt);
+    const int outer = (int)(t2 % (nk ? q.ncnt : q.co));
+    const int slab = (int)(t2 / (nk ? q.ncnt : q.co));
+    const int k = nk ? inner : outer, n = nk ? outer : inner;
+    const float v = q.w[((long long)k * q.ci + q.n0 + n) * 9 + (8 - slab)];
+    const long long d = nk ? ((long long)slab * q.ncnt + n) * q.ktot + q.koff + k : ((long long)slab * q.ktot + q.koff + k) * q.ncnt + n;
+    reinterpret_cast<T*>(q.dst)[d] = (T)v;
+}
 template <typename T>
 __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1359,10 +1372,14 @@ __global__ void k_pack_group(const __grid_constant__ PackGroup G) {
     while (k + 1 < G.njobs && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
     const PackJob& q = G.j[k];
     long long i = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x;
-    const long long total = pack_total_dev(q.co, q.ci, q.mode);
+    const long long total = q.sub ? (long long)9 * q.co * q.ncnt : pack_total_dev(q.co, q.ci, q.mode);
 #pragma unroll
-    for (int u = 0; u < 4; u++, i += 256)
-        if (i < total) pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
+    for (int u = 0; u < 4; u++, i += 256) {
+        if (i < total) {
+            if (q.sub) pack_sub<T>(q, i);
+            else pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
+        }
+    }
 }
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st) {
     AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_PACK, "pack_weights_group: %d jobs (max %d)", njobs, AFI_MAX_PACK);
@@ -1370,7 +1387,11 @@ int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t 
     PackGroup G; memset(&G, 0, sizeof(G));
     G.njobs = njobs;
     int b = 0;
-    for (int k = 0; k < njobs; k++) { G.j[k] = jobs[k]; G.block_begin[k] = b; b += cdiv(pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode), 1024); }
+    for (int k = 0; k < njobs; k++) {
+        G.j[k] = jobs[k]; G.block_begin[k] = b;
+        if (jobs[k].sub) AFI_REQUIRE((jobs[k].mode >> 1) == 1, "pack_weights_group: sub-block packing is a dgrad mode");
+        b += cdiv(jobs[k].sub ? (long long)9 * jobs[k].co * jobs[k].ncnt : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode), 1024);
+    }
     G.block_begin[njobs] = b;
     if (dst_dt == DT_F32) k_pack_group<float><<<b, 256, 0, st>>>(G);
     else k_pack_group<bf16><<<b, 256, 0, st>>>(G);
