@@ -796,7 +796,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         }
         const void* g9b[AFI_MAX_PROB];
         for (int k = 0; k < ncalls; k++) g9b[k] = W[k].G9;
-        static const int head_mma = getenv("AFIGAN_DHEAD_MMA") ? atoi(getenv("AFIGAN_DHEAD_MMA")) : 1;
+        const int head_mma = getenv("AFIGAN_DHEAD_MMA") ? atoi(getenv("AFIGAN_DHEAD_MMA")) : 1;     // read per call: tests switch in-process
         for (int pass = 1; pass <= 2; pass++) {
             if (head_mma && dt == DT_BF16)
                 AFI_TRY(dhead_backward_group_mma(pass, ncalls, g9b, Z3, DZ3, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
@@ -856,7 +856,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             // opt-in (AFIGAN_FUSE_BWD_STATS=1): the long-K dgrads can also emit sum(dy) and sum(dy * xhat) of the layer below (its
             // BatchNorm-backward reductions) from their epilogue.  Measured 0.4 ms/step SLOWER than the separate grouped reduction
             // pass (42.7 vs 42.3 ms): the extra operand stream and shuffles cost the GEMM more than the 0.37 ms pass they replace.
-            static const int fuse_bwd = getenv("AFIGAN_FUSE_BWD_STATS") ? atoi(getenv("AFIGAN_FUSE_BWD_STATS")) : 0;
+            const int fuse_bwd = getenv("AFIGAN_FUSE_BWD_STATS") ? atoi(getenv("AFIGAN_FUSE_BWD_STATS")) : 0;
             stats_ready = tc && fuse_bwd && 9 * co >= 4096;
             if (stats_ready) {
                 AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
