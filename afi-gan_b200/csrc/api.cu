@@ -411,6 +411,8 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     GGradAcc GL = g_gradacc_layout(nr);
     const char* pk = (const char*)packed;
     ConvArgs a;
+    int dn[AFI_MAX_PROB], dh[AFI_MAX_PROB], dw_[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) { dn[k] = d1[k].n; dh[k] = d1[k].h; dw_[k] = d1[k].w; }
 
     // dL/d(branch) on the full 2h x 2w grid: the crop's complement gets zero gradient
     for (int k = 0; k < ncalls; k++) {
@@ -496,12 +498,12 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             const int n = d1[k].n, h = d1[k].h, w = d1[k].w;
             Br[k] = pview(W[k].B[r], h, w, CB);
             GA[k] = pview(W[k].GA[cur], h, w, CB);
-            // dc5 = 0.2 * d_out (GEMM operand in storage dtype)
-            AFI_TRY(ew_combine(DC5[k], dt, d_out[k], DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, 0.2f * d_scale, n, h, w, C, st));
-            // GA[:, 0:256] = d_out, GA[:, 256:384] = 0; the conv5 dgrad below accumulates over all 384 channels
+            // GA[:, 256:384] = 0 (the conv5 dgrad below accumulates over all 384 channels)
             AFI_CUDA(cudaMemsetAsync(W[k].GA[cur], 0, (size_t)n * h * w * CB * 4, st));
-            AFI_TRY(ew_combine(GA[k], DT_F32, d_out[k], DT_F32, pview_null(), 0, pview_null(), 0, 0.2f, d_scale, n, h, w, C, st));
         }
+        // dc5 = 0.2 * d_out (GEMM operand in storage dtype); GA[:, 0:256] = d_out -- one grouped launch each over all levels
+        AFI_TRY(ew_combine_group(ncalls, DC5, dt, d_out, DT_F32, nullptr, 0, nullptr, 0, 0.2f, 0.2f * d_scale, dn, dh, dw_, C, st));
+        AFI_TRY(ew_combine_group(ncalls, GA, DT_F32, d_out, DT_F32, nullptr, 0, nullptr, 0, 0.2f, d_scale, dn, dh, dw_, C, st));
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, CB, DC5, C, gradacc + GL.rdb_w[r][4], st));
         conv_std(a, ncalls, d1, C, CB, pk + L.rdb_d[r][4] * es);
         a.out_dt = DT_F32;
@@ -512,9 +514,9 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             // g = GA[:, slice_i] * lrelu'(c_{i+1})
             // (the four masked growth gradients sit side by side in one 128-channel buffer: slice i feeds this dgrad, all four feed ONE
             //  weight-gradient GEMM below)
-            for (int k = 0; k < ncalls; k++)
-                AFI_TRY(ew_combine(pview_ch(GC[k], GR * i, es), dt, pview_ch(GA[k], cin_f, 4), DT_F32, pview_null(), 0, pview_ch(Br[k], cin_f, es), dt,
-                                   0.2f, 1.f, d1[k].n, d1[k].h, d1[k].w, GR, st));
+            PView gdst[AFI_MAX_PROB], gsrc[AFI_MAX_PROB], gmask[AFI_MAX_PROB];
+            for (int k = 0; k < ncalls; k++) { gdst[k] = pview_ch(GC[k], GR * i, es); gsrc[k] = pview_ch(GA[k], cin_f, 4); gmask[k] = pview_ch(Br[k], cin_f, es); }
+            AFI_TRY(ew_combine_group(ncalls, gdst, dt, gsrc, DT_F32, nullptr, 0, gmask, dt, 0.2f, 1.f, dn, dh, dw_, GR, st));
             if (i > 0) {      // the part of this conv's dgrad that the remaining masks depend on: growth channels [256, 256 + 32 i)
                 conv_std(a, ncalls, d1, GR, GR * i, pk + L.rdb_cd[r][i] * es);
                 a.out_dt = DT_F32;
@@ -536,9 +538,11 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         d_scale = 1.f; cur ^= 1;
     }
     // head conv: g_head = (d_out + dH1) * lrelu'(h0)
-    for (int k = 0; k < ncalls; k++)
-        AFI_TRY(ew_combine(GH[k], dt, d_out[k], DT_F32, dH1[k], DT_F32, pview(W[k].B[0], d1[k].h, d1[k].w, CB), dt, 0.2f, 1.f, d1[k].n, d1[k].h,
-                           d1[k].w, C, st));
+    {
+        PView hmask[AFI_MAX_PROB];
+        for (int k = 0; k < ncalls; k++) hmask[k] = pview(W[k].B[0], d1[k].h, d1[k].w, CB);
+        AFI_TRY(ew_combine_group(ncalls, GH, dt, d_out, DT_F32, dH1, DT_F32, hmask, dt, 0.2f, 1.f, dn, dh, dw_, C, st));
+    }
     AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, X0, C, GH, C, gradacc + GL.head_w, st));
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(GH[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.head_b, st));
     if (calls[0].dx) {

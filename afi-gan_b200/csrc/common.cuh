@@ -140,6 +140,8 @@ template <typename T> int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int s
 // dst = scale * (a + b) * mask ; a,b f32 or T views (dtype flags), mask T view (optional), dst T or f32
 int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt, float mask_slope,
                float scale, int n, int h, int w, int c, cudaStream_t st);
+int ew_combine_group(int nprob, const PView* dst, int dst_dt, const PView* a, int a_dt, const PView* b, int b_dt, const PView* mask, int mask_dt,
+                     float mask_slope, float scale, const int* n, const int* h, const int* w, int c, cudaStream_t st);
 // per-channel sums over all pixels of a view: sum[c] += x, sumsq[c] += x*x (double accumulators, sumsq may be null)
 int col_stats(PView x, int dt, int n, int h, int w, int c, double* sum, double* sumsq, cudaStream_t st);
 // float accumulate variant for bias gradients: out[c] += sum_p x[p][c]

@@ -228,6 +228,46 @@ int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PVie
     return AFI_OK;
 }
 
+// the same op over up to AFI_MAX_PROB problems (the pyramid levels of a generator backward) in ONE launch: most of these are a few
+// hundred KB, i.e. launch-bound on their own
+struct EwProb { PView dst, a, b, mask; int H, W; long long total; int block_begin, pad_; };
+struct EwGroup { int nprob; EwProb p[AFI_MAX_PROB + 1]; };
+__global__ void k_ew_combine_group(const __grid_constant__ EwGroup G, int dst_dt, int a_dt, int b_dt, int mask_dt, float mslope, float scale, int cq) {
+    int k = 0;
+    while (k + 1 < G.nprob && (int)blockIdx.x >= G.p[k + 1].block_begin) k++;
+    const EwProb& e = G.p[k];
+    long long i = (long long)(blockIdx.x - e.block_begin) * blockDim.x + threadIdx.x;
+    if (i >= e.total) return;
+    int c = (int)(i % cq) * 4;
+    PixIdx q = decode_pixel(i / cq, e.H, e.W);
+    float4 v = ld4(e.a.ptr, voff(e.a, q) + c, a_dt);
+    if (e.b.ptr) { float4 t = ld4(e.b.ptr, voff(e.b, q) + c, b_dt); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (e.mask.ptr) {
+        float4 m = ld4(e.mask.ptr, voff(e.mask, q) + c, mask_dt);
+        v.x *= lmaskf(m.x, mslope); v.y *= lmaskf(m.y, mslope); v.z *= lmaskf(m.z, mslope); v.w *= lmaskf(m.w, mslope);
+    }
+    st4(e.dst.ptr, voff(e.dst, q) + c, dst_dt, v);
+}
+int ew_combine_group(int nprob, const PView* dst, int dst_dt, const PView* a, int a_dt, const PView* b, int b_dt, const PView* mask, int mask_dt,
+                     float mask_slope, float scale, const int* n, const int* h, const int* w, int c, cudaStream_t st) {
+    AFI_REQUIRE(nprob >= 1 && nprob <= AFI_MAX_PROB, "ew_combine_group: bad problem count %d", nprob);
+    EwGroup G; memset(&G, 0, sizeof(G));
+    G.nprob = nprob;
+    int blocks = 0;
+    for (int k = 0; k < nprob; k++) {
+        EwProb& e = G.p[k];
+        e.dst = dst[k]; e.a = a[k]; e.b = b ? b[k] : pview_null(); e.mask = mask ? mask[k] : pview_null();
+        e.H = h[k]; e.W = w[k]; e.total = (long long)n[k] * h[k] * w[k] * (c / 4); e.block_begin = blocks;
+        blocks += cdiv(e.total, 256);
+    }
+    G.p[nprob].block_begin = blocks;
+    if (blocks == 0) return AFI_OK;
+    k_ew_combine_group<<<blocks, 256, 0, st>>>(G, dst_dt, a_dt, b_dt, mask_dt, mask_slope, scale, c / 4);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // per-channel reductions over pixels.  Block = 256 threads = (c/4 channel quads) x (pixel lanes); each block
 // owns a chunk of pixels, accumulates in fp32 registers, reduces lanes through shared memory and issues one
