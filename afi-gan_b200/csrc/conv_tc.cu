@@ -145,6 +145,11 @@ __device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint32_
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -840,66 +845,99 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
 // weight-gradient kernel.  Work item = (tap, cout tile of 128, cin tile of bn, k split); K tile = TH x TW = 64 pixels.
 // smem stage: A = two [64 px][64 co] SW128 boxes (8 KB each), B = bn/64 [64 px][64 ci] boxes.
 // ---------------------------------------------------------------------------------------------------
+// PAIR: the two CTAs of a cluster run one cta_group::2 MMA stream with M = 256 couts (128 per CTA) x N = bn cins: each CTA stages its own
+// dY tile and HALF of the X tile (bn/2 channels), i.e. 32 KB instead of 48 KB per 64-pixel K tile, and the ring gets six stages.  Same
+// barrier protocol as the pair convolution kernel.
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs a, const __grid_constant__ Tiling tl) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t tmem_base = setup(s, maps, EPI_THREADS / 32, warp, lane);
-    const int nb = tl.bn / 64;    // B boxes per stage
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES_MAX; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), (PAIR ? 2 : 1) * (EPI_THREADS / 32)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int nb = tl.bn / 64;                      // 64-channel X boxes per K tile (both halves together in pair mode)
+    const int nbl = PAIR ? nb / 2 : nb;             // ... staged by THIS CTA
     const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
+    const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     // the producer and MMA warps run their loops CONVERGED; only the TMA / tcgen05 instruction issue is elected (see elect_one())
     if (warp == 0) {
-        {
-            int stage = 0; uint32_t phase = 0;
-            const uint32_t tx_bytes = A_BYTES + nb * 8192;
-            for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
-                int ks = item % tl.ksplit; int r = item / tl.ksplit;
-                int nt = r % tl.n_tiles; r /= tl.n_tiles;
-                int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
-                const Tap t = a.taps[tp];
-                int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
-                // position of K tile k0: (problem, image, patch row, patch column); advanced incrementally below -- integer divisions
-                // per stage in this single producer thread were eating the 512-cycle stage budget
-                int ti = 0;
-                while (k0 >= tl.p[ti + 1].begin) ti++;
-                int lk0 = k0 - tl.p[ti].begin;
-                int tpi = tl.p[ti].tiles_x * tl.p[ti].tiles_y;
-                int img = lk0 / tpi, rr0 = lk0 % tpi;
-                int ty_ = rr0 / tl.p[ti].tiles_x, tx_ = rr0 % tl.p[ti].tiles_x;
-                for (int kt = k0; kt < k1; kt++) {
-                    const TileP& tp_ = tl.p[ti];
-                    const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
-                    mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
-                    uint32_t fb = smem_u32(&s.full[stage]);
-                    uint32_t sa = tiles0 + stage * stage_bytes;
-                    if (elect_one()) {
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (A_BYTES + nbl * 8192);      // bytes of both CTAs land on the leader's barrier
+        for (int item = item0; item < tl.total; item += item_stride) {
+            int ks = item % tl.ksplit; int r = item / tl.ksplit;
+            int nt = r % tl.n_tiles; r /= tl.n_tiles;
+            int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
+            if (PAIR) mt = 2 * mt + rank;               // m_tiles counts PAIRS of 128-cout tiles
+            const Tap t = a.taps[tp];
+            int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
+            // position of K tile k0: (problem, image, patch row, patch column); advanced incrementally below -- integer divisions
+            // per stage in this serial loop were eating the 512-cycle stage budget
+            int ti = 0;
+            while (k0 >= tl.p[ti + 1].begin) ti++;
+            int lk0 = k0 - tl.p[ti].begin;
+            int tpi = tl.p[ti].tiles_x * tl.p[ti].tiles_y;
+            int img = lk0 / tpi, rr0 = lk0 % tpi;
+            int ty_ = rr0 / tl.p[ti].tiles_x, tx_ = rr0 % tl.p[ti].tiles_x;
+            for (int kt = k0; kt < k1; kt++) {
+                const TileP& tp_ = tl.p[ti];
+                const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
+                mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
+                uint32_t fb = smem_u32(&s.full[stage]);
+                uint32_t sa = tiles0 + stage * stage_bytes;
+                if (elect_one()) {
+                    // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
+                    if (PAIR) {
+                        if (leader) mbar_expect_tx(fb, tx_bytes);
+                        tma_load_5d_pair(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
+                        tma_load_5d_pair(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb + rank * nbl, img);
+                    } else {
                         mbar_expect_tx(fb, tx_bytes);
-                        // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
                         tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
                         tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
                     }
-                    __syncwarp();
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
-                    if (++tx_ == tp_.tiles_x) {
-                        tx_ = 0;
-                        if (++ty_ == tp_.tiles_y) {
-                            ty_ = 0;
-                            if (kt + 1 >= tl.p[ti + 1].begin) { ti++; img = 0; } else img++;
-                        }
+                }
+                __syncwarp();
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
+                if (++tx_ == tp_.tiles_x) {
+                    tx_ = 0;
+                    if (++ty_ == tp_.tiles_y) {
+                        ty_ = 0;
+                        if (kt + 1 >= tl.p[ti + 1].begin) { ti++; img = 0; } else img++;
                     }
                 }
             }
         }
+        if (PAIR) {     // producer tail: every release the leader multicast to this CTA has landed before the CTA may exit
+            for (int i = 0; i < nstages; i++) { mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 15); if (++stage == nstages) { stage = 0; phase ^= 1; } }
+        }
     } else if (warp == 1) {
-        {
+        if (leader) {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            const uint32_t idesc = make_idesc(tl.bn, 1, 1);
-            for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
+            const uint32_t idesc = make_idesc(tl.bn, 1, 1, PAIR ? 256 : 128);
+            for (int item = item0; item < tl.total; item += item_stride) {
                 int ks = item % tl.ksplit;
                 int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
                 mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 12);
@@ -913,14 +951,16 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     uint64_t ad = make_desc(sa, 8192, 1024), bd = make_desc(sa + A_BYTES, 8192, 1024);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++)     // 16 pixels = 2048 B per MMA
-                            umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
-                        umma_commit(smem_u32(&s.empty[stage]));
+                        for (int k = 0; k < 4; k++) {     // 16 pixels = 2048 B per MMA
+                            if (PAIR) umma_bf16_pair(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
+                            else umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
+                        }
+                        if (PAIR) umma_commit_pair(smem_u32(&s.empty[stage])); else umma_commit(smem_u32(&s.empty[stage]));
                     }
                     __syncwarp();
                     if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
+                if (elect_one()) { if (PAIR) umma_commit_pair(smem_u32(&s.acc_full[as])); else umma_commit(smem_u32(&s.acc_full[as])); }
                 __syncwarp();
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
@@ -930,10 +970,11 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
         const int half = (warp - 2) >> 2;       // the two warps of a lane quarter interleave the 16-column chunks
         const int row = q * 32 + lane;
         int as = 0; uint32_t aphase = 0;
-        for (int item = blockIdx.x; item < tl.total; item += gridDim.x) {
+        for (int item = item0; item < tl.total; item += item_stride) {
             int ks = item % tl.ksplit; int r = item / tl.ksplit;
             int nt = r % tl.n_tiles; r /= tl.n_tiles;
             int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
+            if (PAIR) mt = 2 * mt + rank;
             int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
             const int co = mt * 128 + row;
             float* dst = a.dw + ((long long)a.taps[tp].slab * a.cout + co) * a.cin;
@@ -951,11 +992,18 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s.acc_empty[as]));
+            if (lane == 0) { if (PAIR) mbar_arrive_cta0(smem_u32(&s.acc_empty[as])); else mbar_arrive(smem_u32(&s.acc_empty[as])); }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
-    teardown(tmem_base, warp);
+    tc_fence_before();
+    __syncwarp();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -1042,7 +1090,8 @@ int tc_init(afi_ctx* ctx) {
     ctx->encode_tiled = fn;
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     // halo-tile kernels: everything the SM has beyond their static shared memory (statistics scratch + barriers)
     cudaFuncAttributes fa;
     AFI_CUDA(cudaFuncGetAttributes(&fa, tc::k_conv_halo<4, true>));
@@ -1206,6 +1255,10 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     tl.m_tiles = (a.cout + 127) / 128;
     tl.n_tiles = (a.cin + 255) / 256;
     tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
+    // CTA pairs (M = 256 couts per MMA, X tile split across the pair) when the shape allows: whole 256-cout tiles and an even number of
+    // 64-channel X boxes per N tile; AFIGAN_WGRAD_PAIR=0 keeps one CTA per tile
+    const char* wp = getenv("AFIGAN_WGRAD_PAIR");
+    const bool pair = (!wp || atoi(wp) != 0) && a.cout % 256 == 0 && (tl.bn / 64) % 2 == 0;
     Maps maps;
     int begin = 0, np = 0;
     for (int oi = 0; oi < a.nprob; oi++) {
@@ -1219,27 +1272,37 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
         t.prob = order[oi];
         begin += pr.N * t.tiles_x * t.tiles_y;
         AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][0], pr.dy, a.cout, pr.W, pr.H, pr.N, t.TW, t.TH, 2));
-        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N, t.TW, t.TH, tl.bn / 64));
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N, t.TW, t.TH, pair ? tl.bn / 128 : tl.bn / 64));
         np++;
     }
     tl.nprob = np;
     tl.p[np].begin = begin;
     tl.ktiles = begin;
     maps.b = maps.a[tl.p[0].prob][0];
-    // split-K so that the work items fill (at most) two full waves of the persistent grid: base * ks <= 2 * SMs
+    if (pair) tl.m_tiles = a.cout / 256;
+    const int workers = pair ? ctx->sm_count / 2 : ctx->sm_count;
+    // split-K so that the work items fill (at most) two full waves of the persistent grid: base * ks <= 2 * workers
     int base = a.ntaps * tl.m_tiles * tl.n_tiles;
-    int ks = (2 * ctx->sm_count) / base;
+    int ks = (2 * workers) / base;
     if (ks > tl.ktiles) ks = tl.ktiles;
     if (ks < 1) ks = 1;
     int kper = (tl.ktiles + ks - 1) / ks;
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
-    tl.stage_bytes = A_BYTES + (tl.bn / 64) * 8192;
+    tl.stage_bytes = A_BYTES + (tl.bn / 64) * (pair ? 4096 : 8192);
     tl.nstages = (SMEM_BYTES - 1024) / tl.stage_bytes;
     if (tl.nstages > STAGES_MAX) tl.nstages = STAGES_MAX;
-    int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
+    int grid = tl.total < workers ? tl.total : workers;
     ProfScope prof(PROF_WGRAD_TC, 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
-    k_wgrad_tc<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
+    if (pair) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(2 * grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        AFI_CUDA(cudaLaunchKernelEx(&cfg, k_wgrad_tc<true>, maps, a, tl));
+    } else k_wgrad_tc<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
