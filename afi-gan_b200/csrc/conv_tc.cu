@@ -1147,10 +1147,11 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     // fused statistics below K = 8192 (measured: 512 -> 1024 with statistics on four warps is epilogue-bound in pair mode)
     const int K = a.ntaps * tl.kchunks * 64;
     const int epi8 = (K < 4096 || (a.stat_mode && K < 8192)) ? 1 : 0;
-    // halo tiles on CTA pairs pay off on the long-K layers (weight-tile traffic per FLOP halves); the short-K layers are bound by
-    // tile granularity and epilogue overlap, where the single-CTA per-tap kernel measured slightly faster
+    // halo tiles on CTA pairs: every 3x3 layer except the narrow ones (N tile < 128 or 32 input channels: the dense blocks' growth
+    // convs and their dgrads), where the per-tap kernel measured 10-15 % faster (a pair halves the number of schedulable tiles and
+    // an N = 32 MMA is bound by its A-operand read either way)
     int hmode = halo_eligible(a) ? halo_mode() : 0;
-    if (hmode == 2 && K < 4096 && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
+    if (hmode == 2 && K < 4096 && (tl.bn < 128 || a.cin < 64) && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
     const bool pair = hmode == 2;
     tl.rot = getenv("AFIGAN_CONV_ROT") ? atoi(getenv("AFIGAN_CONV_ROT")) : 0;   // measured: no effect (the weight tiles are not an L2 hot spot)
     if (getenv("AFIGAN_HALO_DBG")) {
