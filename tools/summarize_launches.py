@@ -8,7 +8,7 @@ path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv"
 lines = [l for l in open(path) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 n = len(rows)
-half = rows[n // 2:]
+half = rows[n // 2:] if "--all" not in sys.argv else rows
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for row in half:
     name = re.sub(r"\(.*", "", row["Kernel Name"])
