@@ -707,8 +707,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
             Zv[k] = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); Av[k] = pview(W[k].A[i + 1], d[k].h, d[k].w, DC[i + 1]);
         }
         if (training) AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
-        static const int fuse_min_cin = getenv("AFIGAN_FUSE_STATS_MIN_CIN") ? atoi(getenv("AFIGAN_FUSE_STATS_MIN_CIN")) : 512;
-        const bool fuse_stats = training && tc && DC[i] >= fuse_min_cin;   // long-K layers hide the extra epilogue work behind the MMAs
+        const bool fuse_stats = training && tc && DC[i] >= 512;   // long-K layers hide the extra epilogue work behind the MMAs
         if (fuse_stats) {   // tensor-core engine: the per-channel sum / sum of squares come out of the GEMM epilogue
             a.stat_mode = 1;
             for (int k = 0; k < ncalls; k++) { a.p[k].stat0 = W[k].sums; a.p[k].stat1 = W[k].sums + 1024; }

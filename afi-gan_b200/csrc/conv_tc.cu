@@ -56,7 +56,7 @@ struct Tiling {
     int m_tiles, ksplit, ktiles;      // wgrad only
     int nstages, stage_bytes;         // per-tap conv and wgrad: operand ring (a narrow N tile leaves room for more, smaller stages)
     // halo-tile convolution only: B ring of `sb` slots of b_slot bytes (one (tap, chunk) weight tile, or half of it in pair mode)
-    int sb, b_slot, nviews, rot;
+    int sb, b_slot, nviews;
     int view_slab0[4];                // first weight slab of view v (its nine taps use slab0 .. slab0 + 8 in standard order)
     long long* dbg;                   // optional [grid][8] stall-cycle counters (AFIGAN_HALO_DBG)
     TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
@@ -527,9 +527,6 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             int stage = 0; uint32_t phase = 0;
             long long w_e = 0, w_l = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
             const uint32_t tx_bytes = A_BYTES + tl.bn * 128;
-            // every CTA walks the (tap, channel chunk) reduction in its own rotation, so that at any moment the CTAs read DIFFERENT weight
-            // tiles: in lock-step all of them hit the same L2 lines at once
-            const int rot_k = tl.rot ? (int)(blockIdx.x % tl.kchunks) : 0, rot_t = tl.rot ? (int)((blockIdx.x / tl.kchunks) % a.ntaps) : 0;
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
                 int ti = 0;
                 while (tile >= tl.p[ti + 1].begin) ti++;
@@ -540,15 +537,10 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 int img = mt / tiles_per_img, r = mt % tiles_per_img;
                 int y0 = (r / tp_.tiles_x) * tp_.TH, x0 = (r % tp_.tiles_x) * tp_.TW;
                 int n0 = nt * tl.bn;
-                int tpr = rot_t;
                 for (int tp = 0; tp < a.ntaps; tp++) {
-                    const Tap t = a.taps[tpr];
-                    if (++tpr == a.ntaps) tpr = 0;
+                    const Tap t = a.taps[tp];
                     const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
-                    int kc = rot_k;
-                    for (int kci = 0; kci < tl.kchunks; kci++) {
-                        const int kc_ = kc;
-                        if (++kc == tl.kchunks) kc = 0;
+                    for (int kc_ = 0; kc_ < tl.kchunks; kc_++) {
                         mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
                         uint32_t fb = smem_u32(&s.full[stage]);
                         uint32_t sa = tiles0 + stage * stage_bytes;
@@ -673,10 +665,6 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int total = tl.total;
     const bool dbg_on = tl.dbg != nullptr;
-    // every CTA (pair) walks the channel chunks in its own rotation: in lock-step all CTAs would read the same weight tile, i.e. hit
-    // the same L2 lines, at the same moment
-    const int rot = tl.rot ? item0 % nchunks : 0;
-    const int rot_v = rot / kchunks, rot_k = rot % kchunks;
 
     if (warp == 0) {
         {
@@ -723,12 +711,12 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             };
             HaloTile cur, nxt;
             int item = item0;
-            if (item < total) { decode(item, cur); issue_a(cur, rot_v, rot_k); }
+            if (item < total) { decode(item, cur); issue_a(cur, 0, 0); }
             while (item < total) {
                 const int nitem = item + item_stride;
                 const bool has_next = nitem < total;
                 if (has_next) decode(nitem, nxt);
-                int view = rot_v, kc = rot_k;
+                int view = 0, kc = 0;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
                     const int slab0 = tl.view_slab0[view];
                     const int kcol = kc * 64, nrow = cur.n0 + brow;
@@ -736,7 +724,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                     if (nkc == kchunks) { nkc = 0; if (++nview == tl.nviews) nview = 0; }
                     // the halo of the NEXT chunk is requested before this chunk's weight tiles (three A slots: its slot was released long ago)
                     if (chunk + 1 < nchunks) issue_a(cur, nview, nkc);
-                    else if (has_next) issue_a(nxt, rot_v, rot_k);
+                    else if (has_next) issue_a(nxt, 0, 0);
 #pragma unroll
                     for (int j = 0; j < 9; j++) {
                         mbar_wait_t(bar_be + 8 * bi, bph ^ 1, 22, w_be, dbg_on);
@@ -784,7 +772,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * ACC_COLS;
                 uint32_t accum = 0;
-                int kc = rot_k;
+                int kc = 0;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
                     int nk = (cin - kc * 64 + 15) >> 4;              // 16-channel MMA steps with data in this chunk
                     if (++kc == kchunks) kc = 0;
@@ -1153,13 +1141,14 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int hmode = halo_eligible(a) ? halo_mode() : 0;
     if (hmode == 2 && K < 4096 && (tl.bn < 128 || a.cin < 64) && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
     const bool pair = hmode == 2;
-    tl.rot = getenv("AFIGAN_CONV_ROT") ? atoi(getenv("AFIGAN_CONV_ROT")) : 0;   // measured: no effect (the weight tiles are not an L2 hot spot)
+#ifdef AFI_STALL_COUNTERS
     if (getenv("AFIGAN_HALO_DBG")) {
         static long long* dbg = nullptr;
         if (!dbg) cudaMalloc(&dbg, 4096 * sizeof(long long));
         cudaMemsetAsync(dbg, 0, 4096 * sizeof(long long), st);
         tl.dbg = dbg;
     }
+#endif
     if (hmode) {
         tl.nviews = nviews;
         tl.b_slot = ((pair ? tl.bn * 64 : tl.bn * 128) + 1023) / 1024 * 1024;
@@ -1226,6 +1215,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         else k_conv_halo<4, false><<<grid, 64 + 32 * 4, dyn, st>>>(maps, a, tl);
     } else if (epi8) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
     else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
+#ifdef AFI_STALL_COUNTERS
     {
         if (tl.dbg) {      // experiment aid: per-CTA stall cycles of the producer / MMA threads
             long long h[256 * 8];
@@ -1238,6 +1228,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
                     a.cin, a.cout, hmode ? HALO_SA : 0, tl.sb, tl.total, sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / mg, sum[4] / mg, sum[5] / mg, sum[6] / mg);
         }
     }
+#endif
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

@@ -289,9 +289,9 @@ def run_ours(args):
             if kind.value in (0, 2, 4, 5) and (top is None or ms.value > top[0]):
                 top = (ms.value, fl.value, cin.value, cout.value, px.value)
         pk = peaks()
-        names = {0: "k_conv_tc (tcgen05 implicit-GEMM conv/dgrad, per-tap tiles: short-K and 1x1 layers)", 1: "k_wgrad_tc (tcgen05 weight gradient)",
+        names = {0: "k_conv_tc (tcgen05 implicit-GEMM conv/dgrad, per-tap tiles: narrow, 1x1 and non-3x3 layers)", 1: "k_wgrad_tc (tcgen05 weight gradient)",
                  2: "k_conv_simt (fp32 FFMA implicit GEMM)", 3: "k_wgrad_simt (fp32 FFMA weight gradient)",
-                 4: "k_conv_halo<PAIR> (tcgen05 cta_group::2 implicit-GEMM conv/dgrad, halo tiles on CTA pairs: long-K layers)",
+                 4: "k_conv_halo<PAIR> (tcgen05 cta_group::2 implicit-GEMM conv/dgrad, halo tiles on CTA pairs)",
                  5: "k_conv_halo (tcgen05 implicit-GEMM conv/dgrad, halo tiles on single CTAs)"}
         dom = max(agg, key=lambda k: agg[k][2])
         cnt, flops, tms = agg[dom]

@@ -1,5 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_short.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-echo "ncu bench launch list exit $?"; tail -c 300 gpurun_out/bench_short.log
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python tools/quick_time.py bf16 10 2>&1 | tail -1
