@@ -144,12 +144,15 @@ class Stage1Step:
                                             C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, self.g_acc.data_ptr(),
                                             N.stream_ptr()))
 
-    def _d_calls(self, xs, tags, save: bool, dlogits=None, stats_only=None):
+    def _d_calls(self, xs, tags, save: bool, dlogits=None, stats_only=None, staged: bool = False):
         calls = (N.DCall * len(xs))()
         logits = []
         for i, (x, tag) in enumerate(zip(xs, tags)):
             n, _, h, w = x.shape
-            ws = self._ws_for("d", n, h, w, save, tag)
+            # one workspace per (level, real / fake) serves both phases of a step (a forward-only call fits into the workspace of a
+            # forward + backward call); `staged`: it still holds this very input in the library's layout from the D phase
+            ws = self._ws_for("d", n, h, w, True, tag)
+            calls[i].input_staged = int(staged)
             lg = self._buf("logit" + tag, (n, 1, h, w))
             c = calls[i]
             # a call whose output nobody reads (the reference's dead D0(hr) of the G phase) runs for its BatchNorm statistics only
@@ -166,11 +169,11 @@ class Stage1Step:
             sub[j] = calls[i]
         return sub
 
-    def _d_phase(self, xs, tags, targets, loss_rows, save: bool, backward: bool):
+    def _d_phase(self, xs, tags, targets, loss_rows, save: bool, backward: bool, staged: bool = False):
         """Discriminator calls `xs` (reference order), BCE against `targets[i]` accumulated into losses[loss_rows[i], level]; with
         backward=True also d(BCE)/d(params) into the packed accumulator.  Calls with even / odd index (real / fake) form the two groups."""
         lib = self.lib
-        calls, logits = self._d_calls(xs, tags, save, stats_only=[r is None and not backward for r in loss_rows])
+        calls, logits = self._d_calls(xs, tags, save, stats_only=[r is None and not backward for r in loss_rows], staged=staged)
         ps = self._ds()
         bn = self.Dstack[0][0].norm
         mom = 0.1 if bn.momentum is None else bn.momentum
@@ -272,7 +275,9 @@ class Stage1Step:
             xs += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                          # D0(tr) BEFORE D0(hr) here (:399-400)
             tags += [f"f{l}", f"r{l}"]
         # adv = BCE(D0(tr).detach(), 1): no gradient (:399); D0(hr) is dead compute kept for its BN running-stat side effect (:400)
-        self._d_phase(xs, tags, [1.0] * len(xs), [2 if i % 2 == 0 else None for i in range(len(xs))], False, False)
+        # (with one G forward per step the G phase feeds the discriminator the tensors the D phase already staged)
+        self._d_phase(xs, tags, [1.0] * len(xs), [2 if i % 2 == 0 else None for i in range(len(xs))], False, False,
+                      staged=self.reuse_g_forward)
         dtrs = []
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             dtr = self._buf(f"dtr{l}", tuple(tr.shape))

@@ -52,7 +52,7 @@ class GCall(C.Structure):
 
 class DCall(C.Structure):
     _fields_ = [("x", View4), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("logits", C.c_void_p), ("dlogits", C.c_void_p),
-                ("dx", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("dx", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("input_staged", C.c_int)]
 
 
 MAX_CALLS = 10

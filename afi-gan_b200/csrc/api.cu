@@ -686,7 +686,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         // logits == NULL: the call is evaluated for its BatchNorm statistics only (stage1_trainer.py:400 computes D(hr) in the G phase and
         // drops the result: what survives is the running-buffer update), so layer 3's normalise pass and the head are skipped
         AFI_REQUIRE(calls[k].logits || (training && !save), "afi_d_forward: call %d: a statistics-only call (logits == NULL) needs training mode and no backward", k);
-        AFI_TRY(to_nhwc(prec, calls[k].x, d[k].n, DC[0], d[k].h, d[k].w, pview(W[k].A[0], d[k].h, d[k].w, DC[0]), st));
+        if (!calls[k].input_staged) AFI_TRY(to_nhwc(prec, calls[k].x, d[k].n, DC[0], d[k].h, d[k].w, pview(W[k].A[0], d[k].h, d[k].w, DC[0]), st));
     }
     const bool tc = prec_tc(prec);
     for (int i = 0; i < 3; i++) {

@@ -141,6 +141,9 @@ typedef struct {
     const float* dlogits;           /* backward: contiguous [n,1,h,w]                  */
     float* dx;                      /* backward: contiguous [n,256,h,w] or NULL           */
     void* ws; size_t ws_bytes;
+    int input_staged;               /* forward: non-zero = ws still holds THIS input in the library's layout from an earlier
+                                     * afi_d_forward on the same ws (the two phases of a stage-1 step feed the same tensors): the
+                                     * layout conversion is skipped                                                          */
 } afi_d_call;
 
 /* Discriminators[0](x) (feature_patch_discriminator.py:32-41 as called at stage1_trainer.py:349-353) for each call, IN CALL
