@@ -1,20 +1,24 @@
-// tcgen05 / TMEM / TMA implicit-GEMM engine (AFI_PREC_BF16): the throughput path of the library.
+// tcgen05 / TMEM / TMA implicit-GEMM engine (AFI_PREC_BF16): the throughput path of the library.  Three kernels:
 //
-//   conv  : D[128 pixels x bn couts] += A[128 px x 64 ci] * B[bn co x 64 ci]^T per (tap, 64-channel chunk).
-//           The M tile is a TH x TW spatial patch of ONE image; the A operand of tap (dy,dx) is the same patch
-//           shifted by (dy,dx), fetched by a 4-D tiled TMA box {64 ch, TW, TH, 1}: out-of-image coordinates are
-//           zero-filled by the TMA unit, which IS the conv padding (and handles ragged 13x21 / 7x11 levels).
-//           Box rows land as 128-byte, 128B-swizzled rows = the UMMA K-major SWIZZLE_128B canonical layout.
-//   wgrad : D[128 couts x bn cins] += dY[64 px x 128 co]^T * X_shift[64 px x bn ci]: both operands MN-major
-//           (channels contiguous), K = pixels; ONE 5-D grouped TMA box per operand per stage, split-K over the concatenated
-//           spatial patches of all problems of the group, fp32 RED into dW.
-//   Both kernels are GROUPED: one launch covers up to AFI_MAX_PROB problems (pyramid levels / discriminator calls) that share the
-//   weights; the persistent CTAs walk a largest-first work list spanning all of them.
+//   k_conv_halo<EPI, PAIR> : every standard 3x3 conv / dgrad.  D[128 pixels x bn couts] per CTA; the M tile is a 16 x 8 (or 8 x 16) patch
+//           of ONE image whose 18 x 10 HALO is fetched once per 64-channel chunk (one 4-D TMA box; out-of-image coordinates are
+//           zero-filled = the conv padding, which also handles ragged 13x21 / 7x11 levels); the nine taps read it in place through
+//           shifted UMMA descriptors.  PAIR: two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 stream (M = 256) and split every
+//           weight tile between them.  See the comment above the kernel.
+//   k_conv_tc<EPI>         : per-tap variant (one shifted A box per tap, cta_group::1) for the narrow layers, 1x1 convs and any
+//           tap set that is not a standard 3x3.
+//   k_wgrad_tc<PAIR>       : D[128 couts x bn cins] += dY[64 px x 128 co]^T * X_shift[64 px x bn ci]: both operands MN-major (channels
+//           contiguous), K = pixels; ONE 5-D grouped TMA box per operand per stage, split-K over the concatenated spatial patches of
+//           all problems of the group, fp32 RED into dW.  PAIR: M = 256 couts across a CTA pair, the X tile split between them.
+//   All are GROUPED: one launch covers up to AFI_MAX_PROB problems (pyramid levels / discriminator calls) that share the weights; the
+//   persistent CTAs walk a largest-first work list spanning all of them.
 //
 // Warp roles (1 CTA/SM, persistent over a static work list):
-//   warp 0   : TMA producer (one lane)      -- 4-stage smem ring, mbarrier full/empty
-//   warp 1   : TMEM allocator + MMA issuer  -- tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128, N=bn (runtime)
-//   warps 2+ : epilogue, 4 warps (long-K convs: 192 threads) or 8 warps (short-K convs and wgrad: 320 threads)
+//   warp 0   : TMA producer   -- mbarrier full/empty rings (4-10 stages depending on the N tile; separate halo / weight rings in
+//                                k_conv_halo)
+//   warp 1   : TMEM allocator + MMA issuer -- tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M = 128 (256 per pair), N = bn (runtime)
+//              Both run their loops as CONVERGED warps and elect one lane only for the instruction issue (elect_one()).
+//   warps 2+ : epilogue, 4 warps (long-K convs: 192 threads) or 8 warps (short-K convs, statistics below K = 8192, wgrad: 320 threads)
 //                                            -- tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x 256 columns)
 //                                               so the epilogue of tile i overlaps the MMAs of tile i+1; optional fused per-channel
 //                                               statistics (BatchNorm sum / sum of squares) via a 16-shuffle butterfly per chunk.
