@@ -148,6 +148,29 @@ class AFInterpolatorFn(torch.autograd.Function):
         return (dx, d_lat_x, d_lat_w, d_lat_b, None, None, None, None, None, *grads)
 
 
+def afi_bifpn_fuse(x: torch.Tensor, cur: torch.Tensor, weight: Optional[torch.Tensor], holder, prec: int, params) -> torch.Tensor:
+    """Forward-only BiFPN fusion site (reference bifpn_sr.py:535-548) in ONE library call:
+    weight[0] * cur + weight[1] * (Generators[0](x) + bilinear2x(x))[:, :, :H, :W]  (weight None: plain sum)."""
+    if not x.is_cuda:
+        raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
+    x, cur = x.float(), cur.float()
+    n, _, h, w = x.shape
+    oh, ow = cur.shape[2:]
+    if tuple(cur.shape[:2]) != (n, CH) or oh > 2 * h or ow > 2 * w:
+        raise ValueError(f"BiFPN fusion: cur {tuple(cur.shape)} does not fit the up-sampled top {(n, CH, 2 * h, 2 * w)}")
+    dev = x.device
+    fw = (weight.detach().float().reshape(2) if weight is not None else torch.ones(2, device=dev)).contiguous()
+    ps = g_param_struct(params, holder.n_rdb)
+    packed = holder.packed.get("g", prec, params, ps, holder.n_rdb)
+    lib, actx = N.lib(), N.context(dev)
+    ws = _u8(lib.afi_g_workspace_bytes(prec, n, h, w, holder.n_rdb, 0, 0), dev)
+    y = torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev)
+    call = N.GCall(x=N.view4(x), n=n, h=h, w=w, y=y.data_ptr(), oh=oh, ow=ow, ws=ws.data_ptr(), ws_bytes=ws.numel(),
+                   fuse_cur=N.view4(cur), fuse_w=fw.data_ptr())
+    N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, 0, N.stream_ptr()))
+    return y
+
+
 class PatchDiscriminatorFn(torch.autograd.Function):
     """Discriminators[0](x) (reference feature_patch_discriminator.py:32-41)."""
 

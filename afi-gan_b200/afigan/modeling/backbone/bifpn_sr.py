@@ -15,7 +15,13 @@ from ..._compat import BACKBONE_REGISTRY, ShapeSpec
 
 def bifpn_feature_fusion(srf_module, cur_feature: torch.Tensor, top_feature: torch.Tensor,
                          weight: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """weight is the 2-element `..._w1` parameter (or None when attention is disabled): w[0]*cur + w[1]*AFI(top)."""
+    """weight is the 2-element `..._w1` parameter (or None when attention is disabled): w[0]*cur + w[1]*AFI(top).
+    Without autograd (inference, BASELINE config C5: 28 of these per image) the whole site is one library call; with autograd the
+    interpolator is the library's autograd Function and the two-term fusion stays in torch."""
+    needs_grad = torch.is_grad_enabled() and (cur_feature.requires_grad or top_feature.requires_grad or (weight is not None and weight.requires_grad)
+                                              or any(p.requires_grad for p in srf_module.parameters()))
+    if not needs_grad and top_feature.is_cuda and hasattr(srf_module, "fuse"):
+        return srf_module.fuse(top_feature, cur_feature, weight)
     up = srf_module(top_feature, out_hw=tuple(cur_feature.shape[2:]))
     if weight is None:
         return cur_feature + up

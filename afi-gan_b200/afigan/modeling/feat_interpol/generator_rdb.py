@@ -96,6 +96,13 @@ class Generator(nn.Module):
         prec = native.PRECISIONS[self.precision or native.default_precision()]
         return AFInterpolatorFn.apply(features, None, None, None, self._native, prec, out_hw, 1.0, torch.is_grad_enabled(), *self._params())
 
+    def fuse(self, top_feature: torch.Tensor, cur_feature: torch.Tensor, weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward-only BiFPN fusion site in ONE library call (reference bifpn_sr.py:535-548): weight[0] * cur + weight[1] * self(top)."""
+        from ...functional import afi_bifpn_fuse
+        prec = native.PRECISIONS[self.precision or native.default_precision()]
+        with torch.no_grad():
+            return afi_bifpn_fuse(top_feature, cur_feature, weight, self._native, prec, self._params())
+
     def merge(self, prev_features: torch.Tensor, bottom_up: torch.Tensor, lateral_weight: torch.Tensor,
               lateral_bias: Optional[torch.Tensor] = None, fuse_type: str = "sum") -> torch.Tensor:
         """The top-down merge of the AFI necks in ONE library call (reference fpn_sr.py:151-157, pafpn_sr.py:175-181):

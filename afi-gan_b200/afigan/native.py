@@ -47,7 +47,7 @@ class Lateral(C.Structure):
 class GCall(C.Structure):
     _fields_ = [("x", View4), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("y", C.c_void_p), ("oh", C.c_int), ("ow", C.c_int),
                 ("dy", View4), ("dx", C.c_void_p), ("lateral", C.POINTER(Lateral)), ("lat_dx", C.c_void_p), ("lat_gw", C.c_void_p),
-                ("lat_gb", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+                ("lat_gb", C.c_void_p), ("ws", C.c_void_p), ("ws_bytes", C.c_size_t), ("fuse_cur", View4), ("fuse_w", C.c_void_p)]
 
 
 class DCall(C.Structure):

@@ -74,9 +74,9 @@ static int to_nhwc(int prec, afi_view4 src, int n, int c, int h, int w, PView ds
     return prec == AFI_PREC_FP32 ? nchw_to_nhwc<float>(src, n, c, h, w, dst, st) : nchw_to_nhwc<bf16>(src, n, c, h, w, dst, st);
 }
 static int to_nchw(int prec, PView a, PView lat, afi_view4 skip, int sh, int sw, float scale, int n, int c, int oh, int ow, float* dst,
-                   cudaStream_t st) {
-    return prec == AFI_PREC_FP32 ? nhwc_to_nchw<float>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st)
-                                 : nhwc_to_nchw<bf16>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st);
+                   cudaStream_t st, const afi_view4* add = nullptr, const float* fw = nullptr) {
+    return prec == AFI_PREC_FP32 ? nhwc_to_nchw<float>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st, add, fw)
+                                 : nhwc_to_nchw<bf16>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st, add, fw);
 }
 // forward / dgrad pack modes per engine
 static inline int pm(int prec, int kind) { return kind * 2 + (prec_tc(prec) ? 1 : 0); }
@@ -377,7 +377,10 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
             scale = lat->scale;
         }
         // y = (branch + bilinear2x(x) [+ lateral]) * scale, cropped to oh x ow            :125,130; stage1_trainer.py:437-443
-        AFI_TRY(to_nchw(prec, pview(W[k].Yb, d2[k].h, d2[k].w, C), latv, c.x, c.h, c.w, scale, c.n, C, c.oh, c.ow, c.y, st));
+        // [+ the BiFPN fusion w0 * cur + w1 * y (bifpn_sr.py:535-548) when the call carries one]
+        AFI_REQUIRE(!c.fuse_w || (c.fuse_cur.ptr && !save), "afi_g_forward: call %d: the fused BiFPN site is forward-only and needs fuse_cur", k);
+        AFI_TRY(to_nchw(prec, pview(W[k].Yb, d2[k].h, d2[k].w, C), latv, c.x, c.h, c.w, scale, c.n, C, c.oh, c.ow, c.y, st,
+                        c.fuse_w ? &c.fuse_cur : nullptr, c.fuse_w));
     }
     return AFI_OK;
 }

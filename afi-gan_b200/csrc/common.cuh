@@ -135,8 +135,10 @@ int tc_init(afi_ctx* ctx);
 // ---- elementwise / layout kernels (elementwise.cu) ------------------------------------------------------
 template <typename T> int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st);
 // dst[n,c,y,x] (contiguous [n,c,oh,ow]) = scale * ( a[n,y,x,c] (T) [+ lat[n,y,x,c] (T)] [+ bilinear2x(skip)[n,c,y,x]] )
+// ... optionally followed by dst = fw[0] * add[n,c,y,x] + fw[1] * dst (fw: two device floats; the BiFPN fusion site)
 template <typename T> int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale,
-                                       int n, int c, int oh, int ow, float* dst, cudaStream_t st);
+                                       int n, int c, int oh, int ow, float* dst, cudaStream_t st, const afi_view4* add = nullptr,
+                                       const float* fw = nullptr);
 // dst = scale * (a + b) * mask ; a,b f32 or T views (dtype flags), mask T view (optional), dst T or f32
 int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PView mask, int mask_dt, float mask_slope,
                float scale, int n, int h, int w, int c, cudaStream_t st);

@@ -102,7 +102,7 @@ __device__ __forceinline__ void bilin_coord(int o, int size, int& i0, int& i1, f
 }
 template <typename T>
 __global__ void k_nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int sh, int sw_, float scale, int c, int oh, int ow,
-                               float* __restrict__ dst) {
+                               float* __restrict__ dst, afi_view4 add, const float* __restrict__ fw) {
     __shared__ float tile[32][33];
     int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     int n = blockIdx.z / oh, y = blockIdx.z % oh;
@@ -135,20 +135,24 @@ __global__ void k_nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int sh, int s
                 float v10 = s[y1 * skip.sh + xa * skip.sw], v11 = s[y1 * skip.sh + xb * skip.sw];
                 v += ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
             }
-            dst[(((long long)n * c + cc) * oh + y) * ow + xx] = v * scale;
+            v *= scale;
+            if (fw) v = fw[0] * add.ptr[n * add.sn + cc * add.sc + y * add.sh + xx * add.sw] + fw[1] * v;
+            dst[(((long long)n * c + cc) * oh + y) * ow + xx] = v;
         }
     }
 }
 template <typename T>
 int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale, int n, int c, int oh, int ow,
-                 float* dst, cudaStream_t st) {
+                 float* dst, cudaStream_t st, const afi_view4* add, const float* fw) {
     dim3 grid(cdiv(ow, 32), cdiv(c, 32), n * oh), block(32, 8);
-    k_nhwc_to_nchw<T><<<grid, block, 0, st>>>(a, lat, skip, skip_h, skip_w, scale, c, oh, ow, dst);
+    afi_view4 addv; memset(&addv, 0, sizeof(addv));
+    if (add && fw) addv = *add; else fw = nullptr;
+    k_nhwc_to_nchw<T><<<grid, block, 0, st>>>(a, lat, skip, skip_h, skip_w, scale, c, oh, ow, dst, addv, fw);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
-template int nhwc_to_nchw<float>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t);
-template int nhwc_to_nchw<bf16>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t);
+template int nhwc_to_nchw<float>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t, const afi_view4*, const float*);
+template int nhwc_to_nchw<bf16>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t, const afi_view4*, const float*);
 
 // ---------------------------------------------------------------------------------------------------
 // Input gradient of the interpolator: dx[n,c,i,j] = dXb[n,i,j,c] (head-conv dgrad, NHWC fp32) + bilinear2x^T(dy)[n,c,i,j].

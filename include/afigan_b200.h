@@ -101,6 +101,10 @@ typedef struct {
     const afi_lateral* lateral;     /* optional fused FPN lateral, may be NULL                                          */
     float* lat_dx; float* lat_gw; float* lat_gb; /* backward: d lat_x [n,lat_c,oh,ow], d lat_w [256,lat_c], d lat_b [256] (overwritten; may be NULL) */
     void* ws; size_t ws_bytes;      /* workspace of afi_g_workspace_bytes(); keeps the activations between fwd and bwd  */
+    /* optional (forward only, fuse_w != NULL): the BiFPN fusion site (bifpn_sr.py:535-548) folded into the output pass:
+     * y = fuse_w[0] * fuse_cur + fuse_w[1] * (Generators[0](x) + bilinear2x(x)); fuse_cur is a view of [n,256,oh,ow], fuse_w two
+     * floats ON THE DEVICE (the raw attention weights `BiFPNLayer_*_w1`; {1, 1} for the attention-free sum) */
+    afi_view4 fuse_cur; const float* fuse_w;
 } afi_g_call;
 
 /* Generator.forward (generator_rdb.py:123-130) for each call: y = (Generators[0](x) + bilinear2x(x))[:, :, :oh, :ow]

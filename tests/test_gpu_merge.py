@@ -144,6 +144,15 @@ def test_bifpn_fusion():
     out = bifpn_feature_fusion(G, cur.cuda(), top.cuda(), w.cuda())
     assert rel(out, ref) < 1e-5
     assert rel(bifpn_feature_fusion(G, cur.cuda(), top.cuda()), cur + O.generator_forward(g_sd, top)) < 1e-5
+    # the forward-only site (no autograd: one library call, fusion folded into the output pass) against the same oracle,
+    # incl. a cropped `cur` (odd pyramid sizes) and a strided (channels_last) one
+    with torch.no_grad():
+        fused = bifpn_feature_fusion(G, cur.cuda(), top.cuda(), w.cuda())
+        assert rel(fused, ref) < 1e-5
+        assert rel(bifpn_feature_fusion(G, cur.cuda(), top.cuda()), cur + O.generator_forward(g_sd, top)) < 1e-5
+        cur_odd = torch.randn(1, 256, 7, 11, generator=gen)
+        ref_odd = w[0] * cur_odd + w[1] * O.generator_forward(g_sd, top)[:, :, :7, :11]
+        assert rel(bifpn_feature_fusion(G, cur_odd.cuda().to(memory_format=torch.channels_last), top.cuda(), w.cuda()), ref_odd) < 1e-5
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
