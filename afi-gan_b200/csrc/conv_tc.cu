@@ -977,9 +977,11 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 float v[16];
                 tmem_ld16(taddr + c0, v);
                 const int ci = nt * tl.bn + c0;
-                if (k1 > k0 && co < a.cout && ci < a.cin) {
+                if (k1 > k0 && co < a.cout && ci < a.cin) {      // (cin is a multiple of 16: the whole chunk is inside the row, 16-byte aligned)
 #pragma unroll
-                    for (int i = 0; i < 16; i++) atomicAdd(dst + ci + i, v[i]);
+                    for (int i = 0; i < 16; i += 4)             // one vector reduction per four columns instead of four scalar ones
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + ci + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                                     "f"(v[i + 3]) : "memory");
                 }
             }
             tc_fence_before();
