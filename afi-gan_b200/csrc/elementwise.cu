@@ -1378,19 +1378,6 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, in
     }
     dst[i] = (T)v;
 }
-// dgrad sub-block: dst[slab][n - n0][koff + k] (NK) or dst[slab][koff + k][n - n0] (KN) = w[k][n][8 - slab], k < co, n0 <= n < n0 + ncnt
-template <typename T>
-__device__ __forceinline__ void pack_sub(const PackJob& q, long long i) {
-    const int nk = q.mode & 1;
-    const int inner = (int)(i % (nk ? q.co : q.ncnt));
-    const long long t2 = i / (nk ? q.co : q.ncnt);
-    const int outer = (int)(t2 % (nk ? q.ncnt : q.co));
-    const int slab = (int)(t2 / (nk ? q.ncnt : q.co));
-    const int k = nk ? inner : outer, n = nk ? outer : inner;
-    const float v = q.w[((long long)k * q.ci + q.n0 + n) * 9 + (8 - slab)];
-    const long long d = nk ? ((long long)slab * q.ncnt + n) * q.ktot + q.koff + k : ((long long)slab * q.ktot + q.koff + k) * q.ncnt + n;
-    reinterpret_cast<T*>(q.dst)[d] = (T)v;
-}
 template <typename T>
 __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -1410,20 +1397,45 @@ int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt
 }
 // all the re-layouts of one module in ONE launch (the generator has 38 of them, most far too small to fill a launch of their own)
 struct PackGroup { int njobs; int block_begin[AFI_MAX_PACK + 1]; PackJob j[AFI_MAX_PACK]; };
+// 3x3 forward / dgrad layouts (incl. dgrad sub-blocks): one thread per (gemm-cout, gemm-cin) pair reads its NINE taps as 36 contiguous
+// bytes and scatters them to the nine slabs (the element-wise version re-reads every 32-byte sector of the weights nine times)
+template <typename T>
+__device__ __forceinline__ void pack_taps9(const PackJob& q, long long u) {
+    const int nk = q.mode & 1, dgrad = (q.mode >> 1) == 1;
+    const int gk = q.sub ? q.co : (dgrad ? q.co : q.ci);                 // extent of this job's gemm-cin range
+    const int gn = q.sub ? q.ncnt : (dgrad ? q.ci : q.co);               // ... gemm-cout range
+    const int I = nk ? gk : gn, O = nk ? gn : gk;                        // inner / outer index of a slab
+    const int inner = (int)(u % I), outer = (int)(u / I);
+    const int k = nk ? inner : outer, n = nk ? outer : inner;
+    const float* src = q.w + (dgrad ? ((long long)k * q.ci + (q.sub ? q.n0 : 0) + n) : ((long long)n * q.ci + k)) * 9;
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) v[t] = src[t];
+    T* dst = reinterpret_cast<T*>(q.dst);
+    // destination strides: full slabs [O][I], or the [koff, koff + co) gemm-cin slice of a [ncnt][ktot] (NK) / [ktot][ncnt] (KN) slab
+    const long long slab_sz = q.sub ? (long long)q.ncnt * q.ktot : (long long)O * I;
+    const long long off = q.sub ? (nk ? (long long)n * q.ktot + q.koff + k : (long long)(q.koff + k) * q.ncnt + n) : (long long)outer * I + inner;
+#pragma unroll
+    for (int t = 0; t < 9; t++) dst[(long long)t * slab_sz + off] = (T)v[dgrad ? 8 - t : t];
+}
 template <typename T>
 __global__ void k_pack_group(const __grid_constant__ PackGroup G) {
     int k = 0;
     while (k + 1 < G.njobs && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
     const PackJob& q = G.j[k];
     long long i = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x;
-    const long long total = q.sub ? (long long)9 * q.co * q.ncnt : pack_total_dev(q.co, q.ci, q.mode);
+    const int kind = q.mode >> 1;
+    if (kind <= 1) {
+        const long long units = q.sub ? (long long)q.co * q.ncnt : (long long)q.co * q.ci;
 #pragma unroll
-    for (int u = 0; u < 4; u++, i += 256) {
-        if (i < total) {
-            if (q.sub) pack_sub<T>(q, i);
-            else pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
-        }
+        for (int u = 0; u < 4; u++, i += 256)
+            if (i < units) pack_taps9<T>(q, i);
+        return;
     }
+    const long long total = pack_total_dev(q.co, q.ci, q.mode);
+#pragma unroll
+    for (int u = 0; u < 4; u++, i += 256)
+        if (i < total) pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
 }
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st) {
     AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_PACK, "pack_weights_group: %d jobs (max %d)", njobs, AFI_MAX_PACK);
@@ -1434,7 +1446,10 @@ int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t 
     for (int k = 0; k < njobs; k++) {
         G.j[k] = jobs[k]; G.block_begin[k] = b;
         if (jobs[k].sub) AFI_REQUIRE((jobs[k].mode >> 1) == 1, "pack_weights_group: sub-block packing is a dgrad mode");
-        b += cdiv(jobs[k].sub ? (long long)9 * jobs[k].co * jobs[k].ncnt : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode), 1024);
+        const int kind = jobs[k].mode >> 1;
+        const long long work = kind <= 1 ? (jobs[k].sub ? (long long)jobs[k].co * jobs[k].ncnt : (long long)jobs[k].co * jobs[k].ci)
+                                         : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode);
+        b += cdiv(work, 1024);
     }
     G.block_begin[njobs] = b;
     if (dst_dt == DT_F32) k_pack_group<float><<<b, 256, 0, st>>>(G);
