@@ -8,7 +8,8 @@ pixel-major (NHWC) views plus a few elementwise passes:
 
 This file states that chain in plain torch so that the decomposition identities the kernels rely on
 (transposed conv = 4 phase convs; dgrad = conv with flipped/transposed slabs; deconv dgrad = one
-36-tap conv over 4 phase views; dense-block backward; train-mode BatchNorm backward in closed form;
+36-tap conv over 4 phase views; dense-block backward with the growth convs' dgrads split by destination and their
+weight gradients in one GEMM; train-mode BatchNorm backward in closed form; the head backward's mask from bn3(z3);
 the 1024->1 logit conv as 9 per-pixel dot products + a 3x3 shift-sum) are checked against the oracle's
 autograd on the CPU (tests/test_kernel_model.py).  csrc/api.cu is a transliteration of the
 g_forward / g_backward / d_forward / d_backward functions below.
@@ -184,11 +185,22 @@ def g_backward(sd, saved, dy_nchw: torch.Tensor, n_rdb: int = 3, need_dx: bool =
         grads[p + "conv5.weight"] = unpack_wgrad(wgrad_taps(dc5, B[r], TAPS9, C + 128))
         GA = conv_taps([dc5], std_taps(), pack_dgrad(sd[p + "conv5.weight"]), C)      # [.., 384]
         GA[..., :C] += d_out
+        # The four masked growth gradients sit side by side in ONE 128-channel buffer GC.  Their dgrads are split by destination:
+        #   * the part that reaches the EARLIER growth channels [C, C + 32 (i-1)) feeds the remaining masks: three small convs, in order;
+        #   * the part that reaches the block input x [0, C) is one conv with gemm-cin = 128 (all four at once), at the end.
+        # Their weight gradients are one [9][128][C + 96] GEMM whose non-causal blocks are ignored.
+        GC = torch.zeros(N, H, W, 128, dtype=X0.dtype)
         for i in (4, 3, 2, 1):
             cin = C + 32 * (i - 1)
-            g = GA[..., cin:cin + 32] * lmask(B[r][..., cin:cin + 32])
-            grads[p + f"conv{i}.0.weight"] = unpack_wgrad(wgrad_taps(g, B[r], TAPS9, cin))
-            GA[..., :cin] += conv_taps([g], std_taps(), pack_dgrad(sd[p + f"conv{i}.0.weight"]), 32)
+            GC[..., 32 * (i - 1):32 * i] = GA[..., cin:cin + 32] * lmask(B[r][..., cin:cin + 32])
+            if i > 1:
+                wd = pack_dgrad(sd[p + f"conv{i}.0.weight"])                    # [9][cin][32]
+                GA[..., C:cin] += conv_taps([GC[..., 32 * (i - 1):32 * i]], std_taps(), wd[:, C:cin, :], 32)
+        wx = torch.cat([pack_dgrad(sd[p + f"conv{i}.0.weight"])[:, :C, :] for i in (1, 2, 3, 4)], dim=2)   # [9][C][128]
+        GA[..., :C] += conv_taps([GC], std_taps(), wx, 128)
+        dw_all = wgrad_taps(GC, B[r], TAPS9, C + 96)                             # [9][128][C + 96]
+        for i in (1, 2, 3, 4):
+            grads[p + f"conv{i}.0.weight"] = unpack_wgrad(dw_all[:, 32 * (i - 1):32 * i, :C + 32 * (i - 1)])
         d_out = GA[..., :C]
     g_head = (d_out + dH1) * lmask(B[0][..., :C])
     grads["Generators.0.0.0.weight"] = unpack_wgrad(wgrad_taps(g_head, X0, TAPS9, C))
@@ -257,8 +269,13 @@ def d_backward(sd, saved, dlogit_nchw):
         p = f"Discriminators.0.{n}.0."
         mean, rstd, _ = stats[n]
         gamma = sd[p + "norm.weight"]
-        dyv = dA * lmask(A[n + 1])
         xhat = (Z[n] - mean) * rstd
+        if n == 2:
+            # layer 3 (tensor-core engine): dy3 is never stored.  Two passes over z3 recompute the 9-tap product gs @ w4^T, and the
+            # LeakyReLU mask comes from bn3(z3) (same sign as the stored activation), not from A[3]
+            dyv = dA * lmask(xhat * gamma + sd[p + "norm.bias"])
+        else:
+            dyv = dA * lmask(A[n + 1])
         M = dyv.numel() // dyv.shape[-1]
         s_dy, s_dyx = dyv.sum((0, 1, 2)), (dyv * xhat).sum((0, 1, 2))
         grads[p + "norm.weight"], grads[p + "norm.bias"] = s_dyx, s_dy
