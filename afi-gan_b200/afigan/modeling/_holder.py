@@ -1,4 +1,4 @@
-from ..functional import PackedWeights
+from ..functional import InferenceGraphs, PackedWeights
 
 
 class Holder:
@@ -7,6 +7,7 @@ class Holder:
     def __init__(self, n_rdb: int = 0):
         self.n_rdb = n_rdb
         self.packed = PackedWeights()
+        self.graphs = InferenceGraphs()
 
     def __deepcopy__(self, memo):
         return Holder(self.n_rdb)

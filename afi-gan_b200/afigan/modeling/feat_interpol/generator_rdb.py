@@ -94,13 +94,25 @@ class Generator(nn.Module):
     def forward(self, features: torch.Tensor, out_hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         """features [N,256,H,W] -> [N,256,2H,2W] (or its top-left out_hw crop: the _reshape_stage1 of the trainers)."""
         prec = native.PRECISIONS[self.precision or native.default_precision()]
+        if self._use_graphs(features):
+            return self._native.graphs.run(self._native, prec, self._params(), features, out_hw)
         return AFInterpolatorFn.apply(features, None, None, None, self._native, prec, out_hw, 1.0, torch.is_grad_enabled(), *self._params())
+
+    def _use_graphs(self, x: torch.Tensor) -> bool:
+        """Forward-only calls (inference: no autograd) replay CUDA graphs: eagerly issued they are host-bound (functional.InferenceGraphs).
+        AFIGAN_INFER_GRAPH=0 or a stream capture already in progress keeps the eager path."""
+        import os
+        return (not torch.is_grad_enabled() and x.is_cuda and os.environ.get("AFIGAN_INFER_GRAPH", "1") != "0"
+                and not torch.cuda.is_current_stream_capturing())
 
     def fuse(self, top_feature: torch.Tensor, cur_feature: torch.Tensor, weight: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Forward-only BiFPN fusion site in ONE library call (reference bifpn_sr.py:535-548): weight[0] * cur + weight[1] * self(top)."""
         from ...functional import afi_bifpn_fuse
         prec = native.PRECISIONS[self.precision or native.default_precision()]
         with torch.no_grad():
+            if self._use_graphs(top_feature):
+                oh, ow = cur_feature.shape[2:]
+                return self._native.graphs.run(self._native, prec, self._params(), top_feature, (oh, ow), fuse=(cur_feature.float(), weight))
             return afi_bifpn_fuse(top_feature, cur_feature, weight, self._native, prec, self._params())
 
     def merge(self, prev_features: torch.Tensor, bottom_up: torch.Tensor, lateral_weight: torch.Tensor,
@@ -111,5 +123,8 @@ class Generator(nn.Module):
         prec = native.PRECISIONS[self.precision or native.default_precision()]
         oh, ow = bottom_up.shape[2:]
         w2 = lateral_weight.reshape(lateral_weight.shape[0], lateral_weight.shape[1])
+        if self._use_graphs(prev_features) and lateral_weight.is_contiguous() and lateral_weight.dtype == torch.float32:
+            return self._native.graphs.run(self._native, prec, self._params(), prev_features, (oh, ow),
+                                           lat=(bottom_up.float(), w2, lateral_bias, 0.5 if fuse_type == "avg" else 1.0))
         return AFInterpolatorFn.apply(prev_features, bottom_up, w2, lateral_bias, self._native, prec, (oh, ow),
                                       0.5 if fuse_type == "avg" else 1.0, torch.is_grad_enabled(), *self._params())

@@ -1128,9 +1128,17 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);
     Tiling tl{};
-    tl.n_tiles = (a.cout + 255) / 256;
-    // (halving the N tile to get more waves on the generator's small levels was measured SLOWER: 806 -> 605 TFLOP/s on 256->256;
-    //  those layers are bound by L2 -> SM operand traffic, which a narrower tile increases)
+    // N tile: 256 columns whenever the problem has at least one M tile per SM (a narrower tile was measured SLOWER on the training shapes:
+    // 806 -> 605 TFLOP/s on 256->256).  SMALL problems -- inference on the coarse pyramid levels: a handful of M tiles -- are latency-
+    // bound by the serial K loop of each tile (36 taps x 4 MMAs x 128 cycles = 10 us for a 256-column tile with one SM busy per tile):
+    // there the N tile shrinks (128, 64) until the tiles cover the SMs, which shortens every tile's K loop proportionally.
+    int bn_cap = 256;
+    {
+        const long long m_tiles_est = (pixels + 127) / 128;
+        while (bn_cap > 64 && m_tiles_est * ((a.cout + bn_cap - 1) / bn_cap) < ctx->sm_count && a.cout > bn_cap / 2) bn_cap /= 2;
+        if (getenv("AFIGAN_FIXED_NTILE")) bn_cap = 256;
+    }
+    tl.n_tiles = (a.cout + bn_cap - 1) / bn_cap;
     tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
     tl.kchunks = (a.cin + 63) / 64;
     int nviews = 0;
