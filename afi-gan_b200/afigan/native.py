@@ -97,6 +97,7 @@ _SIGNATURES = {
                                C.c_void_p]),
     "afi_sgd_step_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                      C.c_int, C.c_void_p]),
+    "afi_sizeof": (C.c_size_t, [C.c_int]),
     "afi_zero": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
     "afi_conv3x3": (C.c_int, [C.c_void_p, C.c_int, View4, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

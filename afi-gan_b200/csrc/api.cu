@@ -192,6 +192,19 @@ using namespace afi;
 extern "C" {
 
 int afi_abi_version(void) { return AFI_ABI_VERSION; }
+size_t afi_sizeof(int which) {
+    switch (which) {
+        case 0: return sizeof(afi_view4);
+        case 1: return sizeof(afi_g_params);
+        case 2: return sizeof(afi_lateral);
+        case 3: return sizeof(afi_g_call);
+        case 4: return sizeof(afi_d_params);
+        case 5: return sizeof(afi_d_call);
+        case 6: return sizeof(afi_g_grads);
+        case 7: return sizeof(afi_d_grads);
+        default: return 0;
+    }
+}
 const char* afi_last_error(void) { return g_err; }
 long long afi_launch_count(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
 

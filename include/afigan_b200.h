@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AFI_ABI_VERSION 1
+#define AFI_ABI_VERSION 2   /* 2: afi_d_call.input_staged, afi_g_call.fuse_cur / fuse_w, afi_sgd_step_multi, afi_sizeof */
 
 #define AFI_OK 0
 #define AFI_ERR_INVALID (-1)   /* bad argument / unsupported shape */
@@ -52,6 +52,9 @@ typedef struct {
 
 /* ---- library ------------------------------------------------------------------------------------ */
 int afi_abi_version(void);
+/* sizeof() of the boundary structs as this library was built (which: 0 afi_view4, 1 afi_g_params, 2 afi_lateral, 3 afi_g_call,
+ * 4 afi_d_params, 5 afi_d_call, 6 afi_g_grads, 7 afi_d_grads; 0 for anything else): lets a binding check its own struct layouts */
+size_t afi_sizeof(int which);
 const char* afi_last_error(void);
 /* Binds to the CURRENT device; fails with AFI_ERR_ARCH unless it is compute capability 10.x. */
 int afi_create(afi_ctx** out);

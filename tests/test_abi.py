@@ -24,7 +24,18 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/afigan_b200.h but not exported"
     assert set(native.EXPORTED_SYMBOLS) == set(names), set(native.EXPORTED_SYMBOLS) ^ set(names)
-    assert native.lib().afi_abi_version() == 1
+    assert native.lib().afi_abi_version() == 2
+
+
+def test_ctypes_structs_match_the_library():
+    """The ctypes mirror of every boundary struct has the size the library was compiled with (a field added on one side only shows here,
+    on the CPU, instead of as memory corruption on the GPU)."""
+    from afigan import native
+    lib = native.lib()
+    mirrors = [native.View4, native.GParams, native.Lateral, native.GCall, native.DParams, native.DCall, native.GGrads, native.DGrads]
+    for which, cls in enumerate(mirrors):
+        assert lib.afi_sizeof(which) == ctypes.sizeof(cls), (which, cls.__name__, lib.afi_sizeof(which), ctypes.sizeof(cls))
+    assert lib.afi_sizeof(99) == 0
 
 
 def test_size_queries_without_gpu():
