@@ -206,3 +206,29 @@ def test_stage2_loss_block(precision):
     for a, b in zip(ups_c, ups):
         assert rel(a.grad, b.grad) < 1e-5          # sign(fake-real)/numel inside the crop, zero outside
     assert int(D.state_dict()["Discriminators.0.0.0.norm.num_batches_tracked"]) == 8   # (2 + 2) D calls x 2 levels
+
+
+def test_inference_graphs_match_the_eager_path():
+    """Forward-only calls replay CUDA graphs with static buffers (functional.InferenceGraphs): same numbers as the eager autograd path, across
+    repeated calls with fresh inputs on the same shape, for the plain forward, the fused FPN merge and the BiFPN fusion site, and after an
+    in-place weight update (the packed weights are refreshed in place, the graph keeps pointing at them)."""
+    G, _ = _gen("fp32")
+    gen = torch.Generator().manual_seed(31)
+    lat_w = (torch.randn(256, 512, 1, 1, generator=gen) * 0.05).cuda()
+    lat_b = torch.randn(256, generator=gen).cuda()
+    w = torch.tensor([0.6, 1.4]).cuda()
+    for rep in range(3):
+        x = torch.randn(1, 256, 7, 11, generator=gen).cuda()
+        c = torch.randn(1, 512, 13, 21, generator=gen).cuda()
+        cur = torch.randn(1, 256, 13, 21, generator=gen).cuda()
+        eager = (G(x), G(x, out_hw=(13, 21)), G.merge(x, c, lat_w, lat_b, "avg"))           # autograd enabled: eager launches
+        with torch.no_grad():
+            graphed = (G(x), G(x, out_hw=(13, 21)), G.merge(x, c, lat_w, lat_b, "avg"))
+            fused = G.fuse(x, cur, w)
+        for a, b in zip(graphed, eager):
+            assert rel(a, b.detach()) < 1e-6
+        assert rel(fused, (w[0] * cur + w[1] * eager[1]).detach()) < 1e-5
+        if rep == 1:                                # in-place update of a weight: later calls must see it
+            with torch.no_grad():
+                G.Generators[0][4][0].weight.mul_(1.5)
+    assert len(G._native.graphs.entries) == 4       # one graph per (shape, operands) -- not one per call
