@@ -352,7 +352,18 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H1, d1[k].h, d1[k].w, C); a.p[k].out = pview(W[k].H2, d1[k].h, d1[k].w, C); }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [3] ConvTranspose2d k6 s2 p2 == four 3x3 sub-pixel convs with interleaved stores      :101-105, App. G
-    for (int ph = 0; ph < 4; ph++) {
+    if (prec_tc(prec)) {      // tensor-core engine: the four phases are the four N tiles of ONE launch (the input tile is staged once)
+        conv_std(a, ncalls, d1, C, C, pk + L.up_f * es, 0);
+        a.bias = p->up_b; a.act = 1; a.out_dt = dt; a.nphase = 4;
+        for (int k = 0; k < ncalls; k++) {
+            const int H2x = d2[k].h, W2x = d2[k].w;
+            a.p[k].in[0] = pview(W[k].H2, d1[k].h, d1[k].w, C);
+            PView o; o.ptr = W[k].H3;
+            o.sx = 2 * C; o.sy = (long long)2 * W2x * C; o.sn = (long long)H2x * W2x * C;
+            a.p[k].out = o;
+        }
+        AFI_TRY(run_conv(ctx, prec, a, st));
+    } else for (int ph = 0; ph < 4; ph++) {
         int pa = ph >> 1, pb = ph & 1;
         conv_std(a, ncalls, d1, C, C, pk + L.up_f * es, 9 * ph);
         a.bias = p->up_b; a.act = 1; a.out_dt = dt;

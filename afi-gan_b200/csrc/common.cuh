@@ -91,6 +91,10 @@ struct ConvArgs {
     // 0: none.  1: stat0[c] += sum_p v, stat1[c] += sum_p v^2 (BatchNorm batch statistics of a conv output).
     // 2: stat0[c] += sum_p v, stat1[c] += sum_p v * (bnz - bn_mean[c]) * bn_rstd[c]  (the two reductions of BatchNorm backward).
     int stat_mode;
+    // nphase = 4 (tensor-core engine only): FOUR convolutions of the same input in one launch -- the sub-pixel phases of the stride-2
+    // transposed conv.  N tile p uses the slabs 9 p + tap.slab and stores its cout columns at out + (p >> 1) * out.sy / 2 +
+    // (p & 1) * out.sx / 2 (out is the stride-2 view of phase 0 in the 2h x 2w map).  0 = a single convolution.
+    int nphase;
     ConvProb p[AFI_MAX_PROB];
 };
 

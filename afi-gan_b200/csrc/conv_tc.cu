@@ -371,7 +371,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         const int ty = tp_.orient ? (row & 7) : row / tp_.TW, tx = tp_.orient ? (row >> 3) : row % tp_.TW;
         int y = (r / tp_.tiles_x) * tp_.TH + ty, x = (r % tp_.tiles_x) * tp_.TW + tx;
         const bool ok = tile_valid && (y < pr.H) && (x < pr.W);
-        const int n0 = nt * tl.bn;
+        const int n0 = a.nphase ? 0 : nt * tl.bn;                                                   // phase mode: every N tile is a whole conv
+        const long long out_off = a.nphase ? (nt >> 1) * (pr.out.sy >> 1) + (nt & 1) * (pr.out.sx >> 1) : 0;
         // Auxiliary epilogue operands (residuals / mask / BN input / fp32 accumulate-in) are prefetched one chunk ahead of their
         // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
         const long long offA = pr.mask.ptr ? img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx
@@ -446,7 +447,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
                     }
                     if (a.stat_mode == 2) unpack16(ax.c, ax.d, zbn);
                 }
-                st16(pr.out.ptr, img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
+                st16(pr.out.ptr, out_off + img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
             }
             if (a.stat_mode) {      // warp-uniform: every lane takes part in the shuffles, invalid rows contribute zeros
                 float s0[16], s1[16];
@@ -540,7 +541,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 int tiles_per_img = tp_.tiles_x * tp_.tiles_y;
                 int img = mt / tiles_per_img, r = mt % tiles_per_img;
                 int y0 = (r / tp_.tiles_x) * tp_.TH, x0 = (r % tp_.tiles_x) * tp_.TW;
-                int n0 = nt * tl.bn;
+                const int n0 = a.nphase ? 0 : nt * tl.bn, sl0 = a.nphase ? 9 * nt : 0;
                 for (int tp = 0; tp < a.ntaps; tp++) {
                     const Tap t = a.taps[tp];
                     const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
@@ -551,7 +552,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                         if (elect_one()) {
                             mbar_expect_tx(fb, tx_bytes);
                             tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
-                            tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, t.slab);
+                            tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, sl0 + t.slab);
                         }
                         __syncwarp();
                         if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -626,7 +627,7 @@ struct SmemH {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
-struct HaloTile { int prob, img, c1, c2, n0; };      // c1 / c2: TMA coordinates of the halo's first pixel along its fast / slow axis
+struct HaloTile { int prob, img, c1, c2, n0, sl0; };      // c1 / c2: TMA coordinates of the halo's first pixel along its fast / slow axis
 
 template <int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
@@ -694,7 +695,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 const int r = mt % tiles_per_img;
                 h.prob = tp_.prob; h.img = mt / tiles_per_img;
                 const int y0 = (r / tp_.tiles_x) * tp_.TH - 1, x0 = (r % tp_.tiles_x) * tp_.TW - 1;
-                h.c1 = tp_.orient ? y0 : x0; h.c2 = tp_.orient ? x0 : y0; h.n0 = nt * tl.bn;
+                h.c1 = tp_.orient ? y0 : x0; h.c2 = tp_.orient ? x0 : y0;
+                h.n0 = a.nphase ? 0 : nt * tl.bn; h.sl0 = a.nphase ? 9 * nt : 0;
             };
             auto issue_a = [&](const HaloTile& h, int view, int kc) {
                 mbar_wait_t(bar_ae + 8 * ai, aph ^ 1, 21, w_ae, dbg_on);
@@ -722,7 +724,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 if (has_next) decode(nitem, nxt);
                 int view = 0, kc = 0;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
-                    const int slab0 = tl.view_slab0[view];
+                    const int slab0 = tl.view_slab0[view] + cur.sl0;
                     const int kcol = kc * 64, nrow = cur.n0 + brow;
                     int nview = view, nkc = kc + 1;
                     if (nkc == kchunks) { nkc = 0; if (++nview == tl.nviews) nview = 0; }
@@ -1140,6 +1142,11 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     }
     tl.n_tiles = (a.cout + bn_cap - 1) / bn_cap;
     tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
+    if (a.nphase) {      // one N tile per phase
+        AFI_REQUIRE(a.nphase == 4 && a.cout <= 256 && !a.stat_mode, "conv_tc: phase mode needs four phases of <= 256 couts without statistics");
+        tl.n_tiles = a.nphase;
+        tl.bn = (a.cout + 15) / 16 * 16;
+    }
     tl.kchunks = (a.cin + 63) / 64;
     int nviews = 0;
     for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
@@ -1200,6 +1207,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     tl.total = begin;
     int nslab = 0;
     for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
+    if (a.nphase) nslab += 9 * (a.nphase - 1);
     {
         cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
@@ -1211,7 +1219,8 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     if (tl.nstages > STAGES_MAX) tl.nstages = STAGES_MAX;
     int grid = tl.total < ctx->sm_count ? tl.total : ctx->sm_count;
     if (pair) { int ncl = ctx->sm_count / 2; grid = 2 * (tl.total < ncl ? tl.total : ncl); }
-    ProfScope prof(pair ? PROF_CONV_PAIR : (hmode ? PROF_CONV_HALO : PROF_CONV_TC), 2.0 * pixels * (double)a.ntaps * a.cin * a.cout, a.cin, a.cout, pixels, st);
+    ProfScope prof(pair ? PROF_CONV_PAIR : (hmode ? PROF_CONV_HALO : PROF_CONV_TC), 2.0 * pixels * (double)a.ntaps * a.cin * a.cout * (a.nphase ? a.nphase : 1),
+                   a.cin, a.cout * (a.nphase ? a.nphase : 1), pixels, st);
     // short-K layers (K = taps x cin < 4096) get eight epilogue warps
     if (pair) {
         const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
