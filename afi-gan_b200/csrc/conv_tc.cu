@@ -165,6 +165,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Programmatic dependent launch (no-ops unless the kernel was launched with the programmatic-serialization attribute): pdl_launch() lets
+// the NEXT kernel of the stream start its prologue (CTA launch, barrier / TMEM set-up) on idle SMs while this one still runs; pdl_wait()
+// blocks until the PREVIOUS kernel has completed and its writes are visible -- it precedes every global-memory access.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // one lane of a CONVERGED warp (the whole warp runs the role loop; only the instruction issue is elected -- the code the compiler emits
 // for tcgen05 / TMA instructions inside a divergent `if (lane == 0)` region wraps each of them in an ELECT / branch loop)
 __device__ __forceinline__ bool elect_one() {
@@ -526,6 +531,8 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     const uint32_t tmem_base = setup(s, maps, EPI_WARPS, warp, lane);
     const int iters = a.ntaps * tl.kchunks;
     const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
+    pdl_launch();
+    if (warp != 1) pdl_wait();        // the producer and epilogue warps touch global memory; the MMA warp does not
 
     if (warp == 0) {
         {
@@ -665,6 +672,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
+    pdl_launch();
+    if (warp != 1) pdl_wait();        // the producer and epilogue warps touch global memory; the MMA warp does not
     const int kchunks = tl.kchunks;
     const int nchunks = tl.nviews * kchunks;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -1222,22 +1231,33 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     ProfScope prof(pair ? PROF_CONV_PAIR : (hmode ? PROF_CONV_HALO : PROF_CONV_TC), 2.0 * pixels * (double)a.ntaps * a.cin * a.cout * (a.nphase ? a.nphase : 1),
                    a.cin, a.cout * (a.nphase ? a.nphase : 1), pixels, st);
     // short-K layers (K = taps x cin < 4096) get eight epilogue warps
-    if (pair) {
-        const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
+    // AFIGAN_PDL=1: programmatic dependent launch (the kernel may start its prologue before its predecessor in the stream has finished)
+    const char* pe = getenv("AFIGAN_PDL");
+    const bool pdl = pe && atoi(pe) != 0;
+    {
         cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * (epi8 ? 8 : 4)); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, true>, maps, a, tl));
-        else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, true>, maps, a, tl));
-    } else if (hmode) {
-        const int dyn = 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot;
-        if (epi8) k_conv_halo<8, false><<<grid, 64 + 32 * 8, dyn, st>>>(maps, a, tl);
-        else k_conv_halo<4, false><<<grid, 64 + 32 * 4, dyn, st>>>(maps, a, tl);
-    } else if (epi8) k_conv_tc<8><<<grid, 64 + 32 * 8, SMEM_BYTES, st>>>(maps, a, tl);
-    else k_conv_tc<4><<<grid, 64 + 32 * 4, SMEM_BYTES, st>>>(maps, a, tl);
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (pair) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            na++;
+        }
+        if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * (epi8 ? 8 : 4)); cfg.stream = st;
+        cfg.dynamicSmemBytes = hmode ? 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot : SMEM_BYTES;
+        cfg.attrs = attr; cfg.numAttrs = na;
+        if (pair) {
+            if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, true>, maps, a, tl));
+            else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, true>, maps, a, tl));
+        } else if (hmode) {
+            if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, false>, maps, a, tl));
+            else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, false>, maps, a, tl));
+        } else {
+            if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<8>, maps, a, tl));
+            else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<4>, maps, a, tl));
+        }
+    }
 #ifdef AFI_STALL_COUNTERS
     {
         if (tl.dbg) {      // experiment aid: per-CTA stall cycles of the producer / MMA threads
