@@ -134,3 +134,18 @@ def test_checkpoint_key_remap_and_lr_schedule():
     # WarmupMultiStepLR of the stage-1 recipe
     assert abs(warmup_multistep_lr(0) - 1e-6) < 1e-12 and abs(warmup_multistep_lr(500) - 1e-3 * (0.001 * 0.5 + 0.5)) < 1e-12
     assert warmup_multistep_lr(1000) == 1e-3 and warmup_multistep_lr(269999) == 1e-3 and abs(warmup_multistep_lr(270000) - 1e-4) < 1e-12
+
+
+def test_bench_flop_accounting_matches_the_survey():
+    """bench.py's op counts: G forward 19 206 144 FLOP per input pixel, D forward 30 689 280 per pixel, a config-1 stage-1 step
+    2.332e13 FLOP per image; the step that evaluates G(lr) once executes exactly one generator forward less."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    assert bench.G_FWD_FLOP_PER_INPUT_PX == 2 * 1_179_648 + 3 * 2_469_888 + 4_718_592 + 4_718_592 == 19_206_144
+    assert bench.D_FWD_FLOP_PER_PX == 2_359_296 + 9_437_184 + 18_874_368 + 18_432 == 30_689_280
+    lr_px, hr_px = 2 * 23_282, 2 * 89_523
+    ref = bench.stage1_step_flops(lr_px, hr_px)
+    assert abs(ref / 2 - 2.332e13) < 0.001e13                         # per image (batch 2)
+    assert ref - bench.stage1_step_flops(lr_px, hr_px, 1) == bench.G_FWD_FLOP_PER_INPUT_PX * lr_px
+    assert sum(h * w for h, w in bench.C1_LR_SHAPES) == 23_282 and sum(h * w for h, w in bench.C1_HR_SHAPES) == 89_523
