@@ -55,31 +55,54 @@ struct Carver {
     void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += align_up(bytes); return p; }
 };
 
-static inline bool prec_ok(int prec) { return prec == AFI_PREC_FP32 || prec == AFI_PREC_BF16 || prec == AFI_PREC_BF16_SIMT; }
-static inline int prec_dt(int prec) { return prec == AFI_PREC_FP32 ? DT_F32 : DT_BF16; }
+static inline bool prec_ok(int prec) { return prec == AFI_PREC_FP32 || prec == AFI_PREC_BF16 || prec == AFI_PREC_BF16_SIMT || prec == AFI_PREC_SPLIT; }
+// activation storage dtype: AFI_PREC_SPLIT keeps every tensor fp32 in HBM (its elementwise passes are the fp32 mode's); only the GEMM
+// operands are staged as bf16 planes
+static inline int prec_dt(int prec) { return (prec == AFI_PREC_FP32 || prec == AFI_PREC_SPLIT) ? DT_F32 : DT_BF16; }
 static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+// tcgen05 engine with bf16 storage: the tensor-core formulations of the discriminator head and the fused statistics epilogues
 static inline bool prec_tc(int prec) { return prec == AFI_PREC_BF16; }
+// tcgen05 GEMM engine (bf16 or split-precision operands): [slab][cout][cin] weight / gradient layouts, four-phase transposed conv
+static inline bool prec_nk(int prec) { return prec == AFI_PREC_BF16 || prec == AFI_PREC_SPLIT; }
+// packed weights: dtype tag and bytes per logical element (split: three bf16 planes)
+static inline int prec_wdt(int prec) { return prec == AFI_PREC_SPLIT ? DT_BF16X3 : prec_dt(prec); }
+static inline size_t prec_wes(int prec) { return prec == AFI_PREC_SPLIT ? 6 : dt_size(prec_dt(prec)); }
+
+// AFI_PREC_SPLIT operand scratch of the API call in flight: problem k of a grouped launch stages its operands in the scratch of call
+// k0 + k (k0 != 0 only for the single-problem launches issued per call)
+struct SplitScratch { void* p[AFI_MAX_PROB]; size_t n[AFI_MAX_PROB]; int k0; };
+static thread_local SplitScratch g_ss;
 
 static int run_conv(afi_ctx* ctx, int prec, const ConvArgs& a, cudaStream_t st) {
     if (prec == AFI_PREC_FP32) return conv_simt<float>(a, st);
     if (prec == AFI_PREC_BF16_SIMT) return conv_simt<bf16>(a, st);
+    if (prec == AFI_PREC_SPLIT) {
+        ConvArgs b = a;
+        for (int k = 0; k < b.nprob; k++) { b.p[k].sws = g_ss.p[g_ss.k0 + k]; b.p[k].sws_bytes = g_ss.n[g_ss.k0 + k]; }
+        return conv_tc_split(ctx, b, st);
+    }
     return conv_tc(ctx, a, st);
 }
 static int run_wgrad(afi_ctx* ctx, int prec, const WgradArgs& a, cudaStream_t st) {
     if (prec == AFI_PREC_FP32) return wgrad_simt<float>(a, st);
     if (prec == AFI_PREC_BF16_SIMT) return wgrad_simt<bf16>(a, st);
+    if (prec == AFI_PREC_SPLIT) {
+        WgradArgs b = a;
+        for (int k = 0; k < b.nprob; k++) { b.p[k].sws = g_ss.p[g_ss.k0 + k]; b.p[k].sws_bytes = g_ss.n[g_ss.k0 + k]; }
+        return wgrad_tc_split(ctx, b, st);
+    }
     return wgrad_tc(ctx, a, st);
 }
 static int to_nhwc(int prec, afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st) {
-    return prec == AFI_PREC_FP32 ? nchw_to_nhwc<float>(src, n, c, h, w, dst, st) : nchw_to_nhwc<bf16>(src, n, c, h, w, dst, st);
+    return prec_dt(prec) == DT_F32 ? nchw_to_nhwc<float>(src, n, c, h, w, dst, st) : nchw_to_nhwc<bf16>(src, n, c, h, w, dst, st);
 }
 static int to_nchw(int prec, PView a, PView lat, afi_view4 skip, int sh, int sw, float scale, int n, int c, int oh, int ow, float* dst,
                    cudaStream_t st, const afi_view4* add = nullptr, const float* fw = nullptr) {
-    return prec == AFI_PREC_FP32 ? nhwc_to_nchw<float>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st, add, fw)
+    return prec_dt(prec) == DT_F32 ? nhwc_to_nchw<float>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st, add, fw)
                                  : nhwc_to_nchw<bf16>(a, lat, skip, sh, sw, scale, n, c, oh, ow, dst, st, add, fw);
 }
 // forward / dgrad pack modes per engine
-static inline int pm(int prec, int kind) { return kind * 2 + (prec_tc(prec) ? 1 : 0); }
+static inline int pm(int prec, int kind) { return kind * 2 + (prec_nk(prec) ? 1 : 0); }
 
 // standard 3x3 weight gradient over a group of problems (dims / views per problem)
 struct Dim3 { int n, h, w; };
@@ -156,24 +179,30 @@ struct GWs {
     void *X0, *B[AFI_MAX_RDB], *H1, *H2, *H3, *Yb, *LX, *LAT;           // forward (X0..H3 saved for backward)
     void *G0, *G1, *G2, *dH1, *GA[2], *DC5, *GC, *GH, *DXb, *LW;        // backward scratch
     void *LWD, *LWG, *LDX;                                              // lateral backward: dgrad pack, wgrad accumulator, d(lat_x) NHWC
+    void* SPL; size_t spl_bytes;                                        // AFI_PREC_SPLIT: bf16 operand planes of the GEMM in flight
     size_t total;
 };
 static GWs g_ws_layout(void* base, int prec, int n, int h, int w, int n_rdb, int lat_c, int backward) {
     GWs W; memset(&W, 0, sizeof(W));
     Carver cv(base);
-    size_t es = dt_size(prec_dt(prec));
+    size_t es = dt_size(prec_dt(prec)), wes = prec_wes(prec);
     size_t P = (size_t)n * h * w, P4 = 4 * P;
     W.X0 = cv.take(P * C * es);
     for (int r = 0; r < n_rdb; r++) W.B[r] = cv.take(P * CB * es);
     W.H1 = cv.take(P * C * es); W.H2 = cv.take(P * C * es); W.H3 = cv.take(P4 * C * es);
     W.Yb = cv.take(P4 * C * es);
-    if (lat_c > 0) { W.LX = cv.take(P4 * lat_c * es); W.LAT = cv.take(P4 * C * es); W.LW = cv.take((size_t)C * lat_c * es); }
+    if (lat_c > 0) { W.LX = cv.take(P4 * lat_c * es); W.LAT = cv.take(P4 * C * es); W.LW = cv.take((size_t)C * lat_c * wes); }
     if (backward) {
         W.G0 = cv.take(P4 * C * es); W.G1 = cv.take(P4 * C * es); W.G2 = cv.take(P * C * es);
         W.dH1 = cv.take(P * C * 4); W.GA[0] = cv.take(P * CB * 4); W.GA[1] = cv.take(P * CB * 4);
         W.DC5 = cv.take(P * C * es); W.GC = cv.take(P * 4 * GR * es); W.GH = cv.take(P * C * es);
         W.DXb = cv.take(P * C * 4);
-        if (lat_c > 0) { W.LWD = cv.take((size_t)C * lat_c * es); W.LWG = cv.take((size_t)C * lat_c * 4); W.LDX = cv.take(P4 * lat_c * 4); }
+        if (lat_c > 0) { W.LWD = cv.take((size_t)C * lat_c * wes); W.LWG = cv.take((size_t)C * lat_c * 4); W.LDX = cv.take(P4 * lat_c * 4); }
+    }
+    if (prec == AFI_PREC_SPLIT) {
+        // the widest GEMM of a call: the output conv's weight gradient (x and dy on the 2h x 2w grid), or the lateral's
+        W.spl_bytes = 2 * split_planes_bytes((long long)P4, lat_c > C ? lat_c : C);
+        W.SPL = cv.take(W.spl_bytes);
     }
     W.total = cv.off;
     return W;
@@ -252,7 +281,7 @@ int afi_create(afi_ctx** out) {
 }
 void afi_destroy(afi_ctx* ctx) { delete ctx; }
 
-size_t afi_g_packed_bytes(int prec, int n_rdb) { return g_packed_layout(n_rdb).total * dt_size(prec_dt(prec)); }
+size_t afi_g_packed_bytes(int prec, int n_rdb) { return g_packed_layout(n_rdb).total * prec_wes(prec); }
 size_t afi_g_gradacc_bytes(int n_rdb) { return g_gradacc_layout(n_rdb).total * 4; }
 size_t afi_g_workspace_bytes(int prec, int n, int h, int w, int n_rdb, int lat_c, int save_for_backward) {
     return g_ws_layout(nullptr, prec, n, h, w, n_rdb, lat_c, save_for_backward).total;
@@ -263,7 +292,7 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     AFI_REQUIRE(ctx && p && packed, "afi_g_pack: null argument");
     AFI_TRY(g_check(prec, 1, 1, 1, p->n_rdb));
     GPacked L = g_packed_layout(p->n_rdb);
-    int dt = prec_dt(prec); size_t es = dt_size(dt);
+    const int dt = prec_wdt(prec); const size_t es = prec_wes(prec);
     char* b = (char*)packed;
     PackJob jobs[AFI_MAX_PACK]; int nj = 0;     // forward + dgrad layouts of every conv: one grouped launch
     auto add = [&](const float* w, int co, int ci, int kind, size_t off) {
@@ -296,9 +325,10 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
     AFI_REQUIRE(ctx && p && packed && calls, "afi_g_forward: null argument");
     AFI_REQUIRE(ncalls >= 1 && ncalls <= AFI_MAX_PROB, "afi_g_forward: %d calls per group (max %d)", ncalls, AFI_MAX_PROB);
     const int nr = p->n_rdb, dt = prec_dt(prec);
-    const int es = (int)dt_size(dt);
+    const int es = (int)dt_size(dt), wes = (int)prec_wes(prec);
     GWs W[AFI_MAX_PROB];
     Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
+    g_ss.k0 = 0;
     for (int k = 0; k < ncalls; k++) {
         const afi_g_call& c = calls[k];
         AFI_REQUIRE(c.x.ptr && c.y && c.ws, "afi_g_forward: call %d has a null pointer", k);
@@ -310,6 +340,7 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
         if (c.lateral) AFI_REQUIRE(lat_c % 32 == 0 && lat_c <= 2048 && c.lateral->lat_x.ptr && c.lateral->lat_w, "afi_g_forward: bad lateral");
         W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, lat_c, save);
         if (W[k].total > c.ws_bytes) { set_error("afi_g_forward: workspace %zu B < required %zu B", c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        g_ss.p[k] = W[k].SPL; g_ss.n[k] = W[k].spl_bytes;
         d1[k] = {c.n, c.h, c.w};
         d2[k] = {c.n, 2 * c.h, 2 * c.w};
     }
@@ -319,14 +350,14 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
 
     for (int k = 0; k < ncalls; k++) AFI_TRY(to_nhwc(prec, calls[k].x, calls[k].n, C, calls[k].h, calls[k].w, pview(W[k].X0, calls[k].h, calls[k].w, C), st));
     // [0] head conv + bias + LeakyReLU -> B0[:, 0:256]                                   generator_rdb.py:91-93
-    conv_std(a, ncalls, d1, C, C, pk + L.head_f * es);
+    conv_std(a, ncalls, d1, C, C, pk + L.head_f * wes);
     a.bias = p->head_b; a.act = 1; a.out_dt = dt;
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].X0, d1[k].h, d1[k].w, C); a.p[k].out = pview(W[k].B[0], d1[k].h, d1[k].w, CB); }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [1] residual-in-residual: dense blocks write their growth channels into slices of one 384-ch buffer   :39-71
     for (int r = 0; r < nr; r++) {
         for (int i = 0; i < 4; i++) {
-            conv_std(a, ncalls, d1, C + GR * i, GR, pk + L.rdb_f[r][i] * es);
+            conv_std(a, ncalls, d1, C + GR * i, GR, pk + L.rdb_f[r][i] * wes);
             a.act = 1; a.out_dt = dt;
             for (int k = 0; k < ncalls; k++) {
                 PView Br = pview(W[k].B[r], d1[k].h, d1[k].w, CB);
@@ -334,7 +365,7 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
             }
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
-        conv_std(a, ncalls, d1, CB, C, pk + L.rdb_f[r][4] * es);
+        conv_std(a, ncalls, d1, CB, C, pk + L.rdb_f[r][4] * wes);
         a.out_dt = dt; a.r1_dt = dt; a.r2_dt = dt;
         if (r + 1 < nr) { a.alpha = 0.2f; a.beta1 = 1.f; }           // x_{r+1} = x_r + 0.2 * conv5
         else { a.alpha = 0.04f; a.beta1 = 0.2f; a.beta2 = 1.f; }      // h1 = 0.2 * (x + 0.2 conv5) + h0            :27-30
@@ -347,13 +378,13 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
         AFI_TRY(run_conv(ctx, prec, a, st));
     }
     // [2] post conv + bias + LeakyReLU                                                   :97-99
-    conv_std(a, ncalls, d1, C, C, pk + L.post_f * es);
+    conv_std(a, ncalls, d1, C, C, pk + L.post_f * wes);
     a.bias = p->post_b; a.act = 1; a.out_dt = dt;
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H1, d1[k].h, d1[k].w, C); a.p[k].out = pview(W[k].H2, d1[k].h, d1[k].w, C); }
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [3] ConvTranspose2d k6 s2 p2 == four 3x3 sub-pixel convs with interleaved stores      :101-105, App. G
-    if (prec_tc(prec)) {      // tensor-core engine: the four phases are the four N tiles of ONE launch (the input tile is staged once)
-        conv_std(a, ncalls, d1, C, C, pk + L.up_f * es, 0);
+    if (prec_nk(prec)) {      // tensor-core engine: the four phases are the four N tiles of ONE launch (the input tile is staged once)
+        conv_std(a, ncalls, d1, C, C, pk + L.up_f * wes, 0);
         a.bias = p->up_b; a.act = 1; a.out_dt = dt; a.nphase = 4;
         for (int k = 0; k < ncalls; k++) {
             const int H2x = d2[k].h, W2x = d2[k].w;
@@ -365,7 +396,7 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
         AFI_TRY(run_conv(ctx, prec, a, st));
     } else for (int ph = 0; ph < 4; ph++) {
         int pa = ph >> 1, pb = ph & 1;
-        conv_std(a, ncalls, d1, C, C, pk + L.up_f * es, 9 * ph);
+        conv_std(a, ncalls, d1, C, C, pk + L.up_f * wes, 9 * ph);
         a.bias = p->up_b; a.act = 1; a.out_dt = dt;
         for (int k = 0; k < ncalls; k++) {
             const int H2x = d2[k].h, W2x = d2[k].w;
@@ -377,7 +408,7 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
         AFI_TRY(run_conv(ctx, prec, a, st));
     }
     // [4] output conv + bias on the 2h x 2w grid                                           :107-108
-    conv_std(a, ncalls, d2, C, C, pk + L.out_f * es);
+    conv_std(a, ncalls, d2, C, C, pk + L.out_f * wes);
     a.bias = p->out_b; a.out_dt = dt;
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H3, d2[k].h, d2[k].w, C); a.p[k].out = pview(W[k].Yb, d2[k].h, d2[k].w, C); }
     AFI_TRY(run_conv(ctx, prec, a, st));
@@ -389,14 +420,16 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
             const afi_lateral* lat = c.lateral;
             const int lat_c = lat->lat_c;
             AFI_TRY(to_nhwc(prec, lat->lat_x, c.n, lat_c, c.oh, c.ow, pview(W[k].LX, c.oh, c.ow, lat_c), st));
-            AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W[k].LW, dt, st));
+            AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W[k].LW, prec_wdt(prec), st));
             conv_args_init(a);
             a.cin = lat_c; a.cout = C; a.ntaps = 1; a.nprob = 1;
             a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0;
             a.p[0].N = c.n; a.p[0].H = c.oh; a.p[0].W = c.ow;
             a.p[0].in[0] = pview(W[k].LX, c.oh, c.ow, lat_c); a.w = W[k].LW; a.bias = lat->lat_b;
             a.p[0].out = pview(W[k].LAT, c.oh, c.ow, C); a.out_dt = dt;
+            g_ss.k0 = k;
             AFI_TRY(run_conv(ctx, prec, a, st));
+            g_ss.k0 = 0;
             latv = pview(W[k].LAT, c.oh, c.ow, C);
             scale = lat->scale;
         }
@@ -415,9 +448,10 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     AFI_REQUIRE(ctx && p && packed && calls && gradacc, "afi_g_backward: null argument");
     AFI_REQUIRE(ncalls >= 1 && ncalls <= AFI_MAX_PROB, "afi_g_backward: %d calls per group (max %d)", ncalls, AFI_MAX_PROB);
     const int nr = p->n_rdb, dt = prec_dt(prec);
-    const int es = (int)dt_size(dt);
+    const int es = (int)dt_size(dt), wes = (int)prec_wes(prec);
     GWs W[AFI_MAX_PROB];
     Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
+    g_ss.k0 = 0;
     PView X0[AFI_MAX_PROB], H1[AFI_MAX_PROB], H2[AFI_MAX_PROB], H3[AFI_MAX_PROB], G0[AFI_MAX_PROB], G1[AFI_MAX_PROB], G2[AFI_MAX_PROB],
         dH1[AFI_MAX_PROB], DC5[AFI_MAX_PROB], GC[AFI_MAX_PROB], GH[AFI_MAX_PROB], tmpx[AFI_MAX_PROB], tmpy[AFI_MAX_PROB];
     for (int k = 0; k < ncalls; k++) {
@@ -427,6 +461,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         AFI_TRY(g_check(prec, c.n, c.h, c.w, nr));
         W[k] = g_ws_layout(c.ws, prec, c.n, c.h, c.w, nr, c.lateral ? c.lateral->lat_c : 0, 1);
         if (W[k].total > c.ws_bytes) { set_error("afi_g_backward: workspace %zu B < required %zu B", c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        g_ss.p[k] = W[k].SPL; g_ss.n[k] = W[k].spl_bytes;
         const int h = c.h, w = c.w, H2x = 2 * h, W2x = 2 * w;
         d1[k] = {c.n, h, w};
         d2[k] = {c.n, H2x, W2x};
@@ -450,6 +485,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             // y = scale * (lateral_conv(lat_x) + G(x)): both branches see scale * dy                       fpn_sr.py:152-157
             const afi_lateral* lat = c.lateral;
             const int lat_c = lat->lat_c;
+            g_ss.k0 = k;
             if (lat->scale != 1.f)
                 AFI_TRY(ew_combine(G0[k], dt, G0[k], dt, pview_null(), 0, pview_null(), 0, 0.2f, lat->scale, c.n, 2 * c.h, 2 * c.w, C, st));
             PView G0c = G0[k];                                   // the oh x ow crop of the 2h x 2w gradient buffer (same strides)
@@ -462,14 +498,14 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
                 g.cin = lat_c; g.cout = C; g.ntaps = 1; g.nprob = 1; g.dw = (float*)W[k].LWG;
                 g.p[0].N = dc.n; g.p[0].H = dc.h; g.p[0].W = dc.w; g.p[0].x = LX; g.p[0].dy = G0c;
                 AFI_TRY(run_wgrad(ctx, prec, g, st));
-                AFI_TRY(unpack_1x1((const float*)W[k].LWG, C, lat_c, prec_tc(prec) ? 1 : 0, c.lat_gw, 1.f, 0, st));
+                AFI_TRY(unpack_1x1((const float*)W[k].LWG, C, lat_c, prec_nk(prec) ? 1 : 0, c.lat_gw, 1.f, 0, st));
             }
             if (c.lat_gb) {
                 AFI_CUDA(cudaMemsetAsync(c.lat_gb, 0, C * sizeof(float), st));
                 AFI_TRY(col_sum_f32(G0c, dt, dc.n, dc.h, dc.w, C, c.lat_gb, st));
             }
             if (c.lat_dx) {
-                AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 5), W[k].LWD, dt, st));
+                AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 5), W[k].LWD, prec_wdt(prec), st));
                 conv_args_init(a);
                 a.cin = C; a.cout = lat_c; a.ntaps = 1; a.nprob = 1; a.w = W[k].LWD; a.out_dt = DT_F32;
                 a.p[0].N = dc.n; a.p[0].H = dc.h; a.p[0].W = dc.w;
@@ -478,12 +514,13 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
                 afi_view4 none; memset(&none, 0, sizeof(none));
                 AFI_TRY(nhwc_to_nchw<float>(pview(W[k].LDX, dc.h, dc.w, lat_c), pview_null(), none, 0, 0, 1.f, dc.n, lat_c, dc.h, dc.w, c.lat_dx, st));
             }
+            g_ss.k0 = 0;
         }
     }
     // output conv
     AFI_TRY(wgrad_std(ctx, prec, ncalls, d2, H3, C, G0, C, gradacc + GL.out_w, st));
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G0[k], dt, d2[k].n, d2[k].h, d2[k].w, C, gradacc + GL.out_b, st));
-    conv_std(a, ncalls, d2, C, C, pk + L.out_d * es);
+    conv_std(a, ncalls, d2, C, C, pk + L.out_d * wes);
     a.out_dt = dt;
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = G0[k]; a.p[k].mask = H3[k]; a.p[k].out = G1[k]; }
     AFI_TRY(run_conv(ctx, prec, a, st));
@@ -501,7 +538,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     }
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G1[k], dt, d2[k].n, d2[k].h, d2[k].w, C, gradacc + GL.up_b, st));
     conv_args_init(a);
-    a.cin = C; a.cout = C; a.ntaps = 36; a.nprob = ncalls; a.w = pk + L.up_d * es; a.out_dt = dt;
+    a.cin = C; a.cout = C; a.ntaps = 36; a.nprob = ncalls; a.w = pk + L.up_d * wes; a.out_dt = dt;
     for (int i = 0; i < 4; i++) set_std_taps(a.taps + 9 * i, i, 9 * i);
     for (int k = 0; k < ncalls; k++) {
         a.p[k].N = d1[k].n; a.p[k].H = d1[k].h; a.p[k].W = d1[k].w;
@@ -512,7 +549,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     // post conv
     AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, H1, C, G2, C, gradacc + GL.post_w, st));
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(G2[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.post_b, st));
-    conv_std(a, ncalls, d1, C, C, pk + L.post_d * es);
+    conv_std(a, ncalls, d1, C, C, pk + L.post_d * wes);
     a.out_dt = DT_F32;
     for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = G2[k]; a.p[k].out = dH1[k]; }
     AFI_TRY(run_conv(ctx, prec, a, st));
@@ -532,7 +569,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
         AFI_TRY(ew_combine_group(ncalls, DC5, dt, d_out, DT_F32, nullptr, 0, nullptr, 0, 0.2f, 0.2f * d_scale, dn, dh, dw_, C, st));
         AFI_TRY(ew_combine_group(ncalls, GA, DT_F32, d_out, DT_F32, nullptr, 0, nullptr, 0, 0.2f, d_scale, dn, dh, dw_, C, st));
         AFI_TRY(wgrad_std(ctx, prec, ncalls, d1, Br, CB, DC5, C, gradacc + GL.rdb_w[r][4], st));
-        conv_std(a, ncalls, d1, C, CB, pk + L.rdb_d[r][4] * es);
+        conv_std(a, ncalls, d1, C, CB, pk + L.rdb_d[r][4] * wes);
         a.out_dt = DT_F32;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DC5[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
         AFI_TRY(run_conv(ctx, prec, a, st));
@@ -545,7 +582,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             for (int k = 0; k < ncalls; k++) { gdst[k] = pview_ch(GC[k], GR * i, es); gsrc[k] = pview_ch(GA[k], cin_f, 4); gmask[k] = pview_ch(Br[k], cin_f, es); }
             AFI_TRY(ew_combine_group(ncalls, gdst, dt, gsrc, DT_F32, nullptr, 0, gmask, dt, 0.2f, 1.f, dn, dh, dw_, GR, st));
             if (i > 0) {      // the part of this conv's dgrad that the remaining masks depend on: growth channels [256, 256 + 32 i)
-                conv_std(a, ncalls, d1, GR, GR * i, pk + L.rdb_cd[r][i] * es);
+                conv_std(a, ncalls, d1, GR, GR * i, pk + L.rdb_cd[r][i] * wes);
                 a.out_dt = DT_F32;
                 for (int k = 0; k < ncalls; k++) {
                     a.p[k].in[0] = pview_ch(GC[k], GR * i, es); a.p[k].accin = pview_ch(GA[k], C, 4); a.p[k].out = pview_ch(GA[k], C, 4);
@@ -554,7 +591,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
             }
         }
         // ... and the part that reaches the block input x, for all four growth convs in ONE GEMM (K = 4 x 32 channels per tap, N = 256)
-        conv_std(a, ncalls, d1, 4 * GR, C, pk + L.rdb_xd[r] * es);
+        conv_std(a, ncalls, d1, 4 * GR, C, pk + L.rdb_xd[r] * wes);
         a.out_dt = DT_F32;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GC[k]; a.p[k].accin = GA[k]; a.p[k].out = GA[k]; }
         AFI_TRY(run_conv(ctx, prec, a, st));
@@ -574,7 +611,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(GH[k], dt, d1[k].n, d1[k].h, d1[k].w, C, gradacc + GL.head_b, st));
     if (calls[0].dx) {
         // dx = dgrad(head conv)(g_head) + scale * bilinear2x^T(dy)   (needed when the interpolator sits inside a detector: stage 2/3)
-        conv_std(a, ncalls, d1, C, C, pk + L.head_d * es);
+        conv_std(a, ncalls, d1, C, C, pk + L.head_d * wes);
         a.out_dt = DT_F32;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = GH[k]; a.p[k].out = pview(W[k].DXb, d1[k].h, d1[k].w, C); }
         AFI_TRY(run_conv(ctx, prec, a, st));
@@ -592,7 +629,7 @@ int afi_g_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_g
     AFI_REQUIRE(ctx && gradacc && g, "afi_g_unpack_grads: null argument");
     AFI_TRY(g_check(prec, 1, 1, 1, g->n_rdb));
     GGradAcc GL = g_gradacc_layout(g->n_rdb);
-    int nk = prec_tc(prec) ? 1 : 0;
+    int nk = prec_nk(prec) ? 1 : 0;
     if (g->head_w) AFI_TRY(unpack_wgrad(gradacc + GL.head_w, C, C, nk, 0, g->head_w, scale, accumulate, st));
     if (g->head_b) AFI_TRY(axpby_f32(gradacc + GL.head_b, g->head_b, C, scale, accumulate, st));
     for (int r = 0; r < g->n_rdb; r++) {
@@ -641,6 +678,7 @@ struct DWs {
     double* sums;          // [2][1024]
     void *DY[3], *DXb, *G9;
     float* G9F;            // fp32 copy [P][12] of the shifted head gradients
+    void* SPL; size_t spl_bytes;   // AFI_PREC_SPLIT: bf16 operand planes of the GEMM in flight
     size_t total;
 };
 static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) {
@@ -658,6 +696,10 @@ static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) 
         W.G9 = cv.take(P * 16 * 2);
         W.G9F = (float*)cv.take(P * 12 * 4);
     }
+    if (prec == AFI_PREC_SPLIT) {      // the widest GEMM: layer 3's weight gradient (x and dy of 1024 channels); forward only: one 1024-ch input
+        W.spl_bytes = (backward ? 2 : 1) * split_planes_bytes((long long)P, 1024);
+        W.SPL = cv.take(W.spl_bytes);
+    }
     W.total = cv.off;
     return W;
 }
@@ -665,7 +707,7 @@ static DWs d_ws_layout(void* base, int prec, int n, int h, int w, int backward) 
 
 extern "C" {
 
-size_t afi_d_packed_bytes(int prec) { return d_packed_layout().total * dt_size(prec_dt(prec)); }
+size_t afi_d_packed_bytes(int prec) { return d_packed_layout().total * prec_wes(prec); }
 size_t afi_d_gradacc_bytes(void) { return d_gradacc_layout().total * 4; }
 size_t afi_d_workspace_bytes(int prec, int n, int h, int w, int save_for_backward) { return d_ws_layout(nullptr, prec, n, h, w, save_for_backward).total; }
 
@@ -673,17 +715,17 @@ int afi_d_pack(afi_ctx* ctx, int prec, const afi_d_params* p, void* packed, void
     cudaStream_t st = (cudaStream_t)stream;
     AFI_REQUIRE(ctx && p && packed && prec_ok(prec), "afi_d_pack: bad argument");
     DPacked L = d_packed_layout();
-    int dt = prec_dt(prec); size_t es = dt_size(dt);
+    const int dt = prec_wdt(prec); const size_t wes = prec_wes(prec);
     PackJob jobs[6];
     for (int i = 0; i < 3; i++) {
         memset(&jobs[2 * i], 0, 2 * sizeof(PackJob));
         jobs[2 * i].w = jobs[2 * i + 1].w = p->w[i];
-        jobs[2 * i].dst = (char*)packed + L.f[i] * es; jobs[2 * i + 1].dst = (char*)packed + L.d[i] * es;
+        jobs[2 * i].dst = (char*)packed + L.f[i] * wes; jobs[2 * i + 1].dst = (char*)packed + L.d[i] * wes;
         jobs[2 * i].co = jobs[2 * i + 1].co = DC[i + 1]; jobs[2 * i].ci = jobs[2 * i + 1].ci = DC[i];
         jobs[2 * i].mode = pm(prec, 0); jobs[2 * i + 1].mode = pm(prec, 1);
     }
     AFI_TRY(pack_weights_group(6, jobs, dt, st));
-    if (prec_tc(prec)) AFI_TRY(dhead_pack_tc(p->w[3], DC[3], (char*)packed + L.hf * es, (char*)packed + L.hb * es, st));
+    if (prec_tc(prec)) AFI_TRY(dhead_pack_tc(p->w[3], DC[3], (char*)packed + L.hf * wes, (char*)packed + L.hb * wes, st));
     return AFI_OK;
 }
 
@@ -695,8 +737,10 @@ static int d_calls_check(const char* who, int prec, const afi_d_call* calls, int
         AFI_REQUIRE(c.ws && c.n >= 1 && c.h >= 1 && c.w >= 1, "%s: call %d: bad shape n=%d h=%d w=%d or null workspace", who, k, c.n, c.h, c.w);
         W[k] = d_ws_layout(c.ws, prec, c.n, c.h, c.w, save);
         if (W[k].total > c.ws_bytes) { set_error("%s: workspace %zu B < required %zu B", who, c.ws_bytes, W[k].total); return AFI_ERR_WORKSPACE; }
+        g_ss.p[k] = W[k].SPL; g_ss.n[k] = W[k].spl_bytes;
         d[k] = {c.n, c.h, c.w};
     }
+    g_ss.k0 = 0;
     return AFI_OK;
 }
 
@@ -706,7 +750,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
     AFI_REQUIRE(ctx && p && packed, "afi_d_forward: null argument");
     DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
     AFI_TRY(d_calls_check("afi_d_forward", prec, calls, ncalls, save, W, d));
-    const int dt = prec_dt(prec); const size_t es = dt_size(dt);
+    const int dt = prec_dt(prec); const size_t wes = prec_wes(prec);
     DPacked L = d_packed_layout();
     for (int k = 0; k < ncalls; k++) {
         AFI_REQUIRE(calls[k].x.ptr, "afi_d_forward: call %d has a null input", k);
@@ -720,7 +764,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
         // Conv2d 3x3 + bias (all calls in one grouped launch) -> per call: BatchNorm with THIS call's batch statistics
         // -> LeakyReLU(0.2)                                                         feature_patch_discriminator.py:36-38
         ConvArgs a;
-        conv_std(a, ncalls, d, DC[i], DC[i + 1], (const char*)packed + L.f[i] * es);
+        conv_std(a, ncalls, d, DC[i], DC[i + 1], (const char*)packed + L.f[i] * wes);
         a.bias = p->b[i]; a.out_dt = dt;
         for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].A[i], d[k].h, d[k].w, DC[i]); a.p[k].out = pview(W[k].Z[i], d[k].h, d[k].w, DC[i + 1]); }
         void* sums_p[AFI_MAX_PROB]; const double* sum_c[AFI_MAX_PROB]; const double* sq_c[AFI_MAX_PROB]; double* sum_m[AFI_MAX_PROB]; double* sq_m[AFI_MAX_PROB];
@@ -760,7 +804,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
     if (tc) {
         ConvArgs a;
         conv_args_init(a);
-        a.cin = DC[3]; a.cout = 16; a.ntaps = 1; a.nprob = ncalls; a.w = (const char*)packed + L.hf * es; a.out_dt = DT_F32;
+        a.cin = DC[3]; a.cout = 16; a.ntaps = 1; a.nprob = ncalls; a.w = (const char*)packed + L.hf * wes; a.out_dt = DT_F32;
         for (int k = 0; k < ncalls; k++) {
             a.p[k].N = calls[k].logits ? d[k].n : 0; a.p[k].H = d[k].h; a.p[k].W = d[k].w;
             a.p[k].in[0] = pview(W[k].A[3], d[k].h, d[k].w, DC[3]); a.p[k].out = pview(W[k].T9, d[k].h, d[k].w, 16);
@@ -794,7 +838,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
     AFI_REQUIRE(ctx && p && packed && gradacc, "afi_d_backward: null argument");
     DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
     AFI_TRY(d_calls_check("afi_d_backward", prec, calls, ncalls, 1, W, d));
-    const int dt = prec_dt(prec); const size_t es = dt_size(dt);
+    const int dt = prec_dt(prec); const size_t wes = prec_wes(prec);
     DPacked L = d_packed_layout();
     DGradAcc GL = d_gradacc_layout();
     PView X[AFI_MAX_PROB], DYv[AFI_MAX_PROB];
@@ -870,7 +914,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         if (!training) for (int k = 0; k < ncalls; k++) AFI_TRY(col_sum_f32(DYv[k], dt, d[k].n, d[k].h, d[k].w, co, gradacc + GL.b[i], st));
         if (i == 0 && calls[0].dx) {   // input gradient (never needed by the stage-1/2 trainers, which detach D's input; kept for autograd completeness)
             ConvArgs a;
-            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[0] * es);
+            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[0] * wes);
             a.out_dt = DT_F32;
             for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].out = pview(W[k].DXb, d[k].h, d[k].w, ci); }
             AFI_TRY(run_conv(ctx, prec, a, st));
@@ -880,7 +924,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         }
         if (i > 0) {   // dA_i * lrelu'(a_i) -> DY[i-1]
             ConvArgs a;
-            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * es);
+            conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * wes);
             a.out_dt = dt;
             for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].mask = X[k]; a.p[k].out = pview(W[k].DY[i - 1], d[k].h, d[k].w, ci); }
             // opt-in (AFIGAN_FUSE_BWD_STATS=1): the long-K dgrads can also emit sum(dy) and sum(dy * xhat) of the layer below (its
@@ -906,7 +950,7 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
     cudaStream_t st = (cudaStream_t)stream;
     AFI_REQUIRE(ctx && gradacc && g && prec_ok(prec), "afi_d_unpack_grads: bad argument");
     DGradAcc GL = d_gradacc_layout();
-    int nk = prec_tc(prec) ? 1 : 0;
+    const int nk = prec_nk(prec) ? 1 : 0, head_tc = prec_tc(prec) ? 1 : 0;
     for (int i = 0; i < 3; i++) {
         if (g->w[i]) AFI_TRY(unpack_wgrad(gradacc + GL.w[i], DC[i + 1], DC[i], nk, 0, g->w[i], scale, accumulate, st));
         if (g->b[i]) AFI_TRY(axpby_f32(gradacc + GL.b[i], g->b[i], DC[i + 1], scale, accumulate, st));
@@ -914,7 +958,7 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
         if (g->beta[i]) AFI_TRY(axpby_f32(gradacc + GL.beta[i], g->beta[i], DC[i + 1], scale, accumulate, st));
     }
     if (g->w[3]) {
-        if (nk) AFI_TRY(dhead_unpack_tc(gradacc + GL.w[3], DC[3], g->w[3], scale, accumulate, st));
+        if (head_tc) AFI_TRY(dhead_unpack_tc(gradacc + GL.w[3], DC[3], g->w[3], scale, accumulate, st));
         else AFI_TRY(axpby_f32(gradacc + GL.w[3], g->w[3], 9 * DC[3], scale, accumulate, st));
     }
     if (g->b[3]) AFI_TRY(axpby_f32(gradacc + GL.b[3], g->b[3], 1, scale, accumulate, st));
@@ -926,9 +970,10 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
 // =====================================================================================================
 static inline int pad64(int c) { return c <= 64 ? c : (c + 63) / 64 * 64; }
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) {
-    size_t es = dt_size(prec_dt(prec)), P = (size_t)n * h * w;
-    return align_up(P * pad64(cin) * es) + 2 * align_up(P * pad64(cout) * es) + 2 * align_up((size_t)9 * cin * cout * es) +
-           align_up((size_t)9 * cin * cout * 4) + align_up(P * cin * 4) + 4096;
+    size_t es = dt_size(prec_dt(prec)), wes = prec_wes(prec), P = (size_t)n * h * w;
+    return align_up(P * pad64(cin) * es) + 2 * align_up(P * pad64(cout) * es) + 2 * align_up((size_t)9 * cin * cout * wes) +
+           align_up((size_t)9 * cin * cout * 4) + align_up(P * cin * 4) + 4096 +
+           (prec == AFI_PREC_SPLIT ? split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout) + 256 : 0);
 }
 int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
                 int lrelu, float* y, void* ws, size_t ws_bytes, void* stream) {
@@ -936,12 +981,14 @@ int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int 
     AFI_REQUIRE(ctx && x.ptr && weight && y && ws && prec_ok(prec), "afi_conv3x3: bad argument");
     AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv3x3: channels must be multiples of 32");
     if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3: workspace too small"); return AFI_ERR_WORKSPACE; }
-    int dt = prec_dt(prec); size_t es = dt_size(dt), P = (size_t)n * h * w;
+    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w;
     Carver cv(ws);
     void* X = cv.take(P * pad64(cin) * es); void* Y = cv.take(P * pad64(cout) * es); cv.take(P * pad64(cout) * es);
-    void* Wp = cv.take((size_t)9 * cin * cout * es);
+    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
+    cv.take((size_t)9 * cin * cout * 4); cv.take(P * cin * 4);
+    g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
     AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
-    AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, dt, st));
+    AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, prec_wdt(prec), st));
     ConvArgs a;
     Dim3 d = {n, h, w};
     conv_std(a, 1, &d, cin, cout, Wp);
@@ -958,14 +1005,15 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     AFI_REQUIRE(ctx && x.ptr && dy.ptr && weight && dw && ws && prec_ok(prec), "afi_conv3x3_backward: bad argument");
     AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv3x3_backward: channels must be multiples of 32");
     if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3_backward: workspace too small"); return AFI_ERR_WORKSPACE; }
-    int dt = prec_dt(prec); size_t es = dt_size(dt), P = (size_t)n * h * w;
+    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w;
     Carver cv(ws);
     // pixel strides padded to whole 64-channel groups (the tensor-core wgrad reads operands through grouped TMA views)
     const int xs = pad64(cin), ys = pad64(cout);
     void* X = cv.take(P * xs * es); void* DYb = cv.take(P * ys * es); cv.take(P * ys * es);
-    void* Wp = cv.take((size_t)9 * cin * cout * es); cv.take((size_t)9 * cin * cout * es);
+    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
     float* acc = (float*)cv.take((size_t)9 * cin * cout * 4);
     void* DX = cv.take(P * cin * 4);
+    g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
     if (xs != cin) AFI_CUDA(cudaMemsetAsync(X, 0, P * xs * es, st));
     if (ys != cout) AFI_CUDA(cudaMemsetAsync(DYb, 0, P * ys * es, st));
     PView Xv = pview(X, h, w, xs), DYv = pview(DYb, h, w, ys);
@@ -974,13 +1022,13 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     AFI_CUDA(cudaMemsetAsync(acc, 0, (size_t)9 * cin * cout * 4, st));
     Dim3 d = {n, h, w};
     AFI_TRY(wgrad_std(ctx, prec, 1, &d, &Xv, cin, &DYv, cout, acc, st));
-    AFI_TRY(unpack_wgrad(acc, cout, cin, prec_tc(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
+    AFI_TRY(unpack_wgrad(acc, cout, cin, prec_nk(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
     if (db) {
         AFI_CUDA(cudaMemsetAsync(db, 0, cout * sizeof(float), st));
         AFI_TRY(col_sum_f32(DYv, dt, n, h, w, cout, db, st));
     }
     if (dxo) {
-        AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, dt, st));
+        AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, prec_wdt(prec), st));
         ConvArgs a;
         conv_std(a, 1, &d, cout, cin, Wp);
         a.out_dt = DT_F32;

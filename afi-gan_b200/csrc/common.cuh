@@ -49,7 +49,9 @@ struct PView {
     void* ptr;
     long long sn, sy, sx;
 };
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
+// DT_BF16X3: an fp32 value stored as THREE bf16 planes hi + mid + lo (AFI_PREC_SPLIT GEMM operands; plane p of a tensor follows
+// plane p - 1 after `plane stride` elements)
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_BF16X3 = 2 };
 
 static inline PView pview(void* p, int h, int w, int cs) {
     PView v; v.ptr = p; v.sx = cs; v.sy = (long long)w * cs; v.sn = (long long)h * w * cs; return v;
@@ -78,6 +80,8 @@ struct ConvProb {
     // fused per-channel reductions of the stored output v (tensor-core engine only; see ConvArgs.stat_mode)
     double* stat0; double* stat1;
     PView bnz; const float* bn_mean; const float* bn_rstd;
+    // AFI_PREC_SPLIT only: caller-owned scratch in which the fp32 input views of THIS problem are split into bf16 planes
+    void* sws; size_t sws_bytes;
 };
 struct ConvArgs {
     int cin, cout;
@@ -95,6 +99,12 @@ struct ConvArgs {
     // transposed conv.  N tile p uses the slabs 9 p + tap.slab and stores its cout columns at out + (p >> 1) * out.sy / 2 +
     // (p & 1) * out.sx / 2 (out is the stride-2 view of phase 0 in the 2h x 2w map).  0 = a single convolution.
     int nphase;
+    // split-precision operands (set by conv_tc_split, never by callers): 0 = plain bf16; 3 = every input view is three bf16 planes
+    // [hi | mid | lo] stacked along the image axis (plane p of image n = image p * N + n of the view), the packed weights are three
+    // planes stacked along the slab axis, and the product is evaluated as the six plane pairs whose weight is >= 2^-16 (hi hi, hi mid,
+    // mid hi, mid mid, hi lo, lo hi) with fp32 accumulation in TMEM: fp32-accurate products on the bf16 tensor cores.
+    int split;
+    int aux_f32;          // residual / mask operands are fp32 (split mode: activations stay fp32 in HBM)
     ConvProb p[AFI_MAX_PROB];
 };
 
@@ -104,12 +114,14 @@ struct WgradProb {
     int N, H, W, pad_;
     PView x;              // T
     PView dy;             // T
+    void* sws; size_t sws_bytes;   // AFI_PREC_SPLIT: scratch for the bf16 planes of x and dy
 };
 struct WgradArgs {
     int cin, cout;
     int ntaps, nprob;
     Tap taps[9];          // .view unused, .slab = output slab
     float* dw;
+    int split;            // see ConvArgs.split (set by wgrad_tc_split)
     WgradProb p[AFI_MAX_PROB];
 };
 
@@ -134,6 +146,17 @@ template <typename T> int conv_simt(const ConvArgs& a, cudaStream_t st);
 template <typename T> int wgrad_simt(const WgradArgs& a, cudaStream_t st);
 int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st);
 int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st);
+// AFI_PREC_SPLIT: fp32 views in / fp32 out.  The input views are split into bf16 planes (p[k].sws scratch), then the tcgen05 engine
+// runs the six-pair product.  a.w points at the packed [3 planes][slab][cout][cin] bf16 weights.
+int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st);
+int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st);
+// bytes of split scratch one problem needs: conv (nviews input views of cin channels) / wgrad (x of cin + dy of cout channels)
+size_t split_planes_bytes(long long pixels, int channels);
+// fp32 strided views -> dense bf16 planes [3][pixels][cpad] (cpad = split_cpad(c); pad channels zeroed), all jobs in ONE launch
+struct SplitJob { PView src; int n, h, w, c; void* dst; };
+#define AFI_MAX_SPLIT 40
+int split_cpad(int c);
+int split3_group(int njobs, const SplitJob* jobs, cudaStream_t st);
 int tc_init(afi_ctx* ctx);
 
 // ---- elementwise / layout kernels (elementwise.cu) ------------------------------------------------------
@@ -161,7 +184,8 @@ int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt
 #define AFI_MAX_SGD 48
 // sub != 0 (dgrad modes only): pack the gemm-cout range [n0, n0 + ncnt) of this weight into the gemm-cin slice [koff, koff + co) of a
 // destination whose gemm-cin extent is ktot (several convs that read the same gradient buffer share one packed operand)
-struct PackJob { const float* w; void* dst; int co, ci, mode, sub; int n0, ncnt, koff, ktot; };
+// pstride (DT_BF16X3 destinations): elements between the three planes of the destination
+struct PackJob { const float* w; void* dst; int co, ci, mode, sub; int n0, ncnt, koff, ktot; long long pstride; };
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st);
 // gradient un-layout (fp32): torch-layout grad = [grad +] scale * packed ; layout_nk: packed is [slab][cout][cin]
 int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv, float* dst, float scale, int accumulate, cudaStream_t st);

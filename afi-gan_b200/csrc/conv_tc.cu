@@ -62,6 +62,10 @@ struct Tiling {
     // halo-tile convolution only: B ring of `sb` slots of b_slot bytes (one (tap, chunk) weight tile, or half of it in pair mode)
     int sb, b_slot, nviews;
     int view_slab0[4];                // first weight slab of view v (its nine taps use slab0 .. slab0 + 8 in standard order)
+    // split-precision operands (ConvArgs.split): the K loop runs once per plane pair (pa[i], pb[i]); plane p of image n of an A view
+    // is image p * N + n, plane p of weight slab s is slab p * nslab_total + s.  npairs = 1, pa = pb = {0} for plain bf16 operands.
+    int npairs, nslab_total;
+    int pa[6], pb[6];
     long long* dbg;                   // optional [grid][8] stall-cycle counters (AFIGAN_HALO_DBG)
     TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
 };
@@ -224,6 +228,9 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
 }
 
 struct Aux { uint4 a, b, c, d; };   // one 16-column chunk of auxiliary epilogue operands (64 B per thread)
+struct Aux2 { Aux x, y; };          // fp32 auxiliary operands (split-precision mode): 16 floats of the r1 | mask slot, 16 of the r2 slot
+template <bool AUX32> struct AuxSel { typedef Aux type; };
+template <> struct AuxSel<true> { typedef Aux2 type; };
 
 struct Smem {
     uint64_t full[STAGES_MAX];
@@ -321,7 +328,7 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 // PAIR: the CTA is one half of a cta_group::2 pair.  Work items are (pair of M tiles, N tile); this CTA owns M tile 2 * pair + rank
 // (a duplicate of the last tile, with stores and statistics masked, when the problem has an odd tile count) and releases the
 // accumulator stage on the LEADER's barrier, which counts the epilogue warps of both CTAs.
-template <int EPI_WARPS, bool PAIR = false>
+template <int EPI_WARPS, bool PAIR = false, bool AUX32 = false>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& tl, uint64_t* acc_full, uint64_t* acc_empty,
                                               float (*sstat)[2][ACC_COLS], const uint32_t tmem_base, const int warp, const int lane,
                                               const int rank = 0) {
@@ -384,19 +391,32 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
                                            : (pr.r1.ptr ? img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx : 0);
         const long long offB = pr.bnz.ptr && a.stat_mode == 2 ? img * pr.bnz.sn + y * pr.bnz.sy + x * pr.bnz.sx
                                                               : (pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0);
-        const bf16* pA = pr.mask.ptr ? (const bf16*)pr.mask.ptr + offA : (pr.r1.ptr ? (const bf16*)pr.r1.ptr + offA : nullptr);
-        const bf16* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const bf16*)pr.bnz.ptr + offB : (pr.r2.ptr ? (const bf16*)pr.r2.ptr + offB : nullptr);
+        typedef typename AuxSel<AUX32>::type AuxT;
+        // element offsets are the same for bf16 and fp32 operands; the byte address depends on AUX32
+        const char* pA = pr.mask.ptr ? (const char*)pr.mask.ptr + offA * (AUX32 ? 4 : 2) : (pr.r1.ptr ? (const char*)pr.r1.ptr + offA * (AUX32 ? 4 : 2) : nullptr);
+        const char* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const char*)pr.bnz.ptr + offB * (AUX32 ? 4 : 2)
+                                                          : (pr.r2.ptr ? (const char*)pr.r2.ptr + offB * (AUX32 ? 4 : 2) : nullptr);
         const float* pC = pr.accin.ptr ? (const float*)pr.accin.ptr + img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx : nullptr;
         const int nchunks = tl.bn >> 4;
-        auto aux_load = [&](int ch, Aux& r) {
+        auto aux_load = [&](int ch, AuxT& r) {
             const int col = n0 + (ch << 4);
             if (ch < nchunks && ok && col < a.cout) {
-                if (pC) {
-                    const uint4* g = reinterpret_cast<const uint4*>(pC + col);
-                    r.a = g[0]; r.b = g[1]; r.c = g[2]; r.d = g[3];
+                if constexpr (AUX32) {
+                    if (pC) {
+                        const uint4* g = reinterpret_cast<const uint4*>(pC + col);
+                        r.x.a = g[0]; r.x.b = g[1]; r.x.c = g[2]; r.x.d = g[3];
+                    } else {
+                        if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + (size_t)col * 4); r.x.a = g[0]; r.x.b = g[1]; r.x.c = g[2]; r.x.d = g[3]; }
+                        if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + (size_t)col * 4); r.y.a = g[0]; r.y.b = g[1]; r.y.c = g[2]; r.y.d = g[3]; }
+                    }
                 } else {
-                    if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + col); r.a = g[0]; r.b = g[1]; }
-                    if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + col); r.c = g[0]; r.d = g[1]; }
+                    if (pC) {
+                        const uint4* g = reinterpret_cast<const uint4*>(pC + col);
+                        r.a = g[0]; r.b = g[1]; r.c = g[2]; r.d = g[3];
+                    } else {
+                        if (pA) { const uint4* g = reinterpret_cast<const uint4*>(pA + (size_t)col * 2); r.a = g[0]; r.b = g[1]; }
+                        if (pB) { const uint4* g = reinterpret_cast<const uint4*>(pB + (size_t)col * 2); r.c = g[0]; r.d = g[1]; }
+                    }
                 }
             }
         };
@@ -405,12 +425,36 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
 #pragma unroll
             for (int j = 0; j < 8; j++) { t[2 * j] = __uint_as_float(w[j] << 16); t[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u); }
         };
+        auto asfloat16 = [](const Aux& q, float* t) {
+            const uint4 q4[4] = {q.a, q.b, q.c, q.d};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                t[4 * i] = __uint_as_float(q4[i].x); t[4 * i + 1] = __uint_as_float(q4[i].y);
+                t[4 * i + 2] = __uint_as_float(q4[i].z); t[4 * i + 3] = __uint_as_float(q4[i].w);
+            }
+        };
+        // the 16 values of the r1 | mask slot (which = 0), the r2 | bnz slot (1) or the fp32 accumulate-in operand (2) of this chunk
+        auto aux_get = [&](const AuxT& ax, int which, float* t) {
+            if constexpr (AUX32) {
+                asfloat16(which == 1 ? ax.y : ax.x, t);
+            } else {
+                if (which == 2) asfloat16(ax, t);
+                else if (which == 0) unpack16(ax.a, ax.b, t);
+                else unpack16(ax.c, ax.d, t);
+            }
+        };
         // chunk ownership: the two warps of a TMEM lane quarter interleave the 16-column chunks (half = 0 / 1)
         const uint32_t taddr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
-        auto process = [&](int ch, const Aux& ax) {
+        auto process = [&](int ch, const AuxT& ax) {
             const int c0 = ch << 4;
             float v[16];
             tmem_ld16(taddr + c0, v);
+            if constexpr (AUX32) {      // split mode: the K loop alternated between the two accumulators (see DUAL_ACC below)
+                float v2[16];
+                tmem_ld16(taddr + ACC_COLS + c0, v2);
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] += v2[i];
+            }
             const int col = n0 + c0;
             const bool valid = ok && col < a.cout;
             float zbn[16];
@@ -428,29 +472,26 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
                 for (int i = 0; i < 16; i++) v[i] *= a.alpha;
                 float t[16];
                 if (pC) {
-                    const uint4 q4[4] = {ax.a, ax.b, ax.c, ax.d};
+                    aux_get(ax, 2, t);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        v[4 * i] += __uint_as_float(q4[i].x); v[4 * i + 1] += __uint_as_float(q4[i].y);
-                        v[4 * i + 2] += __uint_as_float(q4[i].z); v[4 * i + 3] += __uint_as_float(q4[i].w);
-                    }
+                    for (int i = 0; i < 16; i++) v[i] += t[i];
                 } else {
                     if (pr.r1.ptr) {
-                        unpack16(ax.a, ax.b, t);
+                        aux_get(ax, 0, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] += a.beta1 * t[i];
                     }
                     if (pr.r2.ptr) {
-                        unpack16(ax.c, ax.d, t);
+                        aux_get(ax, 1, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] += a.beta2 * t[i];
                     }
                     if (pr.mask.ptr) {
-                        unpack16(ax.a, ax.b, t);
+                        aux_get(ax, 0, t);
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
                     }
-                    if (a.stat_mode == 2) unpack16(ax.c, ax.d, zbn);
+                    if (a.stat_mode == 2) aux_get(ax, 1, zbn);
                 }
                 st16(pr.out.ptr, out_off + img * pr.out.sn + y * pr.out.sy + x * pr.out.sx + col, a.out_dt, v);
             }
@@ -489,8 +530,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         // two-deep ring of auxiliary-operand buffers per warp: chunk j of this warp lives in buffer j % 2 and is re-filled for
         // chunk j + 2 right after it has been consumed (no register rotation, so no load is waited on early).  With eight
         // epilogue warps that keeps 256 threads x 128 B = 32 KB of loads in flight per SM (~HBM latency x per-SM bandwidth).
-        Aux bA, bB;
-        bA.a = bA.b = bA.c = bA.d = make_uint4(0, 0, 0, 0);
+        AuxT bA, bB;
+        memset(&bA, 0, sizeof(bA));
         bB = bA;
         aux_load(half, bA);
         aux_load(half + HALVES, bB);
@@ -507,7 +548,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             if (PAIR) mbar_arrive_cta0(smem_u32(&acc_empty[as]));
             else mbar_arrive(smem_u32(&acc_empty[as]));
         }
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (AUX32) aphase ^= 1;            // split mode: ONE accumulator stage (both TMEM halves belong to the tile in flight)
+        else if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
 }
@@ -518,7 +560,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
 // EPI_WARPS = 4: one epilogue warp per TMEM lane quarter (long-K layers: the MMA main loop hides the epilogue; 192 threads leave
 // 255 registers per thread).  EPI_WARPS = 8: two warps per quarter interleave the 16-column chunks (short-K layers whose
 // epilogue -- residual / mask loads, statistics -- would otherwise be the critical path).
-template <int EPI_WARPS>
+template <int EPI_WARPS, bool AUX32 = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
@@ -529,7 +571,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tmem_base = setup(s, maps, EPI_WARPS, warp, lane);
-    const int iters = a.ntaps * tl.kchunks;
+    const int iters = tl.npairs * a.ntaps * tl.kchunks;
     const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
     pdl_launch();
     if (warp != 1) pdl_wait();        // the producer and epilogue warps touch global memory; the MMA warp does not
@@ -549,20 +591,24 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 int img = mt / tiles_per_img, r = mt % tiles_per_img;
                 int y0 = (r / tp_.tiles_x) * tp_.TH, x0 = (r % tp_.tiles_x) * tp_.TW;
                 const int n0 = a.nphase ? 0 : nt * tl.bn, sl0 = a.nphase ? 9 * nt : 0;
-                for (int tp = 0; tp < a.ntaps; tp++) {
-                    const Tap t = a.taps[tp];
-                    const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
-                    for (int kc_ = 0; kc_ < tl.kchunks; kc_++) {
-                        mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
-                        uint32_t fb = smem_u32(&s.full[stage]);
-                        uint32_t sa = tiles0 + stage * stage_bytes;
-                        if (elect_one()) {
-                            mbar_expect_tx(fb, tx_bytes);
-                            tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img);
-                            tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, sl0 + t.slab);
+                const int nimg = a.p[tp_.prob].N;
+                for (int pr = 0; pr < tl.npairs; pr++) {      // plane pairs of split-precision operands (one pass for plain bf16)
+                    const int img_p = img + tl.pa[pr] * nimg, sl_p = sl0 + tl.pb[pr] * tl.nslab_total;
+                    for (int tp = 0; tp < a.ntaps; tp++) {
+                        const Tap t = a.taps[tp];
+                        const CUtensorMap* amap = &maps.a[tp_.prob][t.view];
+                        for (int kc_ = 0; kc_ < tl.kchunks; kc_++) {
+                            mbar_wait_t(smem_u32(&s.empty[stage]), phase ^ 1, 1, w_e, dbg_on);
+                            uint32_t fb = smem_u32(&s.full[stage]);
+                            uint32_t sa = tiles0 + stage * stage_bytes;
+                            if (elect_one()) {
+                                mbar_expect_tx(fb, tx_bytes);
+                                tma_load_4d(amap, fb, sa, kc_ * 64, x0 + t.dx, y0 + t.dy, img_p);
+                                tma_load_3d(&maps.b, fb, sa + A_BYTES, kc_ * 64, n0, sl_p + t.slab);
+                            }
+                            __syncwarp();
+                            if (++stage == nstages) { stage = 0; phase ^= 1; }
                         }
-                        __syncwarp();
-                        if (++stage == nstages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -577,15 +623,21 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
                 mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 2, w_acc, dbg_on);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+                // DUAL_ACC (split mode): the tensor cores add into the fp32 accumulator with TRUNCATION, a bias of ~3e-8 of the
+                // running sum per MMA that grows linearly with the length of the accumulation chain (measured: 1e-5 at K = 9216).
+                // Alternating the K steps between the two 256-column accumulators halves every chain and decorrelates the bias; the
+                // epilogue adds the halves in registers (round-to-nearest).  Costs the epilogue / main-loop overlap, which a six-pass
+                // main loop does not need.
                 for (int it = 0; it < iters; it++) {
+                    const uint32_t d_tmem = tmem_base + (AUX32 ? (it & 1) : as) * ACC_COLS;
                     mbar_wait_t(smem_u32(&s.full[stage]), phase, 3, w_f, dbg_on);
                     tc_fence_after();
                     uint32_t sa = tiles0 + stage * stage_bytes;
                     uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
+                    const int first = AUX32 ? (it >> 1) : it;       // 0 on the first K step into this accumulator
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it | k) != 0);
+                        for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first | k) != 0);
                         umma_commit(smem_u32(&s.empty[stage]));
                     }
                     __syncwarp();
@@ -593,12 +645,13 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 }
                 if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (AUX32) aphase ^= 1;
+                else if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
-        conv_epilogue<EPI_WARPS>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
+        conv_epilogue<EPI_WARPS, false, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
     }
     teardown(tmem_base, warp);
 }
@@ -634,9 +687,9 @@ struct SmemH {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
-struct HaloTile { int prob, img, c1, c2, n0, sl0; };      // c1 / c2: TMA coordinates of the halo's first pixel along its fast / slow axis
+struct HaloTile { int prob, img, c1, c2, n0, sl0, nimg; };      // c1 / c2: TMA coordinates of the halo's first pixel along its fast / slow axis
 
-template <int EPI_WARPS, bool PAIR>
+template <int EPI_WARPS, bool PAIR, bool AUX32 = false>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a, const __grid_constant__ Tiling tl) {
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
@@ -675,7 +728,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     pdl_launch();
     if (warp != 1) pdl_wait();        // the producer and epilogue warps touch global memory; the MMA warp does not
     const int kchunks = tl.kchunks;
-    const int nchunks = tl.nviews * kchunks;
+    const int nchunks = tl.npairs * tl.nviews * kchunks;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int total = tl.total;
     const bool dbg_on = tl.dbg != nullptr;
@@ -702,12 +755,12 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                     if (mt >= m_tiles) mt = m_tiles - 1;     // odd tile count: this CTA recomputes the last tile (its epilogue is masked)
                 }
                 const int r = mt % tiles_per_img;
-                h.prob = tp_.prob; h.img = mt / tiles_per_img;
+                h.prob = tp_.prob; h.img = mt / tiles_per_img; h.nimg = a.p[tp_.prob].N;
                 const int y0 = (r / tp_.tiles_x) * tp_.TH - 1, x0 = (r % tp_.tiles_x) * tp_.TW - 1;
                 h.c1 = tp_.orient ? y0 : x0; h.c2 = tp_.orient ? x0 : y0;
                 h.n0 = a.nphase ? 0 : nt * tl.bn; h.sl0 = a.nphase ? 9 * nt : 0;
             };
-            auto issue_a = [&](const HaloTile& h, int view, int kc) {
+            auto issue_a = [&](const HaloTile& h, int view, int kc, int plane) {
                 mbar_wait_t(bar_ae + 8 * ai, aph ^ 1, 21, w_ae, dbg_on);
                 const uint32_t fb = bar_af + 8 * ai;
                 const uint32_t dst = a0 + ai * HALO_SLOT;
@@ -715,10 +768,10 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 if (elect_one()) {
                     if (PAIR) {
                         if (leader) mbar_expect_tx(fb, 2 * HALO_BYTES);
-                        tma_load_4d_pair(amap, fb, dst, kc * 64, h.c1, h.c2, h.img);
+                        tma_load_4d_pair(amap, fb, dst, kc * 64, h.c1, h.c2, h.img + plane * h.nimg);
                     } else {
                         mbar_expect_tx(fb, HALO_BYTES);
-                        tma_load_4d(amap, fb, dst, kc * 64, h.c1, h.c2, h.img);
+                        tma_load_4d(amap, fb, dst, kc * 64, h.c1, h.c2, h.img + plane * h.nimg);
                     }
                 }
                 __syncwarp();
@@ -726,20 +779,20 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             };
             HaloTile cur, nxt;
             int item = item0;
-            if (item < total) { decode(item, cur); issue_a(cur, 0, 0); }
+            if (item < total) { decode(item, cur); issue_a(cur, 0, 0, tl.pa[0]); }
             while (item < total) {
                 const int nitem = item + item_stride;
                 const bool has_next = nitem < total;
                 if (has_next) decode(nitem, nxt);
-                int view = 0, kc = 0;
+                int pr = 0, view = 0, kc = 0;       // (plane pair of split-precision operands, input view, 64-channel chunk)
                 for (int chunk = 0; chunk < nchunks; chunk++) {
-                    const int slab0 = tl.view_slab0[view] + cur.sl0;
+                    const int slab0 = tl.view_slab0[view] + cur.sl0 + tl.pb[pr] * tl.nslab_total;
                     const int kcol = kc * 64, nrow = cur.n0 + brow;
-                    int nview = view, nkc = kc + 1;
-                    if (nkc == kchunks) { nkc = 0; if (++nview == tl.nviews) nview = 0; }
+                    int npr = pr, nview = view, nkc = kc + 1;
+                    if (nkc == kchunks) { nkc = 0; if (++nview == tl.nviews) { nview = 0; if (++npr == tl.npairs) npr = 0; } }
                     // the halo of the NEXT chunk is requested before this chunk's weight tiles (three A slots: its slot was released long ago)
-                    if (chunk + 1 < nchunks) issue_a(cur, nview, nkc);
-                    else if (has_next) issue_a(nxt, 0, 0);
+                    if (chunk + 1 < nchunks) issue_a(cur, nview, nkc, tl.pa[npr]);
+                    else if (has_next) issue_a(nxt, 0, 0, tl.pa[0]);
 #pragma unroll
                     for (int j = 0; j < 9; j++) {
                         mbar_wait_t(bar_be + 8 * bi, bph ^ 1, 22, w_be, dbg_on);
@@ -757,7 +810,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                         __syncwarp();
                         if (++bi == sb) { bi = 0; bph ^= 1; }
                     }
-                    view = nview; kc = nkc;
+                    pr = npr; view = nview; kc = nkc;
                 }
                 cur = nxt; item = nitem;
             }
@@ -785,10 +838,12 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 const bool orient = tl.p[ti].orient != 0;
                 mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 23, w_acc, dbg_on);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
                 uint32_t accum = 0;
                 int kc = 0;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
+                    // split mode: chunks alternate between the two accumulators (DUAL_ACC, see k_conv_tc); nchunks >= 6 there
+                    const uint32_t d_tmem = tmem_base + (AUX32 ? (chunk & 1) : as) * ACC_COLS;
+                    if (AUX32) accum = chunk >= 2;
                     int nk = (cin - kc * 64 + 15) >> 4;              // 16-channel MMA steps with data in this chunk
                     if (++kc == kchunks) kc = 0;
                     mbar_wait_t(bar_af + 8 * ai, aph, 24, w_af, dbg_on);
@@ -826,12 +881,13 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 }
                 if (elect_one()) commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (AUX32) aphase ^= 1;
+                else if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
-        conv_epilogue<EPI_WARPS, PAIR>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
+        conv_epilogue<EPI_WARPS, PAIR, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
     }
     tc_fence_before();
     __syncwarp();
@@ -883,6 +939,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const bool dual = tl.npairs > 1;      // split mode: both TMEM halves accumulate the item in flight
 
     // the producer and MMA warps run their loops CONVERGED; only the TMA / tcgen05 instruction issue is elected (see elect_one())
     if (warp == 0) {
@@ -897,37 +954,42 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
             // position of K tile k0: (problem, image, patch row, patch column); advanced incrementally below -- integer divisions
             // per stage in this serial loop were eating the 512-cycle stage budget
-            int ti = 0;
-            while (k0 >= tl.p[ti + 1].begin) ti++;
-            int lk0 = k0 - tl.p[ti].begin;
-            int tpi = tl.p[ti].tiles_x * tl.p[ti].tiles_y;
-            int img = lk0 / tpi, rr0 = lk0 % tpi;
-            int ty_ = rr0 / tl.p[ti].tiles_x, tx_ = rr0 % tl.p[ti].tiles_x;
-            for (int kt = k0; kt < k1; kt++) {
-                const TileP& tp_ = tl.p[ti];
-                const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
-                mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
-                uint32_t fb = smem_u32(&s.full[stage]);
-                uint32_t sa = tiles0 + stage * stage_bytes;
-                if (elect_one()) {
-                    // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
-                    if (PAIR) {
-                        if (leader) mbar_expect_tx(fb, tx_bytes);
-                        tma_load_5d_pair(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
-                        tma_load_5d_pair(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb + rank * nbl, img);
-                    } else {
-                        mbar_expect_tx(fb, tx_bytes);
-                        tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img);
-                        tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img);
+            int ti0 = 0;
+            while (k0 >= tl.p[ti0 + 1].begin) ti0++;
+            const int lk0 = k0 - tl.p[ti0].begin;
+            const int tpi = tl.p[ti0].tiles_x * tl.p[ti0].tiles_y;
+            const int img0 = lk0 / tpi, rr0 = lk0 % tpi;
+            for (int pr = 0; pr < tl.npairs; pr++) {     // plane pairs of split-precision operands walk the same K range (one pass for bf16)
+                const int pa = tl.pa[pr], pb = tl.pb[pr];
+                int ti = ti0, img = img0;
+                int ty_ = rr0 / tl.p[ti].tiles_x, tx_ = rr0 % tl.p[ti].tiles_x;
+                for (int kt = k0; kt < k1; kt++) {
+                    const TileP& tp_ = tl.p[ti];
+                    const int y0 = ty_ * tp_.TH, x0 = tx_ * tp_.TW;
+                    const int nimg = a.p[tp_.prob].N;
+                    mbar_wait(smem_u32(&s.empty[stage]), phase ^ 1, 11);
+                    uint32_t fb = smem_u32(&s.full[stage]);
+                    uint32_t sa = tiles0 + stage * stage_bytes;
+                    if (elect_one()) {
+                        // 5-D maps {64 ch, W, H, channel group, N}: ONE box lands as consecutive [64 px][128 B] SW128 blocks per group
+                        if (PAIR) {
+                            if (leader) mbar_expect_tx(fb, tx_bytes);
+                            tma_load_5d_pair(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img + pa * nimg);
+                            tma_load_5d_pair(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb + rank * nbl, img + pb * nimg);
+                        } else {
+                            mbar_expect_tx(fb, tx_bytes);
+                            tma_load_5d(&maps.a[tp_.prob][0], fb, sa, 0, x0, y0, mt * 2, img + pa * nimg);
+                            tma_load_5d(&maps.a[tp_.prob][1], fb, sa + A_BYTES, 0, x0 + t.dx, y0 + t.dy, nt * nb, img + pb * nimg);
+                        }
                     }
-                }
-                __syncwarp();
-                if (++stage == nstages) { stage = 0; phase ^= 1; }
-                if (++tx_ == tp_.tiles_x) {
-                    tx_ = 0;
-                    if (++ty_ == tp_.tiles_y) {
-                        ty_ = 0;
-                        if (kt + 1 >= tl.p[ti + 1].begin) { ti++; img = 0; } else img++;
+                    __syncwarp();
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    if (++tx_ == tp_.tiles_x) {
+                        tx_ = 0;
+                        if (++ty_ == tp_.tiles_y) {
+                            ty_ = 0;
+                            if (kt + 1 >= tl.p[ti + 1].begin) { ti++; img = 0; } else img++;
+                        }
                     }
                 }
             }
@@ -945,8 +1007,11 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
                 mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 12);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-                for (int kt = k0; kt < k1; kt++) {
+                const int ksteps = tl.npairs * (k1 - k0);        // split-precision operands: the K range once per plane pair
+                for (int kt = 0; kt < ksteps; kt++) {
+                    // split mode: K steps alternate between the two accumulators (DUAL_ACC, see k_conv_tc)
+                    const uint32_t d_tmem = tmem_base + (dual ? (kt & 1) : as) * ACC_COLS;
+                    const int kfirst = dual ? (kt >> 1) : kt;
                     mbar_wait(smem_u32(&s.full[stage]), phase, 13);
                     tc_fence_after();
                     uint32_t sa = tiles0 + stage * stage_bytes;
@@ -955,8 +1020,8 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; k++) {     // 16 pixels = 2048 B per MMA
-                            if (PAIR) umma_bf16_pair(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
-                            else umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kt > k0) || (k != 0));
+                            if (PAIR) umma_bf16_pair(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kfirst > 0) || (k != 0));
+                            else umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), idesc, (kfirst > 0) || (k != 0));
                         }
                         if (PAIR) umma_commit_pair(smem_u32(&s.empty[stage])); else umma_commit(smem_u32(&s.empty[stage]));
                     }
@@ -965,7 +1030,8 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
                 }
                 if (elect_one()) { if (PAIR) umma_commit_pair(smem_u32(&s.acc_full[as])); else umma_commit(smem_u32(&s.acc_full[as])); }
                 __syncwarp();
-                if (++as == 2) { as = 0; aphase ^= 1; }
+                if (dual) aphase ^= 1;
+                else if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
     } else {
@@ -987,6 +1053,12 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             for (int c0 = half * 16; c0 < tl.bn; c0 += 32) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
+                if (dual && k1 > k0) {
+                    float v2[16];
+                    tmem_ld16(taddr + ACC_COLS + c0, v2);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] += v2[i];
+                }
                 const int ci = nt * tl.bn + c0;
                 if (k1 > k0 && co < a.cout && ci < a.cin) {      // (cin is a multiple of 16: the whole chunk is inside the row, 16-byte aligned)
 #pragma unroll
@@ -998,7 +1070,8 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_cta0(smem_u32(&s.acc_empty[as])); else mbar_arrive(smem_u32(&s.acc_empty[as])); }
-            if (++as == 2) { as = 0; aphase ^= 1; }
+            if (dual) aphase ^= 1;
+            else if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
     tc_fence_before();
@@ -1028,6 +1101,7 @@ static int encode_map(afi_ctx* ctx, CUtensorMap* m, void* ptr, int rank, const c
     return AFI_OK;
 }
 // halo box {64 ch, 10, 18, 1}; orient 1 swaps the roles of x and y (the 10-pixel axis, along which the 8-pixel swizzle groups run, is y)
+// (N counts images x operand planes: split-precision views stack their three bf16 planes along the image axis)
 static int encode_view_halo(afi_ctx* ctx, CUtensorMap* m, const PView& v, int C, int W, int H, int N, int orient) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(orient ? H : W), (cuuint64_t)(orient ? W : H), (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)(orient ? v.sy : v.sx) * 2, (cuuint64_t)(orient ? v.sx : v.sy) * 2, (cuuint64_t)v.sn * 2};
@@ -1064,6 +1138,14 @@ static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
 }
 
 static int g_halo_dyn_max[2] = {0, 0};
+// plane pairs of a split-precision product, smallest terms first (hi lo, lo hi, mid mid, hi mid, mid hi, hi hi): every pair whose
+// weight is >= 2^-16 of the leading term; the dropped ones (mid lo, lo mid, lo lo) are below fp32's own rounding
+static void set_pairs(Tiling& tl, int split, int nslab_total) {
+    static const int PA[6] = {0, 2, 1, 0, 1, 0}, PB[6] = {2, 0, 1, 1, 0, 0};
+    tl.nslab_total = nslab_total;
+    if (split == 3) { tl.npairs = 6; for (int i = 0; i < 6; i++) { tl.pa[i] = PA[i]; tl.pb[i] = PB[i]; } }
+    else { tl.npairs = 1; tl.pa[0] = tl.pb[0] = 0; }
+}
 // AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tiles, one CTA per tile; 2: halo tiles on CTA pairs (cta_group::2)
 static int halo_mode() {      // read on every call (tests switch variants in-process)
     const char* e = getenv("AFIGAN_CONV_HALO");
@@ -1095,6 +1177,8 @@ int tc_init(afi_ctx* ctx) {
     ctx->encode_tiled = fn;
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     // halo-tile kernels: everything the SM has beyond their static shared memory (statistics scratch + barriers)
@@ -1107,6 +1191,9 @@ int tc_init(afi_ctx* ctx) {
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
     AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
+    // fp32 auxiliary operands (split-precision mode): same shared-memory footprint as their bf16 twins
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[0]));
+    AFI_CUDA(cudaFuncSetAttribute(tc::k_conv_halo<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::g_halo_dyn_max[1]));
     return AFI_OK;
 }
 
@@ -1132,10 +1219,14 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         // the epilogue prefetches its auxiliary operands through two bf16 slots (r1|mask, r2|bnz) or one fp32 slot (accin)
         AFI_REQUIRE(!(q.mask.ptr && q.r1.ptr) && !(q.r2.ptr && a.stat_mode == 2), "conv_tc: unsupported epilogue operand combination");
         AFI_REQUIRE(!q.accin.ptr || !(q.mask.ptr || q.r1.ptr || q.r2.ptr || a.stat_mode == 2), "conv_tc: accin excludes other epilogue operands");
-        AFI_REQUIRE((!q.r1.ptr || a.r1_dt == DT_BF16) && (!q.r2.ptr || a.r2_dt == DT_BF16), "conv_tc: residuals must be bf16");
+        AFI_REQUIRE((!q.r1.ptr || a.r1_dt == (a.aux_f32 ? DT_F32 : DT_BF16)) && (!q.r2.ptr || a.r2_dt == (a.aux_f32 ? DT_F32 : DT_BF16)),
+                    "conv_tc: residuals must be %s", a.aux_f32 ? "fp32" : "bf16");
         if (a.stat_mode) AFI_REQUIRE(q.stat0 && q.stat1 && (a.stat_mode == 1 || (q.bnz.ptr && q.bn_mean && q.bn_rstd)), "conv_tc: missing statistics operands");
     }
     if (pixels == 0) return AFI_OK;
+    AFI_REQUIRE(a.split == 0 || a.split == 3, "conv_tc: split %d", a.split);
+    AFI_REQUIRE(!(a.aux_f32 && a.stat_mode == 2), "conv_tc: the BatchNorm-backward statistics epilogue takes bf16 operands only");
+    const int planes = a.split ? 3 : 1;
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);
     Tiling tl{};
@@ -1164,11 +1255,13 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     // short-K layers (K = taps x cin < 4096) cannot hide their epilogue behind the MMAs: eight epilogue warps; so do the layers with
     // fused statistics below K = 8192 (measured: 512 -> 1024 with statistics on four warps is epilogue-bound in pair mode)
     const int K = a.ntaps * tl.kchunks * 64;
-    const int epi8 = (K < 4096 || (a.stat_mode && K < 8192)) ? 1 : 0;
+    const int Kp = K * (a.split ? 6 : 1);                 // MMA work per tile: what the epilogue has to hide behind
+    const int epi8 = (Kp < 4096 || (a.stat_mode && Kp < 8192)) ? 1 : 0;
     // halo tiles on CTA pairs: every 3x3 layer except the narrow ones (N tile < 128 or 32 input channels: the dense blocks' growth
     // convs and their dgrads), where the per-tap kernel measured 10-15 % faster (a pair halves the number of schedulable tiles and
     // an N = 32 MMA is bound by its A-operand read either way)
     int hmode = halo_eligible(a) ? halo_mode() : 0;
+    if (a.aux_f32 && hmode == 1) hmode = 2;                // (the single-CTA halo kernel has no fp32-operand instantiation)
     if (hmode == 2 && K < 4096 && (tl.bn < 128 || a.cin < 64) && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
     const bool pair = hmode == 2;
 #ifdef AFI_STALL_COUNTERS
@@ -1206,8 +1299,8 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         const int m_tiles = pr.N * t.tiles_x * t.tiles_y;
         begin += (pair ? (m_tiles + 1) / 2 : m_tiles) * tl.n_tiles;
         for (int v = 0; v < nviews; v++) {
-            if (hmode) AFI_TRY(encode_view_halo(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.orient));
-            else AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N, t.TW, t.TH));
+            if (hmode) AFI_TRY(encode_view_halo(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N * planes, t.orient));
+            else AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N * planes, t.TW, t.TH));
         }
         np++;
     }
@@ -1217,8 +1310,9 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int nslab = 0;
     for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
     if (a.nphase) nslab += 9 * (a.nphase - 1);
+    set_pairs(tl, a.split, nslab);
     {
-        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab};
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab * planes};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), 1};
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
@@ -1247,7 +1341,15 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * (epi8 ? 8 : 4)); cfg.stream = st;
         cfg.dynamicSmemBytes = hmode ? 1024 + HALO_SA * HALO_SLOT + tl.sb * tl.b_slot : SMEM_BYTES;
         cfg.attrs = attr; cfg.numAttrs = na;
-        if (pair) {
+        if (a.aux_f32) {
+            if (pair) {
+                if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, true, true>, maps, a, tl));
+                else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, true, true>, maps, a, tl));
+            } else {
+                if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<8, true>, maps, a, tl));
+                else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<4, true>, maps, a, tl));
+            }
+        } else if (pair) {
             if (epi8) AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<8, true>, maps, a, tl));
             else AFI_CUDA(cudaLaunchKernelEx(&cfg, k_conv_halo<4, true>, maps, a, tl));
         } else if (hmode) {
@@ -1286,7 +1388,10 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     if (pixels == 0) return AFI_OK;
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);
+    AFI_REQUIRE(a.split == 0 || a.split == 3, "wgrad_tc: split %d", a.split);
+    const int planes = a.split ? 3 : 1;
     Tiling tl{};
+    set_pairs(tl, a.split, 0);
     tl.m_tiles = (a.cout + 127) / 128;
     tl.n_tiles = (a.cin + 255) / 256;
     tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
@@ -1306,8 +1411,8 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
         t.begin = begin;
         t.prob = order[oi];
         begin += pr.N * t.tiles_x * t.tiles_y;
-        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][0], pr.dy, a.cout, pr.W, pr.H, pr.N, t.TW, t.TH, 2));
-        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N, t.TW, t.TH, pair ? tl.bn / 128 : tl.bn / 64));
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][0], pr.dy, a.cout, pr.W, pr.H, pr.N * planes, t.TW, t.TH, 2));
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N * planes, t.TW, t.TH, pair ? tl.bn / 128 : tl.bn / 64));
         np++;
     }
     tl.nprob = np;
@@ -1322,6 +1427,9 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     if (ks > tl.ktiles) ks = tl.ktiles;
     if (ks < 1) ks = 1;
     int kper = (tl.ktiles + ks - 1) / ks;
+    // split mode: the accumulation chain of one item is capped (64 K tiles = 128 MMAs per accumulator and plane pair): the tensor cores
+    // add into the accumulator with truncation, a bias that grows linearly with the chain; the partial sums meet in fp32 RED adds
+    if (a.split && kper > 64) kper = 64;
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
     tl.stage_bytes = A_BYTES + (tl.bn / 64) * (pair ? 4096 : 8192);
@@ -1340,6 +1448,62 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     } else k_wgrad_tc<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(maps, a, tl);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
+}
+
+
+// ---- split-precision front ends (AFI_PREC_SPLIT): fp32 views -> bf16 planes in the caller's scratch -> six-pair tcgen05 product --------
+int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "conv_tc_split: bad problem count %d", a.nprob);
+    int nviews = 0;
+    for (int i = 0; i < a.ntaps; i++) nviews = a.taps[i].view + 1 > nviews ? a.taps[i].view + 1 : nviews;
+    AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc_split: bad view count");
+    AFI_REQUIRE(a.out_dt == DT_F32 && !a.stat_mode, "conv_tc_split: fp32 output without fused statistics");
+    ConvArgs b = a;
+    SplitJob jobs[AFI_MAX_SPLIT]; int nj = 0;
+    const int cpad = split_cpad(a.cin);
+    for (int k = 0; k < a.nprob; k++) {
+        const ConvProb& q = a.p[k];
+        const long long P = (long long)q.N * q.H * q.W;
+        if (P == 0) continue;
+        const size_t each = split_planes_bytes(P, a.cin);
+        if (!q.sws || each * nviews > q.sws_bytes) {
+            set_error("conv_tc_split: problem %d needs %zu B of split scratch, has %zu", k, each * nviews, q.sws ? q.sws_bytes : (size_t)0);
+            return AFI_ERR_WORKSPACE;
+        }
+        for (int v = 0; v < nviews; v++) {
+            SplitJob& j = jobs[nj++];
+            j.src = q.in[v]; j.n = q.N; j.h = q.H; j.w = q.W; j.c = a.cin; j.dst = (char*)q.sws + each * v;
+            b.p[k].in[v] = pview(j.dst, q.H, q.W, cpad);
+        }
+    }
+    AFI_TRY(split3_group(nj, jobs, st));
+    b.split = 3; b.aux_f32 = 1;
+    return conv_tc(ctx, b, st);
+}
+
+int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
+    AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "wgrad_tc_split: bad problem count %d", a.nprob);
+    WgradArgs b = a;
+    SplitJob jobs[AFI_MAX_SPLIT]; int nj = 0;
+    for (int k = 0; k < a.nprob; k++) {
+        const WgradProb& q = a.p[k];
+        const long long P = (long long)q.N * q.H * q.W;
+        if (P == 0) continue;
+        const size_t bx = split_planes_bytes(P, a.cin), by = split_planes_bytes(P, a.cout);
+        if (!q.sws || bx + by > q.sws_bytes) {
+            set_error("wgrad_tc_split: problem %d needs %zu B of split scratch, has %zu", k, bx + by, q.sws ? q.sws_bytes : (size_t)0);
+            return AFI_ERR_WORKSPACE;
+        }
+        SplitJob& jx = jobs[nj++];
+        jx.src = q.x; jx.n = q.N; jx.h = q.H; jx.w = q.W; jx.c = a.cin; jx.dst = q.sws;
+        SplitJob& jy = jobs[nj++];
+        jy.src = q.dy; jy.n = q.N; jy.h = q.H; jy.w = q.W; jy.c = a.cout; jy.dst = (char*)q.sws + bx;
+        b.p[k].x = pview(jx.dst, q.H, q.W, split_cpad(a.cin));
+        b.p[k].dy = pview(jy.dst, q.H, q.W, split_cpad(a.cout));
+    }
+    AFI_TRY(split3_group(nj, jobs, st));
+    b.split = 3;
+    return wgrad_tc(ctx, b, st);
 }
 
 }  // namespace afi

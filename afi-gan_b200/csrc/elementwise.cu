@@ -1373,13 +1373,28 @@ int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumu
 // deconv dgrad : slab = phase*9 + t, t=(e+1)*3+(f+1) <- w[ci][co][2(1+e)+a][2(1+f)+b], gemm-cin = co, gemm-cout = ci
 // 1x1 forward  : w[co][ci] (lateral conv of the FPN merge), one slab (mode kind 4)
 // ---------------------------------------------------------------------------------------------------
+// destination element types of the packers: float, bf16, or Split3 = three bf16 planes hi + mid + lo (AFI_PREC_SPLIT)
+struct Split3 { bf16 v; };
+__device__ __forceinline__ void split3(float x, bf16& hi, bf16& mid, bf16& lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);       // exact in fp32
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+template <typename T> __device__ __forceinline__ void pack_put(T* dst, long long i, float v, long long) { dst[i] = (T)v; }
+template <> __device__ __forceinline__ void pack_put<Split3>(Split3* dst, long long i, float v, long long pstride) {
+    bf16* d = reinterpret_cast<bf16*>(dst);
+    bf16 h, m, l;
+    split3(v, h, m, l);
+    d[i] = h; d[i + pstride] = m; d[i + 2 * pstride] = l;
+}
 __device__ __forceinline__ long long pack_total_dev(int co, int ci, int mode) {
     int kind = mode >> 1;
     int slabs = (kind == 4 || kind == 5) ? 1 : (kind >= 2 ? 36 : 9);
     return (long long)slabs * co * ci;
 }
 template <typename T>
-__device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long i) {
+__device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long i, long long pstride = 0) {
     int nk = mode & 1, kind = mode >> 1;
     int gk = (kind == 0 || kind == 2 || kind == 4) ? ci : co;   // gemm-cin
     int gn = (kind == 0 || kind == 2 || kind == 4) ? co : ci;   // gemm-cout   (kinds 1, 3, 5 are dgrads: roles swapped)
@@ -1407,12 +1422,12 @@ __device__ __forceinline__ void pack_one(const float* __restrict__ w, int co, in
             v = w[(((long long)n * co + k) * 6 + ky) * 6 + kx];
         }
     }
-    dst[i] = (T)v;
+    pack_put<T>(dst, i, v, pstride);
 }
 template <typename T>
 __global__ void k_pack(const float* __restrict__ w, int co, int ci, int mode, T* __restrict__ dst, long long total) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < total) pack_one<T>(w, co, ci, mode, dst, i);
+    if (i < total) pack_one<T>(w, co, ci, mode, dst, i, total);
 }
 static inline long long pack_total(int co, int ci, int mode) {
     int kind = mode >> 1;
@@ -1422,6 +1437,7 @@ static inline long long pack_total(int co, int ci, int mode) {
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st) {
     long long total = pack_total(co, ci, mode);
     if (dst_dt == DT_F32) k_pack<float><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (float*)dst, total);
+    else if (dst_dt == DT_BF16X3) k_pack<Split3><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (Split3*)dst, total);
     else k_pack<bf16><<<cdiv(total, 256), 256, 0, st>>>(w, co, ci, mode, (bf16*)dst, total);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -1447,7 +1463,7 @@ __device__ __forceinline__ void pack_taps9(const PackJob& q, long long u) {
     const long long slab_sz = q.sub ? (long long)q.ncnt * q.ktot : (long long)O * I;
     const long long off = q.sub ? (nk ? (long long)n * q.ktot + q.koff + k : (long long)(q.koff + k) * q.ncnt + n) : (long long)outer * I + inner;
 #pragma unroll
-    for (int t = 0; t < 9; t++) dst[(long long)t * slab_sz + off] = (T)v[dgrad ? 8 - t : t];
+    for (int t = 0; t < 9; t++) pack_put<T>(dst, (long long)t * slab_sz + off, v[dgrad ? 8 - t : t], q.pstride);
 }
 template <typename T>
 __global__ void k_pack_group(const __grid_constant__ PackGroup G) {
@@ -1466,7 +1482,7 @@ __global__ void k_pack_group(const __grid_constant__ PackGroup G) {
     const long long total = pack_total_dev(q.co, q.ci, q.mode);
 #pragma unroll
     for (int u = 0; u < 4; u++, i += 256)
-        if (i < total) pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i);
+        if (i < total) pack_one<T>(q.w, q.co, q.ci, q.mode, reinterpret_cast<T*>(q.dst), i, q.pstride);
 }
 int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t st) {
     AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_PACK, "pack_weights_group: %d jobs (max %d)", njobs, AFI_MAX_PACK);
@@ -1476,6 +1492,8 @@ int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t 
     int b = 0;
     for (int k = 0; k < njobs; k++) {
         G.j[k] = jobs[k]; G.block_begin[k] = b;
+        // plane stride of a three-plane destination = the whole packed operand of this job
+        G.j[k].pstride = jobs[k].sub ? (long long)9 * jobs[k].ncnt * jobs[k].ktot : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode);
         if (jobs[k].sub) AFI_REQUIRE((jobs[k].mode >> 1) == 1, "pack_weights_group: sub-block packing is a dgrad mode");
         const int kind = jobs[k].mode >> 1;
         const long long work = kind <= 1 ? (jobs[k].sub ? (long long)jobs[k].co * jobs[k].ncnt : (long long)jobs[k].co * jobs[k].ci)
@@ -1484,7 +1502,74 @@ int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t 
     }
     G.block_begin[njobs] = b;
     if (dst_dt == DT_F32) k_pack_group<float><<<b, 256, 0, st>>>(G);
+    else if (dst_dt == DT_BF16X3) k_pack_group<Split3><<<b, 256, 0, st>>>(G);
     else k_pack_group<bf16><<<b, 256, 0, st>>>(G);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AFI_PREC_SPLIT operand staging: fp32 pixel-major views -> dense bf16 planes [3][pixels][cpad].  HBM-bound: 4 B read + 6 B written
+// per element; one thread per 8 channels (32 B in, 3 x 16 B out); every view of every problem of a grouped GEMM in ONE launch.
+// ---------------------------------------------------------------------------------------------------
+int split_cpad(int c) { return c <= 64 ? c : (c + 63) / 64 * 64; }
+size_t split_planes_bytes(long long pixels, int channels) { return ((size_t)pixels * split_cpad(channels) * 2 * 3 + 255) / 256 * 256; }
+struct SplitGroup { int njobs; int block_begin[AFI_MAX_SPLIT + 1]; SplitJob j[AFI_MAX_SPLIT]; };
+__global__ void __launch_bounds__(256) k_split3_group(const __grid_constant__ SplitGroup G) {
+    int k = 0;
+    while (k + 1 < G.njobs && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
+    const SplitJob& q = G.j[k];
+    const int cpad = q.c <= 64 ? q.c : (q.c + 63) / 64 * 64;
+    const int cq = cpad >> 3;
+    const long long P = (long long)q.n * q.h * q.w, units = P * cq;
+    const long long pstride = P * cpad;
+    bf16* d = reinterpret_cast<bf16*>(q.dst);
+    for (long long u = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x, e = u + 1024; u < e && u < units; u += 256) {
+        const int c0 = (int)(u % cq) * 8;
+        const long long pix = u / cq;
+        const int x = (int)(pix % q.w), y = (int)((pix / q.w) % q.h), n = (int)(pix / ((long long)q.w * q.h));
+        float v[8];
+        if (c0 < q.c) {
+            const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q.src.ptr) + n * q.src.sn + y * q.src.sy + x * q.src.sx + c0);
+            const float4 a = s4[0], b = s4[1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = 0.f;
+        }
+        uint32_t ph[4], pm[4], pl[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            bf16 h0, m0, l0, h1, m1, l1;
+            split3(v[2 * i], h0, m0, l0);
+            split3(v[2 * i + 1], h1, m1, l1);
+            ph[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pm[i] = (uint32_t)__bfloat16_as_ushort(m0) | ((uint32_t)__bfloat16_as_ushort(m1) << 16);
+            pl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const long long o = pix * cpad + c0;
+        *reinterpret_cast<uint4*>(d + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4*>(d + pstride + o) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+        *reinterpret_cast<uint4*>(d + 2 * pstride + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+int split3_group(int njobs, const SplitJob* jobs, cudaStream_t st) {
+    AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_SPLIT, "split3_group: %d jobs (max %d)", njobs, AFI_MAX_SPLIT);
+    SplitGroup G; memset(&G, 0, sizeof(G));
+    int b = 0, nj = 0;
+    for (int k = 0; k < njobs; k++) {
+        const SplitJob& q = jobs[k];
+        const long long P = (long long)q.n * q.h * q.w;
+        if (P == 0) continue;
+        AFI_REQUIRE(q.c % 8 == 0 && q.src.sx % 4 == 0 && q.src.sy % 4 == 0 && q.src.sn % 4 == 0 && ((uintptr_t)q.src.ptr & 15) == 0,
+                    "split3_group: view %d is not 16-byte aligned per pixel (c %d)", k, q.c);
+        G.j[nj] = q; G.block_begin[nj] = b;
+        b += cdiv(P * (split_cpad(q.c) / 8), 1024);
+        nj++;
+    }
+    if (nj == 0) return AFI_OK;
+    G.njobs = nj; G.block_begin[nj] = b;
+    k_split3_group<<<b, 256, 0, st>>>(G);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }

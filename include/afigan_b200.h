@@ -33,10 +33,13 @@ extern "C" {
 #define AFI_ERR_ARCH (-3)      /* device is not sm_100 */
 #define AFI_ERR_WORKSPACE (-4) /* workspace too small */
 
-/* Operand modes (bf16 operands cannot meet 1e-3 on gradients, fp32 products can). */
+/* Operand modes (bf16 operands cannot meet 1e-3 on gradients, fp32-accurate products can). */
 #define AFI_PREC_FP32 0      /* fp32 storage + fp32 FFMA implicit GEMM: the parity mode              */
 #define AFI_PREC_BF16 1      /* bf16 storage + tcgen05/TMEM implicit GEMM fed by TMA: throughput mode */
 #define AFI_PREC_BF16_SIMT 2 /* bf16 storage + CUDA-core GEMM: on-device cross-check of mode 1        */
+#define AFI_PREC_SPLIT 3     /* fp32 storage; every GEMM operand split on the fly into three bf16 planes (hi + mid + lo) and
+                              * multiplied on the tcgen05 tensor cores as six plane-pair products with fp32 TMEM accumulation:
+                              * fp32-accurate products at tensor-core rate -- the parity mode that meets north_star's tolerance */
 
 #define AFI_MAX_RDB 4
 #define AFI_MAX_CALLS 10 /* calls per grouped launch */

@@ -21,6 +21,8 @@ TOL = {
     # of ~1e-6 of the elements and each flip moves the norm-wise D gradient error by ~sqrt(1/#elements): 1e-3 is AT the
     # fp32-vs-fp32 noise floor for the discriminator, so the gate is 5e-3 + a cosine bound.
     "fp32": dict(feat=1e-4, logit=2e-4, loss=1e-5, grad=1e-3, dgrad=5e-3, cos=0.99998),
+    # split: fp32 storage, bf16x3 six-term products on the tensor cores -- gated at the fp32 row
+    "split": dict(feat=1e-4, logit=2e-4, loss=1e-5, grad=1e-3, dgrad=5e-3, cos=0.99998),
     "bf16": dict(feat=1e-3, logit=3e-2, loss=5e-3, grad=0.15, dgrad=0.15, cos=0.985),
     "bf16_simt": dict(feat=1e-3, logit=3e-2, loss=5e-3, grad=0.15, dgrad=0.15, cos=0.985),
 }

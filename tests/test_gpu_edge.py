@@ -18,7 +18,7 @@ def _gd(precision, n_rdb=3):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 2, 3), (3, 5, 4), (1, 17, 33)])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 def test_generator_tiny_and_odd_shapes(shape, precision):
     n, h, w = shape
     G, _ = _gd(precision)
@@ -26,7 +26,7 @@ def test_generator_tiny_and_odd_shapes(shape, precision):
     x = torch.randn(n, 256, h, w, generator=torch.Generator().manual_seed(h * 100 + w))
     y = G(x.cuda())
     assert y.shape == (n, 256, 2 * h, 2 * w)                      # exactly 2x for any size (k6 s2 p2), SURVEY §8c (i)
-    assert rel(y, O.generator_forward(g_sd, x)) < (1e-5 if precision == "fp32" else 1e-3)
+    assert rel(y, O.generator_forward(g_sd, x)) < (1e-5 if precision in ("fp32", "split") else 1e-3)
 
 
 def test_generator_two_dense_blocks_default_ctor():
@@ -40,13 +40,13 @@ def test_generator_two_dense_blocks_default_ctor():
     assert rel(G(x.cuda()), O.generator_forward(sd, x)) < 1e-5
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 def test_discriminator_batch_one_and_eval(precision):
     _, D = _gd(precision)
     _, d_sd = O.init_states(0)
     stack = D.Discriminators[0]
     x = torch.randn(1, 256, 9, 7, generator=torch.Generator().manual_seed(5))
-    tol = 2e-4 if precision == "fp32" else 3e-2
+    tol = 2e-4 if precision in ("fp32", "split") else 3e-2
     stack.train()
     with torch.no_grad():
         assert rel(stack(x.cuda()), O.discriminator_forward(d_sd, x, True)) < tol

@@ -18,7 +18,7 @@ def _gen(precision):
     return G, g_sd
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 def test_input_gradient(precision):
     G, g_sd = _gen(precision)
     gen = torch.Generator().manual_seed(21)
@@ -30,10 +30,10 @@ def test_input_gradient(precision):
     (G(xg, out_hw=(11, 17)) * dy.cuda()).sum().backward()
     r = rel(xg.grad, xr.grad)
     # the bilinear-skip adjoint dominates dx at init, so even bf16 operands agree closely
-    assert r < (1e-5 if precision == "fp32" else 2e-3), r
+    assert r < (1e-5 if precision in ("fp32", "split") else 2e-3), r
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 @pytest.mark.parametrize("fuse_type,lat_c", [("sum", 256), ("avg", 512)])
 def test_fpn_topdown_merge_forward_backward(precision, fuse_type, lat_c):
     G, g_sd = _gen(precision)
@@ -55,11 +55,11 @@ def test_fpn_topdown_merge_forward_backward(precision, fuse_type, lat_c):
     pc, fc, lwc, lbc = (t.cuda().requires_grad_(True) for t in (prev, feat, lw, lb))
     out = G.merge(pc, fc, lwc, lbc, fuse_type)
     assert out.shape == ref.shape
-    assert rel(out, ref) < (1e-5 if precision == "fp32" else 8e-3), rel(out, ref)
+    assert rel(out, ref) < (1e-5 if precision in ("fp32", "split") else 8e-3), rel(out, ref)
     dy = torch.randn(ref.shape, generator=gen)
     (ref * dy).sum().backward()
     (out * dy.cuda()).sum().backward()
-    gt = 1e-4 if precision == "fp32" else 1.5e-2
+    gt = 1e-4 if precision in ("fp32", "split") else 1.5e-2
     assert rel(pc.grad, pr.grad) < gt, rel(pc.grad, pr.grad)
     assert rel(fc.grad, fr.grad) < gt, rel(fc.grad, fr.grad)
     assert rel(lwc.grad, lwr.grad) < gt, rel(lwc.grad, lwr.grad)
@@ -155,7 +155,7 @@ def test_bifpn_fusion():
         assert rel(bifpn_feature_fusion(G, cur_odd.cuda().to(memory_format=torch.channels_last), top.cuda(), w.cuda()), ref_odd) < 1e-5
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "split", "bf16"])
 def test_stage2_loss_block(precision):
     from afigan.engine import stage2_discriminator_losses, stage2_generator_losses
     from afigan.modeling import Discriminator
