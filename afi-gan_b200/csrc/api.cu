@@ -70,8 +70,14 @@ static inline size_t prec_wes(int prec) { return prec == AFI_PREC_SPLIT ? 6 : dt
 
 // AFI_PREC_SPLIT operand scratch of the API call in flight: problem k of a grouped launch stages its operands in the scratch of call
 // k0 + k (k0 != 0 only for the single-problem launches issued per call)
-struct SplitScratch { void* p[AFI_MAX_PROB]; size_t n[AFI_MAX_PROB]; int k0; };
+// pairs: plane pairs per product for the convs of the call in flight -- 6 for the forward pass of a call that keeps its activations for a
+// backward pass (pre-activation signs decide the LeakyReLU slopes of the gradients), 3 for forward-only calls and every backward GEMM
+struct SplitScratch { void* p[AFI_MAX_PROB]; size_t n[AFI_MAX_PROB]; int k0; int pairs; };
 static thread_local SplitScratch g_ss;
+static inline int split_pairs_env(int dflt) {      // AFIGAN_SPLIT_PAIRS=6 forces the six-pair product everywhere (accuracy experiments)
+    const char* e = getenv("AFIGAN_SPLIT_PAIRS");
+    return (e && atoi(e) == 6) ? 6 : dflt;
+}
 
 static int run_conv(afi_ctx* ctx, int prec, const ConvArgs& a, cudaStream_t st) {
     if (prec == AFI_PREC_FP32) return conv_simt<float>(a, st);
@@ -79,6 +85,7 @@ static int run_conv(afi_ctx* ctx, int prec, const ConvArgs& a, cudaStream_t st) 
     if (prec == AFI_PREC_SPLIT) {
         ConvArgs b = a;
         for (int k = 0; k < b.nprob; k++) { b.p[k].sws = g_ss.p[g_ss.k0 + k]; b.p[k].sws_bytes = g_ss.n[g_ss.k0 + k]; }
+        b.split_pairs = g_ss.pairs == 3 ? 3 : 6;
         return conv_tc_split(ctx, b, st);
     }
     return conv_tc(ctx, a, st);
@@ -89,6 +96,7 @@ static int run_wgrad(afi_ctx* ctx, int prec, const WgradArgs& a, cudaStream_t st
     if (prec == AFI_PREC_SPLIT) {
         WgradArgs b = a;
         for (int k = 0; k < b.nprob; k++) { b.p[k].sws = g_ss.p[g_ss.k0 + k]; b.p[k].sws_bytes = g_ss.n[g_ss.k0 + k]; }
+        b.split_pairs = split_pairs_env(3);
         return wgrad_tc_split(ctx, b, st);
     }
     return wgrad_tc(ctx, a, st);
@@ -328,7 +336,7 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
     const int es = (int)dt_size(dt), wes = (int)prec_wes(prec);
     GWs W[AFI_MAX_PROB];
     Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
-    g_ss.k0 = 0;
+    g_ss.k0 = 0; g_ss.pairs = split_pairs_env(save ? 6 : 3);
     for (int k = 0; k < ncalls; k++) {
         const afi_g_call& c = calls[k];
         AFI_REQUIRE(c.x.ptr && c.y && c.ws, "afi_g_forward: call %d has a null pointer", k);
@@ -451,7 +459,7 @@ int afi_g_backward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pa
     const int es = (int)dt_size(dt), wes = (int)prec_wes(prec);
     GWs W[AFI_MAX_PROB];
     Dim3 d1[AFI_MAX_PROB], d2[AFI_MAX_PROB];
-    g_ss.k0 = 0;
+    g_ss.k0 = 0; g_ss.pairs = split_pairs_env(3);
     PView X0[AFI_MAX_PROB], H1[AFI_MAX_PROB], H2[AFI_MAX_PROB], H3[AFI_MAX_PROB], G0[AFI_MAX_PROB], G1[AFI_MAX_PROB], G2[AFI_MAX_PROB],
         dH1[AFI_MAX_PROB], DC5[AFI_MAX_PROB], GC[AFI_MAX_PROB], GH[AFI_MAX_PROB], tmpx[AFI_MAX_PROB], tmpy[AFI_MAX_PROB];
     for (int k = 0; k < ncalls; k++) {
@@ -750,6 +758,7 @@ int afi_d_forward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pac
     AFI_REQUIRE(ctx && p && packed, "afi_d_forward: null argument");
     DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
     AFI_TRY(d_calls_check("afi_d_forward", prec, calls, ncalls, save, W, d));
+    g_ss.pairs = split_pairs_env(save ? 6 : 3);
     const int dt = prec_dt(prec); const size_t wes = prec_wes(prec);
     DPacked L = d_packed_layout();
     for (int k = 0; k < ncalls; k++) {
@@ -838,6 +847,7 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
     AFI_REQUIRE(ctx && p && packed && gradacc, "afi_d_backward: null argument");
     DWs W[AFI_MAX_PROB]; Dim3 d[AFI_MAX_PROB];
     AFI_TRY(d_calls_check("afi_d_backward", prec, calls, ncalls, 1, W, d));
+    g_ss.pairs = split_pairs_env(3);
     const int dt = prec_dt(prec); const size_t wes = prec_wes(prec);
     DPacked L = d_packed_layout();
     DGradAcc GL = d_gradacc_layout();
@@ -987,6 +997,7 @@ int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int 
     void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
     cv.take((size_t)9 * cin * cout * 4); cv.take(P * cin * 4);
     g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
+    g_ss.pairs = 6;
     AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
     AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, prec_wdt(prec), st));
     ConvArgs a;
@@ -1014,6 +1025,7 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     float* acc = (float*)cv.take((size_t)9 * cin * cout * 4);
     void* DX = cv.take(P * cin * 4);
     g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
+    g_ss.pairs = split_pairs_env(3);
     if (xs != cin) AFI_CUDA(cudaMemsetAsync(X, 0, P * xs * es, st));
     if (ys != cout) AFI_CUDA(cudaMemsetAsync(DYb, 0, P * ys * es, st));
     PView Xv = pview(X, h, w, xs), DYv = pview(DYb, h, w, ys);

@@ -104,6 +104,11 @@ struct ConvArgs {
     // planes stacked along the slab axis, and the product is evaluated as the six plane pairs whose weight is >= 2^-16 (hi hi, hi mid,
     // mid hi, mid mid, hi lo, lo hi) with fp32 accumulation in TMEM: fp32-accurate products on the bf16 tensor cores.
     int split;
+    // split_pairs = 6: all six plane pairs (fp32-accurate products: the forward convs of a training step, whose pre-activation SIGNS
+    // decide the LeakyReLU slopes of the backward pass -- an error eps there moves the gradients by ~sqrt(eps));
+    // split_pairs = 3: hi hi + hi mid + mid hi only (products accurate to ~2^-17: everything a gradient or a forward-only result depends
+    // on LINEARLY -- dgrads, weight gradients, inference); the lo planes are then neither produced nor read.  Set by run_conv / run_wgrad.
+    int split_pairs;
     int aux_f32;          // residual / mask operands are fp32 (split mode: activations stay fp32 in HBM)
     ConvProb p[AFI_MAX_PROB];
 };
@@ -121,7 +126,7 @@ struct WgradArgs {
     int ntaps, nprob;
     Tap taps[9];          // .view unused, .slab = output slab
     float* dw;
-    int split;            // see ConvArgs.split (set by wgrad_tc_split)
+    int split, split_pairs;   // see ConvArgs.split / split_pairs (set by run_wgrad / wgrad_tc_split)
     WgradProb p[AFI_MAX_PROB];
 };
 
@@ -152,8 +157,8 @@ int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st);
 int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st);
 // bytes of split scratch one problem needs: conv (nviews input views of cin channels) / wgrad (x of cin + dy of cout channels)
 size_t split_planes_bytes(long long pixels, int channels);
-// fp32 strided views -> dense bf16 planes [3][pixels][cpad] (cpad = split_cpad(c); pad channels zeroed), all jobs in ONE launch
-struct SplitJob { PView src; int n, h, w, c; void* dst; };
+// fp32 strided views -> dense bf16 planes [nplanes = 2 | 3][pixels][cpad] (cpad = split_cpad(c); pad channels zeroed), all jobs in ONE launch
+struct SplitJob { PView src; int n, h, w, c; void* dst; int nplanes; };
 #define AFI_MAX_SPLIT 40
 int split_cpad(int c);
 int split3_group(int njobs, const SplitJob* jobs, cudaStream_t st);

@@ -66,6 +66,9 @@ struct Tiling {
     // is image p * N + n, plane p of weight slab s is slab p * nslab_total + s.  npairs = 1, pa = pb = {0} for plain bf16 operands.
     int npairs, nslab_total;
     int pa[6], pb[6];
+    // split mode, long accumulation chains: the K loop alternates between the two TMEM accumulators and the epilogue adds them (DUAL_ACC
+    // in k_conv_tc); the accumulator is then single-buffered (no epilogue / main-loop overlap)
+    int dual;
     long long* dbg;                   // optional [grid][8] stall-cycle counters (AFIGAN_HALO_DBG)
     TileP p[AFI_MAX_PROB + 1];        // p[nprob].begin = end sentinel
 };
@@ -449,7 +452,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             const int c0 = ch << 4;
             float v[16];
             tmem_ld16(taddr + c0, v);
-            if constexpr (AUX32) {      // split mode: the K loop alternated between the two accumulators (see DUAL_ACC below)
+            if (AUX32 && tl.dual) {     // split mode: the K loop alternated between the two accumulators (see DUAL_ACC below)
                 float v2[16];
                 tmem_ld16(taddr + ACC_COLS + c0, v2);
 #pragma unroll
@@ -548,7 +551,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             if (PAIR) mbar_arrive_cta0(smem_u32(&acc_empty[as]));
             else mbar_arrive(smem_u32(&acc_empty[as]));
         }
-        if (AUX32) aphase ^= 1;            // split mode: ONE accumulator stage (both TMEM halves belong to the tile in flight)
+        if (AUX32 && tl.dual) aphase ^= 1; // ONE accumulator stage (both TMEM halves belong to the tile in flight)
         else if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (a.stat_mode && cur_prob >= 0) flush_stats(cur_prob, cur_nt);
@@ -620,6 +623,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             int as = 0; uint32_t aphase = 0;
             long long w_f = 0, w_acc = 0; const bool dbg_on = tl.dbg != nullptr; const long long t_start = clock64();
             const uint32_t idesc = make_idesc(tl.bn, 0, 0);
+            const bool dual = AUX32 && tl.dual;
             for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
                 mbar_wait_t(smem_u32(&s.acc_empty[as]), aphase ^ 1, 2, w_acc, dbg_on);
                 tc_fence_after();
@@ -629,12 +633,12 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 // epilogue adds the halves in registers (round-to-nearest).  Costs the epilogue / main-loop overlap, which a six-pass
                 // main loop does not need.
                 for (int it = 0; it < iters; it++) {
-                    const uint32_t d_tmem = tmem_base + (AUX32 ? (it & 1) : as) * ACC_COLS;
+                    const uint32_t d_tmem = tmem_base + (dual ? (it & 1) : as) * ACC_COLS;
                     mbar_wait_t(smem_u32(&s.full[stage]), phase, 3, w_f, dbg_on);
                     tc_fence_after();
                     uint32_t sa = tiles0 + stage * stage_bytes;
                     uint64_t ad = make_desc(sa, 16, 1024), bd = make_desc(sa + A_BYTES, 16, 1024);
-                    const int first = AUX32 ? (it >> 1) : it;       // 0 on the first K step into this accumulator
+                    const int first = dual ? (it >> 1) : it;        // 0 on the first K step into this accumulator
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; k++) umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (first | k) != 0);
@@ -645,7 +649,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
                 }
                 if (elect_one()) umma_commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
-                if (AUX32) aphase ^= 1;
+                if (dual) aphase ^= 1;
                 else if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
@@ -831,6 +835,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             const uint32_t bar_af = smem_u32(&s.a_full[0]), bar_ae = smem_u32(&s.a_empty[0]);
             const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
             const int cin = a.cin;
+            const bool dual = AUX32 && tl.dual;
             auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int ti = 0;
             for (int item = item0; item < total; item += item_stride) {
@@ -842,8 +847,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 int kc = 0;
                 for (int chunk = 0; chunk < nchunks; chunk++) {
                     // split mode: chunks alternate between the two accumulators (DUAL_ACC, see k_conv_tc); nchunks >= 6 there
-                    const uint32_t d_tmem = tmem_base + (AUX32 ? (chunk & 1) : as) * ACC_COLS;
-                    if (AUX32) accum = chunk >= 2;
+                    const uint32_t d_tmem = tmem_base + (dual ? (chunk & 1) : as) * ACC_COLS;
+                    if (dual) accum = chunk >= 2;
                     int nk = (cin - kc * 64 + 15) >> 4;              // 16-channel MMA steps with data in this chunk
                     if (++kc == kchunks) kc = 0;
                     mbar_wait_t(bar_af + 8 * ai, aph, 24, w_af, dbg_on);
@@ -881,7 +886,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 }
                 if (elect_one()) commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
-                if (AUX32) aphase ^= 1;
+                if (dual) aphase ^= 1;
                 else if (++as == 2) { as = 0; aphase ^= 1; }
             }
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
@@ -939,14 +944,17 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
     const int nstages = tl.nstages; const uint32_t stage_bytes = tl.stage_bytes;
     const int kper = (tl.ktiles + tl.ksplit - 1) / tl.ksplit;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const bool dual = tl.npairs > 1;      // split mode: both TMEM halves accumulate the item in flight
+    const bool dual = tl.dual != 0;       // split mode: both TMEM halves accumulate the item in flight
+    // work item = (k split, tap, cout tile, cin tile) with the K SPLIT SLOWEST: the CTAs that run concurrently stream the same range of
+    // pixel tiles (different taps / channel tiles), so each operand tile is read from HBM once per wave and from L2 by everyone else
+    const int kbase = tl.total / tl.ksplit;
 
     // the producer and MMA warps run their loops CONVERGED; only the TMA / tcgen05 instruction issue is elected (see elect_one())
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;
         const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (A_BYTES + nbl * 8192);      // bytes of both CTAs land on the leader's barrier
         for (int item = item0; item < tl.total; item += item_stride) {
-            int ks = item % tl.ksplit; int r = item / tl.ksplit;
+            int ks = item / kbase; int r = item % kbase;
             int nt = r % tl.n_tiles; r /= tl.n_tiles;
             int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
             if (PAIR) mt = 2 * mt + rank;               // m_tiles counts PAIRS of 128-cout tiles
@@ -1003,7 +1011,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
             int as = 0; uint32_t aphase = 0;
             const uint32_t idesc = make_idesc(tl.bn, 1, 1, PAIR ? 256 : 128);
             for (int item = item0; item < tl.total; item += item_stride) {
-                int ks = item % tl.ksplit;
+                int ks = item / kbase;
                 int k0 = ks * kper, k1 = min(k0 + kper, tl.ktiles);
                 mbar_wait(smem_u32(&s.acc_empty[as]), aphase ^ 1, 12);
                 tc_fence_after();
@@ -1040,7 +1048,7 @@ k_wgrad_tc(const __grid_constant__ Maps maps, const __grid_constant__ WgradArgs 
         const int row = q * 32 + lane;
         int as = 0; uint32_t aphase = 0;
         for (int item = item0; item < tl.total; item += item_stride) {
-            int ks = item % tl.ksplit; int r = item / tl.ksplit;
+            int ks = item / kbase; int r = item % kbase;
             int nt = r % tl.n_tiles; r /= tl.n_tiles;
             int mt = r % tl.m_tiles; int tp = r / tl.m_tiles;
             if (PAIR) mt = 2 * mt + rank;
@@ -1140,11 +1148,15 @@ static void pick_patch(int H, int W, int pixels, int* TH, int* TW) {
 static int g_halo_dyn_max[2] = {0, 0};
 // plane pairs of a split-precision product, smallest terms first (hi lo, lo hi, mid mid, hi mid, mid hi, hi hi): every pair whose
 // weight is >= 2^-16 of the leading term; the dropped ones (mid lo, lo mid, lo lo) are below fp32's own rounding
-static void set_pairs(Tiling& tl, int split, int nslab_total) {
+// (split_pairs = 3: only hi mid, mid hi, hi hi -- products accurate to ~2^-17, for everything a result depends on linearly)
+static void set_pairs(Tiling& tl, int split, int split_pairs, int nslab_total) {
     static const int PA[6] = {0, 2, 1, 0, 1, 0}, PB[6] = {2, 0, 1, 1, 0, 0};
     tl.nslab_total = nslab_total;
-    if (split == 3) { tl.npairs = 6; for (int i = 0; i < 6; i++) { tl.pa[i] = PA[i]; tl.pb[i] = PB[i]; } }
-    else { tl.npairs = 1; tl.pa[0] = tl.pb[0] = 0; }
+    if (split == 3) {
+        const int first = split_pairs == 3 ? 3 : 0;
+        tl.npairs = 6 - first;
+        for (int i = first; i < 6; i++) { tl.pa[i - first] = PA[i]; tl.pb[i - first] = PB[i]; }
+    } else { tl.npairs = 1; tl.pa[0] = tl.pb[0] = 0; }
 }
 // AFIGAN_CONV_HALO = 0: per-tap A tiles (k_conv_tc) everywhere; 1: halo tiles, one CTA per tile; 2: halo tiles on CTA pairs (cta_group::2)
 static int halo_mode() {      // read on every call (tests switch variants in-process)
@@ -1226,7 +1238,8 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     if (pixels == 0) return AFI_OK;
     AFI_REQUIRE(a.split == 0 || a.split == 3, "conv_tc: split %d", a.split);
     AFI_REQUIRE(!(a.aux_f32 && a.stat_mode == 2), "conv_tc: the BatchNorm-backward statistics epilogue takes bf16 operands only");
-    const int planes = a.split ? 3 : 1;
+    AFI_REQUIRE(!a.split || a.split_pairs == 6 || a.split_pairs == 3, "conv_tc: split_pairs %d", a.split_pairs);
+    const int planes = a.split ? (a.split_pairs == 3 ? 2 : 3) : 1;      // operand planes of the A views (the weights always carry three)
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);
     Tiling tl{};
@@ -1255,7 +1268,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     // short-K layers (K = taps x cin < 4096) cannot hide their epilogue behind the MMAs: eight epilogue warps; so do the layers with
     // fused statistics below K = 8192 (measured: 512 -> 1024 with statistics on four warps is epilogue-bound in pair mode)
     const int K = a.ntaps * tl.kchunks * 64;
-    const int Kp = K * (a.split ? 6 : 1);                 // MMA work per tile: what the epilogue has to hide behind
+    const int Kp = K * (a.split ? a.split_pairs : 1);     // MMA work per tile: what the epilogue has to hide behind
     const int epi8 = (Kp < 4096 || (a.stat_mode && Kp < 8192)) ? 1 : 0;
     // halo tiles on CTA pairs: every 3x3 layer except the narrow ones (N tile < 128 or 32 input channels: the dense blocks' growth
     // convs and their dgrads), where the per-tap kernel measured 10-15 % faster (a pair halves the number of schedulable tiles and
@@ -1310,9 +1323,13 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int nslab = 0;
     for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
     if (a.nphase) nslab += 9 * (a.nphase - 1);
-    set_pairs(tl, a.split, nslab);
+    set_pairs(tl, a.split, a.split_pairs, nslab);
+    // six-pair products (the sign-critical forward convs) alternate between the two accumulators; so do three-pair products with chains
+    // of more than 160 MMAs per plane pair (K > 2560).  (Measured on the full-size step: with single accumulators on the generator's
+    // K = 2304 layers the worst sampled generator gradient error rose from 3.7e-4 to 9.2e-4.)
+    tl.dual = (a.split && (a.split_pairs == 6 || a.ntaps * tl.kchunks * 4 > 160) && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) ? 1 : 0;
     {
-        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab * planes};
+        cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab * (a.split ? 3 : 1)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), 1};
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
@@ -1389,9 +1406,11 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     int order[AFI_MAX_PROB];
     order_by_size(a.nprob, size, order);
     AFI_REQUIRE(a.split == 0 || a.split == 3, "wgrad_tc: split %d", a.split);
-    const int planes = a.split ? 3 : 1;
+    AFI_REQUIRE(!a.split || a.split_pairs == 6 || a.split_pairs == 3, "wgrad_tc: split_pairs %d", a.split_pairs);
+    const int planes = a.split ? (a.split_pairs == 3 ? 2 : 3) : 1;
     Tiling tl{};
-    set_pairs(tl, a.split, 0);
+    set_pairs(tl, a.split, a.split_pairs, 0);
+    tl.dual = (a.split && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) ? 1 : 0;
     tl.m_tiles = (a.cout + 127) / 128;
     tl.n_tiles = (a.cin + 255) / 256;
     tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
@@ -1427,9 +1446,13 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     if (ks > tl.ktiles) ks = tl.ktiles;
     if (ks < 1) ks = 1;
     int kper = (tl.ktiles + ks - 1) / ks;
-    // split mode: the accumulation chain of one item is capped (64 K tiles = 128 MMAs per accumulator and plane pair): the tensor cores
-    // add into the accumulator with truncation, a bias that grows linearly with the chain; the partial sums meet in fp32 RED adds
-    if (a.split && kper > 64) kper = 64;
+    // split mode: the accumulation chain of one item is capped at 512 K tiles (1024 MMAs per accumulator and plane pair, a truncation
+    // bias of ~2e-5, see DUAL_ACC in k_conv_tc); the partial sums meet in fp32 RED adds.  A tighter cap costs more than it buys: at
+    // 64 K tiles the RED traffic of the discriminator's weight gradients (1.6 GB per launch) made them 1.75x slower (measured).
+    if (a.split && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) {
+        const int cap = getenv("AFIGAN_SPLIT_KCAP") ? atoi(getenv("AFIGAN_SPLIT_KCAP")) : 512;
+        if (kper > cap) kper = cap;
+    }
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
     tl.stage_bytes = A_BYTES + (tl.bn / 64) * (pair ? 4096 : 8192);
@@ -1459,6 +1482,8 @@ int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     AFI_REQUIRE(nviews >= 1 && nviews <= 4, "conv_tc_split: bad view count");
     AFI_REQUIRE(a.out_dt == DT_F32 && !a.stat_mode, "conv_tc_split: fp32 output without fused statistics");
     ConvArgs b = a;
+    if (b.split_pairs != 3) b.split_pairs = 6;
+    const int nplanes = b.split_pairs == 3 ? 2 : 3;
     SplitJob jobs[AFI_MAX_SPLIT]; int nj = 0;
     const int cpad = split_cpad(a.cin);
     for (int k = 0; k < a.nprob; k++) {
@@ -1472,7 +1497,7 @@ int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         }
         for (int v = 0; v < nviews; v++) {
             SplitJob& j = jobs[nj++];
-            j.src = q.in[v]; j.n = q.N; j.h = q.H; j.w = q.W; j.c = a.cin; j.dst = (char*)q.sws + each * v;
+            j.src = q.in[v]; j.n = q.N; j.h = q.H; j.w = q.W; j.c = a.cin; j.dst = (char*)q.sws + each * v; j.nplanes = nplanes;
             b.p[k].in[v] = pview(j.dst, q.H, q.W, cpad);
         }
     }
@@ -1484,6 +1509,8 @@ int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
 int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     AFI_REQUIRE(a.nprob >= 1 && a.nprob <= AFI_MAX_PROB, "wgrad_tc_split: bad problem count %d", a.nprob);
     WgradArgs b = a;
+    if (b.split_pairs != 6) b.split_pairs = 3;      // a weight gradient depends on its operands linearly
+    const int nplanes = b.split_pairs == 3 ? 2 : 3;
     SplitJob jobs[AFI_MAX_SPLIT]; int nj = 0;
     for (int k = 0; k < a.nprob; k++) {
         const WgradProb& q = a.p[k];
@@ -1495,9 +1522,9 @@ int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
             return AFI_ERR_WORKSPACE;
         }
         SplitJob& jx = jobs[nj++];
-        jx.src = q.x; jx.n = q.N; jx.h = q.H; jx.w = q.W; jx.c = a.cin; jx.dst = q.sws;
+        jx.src = q.x; jx.n = q.N; jx.h = q.H; jx.w = q.W; jx.c = a.cin; jx.dst = q.sws; jx.nplanes = nplanes;
         SplitJob& jy = jobs[nj++];
-        jy.src = q.dy; jy.n = q.N; jy.h = q.H; jy.w = q.W; jy.c = a.cout; jy.dst = (char*)q.sws + bx;
+        jy.src = q.dy; jy.n = q.N; jy.h = q.H; jy.w = q.W; jy.c = a.cout; jy.dst = (char*)q.sws + bx; jy.nplanes = nplanes;
         b.p[k].x = pview(jx.dst, q.H, q.W, split_cpad(a.cin));
         b.p[k].dy = pview(jy.dst, q.H, q.W, split_cpad(a.cout));
     }

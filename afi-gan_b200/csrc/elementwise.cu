@@ -1550,7 +1550,7 @@ __global__ void __launch_bounds__(256) k_split3_group(const __grid_constant__ Sp
         const long long o = pix * cpad + c0;
         *reinterpret_cast<uint4*>(d + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
         *reinterpret_cast<uint4*>(d + pstride + o) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
-        *reinterpret_cast<uint4*>(d + 2 * pstride + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        if (q.nplanes > 2) *reinterpret_cast<uint4*>(d + 2 * pstride + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
 }
 int split3_group(int njobs, const SplitJob* jobs, cudaStream_t st) {

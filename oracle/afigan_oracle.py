@@ -21,7 +21,7 @@ math of App. A of SURVEY.md.
 
 Pinning: the reference ships NO tests, golden vectors or fixtures for this path, so
 parity is pinned the second way the task allows: tests/golden/make_golden.py imports the UNMODIFIED
-reference modules (through tests/_ref_stubs) in the dev container, checks that this restatement
+reference modules (through oracle/_ref_stubs) in the dev container, checks that this restatement
 reproduces their state dicts, outputs, losses and gradients, and commits small fixtures
 (tests/golden/*.npz) that tests/test_oracle.py re-checks everywhere (incl. the GPU box, where
 /root/reference does not exist).

@@ -2,7 +2,7 @@
 
 Run in the dev container only (needs /root/reference):   python tests/golden/make_golden.py
 It (1) imports generator_rdb.py / feature_patch_discriminator.py from /root/reference through
-tests/_ref_stubs, (2) asserts that the oracle reproduces the reference's init (bit-exact state dicts
+oracle/_ref_stubs, (2) asserts that the oracle reproduces the reference's init (bit-exact state dicts
 under the same seed), forward outputs, stage-1 losses and every parameter gradient, and (3) stores
 small fixtures in tests/golden/*.npz: inputs are re-derivable from seeds, so only expected outputs are
 kept (full small tensors, and for the 23 M parameter gradients a norm + a strided sample each).
@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_stubs"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref_stubs"))
 sys.path.insert(0, ROOT)
 from oracle import afigan_oracle as O  # noqa: E402
 

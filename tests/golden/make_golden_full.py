@@ -5,7 +5,7 @@ Run in the dev container only (needs /root/reference; ~2-3 min and ~20 GB of hos
 Batch 2, five pyramid levels (LR 104x168 ... 7x11 -> HR 200x336 ... 13x21, crops 208 -> 200 and 14x22 -> 13x21 as
 stage1_trainer.py:437-443 does them), weights under torch.manual_seed(0) (G first, then D: stage1_trainer.py:505-506),
 features from torch.Generator().manual_seed(1234) -- exactly the tensors bench.py feeds rank 0.  The reference step
-(stage1_trainer.py:334-433, optimiser updates omitted) runs through tests/_ref_stubs on torch CPU fp32; what is kept
+(stage1_trainer.py:334-433, optimiser updates omitted) runs through oracle/_ref_stubs on torch CPU fp32; what is kept
 (tests/golden/stage1_full.npz, < 200 KB): the ten losses, for each of the 33 parameter tensors the gradient norm and a
 257-point strided sample, and the BatchNorm running buffers.  tests/test_gpu_full_size.py compares the CUDA path with it.
 """
@@ -18,7 +18,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(ROOT, "tests", "_ref_stubs"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref_stubs"))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 from make_golden import load_ref, ref_stage1, sample  # noqa: E402

@@ -57,14 +57,18 @@ def test_conv3x3_backward(shape, precision):
 SPLIT_SHAPES = SHAPES + [(1, 1024, 1024, 25, 42), (3, 256, 256, 17, 9), (2, 64, 64, 5, 40), (1, 352, 128, 12, 20)]
 
 
+@pytest.mark.parametrize("pairs", ["default", "six"])
 @pytest.mark.parametrize("shape", SPLIT_SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_split_precision_matches_fp64_on_full_fp32_operands(shape):
-    """The split mode multiplies ARBITRARY fp32 operands (not bf16-representable ones) as six bf16 plane-pair products with fp32 TMEM
-    accumulation: forward, dgrad and wgrad must match an fp64 evaluation as closely as fp32 arithmetic does (the CUDA-core fp32 mode is
-    evaluated next to it).  The tensor cores add into the TMEM accumulator with truncation, which biases a chain of n MMAs by ~3e-8 n
-    (measured 1e-5 at K = 9216 with one accumulator); the kernels alternate between two accumulators, so the split mode may be up to
-    6x worse than FFMA fp32, and must stay below 2e-6 x sqrt(K / 256)."""
+def test_split_precision_matches_fp64_on_full_fp32_operands(shape, pairs, monkeypatch):
+    """The split mode multiplies ARBITRARY fp32 operands (not bf16-representable ones) as bf16 plane-pair products with fp32 TMEM
+    accumulation.  Six pairs (forward convs of a training step; everything with AFIGAN_SPLIT_PAIRS=6) must match an fp64 evaluation as
+    closely as fp32 arithmetic does: the CUDA-core fp32 mode is evaluated next to it.  The tensor cores add into the TMEM accumulator
+    with truncation, which biases a chain of n MMAs by ~2e-8 n (measured 1e-5 at K = 9216 with one accumulator); the kernels alternate
+    between two accumulators, so the split mode may be up to 6x worse than FFMA fp32 and must stay below 2e-6 x sqrt(K / 256).
+    Three pairs (hi hi + hi mid + mid hi: the default for dgrad / wgrad, on which results depend linearly) are accurate to ~2^-17."""
     from afigan.functional import conv3x3, conv3x3_backward
+    if pairs == "six":
+        monkeypatch.setenv("AFIGAN_SPLIT_PAIRS", "6")
     n, cin, cout, h, w = shape
     g = torch.Generator().manual_seed(11 + hash(shape) % 1000)
     x = torch.randn(n, cin, h, w, generator=g)
@@ -80,9 +84,12 @@ def test_split_precision_matches_fp64_on_full_fp32_operands(shape):
         y = conv3x3(x.cuda(), wt.cuda(), b.cuda(), False, precision).cpu()
         dw, dx = conv3x3_backward(x.cuda(), dy.cuda(), wt.cuda(), precision)
         errs[precision] = (rel(y, ref), rel(dx, xd.grad), rel(dw, wd.grad))
-    print(f"{shape}: fp32 {errs['fp32']}, split {errs['split']}")
-    for e32, esp in zip(errs["fp32"], errs["split"]):
-        assert esp < bound and esp < 6 * e32 + 2e-7, (shape, errs)
+    print(f"{shape} [{pairs}]: fp32 {errs['fp32']}, split {errs['split']}")
+    for i, (e32, esp) in enumerate(zip(errs["fp32"], errs["split"])):
+        if i == 0 or pairs == "six":
+            assert esp < bound and esp < 6 * e32 + 2e-7, (shape, errs)
+        else:
+            assert esp < 3e-5, (shape, errs)
 
 
 def test_strided_and_channels_last_inputs():
