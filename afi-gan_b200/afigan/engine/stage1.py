@@ -29,7 +29,7 @@ CH = 256
 class Stage1Step:
     def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
                  precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
-                 reuse_g_forward: Optional[bool] = None):
+                 reuse_g_forward: Optional[bool] = None, overlap_comm: bool = True):
         self.G, self.D = G, D
         self.Dstack = D.Discriminators[0]
         self.lr, self.momentum, self.wd, self.wd_norm = lr, momentum, weight_decay, weight_decay_norm
@@ -53,6 +53,10 @@ class Stage1Step:
         self.g_mom = [torch.zeros_like(p) for p in self.g_params]
         self.d_mom = [torch.zeros_like(p) for p in self.d_params]
         self.steps_done = 0
+        self._mom_restored = False
+        # Gradient all-reduces off the critical path: D's runs while the generator's backward pass (which does not read D) computes, G's
+        # while the G phase's discriminator forwards do; only the optimiser update waits for its collective.
+        self.overlap_comm = overlap_comm
         self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
         self.d_acc = _u8(self.lib.afi_d_gradacc_bytes(), dev)
         self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
@@ -75,8 +79,32 @@ class Stage1Step:
             reuse_g_forward = os.environ.get("AFIGAN_REUSE_G_FORWARD", "1") != "0"
         self.reuse_g_forward = reuse_g_forward
         self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap else []
-        self._pack_g()
-        self._pack_d()
+        self._pack_key = None
+        self._refresh_packed()
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.g_params + self.d_params)
+
+    def _refresh_packed(self):
+        """Re-pack the GEMM-layout weight copies when a parameter changed behind this object's back (load_state_dict, checkpoint interop, an
+        external optimiser, a broadcast): the in-library SGD updates do not bump torch's version counters and re-pack explicitly."""
+        key = self._param_key()
+        if key != self._pack_key:
+            self._pack_g()
+            self._pack_d()
+            self._pack_key = key
+
+    def load_optimizer_state(self, g_momentum: Sequence[torch.Tensor], d_momentum: Sequence[torch.Tensor], steps_done: int):
+        """Resume: restored SGD momentum buffers (state-dict order) and the iteration count (detectron2 checkpoints carry both)."""
+        for dst, src in zip(self.g_mom, g_momentum):
+            dst.copy_(src)
+        for dst, src in zip(self.d_mom, d_momentum):
+            dst.copy_(src)
+        self.steps_done = int(steps_done)
+        self._mom_restored = True
+        if self.distributed:
+            self.g_sync.broadcast_parameters(self.g_mom)
+            self.d_sync.broadcast_parameters(self.d_mom)
 
     # ---- helpers --------------------------------------------------------------------------------------
     def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool, tag="") -> torch.Tensor:
@@ -217,7 +245,7 @@ class Stage1Step:
     def _sgd(self, params, grads, moms, is_norm):
         # parameters are updated in place behind torch's back; the packed GEMM-layout copies are refreshed explicitly by the caller.
         # ONE multi-tensor launch per optimiser; the host-side pointer tables are rebuilt only when a tensor moved.
-        first = int(self.steps_done == 0)
+        first = int(self.steps_done == 0 and not self._mom_restored)
         n = len(params)
         key = tuple(t.data_ptr() for ts in (params, grads, moms) for t in ts) + (self.wd, self.wd_norm)
         tab = self._sgd_tabs.get(id(params))
@@ -237,21 +265,34 @@ class Stage1Step:
 
     # ---- the step ---------------------------------------------------------------------------------------
     @torch.no_grad()
-    def run_step(self, lr_feats: Sequence[torch.Tensor], hr_feats: Sequence[torch.Tensor], apply_updates: bool = True):
-        """Returns the device tensor `losses` [4, 8]: row 0 d_loss_p*, 1 g_loss_p*, 2 adv_loss_p*, 3 content_loss_p* (cols = levels)."""
+    def run_step(self, lr_feats: Sequence[torch.Tensor], hr_feats: Sequence[torch.Tensor], apply_updates: bool = True,
+                 timers: Optional[Dict[str, float]] = None):
+        """Returns the device tensor `losses` [4, 8]: row 0 d_loss_p*, 1 g_loss_p*, 2 adv_loss_p*, 3 content_loss_p* (cols = levels).
+        timers (a dict): filled with the device milliseconds of the step's phases (synchronises; instrumented steps only)."""
         lib, st = self.lib, N.stream_ptr
         nl = len(lr_feats)
         assert nl == len(hr_feats) and nl <= 8
+        self._refresh_packed()
         self.losses.zero_()
         lp = self.losses.data_ptr()
+        marks = []
+
+        def mark(name):
+            if timers is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
 
         def slot(row, col):
             return lp + 4 * (row * 8 + col)
 
+        overlap_comm = self.overlap_comm and self.distributed and self.reuse_g_forward and timers is None
+        mark("start")
         # ------------------------------ D phase (stage1_trainer.py:334-381)
         N.check(lib.afi_zero(self.d_acc.data_ptr(), self.d_acc.numel(), st()))
         # G(lr).detach(), cropped
         trs = self._g_forward(lr_feats, hr_feats, True, "g") if self.reuse_g_forward else self._g_forward(lr_feats, hr_feats, False, "d")
+        mark("g_forward")
         xs, tags = [], []
         for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
             xs += [hi[:, :, :tr.size(2), :tr.size(3)], tr]                          # D0(hr) BEFORE D0(tr)  (:349-350)
@@ -260,41 +301,71 @@ class Stage1Step:
         self._d_phase(xs, tags, [1.0 if i % 2 == 0 else 0.0 for i in range(len(xs))], [0] * len(xs), True, True)
         gs = d_grad_struct(self.d_grads)
         N.check(lib.afi_d_unpack_grads(self.ctx, self.prec, self.d_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
-        self._allreduce(self.d_flat)
-        if apply_updates:
-            self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
-            self._pack_d()
-            self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
+        mark("d_forward_backward")
 
-        # ------------------------------ G phase (stage1_trainer.py:384-433)
-        N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
-        if not self.reuse_g_forward:
-            trs = self._g_forward(lr_feats, hr_feats, True, "g")
-        xs, tags = [], []
-        for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
-            xs += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                          # D0(tr) BEFORE D0(hr) here (:399-400)
-            tags += [f"f{l}", f"r{l}"]
-        # adv = BCE(D0(tr).detach(), 1): no gradient (:399); D0(hr) is dead compute kept for its BN running-stat side effect (:400)
-        # (with one G forward per step the G phase feeds the discriminator the tensors the D phase already staged)
-        self._d_phase(xs, tags, [1.0] * len(xs), [2 if i % 2 == 0 else None for i in range(len(xs))], False, False,
-                      staged=self.reuse_g_forward)
-        dtrs = []
-        for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
-            dtr = self._buf(f"dtr{l}", tuple(tr.shape))
-            hi_c = hi[:, :, :tr.size(2), :tr.size(3)]
-            N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), tr.size(0), CH, tr.size(2), tr.size(3), self._tmp[40 + l:].data_ptr(),
-                                    slot(3, l), 1.0, dtr.data_ptr(), 1.0, st()))
-            dtrs.append(dtr)
-        self._g_backward(lr_feats, hr_feats, dtrs, "g")
+        def d_update():
+            if apply_updates:
+                self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
+                self._pack_d()
+                self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
+
+        def g_backward_pass():
+            # L1(tr, hr) and its gradient; backward through G (reads the activations the ONE forward pass kept; does not read D)
+            N.check(lib.afi_zero(self.g_acc.data_ptr(), self.g_acc.numel(), st()))
+            dtrs = []
+            for l, (tr, hi) in enumerate(zip(trs, hr_feats)):
+                dtr = self._buf(f"dtr{l}", tuple(tr.shape))
+                hi_c = hi[:, :, :tr.size(2), :tr.size(3)]
+                N.check(lib.afi_l1_loss(N.view4(tr), N.view4(hi_c), tr.size(0), CH, tr.size(2), tr.size(3), self._tmp[40 + l:].data_ptr(),
+                                        slot(3, l), 1.0, dtr.data_ptr(), 1.0, st()))
+                dtrs.append(dtr)
+            self._g_backward(lr_feats, hr_feats, dtrs, "g")
+            gsg = g_param_struct(self.g_grads, self.n_rdb)
+            N.check(lib.afi_g_unpack_grads(self.ctx, self.prec, self.g_acc.data_ptr(), C.byref(gsg), 1.0, 0, st()))
+
+        def g_phase_d_forwards(trs_):
+            xs_, tags_ = [], []
+            for l, (tr, hi) in enumerate(zip(trs_, hr_feats)):
+                xs_ += [tr, hi[:, :, :tr.size(2), :tr.size(3)]]                     # D0(tr) BEFORE D0(hr) here (:399-400)
+                tags_ += [f"f{l}", f"r{l}"]
+            # adv = BCE(D0(tr).detach(), 1): no gradient (:399); D0(hr) is dead compute kept for its BN running-stat side effect (:400)
+            # (with one G forward per step the G phase feeds the discriminator the tensors the D phase already staged)
+            self._d_phase(xs_, tags_, [1.0] * len(xs_), [2 if i % 2 == 0 else None for i in range(len(xs_))], False, False,
+                          staged=self.reuse_g_forward)
+
+        if overlap_comm:
+            # Same values as the literal order below (the generator's backward does not depend on D's update, the G phase's discriminator
+            # forwards do not depend on G's gradients); only the ISSUE order changes so that each all-reduce has compute to hide behind.
+            self.d_sync.start()
+            g_backward_pass()
+            self.g_sync.start()
+            self.d_sync.finish()
+            d_update()
+            g_phase_d_forwards(trs)
+            self.g_sync.finish()
+        else:
+            self._allreduce(self.d_flat)
+            d_update()
+            mark("d_allreduce_sgd_pack")
+            # ------------------------------ G phase (stage1_trainer.py:384-433)
+            if not self.reuse_g_forward:
+                trs = self._g_forward(lr_feats, hr_feats, True, "g")
+            g_phase_d_forwards(trs)
+            mark("g_phase_d_forwards")
+            g_backward_pass()
+            mark("l1_g_backward")
+            self._allreduce(self.g_flat)
         self.losses[1, :nl] = 1e-3 * self.losses[2, :nl] + self.losses[3, :nl]
-        gs = g_param_struct(self.g_grads, self.n_rdb)
-        N.check(lib.afi_g_unpack_grads(self.ctx, self.prec, self.g_acc.data_ptr(), C.byref(gs), 1.0, 0, st()))
-        self._allreduce(self.g_flat)
         if apply_updates:
             self._sgd(self.g_params, self.g_grads, self.g_mom, [False] * len(self.g_params))
             self._pack_g()
             self.G._native.packed.key = None
             self.steps_done += 1
+        mark("g_allreduce_sgd_pack")
+        if timers is not None:
+            torch.cuda.synchronize(self.dev)
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                timers[name] = timers.get(name, 0.0) + a.elapsed_time(b)
         return self.losses
 
     def metrics(self, n_levels: int = 5) -> Dict[str, float]:

@@ -27,6 +27,19 @@ class FlatGradSync:
         active = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
         self.enabled = active if enabled is None else enabled
         self.world = dist.get_world_size(process_group) if self.enabled else 1
+        self._work = None
+        if self.enabled:
+            self.broadcast_parameters()
+
+    def broadcast_parameters(self, extra: Sequence[torch.Tensor] = ()):
+        """What DistributedDataParallel does at construction (reference stage1_trainer.py:80-89): rank 0's parameters -- and any `extra`
+        tensors, e.g. restored momentum buffers -- replace every other rank's, so that averaged gradients are applied to IDENTICAL
+        replicas (detectron2 seeds each rank differently).  BatchNorm buffers are left alone: the reference passes broadcast_buffers=False."""
+        if not self.enabled:
+            return
+        for t in list(self.params) + list(extra):
+            dist.broadcast(t.data if isinstance(t, torch.nn.Parameter) else t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0,
+                           group=self.pg)
 
     @property
     def grad_scale(self) -> float:
@@ -36,3 +49,13 @@ class FlatGradSync:
         if self.enabled:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
         return None
+
+    def start(self):
+        """Launch the all-reduce without blocking the issuing stream (NCCL runs it on its own stream once the work queued so far is done);
+        `finish()` makes the current stream wait for it.  Kernels issued in between overlap the collective."""
+        self._work = self.all_reduce(async_op=True)
+
+    def finish(self):
+        if self._work is not None:
+            self._work.wait()
+            self._work = None

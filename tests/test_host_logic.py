@@ -99,6 +99,39 @@ def test_gradient_allreduce_world2_gloo(tmp_path):
         assert float((r0["own"][k] - r1["own"][k]).norm()) > 1e-2 * float(ref.norm())     # the shards really differ
 
 
+def _bcast_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "afi-gan_b200"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from afigan.engine.sync import FlatGradSync
+    torch.manual_seed(100 + rank)                                       # detectron2 seeds each rank differently
+    params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    before = [p.detach().clone() for p in params]
+    mom = [torch.randn(5, 3), torch.randn(7)]
+    sync = FlatGradSync(params)                                         # broadcasts rank 0's parameters, like DDP's constructor
+    sync.broadcast_parameters(mom)                                      # ... and on resume the momentum buffers
+    sync.flat.fill_(float(rank + 1))
+    sync.start()                                                        # asynchronous all-reduce
+    sync.finish()
+    torch.save({"before": before, "after": [p.detach().clone() for p in params], "mom": mom, "flat": sync.flat.clone()}, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_initial_state_is_broadcast_from_rank0_world2_gloo(tmp_path):
+    """replicas that start from different seeds must be made identical before averaged gradients are applied (DDP's constructor
+    broadcast, reference stage1_trainer.py:80-89); the asynchronous all-reduce sums like the blocking one."""
+    out = str(tmp_path / "b")
+    mp.spawn(_bcast_worker, args=(2, 29633, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    for a, b, c0, c1 in zip(r0["after"], r1["after"], r0["before"], r1["before"]):
+        assert torch.equal(a, b) and torch.equal(a, c0) and not torch.equal(c0, c1)
+    for a, b in zip(r0["mom"], r1["mom"]):
+        assert torch.equal(a, b)
+    assert torch.equal(r0["flat"], torch.full_like(r0["flat"], 3.0)) and torch.equal(r1["flat"], r0["flat"])
+
+
 def test_checkpoint_key_remap_and_lr_schedule():
     from afigan._compat import ShapeSpec
     from afigan.engine import (convert_afi_names, load_extractor_into_detector, load_generator_into_extractor, remain_only_afi_names,
