@@ -13,8 +13,17 @@ def get_cfg():
         cfg = CfgNode()
         cfg.MODEL = CfgNode()
         cfg.MODEL.DEVICE = "cuda"
+        cfg.MODEL.PIXEL_MEAN = [103.530, 116.280, 123.675]      # detectron2 defaults [upstream]
+        cfg.MODEL.PIXEL_STD = [1.0, 1.0, 1.0]
+        cfg.INPUT = CfgNode()
+        cfg.INPUT.FORMAT = "BGR"
+        cfg.INPUT.MIN_SIZE_TRAIN = (800,)
+        cfg.INPUT.MAX_SIZE_TRAIN = 1333
+        cfg.INPUT.MIN_SIZE_TRAIN_SAMPLING = "choice"
         cfg.MODEL.RESNETS = CfgNode()
         cfg.MODEL.FPN = CfgNode()
+        cfg.MODEL.RESNETS.DEPTH = 50
+        cfg.MODEL.RESNETS.STRIDE_IN_1X1 = True
         cfg.MODEL.FPN.IN_FEATURES = []
         cfg.MODEL.FPN.OUT_CHANNELS = 256
         cfg.MODEL.FPN.NORM = ""

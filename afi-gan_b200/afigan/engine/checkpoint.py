@@ -9,7 +9,7 @@ Because this package keeps the reference's parameter names and shapes, these fun
 `module.load_state_dict(..., strict=False)` of either implementation (weights trained here load in the reference and vice versa)."""
 from __future__ import annotations
 
-from typing import Dict, Mapping, Tuple
+from typing import Dict, Mapping, Optional, Sequence, Tuple
 
 import torch
 
@@ -72,3 +72,96 @@ def load_extractor_into_detector(model: torch.nn.Module, extractor_ckpt: Mapping
         for mk, ck in mapping.items():
             state[mk].copy_(ckpt[ck])
     return len(mapping)
+
+
+class AFCheckpointer:
+    """File-level counterpart of the reference's `AF_DetectionCheckpointer` (reference afigan/engine/checkpoint.py:14-76, on top of fvcore's
+    `Checkpointer` [upstream]) without the fvcore / detectron2 dependency.  Wire format = `torch.save({"model": state_dict, **checkpointables})`
+    with a `last_checkpoint` text file next to it; `module.` prefixes of DDP-wrapped models are stripped on save and tolerated on load; `.pkl`
+    files in detectron2's model-zoo format (`{"model": {name: ndarray}, "__author__": ...}`) load too.  Files written here load with the
+    reference's checkpointers into the reference's modules and vice versa (tests/test_checkpoint_interop.py)."""
+
+    def __init__(self, model: torch.nn.Module, save_dir: str = "", save_to_disk: bool = True, **checkpointables):
+        self.model = model.module if hasattr(model, "module") and isinstance(model.module, torch.nn.Module) else model
+        self.save_dir, self.save_to_disk, self.checkpointables = save_dir, save_to_disk, dict(checkpointables)
+
+    # ---- save / bookkeeping (fvcore Checkpointer.save / get_checkpoint_file / tag_last_checkpoint [upstream])
+    def save(self, name: str, **extra) -> str:
+        import os
+        if not self.save_dir or not self.save_to_disk:
+            return ""
+        data = {"model": self.model.state_dict()}
+        for k, obj in self.checkpointables.items():
+            data[k] = obj.state_dict() if hasattr(obj, "state_dict") else obj
+        data.update(extra)
+        os.makedirs(self.save_dir, exist_ok=True)
+        path = os.path.join(self.save_dir, f"{name}.pth")
+        torch.save(data, path)
+        with open(os.path.join(self.save_dir, "last_checkpoint"), "w") as f:
+            f.write(os.path.basename(path))
+        return path
+
+    def has_checkpoint(self) -> bool:
+        import os
+        return bool(self.save_dir) and os.path.exists(os.path.join(self.save_dir, "last_checkpoint"))
+
+    def get_checkpoint_file(self) -> str:
+        import os
+        try:
+            with open(os.path.join(self.save_dir, "last_checkpoint")) as f:
+                return os.path.join(self.save_dir, f.read().strip())
+        except OSError:
+            return ""
+
+    # ---- load
+    def _load_file(self, filename: str) -> Dict:
+        """checkpoint.py:29-47."""
+        if filename.endswith(".pkl"):
+            import pickle
+            with open(filename, "rb") as f:
+                data = pickle.load(f, encoding="latin1")
+            if "model" in data and "__author__" in data:
+                data = dict(data)
+                data["model"] = {k: torch.as_tensor(v) for k, v in data["model"].items()}
+                return data
+            raise NotImplementedError("Caffe2 / Detectron1 model-zoo pickles need detectron2's name-matching heuristics (c2_model_loading) [upstream]")
+        loaded = torch.load(filename, map_location="cpu", weights_only=False)
+        if "model" not in loaded:
+            loaded = {"model": loaded}
+        return loaded
+
+    def _load_model(self, checkpoint: Dict) -> Dict[str, list]:
+        """fvcore Checkpointer._load_model [upstream]: strip `module.`, skip shape mismatches, load non-strictly, report what did not match."""
+        state = strip_module_prefix(checkpoint["model"])
+        own = self.model.state_dict()
+        incorrect = [(k, tuple(v.shape), tuple(own[k].shape)) for k, v in state.items() if k in own and tuple(v.shape) != tuple(own[k].shape)]
+        for k, _, _ in incorrect:
+            state.pop(k)
+        res = self.model.load_state_dict(state, strict=False)
+        return {"missing_keys": list(res.missing_keys), "unexpected_keys": list(res.unexpected_keys), "incorrect_shapes": incorrect}
+
+    def load(self, path: str, checkpointables: Optional[Sequence[str]] = None) -> Dict:
+        """Checkpointer.load [upstream]: the model plus the named checkpointables (optimizer, scheduler, ...); returns what is left (`iteration`)."""
+        if not path:
+            return {}
+        checkpoint = self._load_file(path)
+        self.last_incompatible = self._load_model(checkpoint)
+        for k in (self.checkpointables if checkpointables is None else checkpointables):
+            if k in checkpoint and hasattr(self.checkpointables.get(k), "load_state_dict"):
+                self.checkpointables[k].load_state_dict(checkpoint.pop(k))
+        checkpoint.pop("model", None)
+        return checkpoint
+
+    def resume_or_load(self, path: str, resume: bool = True) -> Dict:
+        """Checkpointer.resume_or_load [upstream] as stage1_trainer.py:157-174 uses it."""
+        if resume and self.has_checkpoint():
+            return self.load(self.get_checkpoint_file())
+        return self.load(path, checkpointables=[])
+
+    def _load_AFExtractor_weights_file(self, filename: str) -> int:
+        """checkpoint.py:64-69: a stage-1 generator checkpoint into a detector whose backbone owns `srf_module` (stage 1 -> stage 2)."""
+        return load_generator_into_extractor(self.model, self._load_file(filename)["model"])
+
+    def _load_TargetDetector_weights_file(self, filename: str) -> int:
+        """checkpoint.py:71-76: only the `srf_module` weights of an AF-extractor checkpoint into the target detector (stage 2 -> stage 3)."""
+        return load_extractor_into_detector(self.model, self._load_file(filename)["model"])

@@ -36,8 +36,53 @@ def test_backbone_registry_names():
     cfg = get_cfg()
     cfg.MODEL.GUIDE_ARCHITECTURE = "RCNN_FPN_only"                 # configs/step1_*.yaml:5
     assert callable(GUIDE_ARCH_REGISTRY.get("RCNN_FPN_only"))
-    with pytest.raises(ImportError, match="out of scope"):          # the guide model itself is a producer of the path's inputs
-        build_guide_model(cfg)
+    assert callable(BACKBONE_REGISTRY.get(cfg.MODEL.GUIDE_BACKBONE.NAME))      # build_resnet_fpn_backbone (detectron2's, or the stand-in)
+
+
+def test_guide_model_and_paired_scale_mapper_produce_the_config1_shape_pairs():
+    """an 800x1333 image and its int(0.5 x) copy, padded to 32, give HR levels 200x336 .. 13x21 and LR levels
+    104x168 .. 7x11 (reference rcnn_only.py:34-44, dataset_mapper.py:70-125, transform_gen.py:540-552).  Runs the guide ResNet-50-FPN on
+    the CPU at 1/4 of the image size (the shape arithmetic is the same) and checks the full-size arithmetic without running it."""
+    import numpy as np
+    from afigan.config import get_cfg
+    from afigan.engine import PairedScaleMapper, shortest_edge_size
+    from afigan.modeling import build_guide_model
+    from afigan.modeling.meta_arch import pad_to_divisible
+    assert shortest_edge_size(480, 640, 800, 1333) == (800, 1067) and shortest_edge_size(600, 1000, 800, 1333) == (800, 1333)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 255, size=(150, 250, 3), dtype=np.uint8)
+    annos = [{"bbox": [10.0, 20.0, 110.0, 70.0], "bbox_mode": "XYXY_ABS"}]
+    flipped = plain = None
+    mapper = PairedScaleMapper(min_size=(200,), max_size=333, rng=rng)
+    for _ in range(20):
+        d = mapper({"image_array": img, "annotations": annos})
+        assert tuple(d["image"].shape) == (3, 200, 333) and tuple(d["image_x0.5"].shape) == (3, 100, 166)      # int(0.5 * 333) = 166
+        b, b2 = d["instances"]["gt_boxes"][0], d["instances_x0.5"]["gt_boxes"][0]
+        assert torch.allclose(b2 * torch.tensor([333 / 166, 2.0, 333 / 166, 2.0]), b, atol=1e-3)                 # same flip at both scales
+        if float(b[0]) > 150:
+            flipped = d
+        else:
+            plain = d
+    assert flipped is not None and plain is not None
+    assert torch.equal(flipped["image"], plain["image"].flip(2)) and torch.equal(flipped["image_x0.5"], plain["image_x0.5"].flip(2))
+    # full-size arithmetic (not executed): 800x1333 -> pad 32 -> 800x1344; LR 400x666 -> 416x672
+    for (h, w), want in (((800, 1333), (800, 1344)), ((400, 666), (416, 672))):
+        assert tuple(pad_to_divisible([torch.zeros(1, h, w)], 32).shape[2:]) == want
+    cfg = get_cfg()
+    cfg.MODEL.DEVICE = "cpu"
+    cfg.MODEL.GUIDE_ARCHITECTURE = "RCNN_FPN_only"
+    torch.manual_seed(0)
+    guide = build_guide_model(cfg).eval()
+    assert guide.backbone.size_divisibility == 32
+    keys = set(guide.state_dict())
+    assert {"backbone.bottom_up.stem.conv1.weight", "backbone.bottom_up.res2.0.shortcut.norm.running_var", "backbone.bottom_up.res5.2.conv3.weight",
+            "backbone.fpn_lateral5.weight", "backbone.fpn_output2.bias"} <= keys                                  # detectron2 R-50-FPN key names
+    out = guide([plain], "image")[0]["features"]
+    assert [tuple(out[k].shape[1:]) for k in ("p2", "p3", "p4", "p5", "p6")] == [(256, 56, 88), (256, 28, 44), (256, 14, 22), (256, 7, 11), (256, 4, 6)]
+    lr_f, hr_f = guide.extract_pair([plain, flipped])
+    assert [tuple(t.shape) for t in lr_f] == [(2, 256, 32, 48), (2, 256, 16, 24), (2, 256, 8, 12), (2, 256, 4, 6), (2, 256, 2, 3)]
+    assert all(not t.requires_grad and t.dtype == torch.float32 for t in lr_f + hr_f)
+    assert torch.allclose(hr_f[1][0], out["p3"][0], atol=1e-5)
 
 
 def test_neck_parameter_names_on_cpu():
