@@ -367,5 +367,46 @@ class Conv3x3Fn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class Conv1x1Fn(torch.autograd.Function):
+    """1x1 convolution (+bias) through the library's GEMM engine with autograd: the necks' lateral convs incl. the top-level one (reference
+    fpn_sr.py:79-81, 144-145), the BiFPN's input laterals and the pointwise half of its depthwise-separable convs (bifpn_sr.py:160-183,
+    bifpn_layers/wrappers.py:166-206)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec: int):
+        if not x.is_cuda:
+            raise RuntimeError("conv1x1: input must live on an sm_100a CUDA device (no CPU fallback)")
+        x, weight = x.float(), weight.float().contiguous()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv1x1_workspace_bytes(prec, n, cin, h, w, cout), x.device)
+        y = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+        N.check(lib.afi_conv1x1(actx, prec, N.view4(x), n, cin, h, w, weight.data_ptr(), N.ptr(bias), cout, y.data_ptr(), ws.data_ptr(),
+                                ws.numel(), N.stream_ptr()))
+        ctx.prec, ctx.has_bias = prec, bias is not None
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.float()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv1x1_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
+        dw = torch.empty_like(weight)
+        db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        N.check(lib.afi_conv1x1_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(db),
+                                         N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
+        return dx, dw, db, None
+
+
+def conv1x1_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
+    return Conv1x1Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])
+
+
 def conv3x3_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
     return Conv3x3Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..._compat import BACKBONE_REGISTRY, Backbone, Conv2d, ShapeSpec, c2_xavier_fill, get_norm
-from ...functional import conv3x3_autograd
+from ...functional import conv1x1_autograd, conv3x3_autograd
 from ..feat_interpol import generator_rdb as G_rdb
 
 __all__ = ["build_resnet_fpn_sr_backbone", "build_resnest_fpn_sr_backbone", "FPN_AFIGAN", "LastLevelMaxPool"]
@@ -39,12 +39,27 @@ def output_conv3x3(conv, x, precision=None):
     return conv(x)
 
 
+def lateral_conv1x1(conv, x, precision=None):
+    """A neck's 1x1 lateral conv on its own -- the top-level lateral (fpn_sr.py:144-145), or any lateral that carries a norm (SyncBN
+    configs): the 1x1 conv runs on the library's GEMM engine, norm / activation (if any) stay torch modules."""
+    ok = (x.is_cuda and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.in_channels % 32 == 0
+          and conv.out_channels % 32 == 0)
+    if not ok:
+        return conv(x)
+    y = conv1x1_autograd(x, conv.weight, conv.bias, precision)
+    if getattr(conv, "norm", None) is not None:
+        y = conv.norm(y)
+    if getattr(conv, "activation", None) is not None:
+        y = conv.activation(y)
+    return y
+
+
 def topdown_merge(srf_module, prev_features, features, lateral_conv, fuse_type):
     """One top-down step.  Bare 1x1 lateral (FPN.NORM == ""): fully fused in the library; with a norm in the lateral the conv+norm
     stay in torch and only the interpolator runs in the library (SURVEY.md §7 hard part 7)."""
     if getattr(lateral_conv, "norm", None) is None and getattr(lateral_conv, "activation", None) is None:
         return srf_module.merge(prev_features, features, lateral_conv.weight, lateral_conv.bias, fuse_type)
-    lateral = lateral_conv(features)
+    lateral = lateral_conv1x1(lateral_conv, features, srf_module.precision)
     out = lateral + srf_module(prev_features, out_hw=tuple(lateral.shape[2:]))
     return out / 2 if fuse_type == "avg" else out
 
@@ -111,7 +126,7 @@ class _AFINeck(Backbone):
         """Merged maps, finest first: prev = lateral(C_l) + srf_module(prev) [/2]   (fpn_sr.py:147-157, pafpn_sr.py:172-181)."""
         feats = [bottom_up_features[f] for f in self.in_features[::-1]]
         laterals = self._laterals_bottom_up[::-1]
-        prev = laterals[0](feats[0])
+        prev = lateral_conv1x1(laterals[0], feats[0], self.srf_module.precision)
         merged = [prev]
         for features, lateral_conv in zip(feats[1:], laterals[1:]):
             prev = topdown_merge(self.srf_module, prev, features, lateral_conv, self._fuse_type)

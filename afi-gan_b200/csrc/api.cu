@@ -141,8 +141,10 @@ struct GPacked {   // element offsets into the packed weight buffer (dtype T).  
                    // rdb_xd[r] = [9][256][128], the part of the four growth convs that reaches the block input x (gemm-cin = the four
                    // 32-channel growth gradients side by side); rdb_cd[r][i], i = 1..3 = [9][32 i][32], the part of growth conv i+1 that
                    // reaches the earlier growth channels
-    size_t head_f, head_d, rdb_f[AFI_MAX_RDB][5], rdb_d[AFI_MAX_RDB][5], rdb_xd[AFI_MAX_RDB], rdb_cd[AFI_MAX_RDB][4], post_f, post_d, up_f, up_d,
-        out_f, out_d, total;
+    // Forward operands of a dense block on the tensor-core engines: rdb_fx[r] = [9][128][256], the x part (input channels 0..255) of the four
+    // growth convs as ONE N = 128 GEMM; rdb_fc[r][i], i = 1..3 = [9][32][32 i], the part of growth conv i+1 that reads the earlier growth channels
+    size_t head_f, head_d, rdb_f[AFI_MAX_RDB][5], rdb_d[AFI_MAX_RDB][5], rdb_xd[AFI_MAX_RDB], rdb_cd[AFI_MAX_RDB][4], rdb_fx[AFI_MAX_RDB],
+        rdb_fc[AFI_MAX_RDB][4], post_f, post_d, up_f, up_d, out_f, out_d, total;
 };
 static GPacked g_packed_layout(int n_rdb) {
     GPacked L; size_t o = 0;
@@ -157,6 +159,9 @@ static GPacked g_packed_layout(int n_rdb) {
         L.rdb_xd[r] = take((size_t)9 * C * 4 * GR);
         L.rdb_cd[r][0] = 0;
         for (int i = 1; i < 4; i++) L.rdb_cd[r][i] = take((size_t)9 * GR * i * GR);
+        L.rdb_fx[r] = take((size_t)9 * 4 * GR * C);
+        L.rdb_fc[r][0] = 0;
+        for (int i = 1; i < 4; i++) L.rdb_fc[r][i] = take((size_t)9 * GR * GR * i);
     }
     L.post_f = take(9 * C * C); L.post_d = take(9 * C * C);
     L.up_f = take(36 * C * C); L.up_d = take(36 * C * C);
@@ -185,6 +190,7 @@ static GGradAcc g_gradacc_layout(int n_rdb) {
 }
 struct GWs {
     void *X0, *B[AFI_MAX_RDB], *H1, *H2, *H3, *Yb, *LX, *LAT;           // forward (X0..H3 saved for backward)
+    void* GP;                                                           // fp32 [P][128]: x-part partial sums of a dense block's growth convs
     void *G0, *G1, *G2, *dH1, *GA[2], *DC5, *GC, *GH, *DXb, *LW;        // backward scratch
     void *LWD, *LWG, *LDX;                                              // lateral backward: dgrad pack, wgrad accumulator, d(lat_x) NHWC
     void* SPL; size_t spl_bytes;                                        // AFI_PREC_SPLIT: bf16 operand planes of the GEMM in flight
@@ -199,6 +205,7 @@ static GWs g_ws_layout(void* base, int prec, int n, int h, int w, int n_rdb, int
     for (int r = 0; r < n_rdb; r++) W.B[r] = cv.take(P * CB * es);
     W.H1 = cv.take(P * C * es); W.H2 = cv.take(P * C * es); W.H3 = cv.take(P4 * C * es);
     W.Yb = cv.take(P4 * C * es);
+    W.GP = cv.take(P * 4 * GR * 4);
     if (lat_c > 0) { W.LX = cv.take(P4 * lat_c * es); W.LAT = cv.take(P4 * C * es); W.LW = cv.take((size_t)C * lat_c * wes); }
     if (backward) {
         W.G0 = cv.take(P4 * C * es); W.G1 = cv.take(P4 * C * es); W.G2 = cv.take(P * C * es);
@@ -304,6 +311,7 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     char* b = (char*)packed;
     PackJob jobs[AFI_MAX_PACK]; int nj = 0;     // forward + dgrad layouts of every conv: one grouped launch
     auto add = [&](const float* w, int co, int ci, int kind, size_t off) {
+        if (nj >= AFI_MAX_PACK) return;
         PackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j)); j.w = w; j.dst = b + off * es; j.co = co; j.ci = ci; j.mode = pm(prec, kind);
     };
     auto add_sub = [&](const float* w, int co, int ci, size_t off, int n0, int ncnt, int koff, int ktot) {
@@ -314,7 +322,15 @@ int afi_g_pack(afi_ctx* ctx, int prec, const afi_g_params* p, void* packed, void
     for (int r = 0; r < p->n_rdb; r++)
         for (int i = 0; i < 5; i++) {
             int co = i < 4 ? GR : C, ci = C + GR * i;
-            add(p->rdb_w[r][i], co, ci, 0, L.rdb_f[r][i]);
+            if (i == 4 || !prec_nk(prec)) add(p->rdb_w[r][i], co, ci, 0, L.rdb_f[r][i]);      // (the tensor-core engines read rdb_fx / rdb_fc instead)
+            if (i < 4 && prec_nk(prec)) {       // forward sub-blocks: x part of all four convs in one operand; growth part per conv
+                PackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+                j.w = p->rdb_w[r][i]; j.dst = b + L.rdb_fx[r] * es; j.co = GR; j.ci = ci; j.mode = 1; j.sub = 2; j.n0 = 0; j.ncnt = C; j.koff = GR * i; j.ktot = 4 * GR;
+                if (i > 0) {
+                    PackJob& k2 = jobs[nj++]; memset(&k2, 0, sizeof(k2));
+                    k2.w = p->rdb_w[r][i]; k2.dst = b + L.rdb_fc[r][i] * es; k2.co = GR; k2.ci = ci; k2.mode = 1; k2.sub = 2; k2.n0 = C; k2.ncnt = GR * i; k2.koff = 0; k2.ktot = GR;
+                }
+            }
             if (i == 4) add(p->rdb_w[r][i], co, ci, 1, L.rdb_d[r][i]);
             else {
                 add_sub(p->rdb_w[r][i], GR, ci, L.rdb_xd[r], 0, C, GR * i, 4 * GR);                  // x part: all four convs, one operand
@@ -364,7 +380,29 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
     AFI_TRY(run_conv(ctx, prec, a, st));
     // [1] residual-in-residual: dense blocks write their growth channels into slices of one 384-ch buffer   :39-71
     for (int r = 0; r < nr; r++) {
-        for (int i = 0; i < 4; i++) {
+        if (prec_nk(prec)) {
+            // Tensor-core engines: c_i = L(W_i^x * x + W_i^c * [c_1 .. c_{i-1}]).  The x parts of all four growth convs are ONE GEMM
+            // (K = 2304, N = 128: four N = 32 GEMMs run at a fifth of the rate, each M128 x N32 MMA being bound by its A-operand read);
+            // its epilogue stores c_1 (activated) into the block buffer and the partial sums of c_2 .. c_4 as fp32.  The growth parts
+            // are three short-K convs (K = 288, 576, 864) that add their partial sum and activate in the epilogue.
+            conv_std(a, ncalls, d1, C, 4 * GR, pk + L.rdb_fx[r] * wes);
+            a.out_dt = DT_F32; a.split_col = GR; a.out2_dt = dt;
+            for (int k = 0; k < ncalls; k++) {
+                PView Br = pview(W[k].B[r], d1[k].h, d1[k].w, CB);
+                a.p[k].in[0] = Br; a.p[k].out = pview(W[k].GP, d1[k].h, d1[k].w, 4 * GR); a.p[k].out2 = pview_ch(Br, C, es);
+            }
+            AFI_TRY(run_conv(ctx, prec, a, st));
+            for (int i = 1; i < 4; i++) {
+                conv_std(a, ncalls, d1, GR * i, GR, pk + L.rdb_fc[r][i] * wes);
+                a.act = 1; a.act_post = 1; a.out_dt = dt;
+                for (int k = 0; k < ncalls; k++) {
+                    PView Br = pview(W[k].B[r], d1[k].h, d1[k].w, CB);
+                    a.p[k].in[0] = pview_ch(Br, C, es); a.p[k].accin = pview_ch(pview(W[k].GP, d1[k].h, d1[k].w, 4 * GR), GR * i, 4);
+                    a.p[k].out = pview_ch(Br, C + GR * i, es);
+                }
+                AFI_TRY(run_conv(ctx, prec, a, st));
+            }
+        } else for (int i = 0; i < 4; i++) {
             conv_std(a, ncalls, d1, C + GR * i, GR, pk + L.rdb_f[r][i] * wes);
             a.act = 1; a.out_dt = dt;
             for (int k = 0; k < ncalls; k++) {
@@ -415,37 +453,47 @@ int afi_g_forward(afi_ctx* ctx, int prec, const afi_g_params* p, const void* pac
         }
         AFI_TRY(run_conv(ctx, prec, a, st));
     }
-    // [4] output conv + bias on the 2h x 2w grid                                           :107-108
+    // Lateral 1x1 conv of the FPN / PAFPN merge (fpn_sr.py:152), one problem per call.  Tensor-core engines: it runs BEFORE the output
+    // conv, into LAT laid out on the 2h x 2w grid, and the output conv adds it in its GEMM epilogue (residual operand) -- the merge
+    // `lateral + G(x)` costs no pass of its own.  CUDA-core engines: added by the final layout pass.
+    const bool lat_in_epilogue = prec_nk(prec);
+    PView latv[AFI_MAX_PROB];
+    for (int k = 0; k < ncalls; k++) {
+        const afi_g_call& c = calls[k];
+        latv[k] = pview_null();
+        if (!c.lateral) continue;
+        const afi_lateral* lat = c.lateral;
+        const int lat_c = lat->lat_c;
+        AFI_TRY(to_nhwc(prec, lat->lat_x, c.n, lat_c, c.oh, c.ow, pview(W[k].LX, c.oh, c.ow, lat_c), st));
+        AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W[k].LW, prec_wdt(prec), st));
+        conv_args_init(a);
+        a.cin = lat_c; a.cout = C; a.ntaps = 1; a.nprob = 1;
+        a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0;
+        a.p[0].N = c.n; a.p[0].H = c.oh; a.p[0].W = c.ow;
+        a.p[0].in[0] = pview(W[k].LX, c.oh, c.ow, lat_c); a.w = W[k].LW; a.bias = lat->lat_b;
+        latv[k] = lat_in_epilogue ? pview(W[k].LAT, d2[k].h, d2[k].w, C) : pview(W[k].LAT, c.oh, c.ow, C);
+        a.p[0].out = latv[k]; a.out_dt = dt;
+        g_ss.k0 = k;
+        AFI_TRY(run_conv(ctx, prec, a, st));
+        g_ss.k0 = 0;
+    }
+    // [4] output conv + bias (+ lateral) on the 2h x 2w grid                                :107-108
     conv_std(a, ncalls, d2, C, C, pk + L.out_f * wes);
-    a.bias = p->out_b; a.out_dt = dt;
-    for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = pview(W[k].H3, d2[k].h, d2[k].w, C); a.p[k].out = pview(W[k].Yb, d2[k].h, d2[k].w, C); }
+    a.bias = p->out_b; a.out_dt = dt; a.r1_dt = dt; a.beta1 = 1.f;
+    for (int k = 0; k < ncalls; k++) {
+        a.p[k].in[0] = pview(W[k].H3, d2[k].h, d2[k].w, C); a.p[k].out = pview(W[k].Yb, d2[k].h, d2[k].w, C);
+        // (outside the oh x ow crop LAT holds whatever the workspace held: those outputs are never read)
+        if (lat_in_epilogue && latv[k].ptr) a.p[k].r1 = latv[k];
+    }
     AFI_TRY(run_conv(ctx, prec, a, st));
     for (int k = 0; k < ncalls; k++) {
         const afi_g_call& c = calls[k];
-        PView latv = pview_null();
-        float scale = 1.f;
-        if (c.lateral) {   // lateral 1x1 conv of the FPN merge (fpn_sr.py:152), one problem per call
-            const afi_lateral* lat = c.lateral;
-            const int lat_c = lat->lat_c;
-            AFI_TRY(to_nhwc(prec, lat->lat_x, c.n, lat_c, c.oh, c.ow, pview(W[k].LX, c.oh, c.ow, lat_c), st));
-            AFI_TRY(pack_weights(lat->lat_w, C, lat_c, pm(prec, 4), W[k].LW, prec_wdt(prec), st));
-            conv_args_init(a);
-            a.cin = lat_c; a.cout = C; a.ntaps = 1; a.nprob = 1;
-            a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0;
-            a.p[0].N = c.n; a.p[0].H = c.oh; a.p[0].W = c.ow;
-            a.p[0].in[0] = pview(W[k].LX, c.oh, c.ow, lat_c); a.w = W[k].LW; a.bias = lat->lat_b;
-            a.p[0].out = pview(W[k].LAT, c.oh, c.ow, C); a.out_dt = dt;
-            g_ss.k0 = k;
-            AFI_TRY(run_conv(ctx, prec, a, st));
-            g_ss.k0 = 0;
-            latv = pview(W[k].LAT, c.oh, c.ow, C);
-            scale = lat->scale;
-        }
+        const float scale = c.lateral ? c.lateral->scale : 1.f;
         // y = (branch + bilinear2x(x) [+ lateral]) * scale, cropped to oh x ow            :125,130; stage1_trainer.py:437-443
         // [+ the BiFPN fusion w0 * cur + w1 * y (bifpn_sr.py:535-548) when the call carries one]
         AFI_REQUIRE(!c.fuse_w || (c.fuse_cur.ptr && !save), "afi_g_forward: call %d: the fused BiFPN site is forward-only and needs fuse_cur", k);
-        AFI_TRY(to_nchw(prec, pview(W[k].Yb, d2[k].h, d2[k].w, C), latv, c.x, c.h, c.w, scale, c.n, C, c.oh, c.ow, c.y, st,
-                        c.fuse_w ? &c.fuse_cur : nullptr, c.fuse_w));
+        AFI_TRY(to_nchw(prec, pview(W[k].Yb, d2[k].h, d2[k].w, C), lat_in_epilogue ? pview_null() : latv[k], c.x, c.h, c.w, scale, c.n, C, c.oh,
+                        c.ow, c.y, st, c.fuse_w ? &c.fuse_cur : nullptr, c.fuse_w));
     }
     return AFI_OK;
 }
@@ -979,30 +1027,34 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
 // single-layer entry points (unit tests / kernel benchmarks)
 // =====================================================================================================
 static inline int pad64(int c) { return c <= 64 ? c : (c + 63) / 64 * 64; }
-size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) {
-    size_t es = dt_size(prec_dt(prec)), wes = prec_wes(prec), P = (size_t)n * h * w;
-    return align_up(P * pad64(cin) * es) + 2 * align_up(P * pad64(cout) * es) + 2 * align_up((size_t)9 * cin * cout * wes) +
-           align_up((size_t)9 * cin * cout * 4) + align_up(P * cin * 4) + 4096 +
+static size_t conv_single_ws_bytes(int prec, int ks, int n, int cin, int h, int w, int cout) {
+    size_t es = dt_size(prec_dt(prec)), wes = prec_wes(prec), P = (size_t)n * h * w, nt = (size_t)ks * ks;
+    return align_up(P * pad64(cin) * es) + 2 * align_up(P * pad64(cout) * es) + 2 * align_up(nt * cin * cout * wes) +
+           align_up(nt * cin * cout * 4) + align_up(P * cin * 4) + 4096 +
            (prec == AFI_PREC_SPLIT ? split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout) + 256 : 0);
 }
-int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
-                int lrelu, float* y, void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && x.ptr && weight && y && ws && prec_ok(prec), "afi_conv3x3: bad argument");
-    AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv3x3: channels must be multiples of 32");
-    if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3: workspace too small"); return AFI_ERR_WORKSPACE; }
-    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w;
+static void single_taps(ConvArgs& a, int ks) {
+    if (ks == 1) { a.ntaps = 1; a.taps[0].dy = 0; a.taps[0].dx = 0; a.taps[0].view = 0; a.taps[0].slab = 0; }
+}
+// one stride-1 "same" convolution (ks = 1 or 3) through the GEMM engine of `prec`: y = [lrelu](conv(x, w) + b)
+static int conv_single(afi_ctx* ctx, int prec, int ks, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
+                       int lrelu, float* y, void* ws, size_t ws_bytes, cudaStream_t st) {
+    AFI_REQUIRE(ctx && x.ptr && weight && y && ws && prec_ok(prec), "afi_conv: bad argument");
+    AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv: channels must be multiples of 32");
+    if (ws_bytes < conv_single_ws_bytes(prec, ks, n, cin, h, w, cout)) { set_error("afi_conv: workspace too small"); return AFI_ERR_WORKSPACE; }
+    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w, nt = (size_t)ks * ks;
     Carver cv(ws);
     void* X = cv.take(P * pad64(cin) * es); void* Y = cv.take(P * pad64(cout) * es); cv.take(P * pad64(cout) * es);
-    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
-    cv.take((size_t)9 * cin * cout * 4); cv.take(P * cin * 4);
+    void* Wp = cv.take(nt * cin * cout * wes); cv.take(nt * cin * cout * wes);
+    cv.take(nt * cin * cout * 4); cv.take(P * cin * 4);
     g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
     g_ss.pairs = 6;
     AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
-    AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, prec_wdt(prec), st));
+    AFI_TRY(pack_weights(weight, cout, cin, pm(prec, ks == 1 ? 4 : 0), Wp, prec_wdt(prec), st));
     ConvArgs a;
     Dim3 d = {n, h, w};
     conv_std(a, 1, &d, cin, cout, Wp);
+    single_taps(a, ks);
     a.bias = bias; a.act = lrelu; a.out_dt = dt;
     a.p[0].in[0] = pview(X, h, w, cin); a.p[0].out = pview(Y, h, w, cout);
     AFI_TRY(run_conv(ctx, prec, a, st));
@@ -1010,19 +1062,18 @@ int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int 
     AFI_TRY(to_nchw(prec, pview(Y, h, w, cout), pview_null(), none, 0, 0, 1.f, n, cout, h, w, y, st));
     return AFI_OK;
 }
-int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
-                         float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    AFI_REQUIRE(ctx && x.ptr && dy.ptr && weight && dw && ws && prec_ok(prec), "afi_conv3x3_backward: bad argument");
-    AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv3x3_backward: channels must be multiples of 32");
-    if (ws_bytes < afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3_backward: workspace too small"); return AFI_ERR_WORKSPACE; }
-    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w;
+static int conv_single_backward(afi_ctx* ctx, int prec, int ks, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
+                                float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, cudaStream_t st) {
+    AFI_REQUIRE(ctx && x.ptr && dy.ptr && weight && dw && ws && prec_ok(prec), "afi_conv_backward: bad argument");
+    AFI_REQUIRE(cin % 32 == 0 && cout % 32 == 0, "afi_conv_backward: channels must be multiples of 32");
+    if (ws_bytes < conv_single_ws_bytes(prec, ks, n, cin, h, w, cout)) { set_error("afi_conv_backward: workspace too small"); return AFI_ERR_WORKSPACE; }
+    int dt = prec_dt(prec); size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w, nt = (size_t)ks * ks;
     Carver cv(ws);
     // pixel strides padded to whole 64-channel groups (the tensor-core wgrad reads operands through grouped TMA views)
     const int xs = pad64(cin), ys = pad64(cout);
     void* X = cv.take(P * xs * es); void* DYb = cv.take(P * ys * es); cv.take(P * ys * es);
-    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
-    float* acc = (float*)cv.take((size_t)9 * cin * cout * 4);
+    void* Wp = cv.take(nt * cin * cout * wes); cv.take(nt * cin * cout * wes);
+    float* acc = (float*)cv.take(nt * cin * cout * 4);
     void* DX = cv.take(P * cin * 4);
     g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
     g_ss.pairs = split_pairs_env(3);
@@ -1031,18 +1082,28 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
     PView Xv = pview(X, h, w, xs), DYv = pview(DYb, h, w, ys);
     AFI_TRY(to_nhwc(prec, x, n, cin, h, w, Xv, st));
     AFI_TRY(to_nhwc(prec, dy, n, cout, h, w, DYv, st));
-    AFI_CUDA(cudaMemsetAsync(acc, 0, (size_t)9 * cin * cout * 4, st));
+    AFI_CUDA(cudaMemsetAsync(acc, 0, nt * cin * cout * 4, st));
     Dim3 d = {n, h, w};
-    AFI_TRY(wgrad_std(ctx, prec, 1, &d, &Xv, cin, &DYv, cout, acc, st));
-    AFI_TRY(unpack_wgrad(acc, cout, cin, prec_nk(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
+    if (ks == 1) {
+        WgradArgs g;
+        memset(&g, 0, sizeof(g));
+        g.cin = cin; g.cout = cout; g.ntaps = 1; g.nprob = 1; g.dw = acc;
+        g.p[0].N = n; g.p[0].H = h; g.p[0].W = w; g.p[0].x = Xv; g.p[0].dy = DYv;
+        AFI_TRY(run_wgrad(ctx, prec, g, st));
+        AFI_TRY(unpack_1x1(acc, cout, cin, prec_nk(prec) ? 1 : 0, dw, 1.f, 0, st));
+    } else {
+        AFI_TRY(wgrad_std(ctx, prec, 1, &d, &Xv, cin, &DYv, cout, acc, st));
+        AFI_TRY(unpack_wgrad(acc, cout, cin, prec_nk(prec) ? 1 : 0, 0, dw, 1.f, 0, st));
+    }
     if (db) {
         AFI_CUDA(cudaMemsetAsync(db, 0, cout * sizeof(float), st));
         AFI_TRY(col_sum_f32(DYv, dt, n, h, w, cout, db, st));
     }
     if (dxo) {
-        AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, prec_wdt(prec), st));
+        AFI_TRY(pack_weights(weight, cout, cin, pm(prec, ks == 1 ? 5 : 1), Wp, prec_wdt(prec), st));
         ConvArgs a;
         conv_std(a, 1, &d, cout, cin, Wp);
+        single_taps(a, ks);
         a.out_dt = DT_F32;
         a.p[0].in[0] = DYv; a.p[0].out = pview(DX, h, w, cin);
         AFI_TRY(run_conv(ctx, prec, a, st));
@@ -1050,6 +1111,24 @@ int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int 
         AFI_TRY(nhwc_to_nchw<float>(pview(DX, h, w, cin), pview_null(), none, 0, 0, 1.f, n, cin, h, w, dxo, st));
     }
     return AFI_OK;
+}
+size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) { return conv_single_ws_bytes(prec, 3, n, cin, h, w, cout); }
+int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
+                int lrelu, float* y, void* ws, size_t ws_bytes, void* stream) {
+    return conv_single(ctx, prec, 3, x, n, cin, h, w, weight, bias, cout, lrelu, y, ws, ws_bytes, (cudaStream_t)stream);
+}
+int afi_conv3x3_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
+                         float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream) {
+    return conv_single_backward(ctx, prec, 3, x, dy, n, cin, h, w, weight, cout, dw, db, dxo, ws, ws_bytes, (cudaStream_t)stream);
+}
+size_t afi_conv1x1_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) { return conv_single_ws_bytes(prec, 1, n, cin, h, w, cout); }
+int afi_conv1x1(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
+                float* y, void* ws, size_t ws_bytes, void* stream) {
+    return conv_single(ctx, prec, 1, x, n, cin, h, w, weight, bias, cout, 0, y, ws, ws_bytes, (cudaStream_t)stream);
+}
+int afi_conv1x1_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
+                         float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream) {
+    return conv_single_backward(ctx, prec, 1, x, dy, n, cin, h, w, weight, cout, dw, db, dxo, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

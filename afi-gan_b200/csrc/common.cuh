@@ -82,6 +82,7 @@ struct ConvProb {
     PView bnz; const float* bn_mean; const float* bn_rstd;
     // AFI_PREC_SPLIT only: caller-owned scratch in which the fp32 input views of THIS problem are split into bf16 planes
     void* sws; size_t sws_bytes;
+    PView out2;           // tensor-core engine, ConvArgs.split_col > 0: where the columns below split_col go (dtype ConvArgs.out2_dt)
 };
 struct ConvArgs {
     int cin, cout;
@@ -92,6 +93,11 @@ struct ConvArgs {
     int act; float slope;
     float alpha, beta1, beta2, mask_slope;
     int out_dt, r1_dt, r2_dt;
+    // tensor-core engine only.  act_post: the activation is applied AFTER alpha / residuals / accin (v = lrelu(alpha * acc + accin)).
+    // split_col > 0 (a multiple of 16): output columns [0, split_col) get the LeakyReLU and are stored to p[].out2 (dtype out2_dt);
+    // the columns from split_col on are stored raw to p[].out.  One GEMM then serves several consumers of the same input: the dense
+    // block's x-part GEMM writes growth channel 1 (activated) into the block buffer and the partial sums of channels 2-4 as fp32.
+    int act_post, split_col, out2_dt;
     // 0: none.  1: stat0[c] += sum_p v, stat1[c] += sum_p v^2 (BatchNorm batch statistics of a conv output).
     // 2: stat0[c] += sum_p v, stat1[c] += sum_p v * (bnz - bn_mean[c]) * bn_rstd[c]  (the two reductions of BatchNorm backward).
     int stat_mode;
@@ -185,7 +191,7 @@ enum PackMode { PACK_FWD_KN = 0, PACK_FWD_NK = 1, PACK_DGRAD_KN = 2, PACK_DGRAD_
                 PACK_DECONV_FWD_KN = 4, PACK_DECONV_FWD_NK = 5, PACK_DECONV_DGRAD_KN = 6, PACK_DECONV_DGRAD_NK = 7,
                 PACK_1X1_KN = 8, PACK_1X1_NK = 9, PACK_1X1_DGRAD_KN = 10, PACK_1X1_DGRAD_NK = 11 };
 int pack_weights(const float* w, int co, int ci, int mode, void* dst, int dst_dt, cudaStream_t st);
-#define AFI_MAX_PACK 64
+#define AFI_MAX_PACK 96
 #define AFI_MAX_SGD 48
 // sub != 0 (dgrad modes only): pack the gemm-cout range [n0, n0 + ncnt) of this weight into the gemm-cin slice [koff, koff + co) of a
 // destination whose gemm-cin extent is ktot (several convs that read the same gradient buffer share one packed operand)

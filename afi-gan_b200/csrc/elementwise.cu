@@ -1449,16 +1449,28 @@ struct PackGroup { int njobs; int block_begin[AFI_MAX_PACK + 1]; PackJob j[AFI_M
 template <typename T>
 __device__ __forceinline__ void pack_taps9(const PackJob& q, long long u) {
     const int nk = q.mode & 1, dgrad = (q.mode >> 1) == 1;
+    T* dst = reinterpret_cast<T*>(q.dst);
+    float v[9];
+    if (q.sub == 2) {
+        // forward sub-block (NK only): gemm-cin range [n0, n0 + ncnt) of this conv, all of its couts, into rows [koff, koff + co) of a
+        // [ktot rows][ncnt columns] slab (several convs that read the same input share one packed operand: N = sum of their couts)
+        const int kk = (int)(u % q.ncnt), n = (int)(u / q.ncnt);
+        const float* src = q.w + ((long long)n * q.ci + q.n0 + kk) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; t++) v[t] = src[t];
+        const long long slab_sz = (long long)q.ktot * q.ncnt, off = (long long)(q.koff + n) * q.ncnt + kk;
+#pragma unroll
+        for (int t = 0; t < 9; t++) pack_put<T>(dst, (long long)t * slab_sz + off, v[t], q.pstride);
+        return;
+    }
     const int gk = q.sub ? q.co : (dgrad ? q.co : q.ci);                 // extent of this job's gemm-cin range
     const int gn = q.sub ? q.ncnt : (dgrad ? q.ci : q.co);               // ... gemm-cout range
     const int I = nk ? gk : gn, O = nk ? gn : gk;                        // inner / outer index of a slab
     const int inner = (int)(u % I), outer = (int)(u / I);
     const int k = nk ? inner : outer, n = nk ? outer : inner;
     const float* src = q.w + (dgrad ? ((long long)k * q.ci + (q.sub ? q.n0 : 0) + n) : ((long long)n * q.ci + k)) * 9;
-    float v[9];
 #pragma unroll
     for (int t = 0; t < 9; t++) v[t] = src[t];
-    T* dst = reinterpret_cast<T*>(q.dst);
     // destination strides: full slabs [O][I], or the [koff, koff + co) gemm-cin slice of a [ncnt][ktot] (NK) / [ktot][ncnt] (KN) slab
     const long long slab_sz = q.sub ? (long long)q.ncnt * q.ktot : (long long)O * I;
     const long long off = q.sub ? (nk ? (long long)n * q.ktot + q.koff + k : (long long)(q.koff + k) * q.ncnt + n) : (long long)outer * I + inner;
@@ -1494,7 +1506,8 @@ int pack_weights_group(int njobs, const PackJob* jobs, int dst_dt, cudaStream_t 
         G.j[k] = jobs[k]; G.block_begin[k] = b;
         // plane stride of a three-plane destination = the whole packed operand of this job
         G.j[k].pstride = jobs[k].sub ? (long long)9 * jobs[k].ncnt * jobs[k].ktot : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode);
-        if (jobs[k].sub) AFI_REQUIRE((jobs[k].mode >> 1) == 1, "pack_weights_group: sub-block packing is a dgrad mode");
+        if (jobs[k].sub == 1) AFI_REQUIRE((jobs[k].mode >> 1) == 1, "pack_weights_group: sub-block packing (sub = 1) is a dgrad mode");
+        if (jobs[k].sub == 2) AFI_REQUIRE(jobs[k].mode == 1, "pack_weights_group: forward sub-block packing (sub = 2) takes the NK forward mode");
         const int kind = jobs[k].mode >> 1;
         const long long work = kind <= 1 ? (jobs[k].sub ? (long long)jobs[k].co * jobs[k].ncnt : (long long)jobs[k].co * jobs[k].ci)
                                          : pack_total(jobs[k].co, jobs[k].ci, jobs[k].mode);

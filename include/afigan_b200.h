@@ -206,6 +206,13 @@ int afi_conv3x3(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, 
 int afi_conv3x3_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
                          int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
+/* The same for 1x1 convolutions: the necks' lateral convs incl. the top-level one (fpn_sr.py:79-81,144-145), the pointwise half of the
+ * BiFPN's depthwise-separable convs (bifpn_layers/wrappers.py:166-206) and its input laterals (bifpn_sr.py:160-183).  weight [cout,cin,1,1]. */
+int afi_conv1x1(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, const float* weight, const float* bias, int cout,
+                float* y, void* ws, size_t ws_bytes, void* stream);
+int afi_conv1x1_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
+                         int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
+size_t afi_conv1x1_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
  * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05 per-tap

@@ -1,0 +1,106 @@
+"""BiFPN neck (reference afigan/modeling/backbone/bifpn_sr.py:203-731) against the golden fixture made by running the
+UNMODIFIED reference class on the CPU (tests/golden/make_golden_bifpn.py): same state-dict keys / shapes, and -- with weights derived from
+the keys on both sides -- the same five output maps, with the 28 interpolator fusion sites and every 1x1 conv running in the library."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden_bifpn import keyed_state, sample, tiny_bottom_up  # noqa: E402
+
+FX = np.load(os.path.join(HERE, "golden", "bifpn_small.npz"))
+
+
+def _build(precision=None):
+    from afigan._compat import Backbone
+    from afigan.modeling import BiFPN_AFIGAN
+    from afigan.modeling.backbone import LastLevelP6P7
+    torch.manual_seed(0)
+    net = BiFPN_AFIGAN(tiny_bottom_up(Backbone), ["s2", "s3", "s4"], 256, 3, norm="BN", top_block=LastLevelP6P7(128, 256, "BN"))
+    if precision is not None:
+        net.srf_module.precision = precision
+        for m in net.modules():
+            if hasattr(m, "precision") and m is not net.srf_module:
+                m.precision = precision
+    return net
+
+
+def test_bifpn_state_dict_matches_the_reference_key_for_key():
+    net = _build()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(FX["keys"])
+    assert [str(tuple(v.shape)) for v in sd.values()] == list(FX["shapes"])
+    assert net.size_divisibility == 128 and net._out_features == ["p3", "p4", "p5", "p6", "p7"]
+    from afigan._compat import BACKBONE_REGISTRY
+    assert callable(BACKBONE_REGISTRY.get("build_swint_bifpn_sr_backbone"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["split", "fp32", "bf16"])
+def test_bifpn_forward_vs_reference_golden(precision):
+    net = _build(precision)
+    net.load_state_dict(keyed_state(net.state_dict()), strict=True)
+    net = net.cuda().eval()
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(77)).cuda()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the depthwise convs are cuDNN's: keep them fp32 like the CPU reference (TF32 costs 1.2e-4 here)
+    try:
+        with torch.no_grad():
+            out = net(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    tol = 2e-5 if precision in ("split", "fp32") else 2e-2
+    worst = 0.0
+    for k, v in out.items():
+        v = v.float().cpu()
+        assert tuple(v.shape) == tuple(FX[f"shape/{k}"])
+        if f"full/{k}" in FX:
+            ref = torch.from_numpy(FX[f"full/{k}"])
+            e = float((v - ref).norm() / ref.norm())
+        else:
+            ref = FX[f"sample/{k}"]
+            e = float(np.linalg.norm(sample(v) - ref) / np.linalg.norm(ref))
+            assert abs(float(v.norm()) - float(FX[f"norm/{k}"])) <= tol * float(FX[f"norm/{k}"])
+        worst = max(worst, e)
+        assert e <= tol, (k, e)
+    print(f"[{precision}] BiFPN_AFIGAN forward vs the reference golden: worst rel err {worst:.2e}")
+
+
+@pytest.mark.gpu
+def test_bifpn_training_step_has_gradients_everywhere():
+    """Autograd through the neck (stage 3 trains a detector on top of it): every parameter that takes part gets a finite gradient, and the
+    interpolator's input gradient path (grad w.r.t. the bottom-up features) is live."""
+    net = _build("split")
+    net.load_state_dict(keyed_state(net.state_dict()), strict=True)
+    net = net.cuda().train()
+    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(78)).cuda()
+    out = net(x)
+    sum(v.square().mean() for v in out.values()).backward()
+    missing = [k for k, p in net.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, missing[:8]
+    assert float(net.bottom_up.c[0].weight.grad.abs().sum()) > 0 and float(net.srf_module.Generators[0][0][0].weight.grad.abs().sum()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_conv1x1_autograd_vs_torch(precision):
+    from afigan.functional import conv1x1_autograd
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 512, 13, 21, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(256, 512, 1, 1, generator=g) * 0.05).cuda().requires_grad_(True)
+    b = torch.randn(256, generator=g).cuda().requires_grad_(True)
+    dy = torch.randn(2, 256, 13, 21, generator=g).cuda()
+    conv1x1_autograd(x, w, b, precision).backward(dy)
+    got = [conv1x1_autograd(x, w, b, precision).detach(), x.grad.clone(), w.grad.clone(), b.grad.clone()]
+    x2, w2, b2 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y2 = F.conv2d(x2, w2, b2)
+    y2.backward(dy.double())
+    ref = [y2.detach(), x2.grad, w2.grad, b2.grad]
+    tol = 3e-5 if precision == "split" else 1e-2
+    for a, r in zip(got, ref):
+        assert float((a.double() - r).norm() / r.norm()) < tol
