@@ -408,5 +408,45 @@ def conv1x1_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch
     return Conv1x1Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])
 
 
+class Conv3x3S2Fn(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 convolution (+bias) through the tcgen05 engine: the PANet neck's bottom-up down-sampling convs (reference
+    pafpn_sr.py:103-117, 186-193) -- a 9-tap stride-1 implicit GEMM over the four sub-pixel phase views of the input (no wasted products)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec: int):
+        if not x.is_cuda:
+            raise RuntimeError("conv3x3s2: input must live on an sm_100a CUDA device (no CPU fallback)")
+        x, weight = x.float(), weight.float().contiguous()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv3x3s2_workspace_bytes(prec, n, cin, h, w, cout), x.device)
+        y = torch.empty((n, cout, (h + 1) // 2, (w + 1) // 2), dtype=torch.float32, device=x.device)
+        N.check(lib.afi_conv3x3s2(actx, prec, N.view4(x), n, cin, h, w, weight.data_ptr(), N.ptr(bias), cout, y.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), N.stream_ptr()))
+        ctx.prec, ctx.has_bias = prec, bias is not None
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.float()
+        n, cin, h, w = x.shape
+        cout = weight.shape[0]
+        lib, actx = N.lib(), N.context(x.device)
+        ws = _u8(lib.afi_conv3x3s2_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
+        dw = torch.empty_like(weight)
+        db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        N.check(lib.afi_conv3x3s2_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(),
+                                           N.ptr(db), N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
+        return dx, dw, db, None
+
+
+def conv3x3s2_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
+    return Conv3x3S2Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])
+
+
 def conv3x3_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
     return Conv3x3Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])

@@ -1112,6 +1112,131 @@ static int conv_single_backward(afi_ctx* ctx, int prec, int ks, afi_view4 x, afi
     }
     return AFI_OK;
 }
+// ---- 3x3 / stride 2 / pad 1 convolution (the bottom-up path of the PANet neck, pafpn_sr.py:103-117, 186-193) -----------------------------
+// out[y, x] = sum_{dy, dx in -1..1} w[dy, dx] . in[2y + dy, 2x + dx].  With the four sub-pixel phase views of the input, in_ab[i, j] =
+// in[2i + a, 2j + b] (strided views, no copy), every tap reads ONE phase at an offset of -1 or 0: tap dy -> phase |dy|, offset (dy == -1 ? -1 : 0).
+// So the stride-2 conv is a 9-tap stride-1 implicit GEMM over four views on the OUTPUT grid: no wasted products, the engine's TMA
+// out-of-bounds fill supplies the padding (each view with its own extent: the phases of an odd size differ by one row / column).
+// Backward: the input gradient of phase (a, b) is a conv of dY with the taps |dy| = a, |dx| = b (1, 2, 2 and 4 taps) stored through a
+// strided view; the weight gradient is one K = pixels GEMM per phase view with that phase's taps.
+struct S2Phase { int rows, cols; };
+static inline int s2_off(int d) { return d == -1 ? -1 : 0; }
+static size_t conv_s2_ws_bytes(int prec, int n, int cin, int h, int w, int cout) {
+    size_t es = dt_size(prec_dt(prec)), wes = prec_wes(prec), P = (size_t)n * h * w, Po = (size_t)n * ((h + 1) / 2) * ((w + 1) / 2);
+    return align_up(P * pad64(cin) * es) + align_up(Po * pad64(cout) * es) + 2 * align_up((size_t)9 * cin * cout * wes) +
+           align_up((size_t)9 * cin * cout * 4) + align_up(P * cin * 4) + 4096 +
+           (prec == AFI_PREC_SPLIT ? split_planes_bytes((long long)P, cin) + 4 * 256 + split_planes_bytes((long long)Po, cout) + 256 : 0);
+}
+static PView s2_phase_view(void* base, int a, int b, int h, int w, int cs, size_t es) {
+    PView v; v.ptr = (char*)base + ((size_t)a * w + b) * cs * es; v.sx = 2 * cs; v.sy = (long long)2 * w * cs; v.sn = (long long)h * w * cs; return v;
+}
+static int conv_s2_check(afi_ctx* ctx, int prec, int cin, int cout) {
+    AFI_REQUIRE(ctx && prec_ok(prec), "afi_conv3x3s2: bad argument");
+    AFI_REQUIRE(prec_nk(prec), "afi_conv3x3s2: the stride-2 convolution runs on the tensor-core engines only (precision bf16 or split)");
+    AFI_REQUIRE(cin % 64 == 0 && cout % 32 == 0, "afi_conv3x3s2: cin must be a multiple of 64 and cout of 32");
+    return AFI_OK;
+}
+size_t afi_conv3x3s2_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) { return conv_s2_ws_bytes(prec, n, cin, h, w, cout); }
+int afi_conv3x3s2(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout, float* y,
+                  void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_TRY(conv_s2_check(ctx, prec, cin, cout));
+    AFI_REQUIRE(x.ptr && weight && y && ws && n >= 1 && h >= 1 && w >= 1, "afi_conv3x3s2: bad argument");
+    if (ws_bytes < conv_s2_ws_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3s2: workspace too small"); return AFI_ERR_WORKSPACE; }
+    const int dt = prec_dt(prec), oh = (h + 1) / 2, ow = (w + 1) / 2;
+    const size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w, Po = (size_t)n * oh * ow;
+    Carver cv(ws);
+    void* X = cv.take(P * pad64(cin) * es); void* Y = cv.take(Po * pad64(cout) * es);
+    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
+    cv.take((size_t)9 * cin * cout * 4); cv.take(P * cin * 4);
+    g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + 4 * 256 + split_planes_bytes((long long)Po, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
+    g_ss.pairs = 6;
+    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
+    AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 0), Wp, prec_wdt(prec), st));
+    ConvArgs a;
+    conv_args_init(a);
+    a.cin = cin; a.cout = cout; a.ntaps = 9; a.nprob = 1; a.w = Wp; a.bias = bias; a.out_dt = dt;
+    int t = 0;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++, t++) {
+            a.taps[t].dy = s2_off(dy); a.taps[t].dx = s2_off(dx); a.taps[t].view = (dy != 0) * 2 + (dx != 0); a.taps[t].slab = t;
+        }
+    a.p[0].N = n; a.p[0].H = oh; a.p[0].W = ow;
+    for (int v = 0; v < 4; v++) {
+        const int pa = v >> 1, pb = v & 1;
+        a.p[0].in[v] = s2_phase_view(X, pa, pb, h, w, cin, es);
+        a.p[0].vh[v] = (h - pa + 1) / 2; a.p[0].vw[v] = (w - pb + 1) / 2;
+        if (a.p[0].vh[v] == 0 || a.p[0].vw[v] == 0) { a.p[0].in[v] = pview(X, 1, 1, cin); a.p[0].vh[v] = a.p[0].vw[v] = 1; }   // (h or w == 1: never in range)
+    }
+    a.p[0].out = pview(Y, oh, ow, cout);
+    if (h == 1 || w == 1) AFI_REQUIRE(false, "afi_conv3x3s2: spatial size %dx%d not supported", h, w);
+    AFI_TRY(run_conv(ctx, prec, a, st));
+    afi_view4 none; memset(&none, 0, sizeof(none));
+    AFI_TRY(to_nchw(prec, pview(Y, oh, ow, cout), pview_null(), none, 0, 0, 1.f, n, cout, oh, ow, y, st));
+    return AFI_OK;
+}
+int afi_conv3x3s2_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w, const float* weight, int cout,
+                           float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_TRY(conv_s2_check(ctx, prec, cin, cout));
+    AFI_REQUIRE(x.ptr && dy.ptr && weight && dw && ws && h >= 2 && w >= 2, "afi_conv3x3s2_backward: bad argument");
+    AFI_REQUIRE(cout % 64 == 0, "afi_conv3x3s2_backward: cout must be a multiple of 64");
+    if (ws_bytes < conv_s2_ws_bytes(prec, n, cin, h, w, cout)) { set_error("afi_conv3x3s2_backward: workspace too small"); return AFI_ERR_WORKSPACE; }
+    const int dt = prec_dt(prec), oh = (h + 1) / 2, ow = (w + 1) / 2;
+    const size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w, Po = (size_t)n * oh * ow;
+    Carver cv(ws);
+    void* X = cv.take(P * pad64(cin) * es); void* DYb = cv.take(Po * pad64(cout) * es);
+    void* Wp = cv.take((size_t)9 * cin * cout * wes); cv.take((size_t)9 * cin * cout * wes);
+    float* acc = (float*)cv.take((size_t)9 * cin * cout * 4);
+    float* DX = (float*)cv.take(P * cin * 4);
+    g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, cin) + 4 * 256 + split_planes_bytes((long long)Po, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
+    g_ss.pairs = split_pairs_env(3);
+    PView DYv = pview(DYb, oh, ow, cout);
+    AFI_TRY(to_nhwc(prec, x, n, cin, h, w, pview(X, h, w, cin), st));
+    AFI_TRY(to_nhwc(prec, dy, n, cout, oh, ow, DYv, st));
+    AFI_CUDA(cudaMemsetAsync(acc, 0, (size_t)9 * cin * cout * 4, st));
+    for (int v = 0; v < 4; v++) {       // weight gradient: one GEMM per phase view with that phase's taps
+        const int pa = v >> 1, pb = v & 1;
+        WgradArgs g;
+        memset(&g, 0, sizeof(g));
+        g.cin = cin; g.cout = cout; g.nprob = 1; g.dw = acc;
+        for (int d0 = -1; d0 <= 1; d0++)
+            for (int d1 = -1; d1 <= 1; d1++)
+                if ((d0 != 0) == pa && (d1 != 0) == pb) { Tap& t = g.taps[g.ntaps++]; t.dy = s2_off(d0); t.dx = s2_off(d1); t.view = 0; t.slab = (d0 + 1) * 3 + d1 + 1; }
+        g.p[0].N = n; g.p[0].H = oh; g.p[0].W = ow; g.p[0].dy = DYv;
+        g.p[0].x = s2_phase_view(X, pa, pb, h, w, cin, es); g.p[0].xh = (h - pa + 1) / 2; g.p[0].xw = (w - pb + 1) / 2;
+        AFI_TRY(run_wgrad(ctx, prec, g, st));
+    }
+    AFI_TRY(unpack_wgrad(acc, cout, cin, 1, 0, dw, 1.f, 0, st));
+    if (db) {
+        AFI_CUDA(cudaMemsetAsync(db, 0, cout * sizeof(float), st));
+        AFI_TRY(col_sum_f32(DYv, dt, n, oh, ow, cout, db, st));
+    }
+    if (dxo) {
+        // input gradient, phase by phase: dx[2i + a, 2j + b] = sum over the taps with |dy| = a, |dx| = b of W[dy, dx]^T . dY[i + (dy == -1), j + (dx == -1)]
+        AFI_TRY(pack_weights(weight, cout, cin, pm(prec, 1), Wp, prec_wdt(prec), st));      // dgrad slabs: slab 8 - t holds W[tap t]^T
+        for (int v = 0; v < 4; v++) {
+            const int pa = v >> 1, pb = v & 1;
+            const int rows = (h - pa + 1) / 2, cols = (w - pb + 1) / 2;
+            ConvArgs a;
+            conv_args_init(a);
+            a.cin = cout; a.cout = cin; a.nprob = 1; a.w = Wp; a.out_dt = DT_F32; a.ntaps = 0; a.nslab = 9;
+            for (int d0 = -1; d0 <= 1; d0++)
+                for (int d1 = -1; d1 <= 1; d1++)
+                    if ((d0 != 0) == pa && (d1 != 0) == pb) {
+                        Tap& t = a.taps[a.ntaps++]; t.dy = d0 == -1 ? 1 : 0; t.dx = d1 == -1 ? 1 : 0; t.view = 0; t.slab = 8 - ((d0 + 1) * 3 + d1 + 1);
+                    }
+            a.p[0].N = n; a.p[0].H = rows; a.p[0].W = cols;
+            a.p[0].in[0] = DYv; a.p[0].vh[0] = oh; a.p[0].vw[0] = ow;
+            a.p[0].out = s2_phase_view(DX, pa, pb, h, w, cin, 4);
+            AFI_TRY(run_conv(ctx, prec, a, st));
+        }
+        afi_view4 none; memset(&none, 0, sizeof(none));
+        AFI_TRY(nhwc_to_nchw<float>(pview(DX, h, w, cin), pview_null(), none, 0, 0, 1.f, n, cin, h, w, dxo, st));
+    }
+    return AFI_OK;
+}
+
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) { return conv_single_ws_bytes(prec, 3, n, cin, h, w, cout); }
 int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
                 int lrelu, float* y, void* ws, size_t ws_bytes, void* stream) {

@@ -83,6 +83,9 @@ struct ConvProb {
     // AFI_PREC_SPLIT only: caller-owned scratch in which the fp32 input views of THIS problem are split into bf16 planes
     void* sws; size_t sws_bytes;
     PView out2;           // tensor-core engine, ConvArgs.split_col > 0: where the columns below split_col go (dtype ConvArgs.out2_dt)
+    // tensor-core engine: extent of input view v when it differs from the problem grid (0 = H / W).  Reads outside a view's own extent
+    // are zero (TMA out-of-bounds fill): the sub-pixel phase views of a stride-2 convolution have ceil / floor halves of an odd size.
+    int vh[4], vw[4];
 };
 struct ConvArgs {
     int cin, cout;
@@ -98,6 +101,7 @@ struct ConvArgs {
     // the columns from split_col on are stored raw to p[].out.  One GEMM then serves several consumers of the same input: the dense
     // block's x-part GEMM writes growth channel 1 (activated) into the block buffer and the partial sums of channels 2-4 as fp32.
     int act_post, split_col, out2_dt;
+    int nslab;            // slabs of the packed weight operand when the taps do not use them all (0 = highest slab used + 1)
     // 0: none.  1: stat0[c] += sum_p v, stat1[c] += sum_p v^2 (BatchNorm batch statistics of a conv output).
     // 2: stat0[c] += sum_p v, stat1[c] += sum_p v * (bnz - bn_mean[c]) * bn_rstd[c]  (the two reductions of BatchNorm backward).
     int stat_mode;
@@ -126,6 +130,7 @@ struct WgradProb {
     PView x;              // T
     PView dy;             // T
     void* sws; size_t sws_bytes;   // AFI_PREC_SPLIT: scratch for the bf16 planes of x and dy
+    int xh, xw;                    // tensor-core engine: extent of x when it differs from the dY grid (0 = H / W); reads outside are zero
 };
 struct WgradArgs {
     int cin, cout;

@@ -1320,8 +1320,9 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         const int m_tiles = pr.N * t.tiles_x * t.tiles_y;
         begin += (pair ? (m_tiles + 1) / 2 : m_tiles) * tl.n_tiles;
         for (int v = 0; v < nviews; v++) {
-            if (hmode) AFI_TRY(encode_view_halo(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N * planes, t.orient));
-            else AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, pr.W, pr.H, pr.N * planes, t.TW, t.TH));
+            const int vW = pr.vw[v] ? pr.vw[v] : pr.W, vH = pr.vh[v] ? pr.vh[v] : pr.H;      // the view's own extent (out-of-bounds reads are zero)
+            if (hmode) AFI_TRY(encode_view_halo(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, vW, vH, pr.N * planes, t.orient));
+            else AFI_TRY(encode_view(ctx, &maps.a[t.prob][v], pr.in[v], a.cin, vW, vH, pr.N * planes, t.TW, t.TH));
         }
         np++;
     }
@@ -1331,6 +1332,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int nslab = 0;
     for (int i = 0; i < a.ntaps; i++) nslab = a.taps[i].slab + 1 > nslab ? a.taps[i].slab + 1 : nslab;
     if (a.nphase) nslab += 9 * (a.nphase - 1);
+    if (a.nslab > nslab) nslab = a.nslab;
     set_pairs(tl, a.split, a.split_pairs, nslab);
     // six-pair products (the sign-critical forward convs) alternate between the two accumulators; so do three-pair products with chains
     // of more than 160 MMAs per plane pair (K > 2560).  (Measured on the full-size step: with single accumulators on the generator's
@@ -1441,7 +1443,8 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
         t.prob = order[oi];
         begin += pr.N * t.tiles_x * t.tiles_y;
         AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][0], pr.dy, a.cout, pr.W, pr.H, pr.N * planes, t.TW, t.TH, 2));
-        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.W, pr.H, pr.N * planes, t.TW, t.TH, pair ? tl.bn / 128 : tl.bn / 64));
+        AFI_TRY(encode_view_grouped(ctx, &maps.a[t.prob][1], pr.x, a.cin, pr.xw ? pr.xw : pr.W, pr.xh ? pr.xh : pr.H, pr.N * planes, t.TW, t.TH,
+                                    pair ? tl.bn / 128 : tl.bn / 64));
         np++;
     }
     tl.nprob = np;
@@ -1500,15 +1503,18 @@ int conv_tc_split(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
         const ConvProb& q = a.p[k];
         const long long P = (long long)q.N * q.H * q.W;
         if (P == 0) continue;
-        const size_t each = split_planes_bytes(P, a.cin);
-        if (!q.sws || each * nviews > q.sws_bytes) {
-            set_error("conv_tc_split: problem %d needs %zu B of split scratch, has %zu", k, each * nviews, q.sws ? q.sws_bytes : (size_t)0);
-            return AFI_ERR_WORKSPACE;
-        }
+        size_t off = 0;
         for (int v = 0; v < nviews; v++) {
+            const int vH = q.vh[v] ? q.vh[v] : q.H, vW = q.vw[v] ? q.vw[v] : q.W;
+            const size_t each = split_planes_bytes((long long)q.N * vH * vW, a.cin);
+            if (!q.sws || off + each > q.sws_bytes) {
+                set_error("conv_tc_split: problem %d needs more than %zu B of split scratch", k, q.sws ? q.sws_bytes : (size_t)0);
+                return AFI_ERR_WORKSPACE;
+            }
             SplitJob& j = jobs[nj++];
-            j.src = q.in[v]; j.n = q.N; j.h = q.H; j.w = q.W; j.c = a.cin; j.dst = (char*)q.sws + each * v; j.nplanes = nplanes;
-            b.p[k].in[v] = pview(j.dst, q.H, q.W, cpad);
+            j.src = q.in[v]; j.n = q.N; j.h = vH; j.w = vW; j.c = a.cin; j.dst = (char*)q.sws + off; j.nplanes = nplanes;
+            b.p[k].in[v] = pview(j.dst, vH, vW, cpad);
+            off += each;
         }
     }
     AFI_TRY(split3_group(nj, jobs, st));
@@ -1526,16 +1532,17 @@ int wgrad_tc_split(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
         const WgradProb& q = a.p[k];
         const long long P = (long long)q.N * q.H * q.W;
         if (P == 0) continue;
-        const size_t bx = split_planes_bytes(P, a.cin), by = split_planes_bytes(P, a.cout);
+        const int xH = q.xh ? q.xh : q.H, xW = q.xw ? q.xw : q.W;
+        const size_t bx = split_planes_bytes((long long)q.N * xH * xW, a.cin), by = split_planes_bytes(P, a.cout);
         if (!q.sws || bx + by > q.sws_bytes) {
             set_error("wgrad_tc_split: problem %d needs %zu B of split scratch, has %zu", k, bx + by, q.sws ? q.sws_bytes : (size_t)0);
             return AFI_ERR_WORKSPACE;
         }
         SplitJob& jx = jobs[nj++];
-        jx.src = q.x; jx.n = q.N; jx.h = q.H; jx.w = q.W; jx.c = a.cin; jx.dst = q.sws; jx.nplanes = nplanes;
+        jx.src = q.x; jx.n = q.N; jx.h = xH; jx.w = xW; jx.c = a.cin; jx.dst = q.sws; jx.nplanes = nplanes;
         SplitJob& jy = jobs[nj++];
         jy.src = q.dy; jy.n = q.N; jy.h = q.H; jy.w = q.W; jy.c = a.cout; jy.dst = (char*)q.sws + bx; jy.nplanes = nplanes;
-        b.p[k].x = pview(jx.dst, q.H, q.W, split_cpad(a.cin));
+        b.p[k].x = pview(jx.dst, xH, xW, split_cpad(a.cin));
         b.p[k].dy = pview(jy.dst, q.H, q.W, split_cpad(a.cout));
     }
     AFI_TRY(split3_group(nj, jobs, st));

@@ -213,6 +213,14 @@ int afi_conv1x1(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, 
 int afi_conv1x1_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
                          int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
 size_t afi_conv1x1_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
+/* 3x3 / stride 2 / pad 1 convolution (+bias): the bottom-up down-sampling convs of the PANet neck (pafpn_sr.py:103-117, 186-193).
+ * x [n,cin,h,w] -> y contiguous [n,cout,ceil(h/2),ceil(w/2)]; backward: dw [cout,cin,3,3], db [cout] or NULL, dxo [n,cin,h,w] or NULL.
+ * Tensor-core engines only (AFI_PREC_BF16, AFI_PREC_SPLIT); h, w >= 2. */
+int afi_conv3x3s2(afi_ctx*, int prec, afi_view4 x, int n, int cin, int h, int w_, const float* weight, const float* bias, int cout,
+                  float* y, void* ws, size_t ws_bytes, void* stream);
+int afi_conv3x3s2_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n, int cin, int h, int w_, const float* weight,
+                           int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
+size_t afi_conv3x3s2_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
  * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05 per-tap

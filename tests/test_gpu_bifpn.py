@@ -104,3 +104,30 @@ def test_conv1x1_autograd_vs_torch(precision):
     tol = 3e-5 if precision == "split" else 1e-2
     for a, r in zip(got, ref):
         assert float((a.double() - r).norm() / r.norm()) < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 256, 256, 25, 42), (1, 256, 256, 26, 43), (1, 64, 128, 13, 21), (2, 256, 256, 100, 168), (1, 256, 256, 2, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_conv3x3_stride2_vs_torch(shape, precision):
+    """The PANet neck's down-sampling conv as a 9-tap implicit GEMM over the four sub-pixel phase views (odd sizes: the phases differ by a
+    row / column and the padding comes from each view's own TMA bounds): forward, input gradient, weight and bias gradients vs torch fp64."""
+    from afigan.functional import conv3x3s2_autograd
+    import torch.nn.functional as F
+    n, cin, cout, h, w = shape
+    g = torch.Generator().manual_seed(6 + h)
+    x = torch.randn(n, cin, h, w, generator=g).cuda().requires_grad_(True)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).cuda().requires_grad_(True)
+    b = torch.randn(cout, generator=g).cuda().requires_grad_(True)
+    y = conv3x3s2_autograd(x, wt, b, precision)
+    dy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(dy)
+    x2, w2, b2 = (t.detach().double().requires_grad_(True) for t in (x, wt, b))
+    y2 = F.conv2d(x2, w2, b2, stride=2, padding=1)
+    assert y.shape == y2.shape
+    y2.backward(dy.double())
+    tol = 3e-5 if precision == "split" else 1e-2
+    for name, a, r in (("y", y.detach(), y2.detach()), ("dx", x.grad, x2.grad), ("dw", wt.grad, w2.grad), ("db", b.grad, b2.grad)):
+        e = float((a.double() - r).norm() / r.norm())
+        assert e < tol, (name, e)
