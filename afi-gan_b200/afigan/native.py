@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libafigan_b200.so")
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_SPLIT = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT, "split": PREC_SPLIT}
 MAX_RDB = 4
+ABI_VERSION = 3
 
 
 def default_precision() -> str:
@@ -138,6 +139,12 @@ def lib() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        # a library built from another revision of include/afigan_b200.h must not be driven with these struct layouts
+        if l.afi_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {l.afi_abi_version()}, this binding expects {ABI_VERSION}: rebuild it")
+        for which, st in enumerate((View4, GParams, Lateral, GCall, DParams, DCall, GGrads, DGrads)):
+            if l.afi_sizeof(which) != C.sizeof(st):
+                raise RuntimeError(f"struct {st.__name__}: the library says {l.afi_sizeof(which)} bytes, the binding {C.sizeof(st)}")
         _lib = l
     return _lib
 

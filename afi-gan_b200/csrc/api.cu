@@ -913,10 +913,10 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         memset(&g, 0, sizeof(g));
         g.cin = DC[3]; g.cout = 16; g.ntaps = 1; g.nprob = ncalls; g.dw = gradacc + GL.w[3];
         void* sums_p[AFI_MAX_PROB]; double* s0[AFI_MAX_PROB]; double* s1[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
-        const float* g9f[AFI_MAX_PROB]; long long cnt[AFI_MAX_PROB]; PView Z3[AFI_MAX_PROB], DZ3[AFI_MAX_PROB];
+        long long cnt[AFI_MAX_PROB]; PView Z3[AFI_MAX_PROB], DZ3[AFI_MAX_PROB];
         for (int k = 0; k < ncalls; k++) {
             sums_p[k] = W[k].sums; s0[k] = W[k].sums; s1[k] = W[k].sums + 1024; mean_c[k] = W[k].mean[2]; rstd_c[k] = W[k].rstd[2];
-            g9f[k] = W[k].G9F; cnt[k] = (long long)d[k].n * d[k].h * d[k].w;
+            cnt[k] = (long long)d[k].n * d[k].h * d[k].w;
             Z3[k] = pview(W[k].Z[2], d[k].h, d[k].w, DC[3]); DZ3[k] = pview(W[k].DY[2], d[k].h, d[k].w, DC[3]);
         }
         AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
@@ -928,22 +928,17 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         }
         const void* g9b[AFI_MAX_PROB];
         for (int k = 0; k < ncalls; k++) g9b[k] = W[k].G9;
-        const int head_mma = getenv("AFIGAN_DHEAD_MMA") ? atoi(getenv("AFIGAN_DHEAD_MMA")) : 1;     // read per call: tests switch in-process
-        for (int pass = 1; pass <= 2; pass++) {
-            if (head_mma && dt == DT_BF16)
-                AFI_TRY(dhead_backward_group_mma(pass, ncalls, g9b, Z3, DZ3, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
-                                                 gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
-            else
-                AFI_TRY(dhead_backward_group(pass, ncalls, g9f, Z3, DZ3, dt, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
+        // (an FMA formulation of these two passes was FMA-bound at 0.9 + 0.8 ms per step; the 9-tap product on warp-level MMAs is HBM-bound:
+        //  profiles/r01_hbm_passes.md)
+        for (int pass = 1; pass <= 2; pass++)
+            AFI_TRY(dhead_backward_group_mma(pass, ncalls, g9b, Z3, DZ3, p->w[3], mean_c, rstd_c, p->gamma[2], p->beta[2], s0, s1,
                                              gradacc + GL.gamma[2], gradacc + GL.beta[2], cnt, DC[3], training ? 0 : 1, st));
-        }
         AFI_TRY(run_wgrad(ctx, prec, g, st));
     } else {
         for (int k = 0; k < ncalls; k++)   // head: dW4, db4 and dy3 = dA3 * lrelu'(a3) in one pass over a3
             AFI_TRY(dhead_backward(pview(W[k].A[3], d[k].h, d[k].w, DC[3]), dt, p->w[3], calls[k].dlogits, d[k].n, d[k].h, d[k].w, DC[3],
                                    gradacc + GL.w[3], gradacc + GL.b[3], pview(W[k].DY[2], d[k].h, d[k].w, DC[3]), st));
     }
-    bool stats_ready = false;     // layer i's two BatchNorm-backward reductions already came out of the dgrad GEMM that produced DY[i]
     for (int i = 2; i >= 0; i--) {
         const int co = DC[i + 1], ci = DC[i];
         void* sums_p[AFI_MAX_PROB]; double* s0[AFI_MAX_PROB]; double* s1[AFI_MAX_PROB]; const float* mean_c[AFI_MAX_PROB]; const float* rstd_c[AFI_MAX_PROB];
@@ -958,10 +953,8 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
         // train-mode BatchNorm backward in closed form: two per-channel reductions, then one elementwise pass (in place: DY -> DZ);
         // each pass is one grouped launch over all calls
         if (!(tc && i == 2)) {      // (the tensor-core path did layer 3's BatchNorm backward in the fused head passes above)
-            if (!stats_ready) {
-                AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
-                AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
-            }
+            AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
+            AFI_TRY(col_reduce_group(1, ncalls, DYv, Zv, dt, mean_c, rstd_c, s0, s1, cnt, co, st));
             AFI_TRY(bn_bwd_apply_group(ncalls, DYv, Zv, dt, mean_c, rstd_c, p->gamma[i], s0, s1, gradacc + GL.gamma[i], gradacc + GL.beta[i], cnt, co,
                                        training ? 0 : 1, st));
         }
@@ -985,19 +978,9 @@ int afi_d_backward(afi_ctx* ctx, int prec, const afi_d_params* p, const void* pa
             conv_std(a, ncalls, d, co, ci, (const char*)packed + L.d[i] * wes);
             a.out_dt = dt;
             for (int k = 0; k < ncalls; k++) { a.p[k].in[0] = DYv[k]; a.p[k].mask = X[k]; a.p[k].out = pview(W[k].DY[i - 1], d[k].h, d[k].w, ci); }
-            // opt-in (AFIGAN_FUSE_BWD_STATS=1): the long-K dgrads can also emit sum(dy) and sum(dy * xhat) of the layer below (its
-            // BatchNorm-backward reductions) from their epilogue.  Measured 0.4 ms/step SLOWER than the separate grouped reduction
-            // pass (42.7 vs 42.3 ms): the extra operand stream and shuffles cost the GEMM more than the 0.37 ms pass they replace.
-            const int fuse_bwd = getenv("AFIGAN_FUSE_BWD_STATS") ? atoi(getenv("AFIGAN_FUSE_BWD_STATS")) : 0;
-            stats_ready = tc && fuse_bwd && 9 * co >= 4096;
-            if (stats_ready) {
-                AFI_TRY(zero_group(ncalls, sums_p, 2 * 1024 * sizeof(double), st));
-                a.stat_mode = 2;
-                for (int k = 0; k < ncalls; k++) {
-                    a.p[k].stat0 = W[k].sums; a.p[k].stat1 = W[k].sums + 1024;
-                    a.p[k].bnz = pview(W[k].Z[i - 1], d[k].h, d[k].w, ci); a.p[k].bn_mean = W[k].mean[i - 1]; a.p[k].bn_rstd = W[k].rstd[i - 1];
-                }
-            }
+            // (emitting the layer below's two BatchNorm-backward reductions from this dgrad's epilogue measured 0.4 ms/step SLOWER than the
+            //  separate grouped reduction pass -- 42.7 vs 42.3 ms: the extra operand stream and shuffles cost the GEMM more than the 0.37 ms
+            //  pass they replace; round-1 experiment, removed)
             AFI_TRY(run_conv(ctx, prec, a, st));
         }
     }

@@ -79,7 +79,6 @@ struct ConvProb {
     PView mask;           // dtype T
     // fused per-channel reductions of the stored output v (tensor-core engine only; see ConvArgs.stat_mode)
     double* stat0; double* stat1;
-    PView bnz; const float* bn_mean; const float* bn_rstd;
     // AFI_PREC_SPLIT only: caller-owned scratch in which the fp32 input views of THIS problem are split into bf16 planes
     void* sws; size_t sws_bytes;
     PView out2;           // tensor-core engine, ConvArgs.split_col > 0: where the columns below split_col go (dtype ConvArgs.out2_dt)
@@ -103,7 +102,6 @@ struct ConvArgs {
     int act_post, split_col, out2_dt;
     int nslab;            // slabs of the packed weight operand when the taps do not use them all (0 = highest slab used + 1)
     // 0: none.  1: stat0[c] += sum_p v, stat1[c] += sum_p v^2 (BatchNorm batch statistics of a conv output).
-    // 2: stat0[c] += sum_p v, stat1[c] += sum_p v * (bnz - bn_mean[c]) * bn_rstd[c]  (the two reductions of BatchNorm backward).
     int stat_mode;
     // nphase = 4 (tensor-core engine only): FOUR convolutions of the same input in one launch -- the sub-pixel phases of the stride-2
     // transposed conv.  N tile p uses the slabs 9 p + tap.slab and stores its cout columns at out + (p >> 1) * out.sy / 2 +
@@ -187,8 +185,6 @@ int ew_combine(PView dst, int dst_dt, PView a, int a_dt, PView b, int b_dt, PVie
                float scale, int n, int h, int w, int c, cudaStream_t st);
 int ew_combine_group(int nprob, const PView* dst, int dst_dt, const PView* a, int a_dt, const PView* b, int b_dt, const PView* mask, int mask_dt,
                      float mask_slope, float scale, const int* n, const int* h, const int* w, int c, cudaStream_t st);
-// per-channel sums over all pixels of a view: sum[c] += x, sumsq[c] += x*x (double accumulators, sumsq may be null)
-int col_stats(PView x, int dt, int n, int h, int w, int c, double* sum, double* sumsq, cudaStream_t st);
 // float accumulate variant for bias gradients: out[c] += sum_p x[p][c]
 int col_sum_f32(PView x, int dt, int n, int h, int w, int c, float* out, cudaStream_t st);
 // weight re-layout: dst[slab][r][c] from torch [co][ci][k][k] (see pack modes in elementwise.cu)
@@ -217,14 +213,6 @@ int bn_finalize(const double* sum, const double* sumsq, long long count, int c, 
                 float* mean, float* rstd, float* var_unb, float* running_mean, float* running_var, long long* nbt, cudaStream_t st);
 int bn_update_running(int ncalls, const float* const* mean, const float* const* var, int c, float momentum, float* rmean, float* rvar,
                       long long* nbt, cudaStream_t st);
-// a = lrelu(gamma * (z - mean) * rstd + beta)
-int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                   float slope, int n, int h, int w, int c, cudaStream_t st);
-// reduce: s_dy[c] += dy, s_dyx[c] += dy * xhat (double);  apply: dz = gamma*rstd*(dy - s_dy/M - xhat*s_dyx/M) (in place on dy)
-int bn_bwd_reduce(PView dy, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
-                  double* s_dy, double* s_dyx, cudaStream_t st);
-int bn_bwd_apply(PView dy, PView z, int dt, const float* mean, const float* rstd, const float* gamma, const double* s_dy,
-                 const double* s_dyx, float* dgamma_acc, float* dbeta_acc, int n, int h, int w, int c, cudaStream_t st);
 // discriminator head (1024 -> 1 conv): t9[p][tap] = <a3[p], w4[tap]>, logits = b + 3x3 shift-sum of t9
 int dhead_forward(PView a3, int dt, const float* w4 /*[c][9] torch layout*/, const float* b4, int n, int h, int w, int c,
                   float* t9, float* logits, cudaStream_t st);
@@ -251,10 +239,6 @@ int dhead_build_g9(const float* g, int n, int h, int w, void* g9, float* g9f, cu
 int dhead_stencil16(const float* t9, const float* b4, int n, int h, int w, float* logits, cudaStream_t st);
 int dhead_unpack_tc(const float* acc, int c, float* dst, float scale, int accumulate, cudaStream_t st);
 int sum_f32(const float* x, long long n, float* out, cudaStream_t st);
-// head backward fused with layer 3's BatchNorm backward (pass 1: the two reductions; pass 2: dz3), grouped over calls
-int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PView* z3, const PView* dz3, int dt, const float* w4,
-                         const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
-                         double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st);
 
 // bf16 variant with the 9-tap product on warp-level tensor-core MMAs (g9: the bf16 [P][16] shifted head gradients)
 int dhead_backward_group_mma(int pass, int nprob, const void* const* g9, const PView* z3, const PView* dz3, const float* w4,

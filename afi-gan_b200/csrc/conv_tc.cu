@@ -392,13 +392,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         // use (a dependent global load per chunk made memory-bound epilogues ~8x slower than the MMA main loop).
         const long long offA = pr.mask.ptr ? img * pr.mask.sn + y * pr.mask.sy + x * pr.mask.sx
                                            : (pr.r1.ptr ? img * pr.r1.sn + y * pr.r1.sy + x * pr.r1.sx : 0);
-        const long long offB = pr.bnz.ptr && a.stat_mode == 2 ? img * pr.bnz.sn + y * pr.bnz.sy + x * pr.bnz.sx
-                                                              : (pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0);
+        const long long offB = pr.r2.ptr ? img * pr.r2.sn + y * pr.r2.sy + x * pr.r2.sx : 0;
         typedef typename AuxSel<AUX32>::type AuxT;
         // element offsets are the same for bf16 and fp32 operands; the byte address depends on AUX32
         const char* pA = pr.mask.ptr ? (const char*)pr.mask.ptr + offA * (AUX32 ? 4 : 2) : (pr.r1.ptr ? (const char*)pr.r1.ptr + offA * (AUX32 ? 4 : 2) : nullptr);
-        const char* pB = (pr.bnz.ptr && a.stat_mode == 2) ? (const char*)pr.bnz.ptr + offB * (AUX32 ? 4 : 2)
-                                                          : (pr.r2.ptr ? (const char*)pr.r2.ptr + offB * (AUX32 ? 4 : 2) : nullptr);
+        const char* pB = pr.r2.ptr ? (const char*)pr.r2.ptr + offB * (AUX32 ? 4 : 2) : nullptr;
         const float* pC = pr.accin.ptr ? (const float*)pr.accin.ptr + img * pr.accin.sn + y * pr.accin.sy + x * pr.accin.sx : nullptr;
         const int nchunks = tl.bn >> 4;
         auto aux_load = [&](int ch, AuxT& r) {
@@ -436,7 +434,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
                 t[4 * i + 2] = __uint_as_float(q4[i].z); t[4 * i + 3] = __uint_as_float(q4[i].w);
             }
         };
-        // the 16 values of the r1 | mask slot (which = 0), the r2 | bnz slot (1) or the fp32 accumulate-in operand (2) of this chunk
+        // the 16 values of the r1 | mask slot (which = 0), the r2 slot (1) or the fp32 accumulate-in operand (2) of this chunk
         auto aux_get = [&](const AuxT& ax, int which, float* t) {
             if constexpr (AUX32) {
                 asfloat16(which == 1 ? ax.y : ax.x, t);
@@ -460,7 +458,6 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             }
             const int col = n0 + c0;
             const bool valid = ok && col < a.cout;
-            float zbn[16];
             if (valid) {
                 if (a.bias) {
                     const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
@@ -494,7 +491,6 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] *= t[i] > 0.f ? 1.f : a.mask_slope;
                     }
-                    if (a.stat_mode == 2) aux_get(ax, 1, zbn);
                 }
                 if (a.act_post || col < a.split_col) {
 #pragma unroll
@@ -505,27 +501,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             }
             if (a.stat_mode) {      // warp-uniform: every lane takes part in the shuffles, invalid rows contribute zeros
                 float s0[16], s1[16];
-                if (a.stat_mode == 1) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) { s0[i] = valid ? v[i] : 0.f; s1[i] = valid ? v[i] * v[i] : 0.f; }
-                } else {
-                    float mu[16], rs[16];
-                    if (valid) {
-                        const float4* m4 = reinterpret_cast<const float4*>(pr.bn_mean + col);
-                        const float4* r4 = reinterpret_cast<const float4*>(pr.bn_rstd + col);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            float4 m = __ldg(m4 + i), r = __ldg(r4 + i);
-                            mu[4 * i] = m.x; mu[4 * i + 1] = m.y; mu[4 * i + 2] = m.z; mu[4 * i + 3] = m.w;
-                            rs[4 * i] = r.x; rs[4 * i + 1] = r.y; rs[4 * i + 2] = r.z; rs[4 * i + 3] = r.w;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        s0[i] = valid ? v[i] : 0.f;
-                        s1[i] = valid ? v[i] * (zbn[i] - mu[i]) * rs[i] : 0.f;
-                    }
-                }
+                for (int i = 0; i < 16; i++) { s0[i] = valid ? v[i] : 0.f; s1[i] = valid ? v[i] * v[i] : 0.f; }
                 butterfly16(s0, lane);
                 butterfly16(s1, lane);
                 if ((lane & 1) == 0) {      // 16 lanes own 16 distinct columns of this warp's private accumulator
@@ -1233,17 +1210,16 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     for (int i = 0; i < a.nprob; i++) {
         const ConvProb& q = a.p[i];
         size[i] = (long long)q.N * q.H * q.W; pixels += size[i];
-        // the epilogue prefetches its auxiliary operands through two bf16 slots (r1|mask, r2|bnz) or one fp32 slot (accin)
-        AFI_REQUIRE(!(q.mask.ptr && q.r1.ptr) && !(q.r2.ptr && a.stat_mode == 2), "conv_tc: unsupported epilogue operand combination");
-        AFI_REQUIRE(!q.accin.ptr || !(q.mask.ptr || q.r1.ptr || q.r2.ptr || a.stat_mode == 2), "conv_tc: accin excludes other epilogue operands");
+        // the epilogue prefetches its auxiliary operands through two slots (r1|mask, r2) or one fp32 slot (accin)
+        AFI_REQUIRE(!(q.mask.ptr && q.r1.ptr), "conv_tc: unsupported epilogue operand combination");
+        AFI_REQUIRE(!q.accin.ptr || !(q.mask.ptr || q.r1.ptr || q.r2.ptr), "conv_tc: accin excludes other epilogue operands");
         AFI_REQUIRE((!q.r1.ptr || a.r1_dt == (a.aux_f32 ? DT_F32 : DT_BF16)) && (!q.r2.ptr || a.r2_dt == (a.aux_f32 ? DT_F32 : DT_BF16)),
                     "conv_tc: residuals must be %s", a.aux_f32 ? "fp32" : "bf16");
-        if (a.stat_mode) AFI_REQUIRE(q.stat0 && q.stat1 && (a.stat_mode == 1 || (q.bnz.ptr && q.bn_mean && q.bn_rstd)), "conv_tc: missing statistics operands");
+        if (a.stat_mode) AFI_REQUIRE(a.stat_mode == 1 && q.stat0 && q.stat1, "conv_tc: missing statistics operands");
     }
     if (pixels == 0) return AFI_OK;
     AFI_REQUIRE(a.split == 0 || a.split == 3, "conv_tc: split %d", a.split);
     AFI_REQUIRE(a.split_col % 16 == 0 && (a.split_col == 0 || (!a.nphase && !a.stat_mode && a.split_col <= a.cout)), "conv_tc: bad split_col %d", a.split_col);
-    AFI_REQUIRE(!(a.aux_f32 && a.stat_mode == 2), "conv_tc: the BatchNorm-backward statistics epilogue takes bf16 operands only");
     AFI_REQUIRE(!a.split || a.split_pairs == 6 || a.split_pairs == 3, "conv_tc: split_pairs %d", a.split_pairs);
     const int planes = a.split ? (a.split_pairs == 3 ? 2 : 3) : 1;      // operand planes of the A views (the weights always carry three)
     int order[AFI_MAX_PROB];
@@ -1257,9 +1233,6 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     {
         const long long m_tiles_est = (pixels + 127) / 128;
         while (bn_cap > 64 && m_tiles_est * ((a.cout + bn_cap - 1) / bn_cap) < ctx->sm_count && a.cout > bn_cap / 2) bn_cap /= 2;
-        if (getenv("AFIGAN_FIXED_NTILE")) bn_cap = 256;
-        if (getenv("AFIGAN_NTILE_CAP")) { const int c = atoi(getenv("AFIGAN_NTILE_CAP")); const int kmax = getenv("AFIGAN_NTILE_CAP_K") ? atoi(getenv("AFIGAN_NTILE_CAP_K")) : 4096;
-            if ((c == 64 || c == 128 || c == 256) && a.ntaps * ((a.cin + 63) / 64) * 64 < kmax) bn_cap = c; }
     }
     tl.n_tiles = (a.cout + bn_cap - 1) / bn_cap;
     tl.bn = ((a.cout + tl.n_tiles - 1) / tl.n_tiles + 15) / 16 * 16;
@@ -1337,7 +1310,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     // six-pair products (the sign-critical forward convs) alternate between the two accumulators; so do three-pair products with chains
     // of more than 160 MMAs per plane pair (K > 2560).  (Measured on the full-size step: with single accumulators on the generator's
     // K = 2304 layers the worst sampled generator gradient error rose from 3.7e-4 to 9.2e-4.)
-    tl.dual = (a.split && (a.split_pairs == 6 || a.ntaps * tl.kchunks * 4 > 160) && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) ? 1 : 0;
+    tl.dual = (a.split && (a.split_pairs == 6 || a.ntaps * tl.kchunks * 4 > 160)) ? 1 : 0;
     {
         cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab * (a.split ? 3 : 1)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
@@ -1422,7 +1395,7 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     const int planes = a.split ? (a.split_pairs == 3 ? 2 : 3) : 1;
     Tiling tl{};
     set_pairs(tl, a.split, a.split_pairs, 0);
-    tl.dual = (a.split && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) ? 1 : 0;
+    tl.dual = a.split ? 1 : 0;
     tl.m_tiles = (a.cout + 127) / 128;
     tl.n_tiles = (a.cin + 255) / 256;
     tl.bn = ((a.cin + tl.n_tiles - 1) / tl.n_tiles + 63) / 64 * 64;
@@ -1462,10 +1435,7 @@ int wgrad_tc(afi_ctx* ctx, const WgradArgs& a, cudaStream_t st) {
     // split mode: the accumulation chain of one item is capped at 512 K tiles (1024 MMAs per accumulator and plane pair, a truncation
     // bias of ~2e-5, see DUAL_ACC in k_conv_tc); the partial sums meet in fp32 RED adds.  A tighter cap costs more than it buys: at
     // 64 K tiles the RED traffic of the discriminator's weight gradients (1.6 GB per launch) made them 1.75x slower (measured).
-    if (a.split && !getenv("AFIGAN_SPLIT_SINGLE_ACC")) {
-        const int cap = getenv("AFIGAN_SPLIT_KCAP") ? atoi(getenv("AFIGAN_SPLIT_KCAP")) : 512;
-        if (kper > cap) kper = cap;
-    }
+    if (a.split && kper > 512) kper = 512;
     tl.ksplit = (tl.ktiles + kper - 1) / kper;
     tl.total = base * tl.ksplit;
     tl.stage_bytes = A_BYTES + (tl.bn / 64) * (pair ? 4096 : 8192);

@@ -391,63 +391,6 @@ static inline bool dense_ok(int c) { return c % 8 == 0 && c / 8 <= 256 && 256 % 
 constexpr int DENSE_ROWS = 64;     // rows per block of the elementwise passes
 constexpr int REDUCE_ROWS = 256;   // max rows per block of the column reductions (fewer for small tensors: keep >= ~600 blocks)
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_bn_apply_dense(const T* __restrict__ z, T* __restrict__ a, long long P, int C,
-                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
-    const int tpr = C >> 3, rpb = 256 / tpr;
-    const int c0 = (threadIdx.x % tpr) * 8;
-    float mu[8], rs[8], ga[8], be[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k]; }
-    long long r0 = (long long)blockIdx.x * DENSE_ROWS, r1 = r0 + DENSE_ROWS;
-    if (r1 > P) r1 = P;
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
-        float v[8];
-        V8<T>::ld(z + r * C + c0, v);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            float t = (v[k] - mu[k]) * rs[k] * ga[k] + be[k];    // ATen order: (x - mean) * invstd * weight + bias
-            v[k] = t > 0.f ? t : t * slope;
-        }
-        V8<T>::st(a + r * C + c0, v);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) k_bn_bwd_apply_dense(T* __restrict__ dy, const T* __restrict__ z, long long P, int C,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const float* __restrict__ gamma, const double* __restrict__ s_dy,
-                                                            const double* __restrict__ s_dyx, float* dgamma_acc, float* dbeta_acc, float inv_m) {
-    if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)s_dyx[c]);
-            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)s_dy[c]);
-        }
-    }
-    const int tpr = C >> 3, rpb = 256 / tpr;
-    const int c0 = (threadIdx.x % tpr) * 8;
-    float mu[8], rs[8], gr[8], m1[8], m2[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        mu[k] = mean[c0 + k]; rs[k] = rstd[c0 + k]; gr[k] = gamma[c0 + k] * rs[k];
-        m1[k] = (float)s_dy[c0 + k] * inv_m; m2[k] = (float)s_dyx[c0 + k] * inv_m;
-    }
-    long long r0 = (long long)blockIdx.x * DENSE_ROWS, r1 = r0 + DENSE_ROWS;
-    if (r1 > P) r1 = P;
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.x / tpr; r < r1; r += rpb) {
-        float g[8], zz[8];
-        V8<T>::ld(dy + r * C + c0, g);
-        V8<T>::ld(z + r * C + c0, zz);
-#pragma unroll
-        for (int k = 0; k < 8; k++) g[k] = gr[k] * (g[k] - m1[k] - (zz[k] - mu[k]) * rs[k] * m2[k]);
-        V8<T>::st(dy + r * C + c0, g);
-    }
-}
-
-// MODE 0: sum x, sum x^2 (double out).  MODE 1: sum dy, sum dy*xhat (double out).  MODE 2: sum x (float out).
 template <int MODE, typename T>
 __global__ void __launch_bounds__(256) k_col_reduce_dense(const T* __restrict__ x, const T* __restrict__ z, long long P, int C,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -762,15 +705,8 @@ static int col_reduce_launch(int mode, PView x, PView z, int dt, const float* me
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
-int col_stats(PView x, int dt, int n, int h, int w, int c, double* sum, double* sumsq, cudaStream_t st) {
-    return col_reduce_launch(0, x, pview_null(), dt, nullptr, nullptr, n, h, w, c, sum, sumsq, nullptr, st);
-}
 int col_sum_f32(PView x, int dt, int n, int h, int w, int c, float* out, cudaStream_t st) {
     return col_reduce_launch(2, x, pview_null(), dt, nullptr, nullptr, n, h, w, c, nullptr, nullptr, out, st);
-}
-int bn_bwd_reduce(PView dy, PView z, int dt, const float* mean, const float* rstd, int n, int h, int w, int c,
-                  double* s_dy, double* s_dyx, cudaStream_t st) {
-    return col_reduce_launch(1, dy, z, dt, mean, rstd, n, h, w, c, s_dy, s_dyx, nullptr, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -828,81 +764,6 @@ int bn_update_running(int ncalls, const float* const* mean, const float* const* 
     return AFI_OK;
 }
 
-__global__ void k_bn_apply_lrelu(PView z, PView a, int dt, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, float slope, int H, int W,
-                                 int cq, long long total) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int c = (int)(i % cq) * 4;
-    PixIdx q = decode_pixel(i / cq, H, W);
-    float4 v = ld4(z.ptr, voff(z, q) + c, dt);
-    float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
-    float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-    // same operation order as ATen's batch_norm: (x - mean) * invstd * weight + bias
-    v.x = (v.x - mu.x) * rs.x * g.x + b.x; v.y = (v.y - mu.y) * rs.y * g.y + b.y;
-    v.z = (v.z - mu.z) * rs.z * g.z + b.z; v.w = (v.w - mu.w) * rs.w * g.w + b.w;
-    v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
-    v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
-    st4(a.ptr, voff(a, q) + c, dt, v);
-}
-int bn_apply_lrelu(PView z, PView a, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                   float slope, int n, int h, int w, int c, cudaStream_t st) {
-    long long total = (long long)n * h * w * (c / 4);
-    if (total == 0) return AFI_OK;
-    if (is_dense(z, h, w, c) && is_dense(a, h, w, c) && dense_ok(c)) {
-        long long P = (long long)n * h * w;
-        if (dt == DT_F32) k_bn_apply_dense<float><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((const float*)z.ptr, (float*)a.ptr, P, c, mean, rstd, gamma, beta, slope);
-        else k_bn_apply_dense<bf16><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((const bf16*)z.ptr, (bf16*)a.ptr, P, c, mean, rstd, gamma, beta, slope);
-        AFI_LAUNCH_CHECK();
-        return AFI_OK;
-    }
-    k_bn_apply_lrelu<<<cdiv(total, 256), 256, 0, st>>>(z, a, dt, mean, rstd, gamma, beta, slope, h, w, c / 4, total);
-    AFI_LAUNCH_CHECK();
-    return AFI_OK;
-}
-
-__global__ void k_bn_bwd_apply(PView dy, PView z, int dt, const float* __restrict__ mean, const float* __restrict__ rstd,
-                               const float* __restrict__ gamma, const double* __restrict__ s_dy, const double* __restrict__ s_dyx,
-                               float* dgamma_acc, float* dbeta_acc, int H, int W, int cq, long long total, float inv_m) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0) {   // parameter gradients of the affine part: d gamma = sum dy*xhat, d beta = sum dy
-        for (int c = threadIdx.x; c < cq * 4; c += blockDim.x) {
-            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)s_dyx[c]);
-            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)s_dy[c]);
-        }
-    }
-    if (i >= total) return;
-    int c = (int)(i % cq) * 4;
-    PixIdx q = decode_pixel(i / cq, H, W);
-    long long o = voff(dy, q) + c;
-    float4 g = ld4(dy.ptr, o, dt);
-    float4 zz = ld4(z.ptr, voff(z, q) + c, dt);
-    float r[4] = {g.x, g.y, g.z, g.w}, zv[4] = {zz.x, zz.y, zz.z, zz.w};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float xhat = (zv[k] - mean[c + k]) * rstd[c + k];
-        float m_dy = (float)s_dy[c + k] * inv_m, m_dyx = (float)s_dyx[c + k] * inv_m;
-        r[k] = gamma[c + k] * rstd[c + k] * (r[k] - m_dy - xhat * m_dyx);
-    }
-    st4(dy.ptr, o, dt, make_float4(r[0], r[1], r[2], r[3]));
-}
-int bn_bwd_apply(PView dy, PView z, int dt, const float* mean, const float* rstd, const float* gamma, const double* s_dy,
-                 const double* s_dyx, float* dgamma_acc, float* dbeta_acc, int n, int h, int w, int c, cudaStream_t st) {
-    long long total = (long long)n * h * w * (c / 4);
-    if (total == 0) return AFI_OK;
-    if (is_dense(dy, h, w, c) && is_dense(z, h, w, c) && dense_ok(c)) {
-        long long P = (long long)n * h * w;
-        float inv_m = 1.f / (float)P;
-        if (dt == DT_F32) k_bn_bwd_apply_dense<float><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((float*)dy.ptr, (const float*)z.ptr, P, c, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, inv_m);
-        else k_bn_bwd_apply_dense<bf16><<<cdiv(P, DENSE_ROWS), 256, 0, st>>>((bf16*)dy.ptr, (const bf16*)z.ptr, P, c, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, inv_m);
-        AFI_LAUNCH_CHECK();
-        return AFI_OK;
-    }
-    k_bn_bwd_apply<<<cdiv(total, 256), 256, 0, st>>>(dy, z, dt, mean, rstd, gamma, s_dy, s_dyx, dgamma_acc, dbeta_acc, h, w, c / 4,
-                                                   total, 1.f / (float)((long long)n * h * w));
-    AFI_LAUNCH_CHECK();
-    return AFI_OK;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // discriminator head: Conv2d 1024 -> 1, 3x3 (feature_patch_discriminator.py:40-41).  GEMV-like, HBM-bound:
@@ -1099,107 +960,6 @@ template <> struct V4<bf16> {
 // re-derived from z3 with the SAME fp32 expression bn_apply uses, so it equals the sign of the stored activation.
 // A thread owns 4 channels (its 4 x 9 head weights stay in registers) and keeps ROWS independent 8-byte loads in flight.
 // ---------------------------------------------------------------------------------------------------
-template <int PASS, typename T>
-__global__ void __launch_bounds__(256, 2) k_dhead_bwd_group(const __grid_constant__ DenseGroupD G, const float* __restrict__ w4,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float* dgamma_acc, float* dbeta_acc, float slope, int eval_mode) {
-    constexpr int ROWS = PASS == 1 ? 8 : 4;
-    __shared__ float sm0[PASS == 1 ? 256 * 4 : 1];
-    __shared__ float sm1[PASS == 1 ? 256 * 4 : 1];
-    const int kp = find_prob(G, blockIdx.x);
-    const DenseProbD& q = G.p[kp];
-    const int C = G.C, tpr = C >> 2, rpb = 256 / tpr;
-    const int cq = threadIdx.x % tpr, lane_r = threadIdx.x / tpr;
-    const int c0 = cq * 4;
-    const float* __restrict__ g9 = reinterpret_cast<const float*>(q.a);
-    const T* __restrict__ z = reinterpret_cast<const T*>(q.b);
-    T* __restrict__ dz = reinterpret_cast<T*>(q.out);
-    if (PASS == 2 && (int)blockIdx.x == q.block_begin) {     // d gamma = sum dy*xhat, d beta = sum dy: once per call
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            if (dgamma_acc) atomicAdd(dgamma_acc + c, (float)q.o1[c]);
-            if (dbeta_acc) atomicAdd(dbeta_acc + c, (float)q.o0[c]);
-        }
-    }
-    float wr[4][9], mu[4], rs[4], ga[4], be[4], a0[4], a1[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        mu[k] = q.mean[c0 + k]; rs[k] = q.rstd[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k];
-        if (PASS == 1) { a0[k] = 0.f; a1[k] = 0.f; }
-        else {
-            const float inv_m = 1.f / (float)q.P;
-            a0[k] = eval_mode ? 0.f : (float)q.o0[c0 + k] * inv_m; a1[k] = eval_mode ? 0.f : (float)q.o1[c0 + k] * inv_m;
-        }
-#pragma unroll
-        for (int t = 0; t < 9; t++) wr[k][t] = w4[(c0 + k) * 9 + t];
-    }
-    long long r0 = (long long)(blockIdx.x - q.block_begin) * q.rows_per_block, r1 = r0 + q.rows_per_block;
-    if (r1 > q.P) r1 = q.P;
-    for (long long rb = r0 + lane_r; rb < r1; rb += (long long)ROWS * rpb) {
-        float zv[ROWS][4];
-#pragma unroll
-        for (int j = 0; j < ROWS; j++) {
-            const long long r = rb + (long long)j * rpb;
-            if (r < r1) V4<T>::ld(z + r * C + c0, zv[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < ROWS; j++) {
-            const long long r = rb + (long long)j * rpb;
-            if (r < r1) {
-                const float4* gp = reinterpret_cast<const float4*>(g9 + r * 12);
-                const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
-                const float gt[9] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x};
-                float o[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float d = 0.f;
-#pragma unroll
-                    for (int t = 0; t < 9; t++) d = fmaf(gt[t], wr[k][t], d);
-                    const float xh = (zv[j][k] - mu[k]) * rs[k];
-                    const float y = (zv[j][k] - mu[k]) * rs[k] * ga[k] + be[k];      // == bn_apply's expression: sign(y) is the stored activation's sign
-                    d *= y > 0.f ? 1.f : slope;
-                    if (PASS == 1) { a0[k] += d; a1[k] = fmaf(d, xh, a1[k]); }
-                    else o[k] = ga[k] * rs[k] * (d - a0[k] - xh * a1[k]);
-                }
-                if (PASS == 2) V4<T>::st(dz + r * C + c0, o);
-            }
-        }
-    }
-    if (PASS == 1) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) { sm0[(lane_r * 4 + k) * tpr + cq] = a0[k]; sm1[(lane_r * 4 + k) * tpr + cq] = a1[k]; }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += 256) {
-            int qd = c >> 2, k = c & 3;
-            float t0 = 0.f, t1 = 0.f;
-            for (int l = 0; l < rpb; l++) { t0 += sm0[(l * 4 + k) * tpr + qd]; t1 += sm1[(l * 4 + k) * tpr + qd]; }
-            atomicAdd(q.o0 + c, (double)t0);
-            atomicAdd(q.o1 + c, (double)t1);
-        }
-    }
-}
-int dhead_backward_group(int pass, int nprob, const float* const* g9f, const PView* z3, const PView* dz3, int dt, const float* w4,
-                         const float* const* mean, const float* const* rstd, const float* gamma, const float* beta, double* const* s_dy,
-                         double* const* s_dyx, float* dgamma_acc, float* dbeta_acc, const long long* P, int c, int eval_mode, cudaStream_t st) {
-    AFI_REQUIRE(c % 4 == 0 && c / 4 <= 256 && 256 % (c / 4) == 0, "dhead_backward_group: C/4 must divide 256");
-    DenseGroupD G; memset(&G, 0, sizeof(G));
-    G.nprob = nprob; G.C = c;
-    for (int k = 0; k < nprob; k++) {
-        G.p[k].a = g9f[k]; G.p[k].b = z3[k].ptr; G.p[k].out = dz3[k].ptr; G.p[k].P = P[k]; G.p[k].mean = mean[k]; G.p[k].rstd = rstd[k];
-        G.p[k].o0 = s_dy[k]; G.p[k].o1 = s_dyx[k];
-    }
-    dense_group_blocks(G, pass == 1 ? 128 : 64, pass == 1 ? 1184 : 2368);
-    int grid = G.p[nprob].block_begin;
-    if (grid == 0) return AFI_OK;
-    if (pass == 1) {
-        if (dt == DT_F32) k_dhead_bwd_group<1, float><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
-        else k_dhead_bwd_group<1, bf16><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
-    } else {
-        if (dt == DT_F32) k_dhead_bwd_group<2, float><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
-        else k_dhead_bwd_group<2, bf16><<<grid, 256, 0, st>>>(G, w4, gamma, beta, dgamma_acc, dbeta_acc, 0.2f, eval_mode);
-    }
-    AFI_LAUNCH_CHECK();
-    return AFI_OK;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // The same two passes with the 9-tap product on the tensor cores (bf16 operand mode): dy[16 rows x 8 channels] = g9[16 x 16] * w4^T[16 x 8]

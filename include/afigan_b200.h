@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define AFI_ABI_VERSION 2   /* 2: afi_d_call.input_staged, afi_g_call.fuse_cur / fuse_w, afi_sgd_step_multi, afi_sizeof */
+#define AFI_ABI_VERSION 3   /* 2: afi_d_call.input_staged, afi_g_call.fuse_cur / fuse_w, afi_sgd_step_multi, afi_sizeof
+                             * 3: AFI_PREC_SPLIT, afi_conv1x1*, afi_conv3x3s2* (struct layouts unchanged since 2) */
 
 #define AFI_OK 0
 #define AFI_ERR_INVALID (-1)   /* bad argument / unsupported shape */

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/afigan_b200.h but not exported"
     assert set(native.EXPORTED_SYMBOLS) == set(names), set(native.EXPORTED_SYMBOLS) ^ set(names)
-    assert native.lib().afi_abi_version() == 2
+    assert native.lib().afi_abi_version() == 3
 
 
 def test_ctypes_structs_match_the_library():
@@ -36,6 +36,21 @@ def test_ctypes_structs_match_the_library():
     for which, cls in enumerate(mirrors):
         assert lib.afi_sizeof(which) == ctypes.sizeof(cls), (which, cls.__name__, lib.afi_sizeof(which), ctypes.sizeof(cls))
     assert lib.afi_sizeof(99) == 0
+
+
+def test_integration_snippet():
+    """the ctypes stub printed in INTEGRATION.md must be the struct layout the library was built with -- the block between the
+    binding-begin / binding-end markers is executed as is and its own check_binding() is run against the built library."""
+    from afigan import native
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"# --- binding-begin\n(.*?)# --- binding-end", doc, flags=re.S)
+    assert m, "INTEGRATION.md lost its binding block"
+    ns = {}
+    exec(m.group(1), ns)
+    ns["check_binding"](ctypes.CDLL(native.LIB_PATH))
+    for name in ("View4", "GParams", "Lateral", "GCall", "DParams", "DCall", "DGrads"):
+        assert ctypes.sizeof(ns[name]) == ctypes.sizeof(getattr(native, name)), name
+        assert [f[0] for f in ns[name]._fields_] == [f[0] for f in getattr(native, name)._fields_], name
 
 
 def test_size_queries_without_gpu():

@@ -150,8 +150,8 @@ def _grads_of(step):
 
 
 @pytest.mark.parametrize("env", [
-    {"AFIGAN_DHEAD_MMA": "0"},             # head backward: CUDA-core 9-tap product instead of warp-level tensor-core MMAs
-    {"AFIGAN_FUSE_BWD_STATS": "1"},        # BatchNorm-backward reductions out of the long-K dgrad epilogues
+    {"AFIGAN_PDL": "0"},                   # no programmatic dependent launch
+    {"AFIGAN_WGRAD_PAIR": "0"},            # weight gradients on single CTAs instead of CTA pairs
     {"AFIGAN_CONV_HALO": "0"},             # per-tap tcgen05 conv kernel everywhere
     {"AFIGAN_CONV_HALO": "2", "AFIGAN_PAIR_ALL": "1"},   # CTA-pair kernel on every 3x3 layer
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
