@@ -56,7 +56,8 @@ class Stage1Step:
         self._mom_restored = False
         # Gradient all-reduces off the critical path: D's runs while the generator's backward pass (which does not read D) computes, G's
         # while the G phase's discriminator forwards do; only the optimiser update waits for its collective.
-        self.overlap_comm = overlap_comm
+        import os as _os
+        self.overlap_comm = overlap_comm and _os.environ.get("AFIGAN_OVERLAP_COMM", "1") != "0"
         self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
         self.d_acc = _u8(self.lib.afi_d_gradacc_bytes(), dev)
         self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
