@@ -26,42 +26,26 @@ from .sync import FlatGradSync
 CH = 256
 
 
-class Stage1Step:
-    def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
-                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
-                 reuse_g_forward: Optional[bool] = None, overlap_comm: bool = True):
-        self.G, self.D = G, D
-        self.Dstack = D.Discriminators[0]
+class _StepBase:
+    """State and helpers shared by the fused stage-1 step and the grouped stage-2 loss block: the discriminator side (flat gradient buffer,
+    momentum, packed weights, per-call workspaces, grouped forward / backward over level x {real, fake} calls), the loss slots and the
+    multi-tensor SGD."""
+
+    def _init_common(self, dev, lr, momentum, weight_decay, weight_decay_norm, precision, process_group, overlap, overlap_comm):
+        import os
+        if dev.type != "cuda":
+            raise RuntimeError("the fused training steps need the modules on an sm_100a CUDA device (no CPU fallback)")
+        self.dev = dev
         self.lr, self.momentum, self.wd, self.wd_norm = lr, momentum, weight_decay, weight_decay_norm
-        self.precision = precision or G.precision or N.default_precision()
+        self.precision = precision
         self.prec = N.PRECISIONS[self.precision]
         self.pg = process_group
-        self.g_params: List[torch.nn.Parameter] = G._params()
-        self.d_params: List[torch.nn.Parameter] = self.Dstack._params()
-        dev = self.g_params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("Stage1Step needs the modules on an sm_100a CUDA device (no CPU fallback)")
-        self.dev = dev
-        self.n_rdb = G.n_residual_dense_blocks
         self.lib, self.ctx = N.lib(), N.context(dev)
-        # flat gradient buffers: param.grad are views, so one all-reduce per optimiser covers every parameter
-        self.g_sync = FlatGradSync(self.g_params, process_group, distributed)
-        self.d_sync = FlatGradSync(self.d_params, process_group, distributed)
-        self.g_flat, self.g_grads = self.g_sync.flat, self.g_sync.views
-        self.d_flat, self.d_grads = self.d_sync.flat, self.d_sync.views
-        self.distributed, self.world = self.g_sync.enabled, self.g_sync.world
-        self.g_mom = [torch.zeros_like(p) for p in self.g_params]
-        self.d_mom = [torch.zeros_like(p) for p in self.d_params]
         self.steps_done = 0
         self._mom_restored = False
         # Gradient all-reduces off the critical path: D's runs while the generator's backward pass (which does not read D) computes, G's
         # while the G phase's discriminator forwards do; only the optimiser update waits for its collective.
-        import os as _os
-        self.overlap_comm = overlap_comm and _os.environ.get("AFIGAN_OVERLAP_COMM", "1") != "0"
-        self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
-        self.d_acc = _u8(self.lib.afi_d_gradacc_bytes(), dev)
-        self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
-        self.d_packed = _u8(self.lib.afi_d_packed_bytes(self.prec), dev)
+        self.overlap_comm = overlap_comm and os.environ.get("AFIGAN_OVERLAP_COMM", "1") != "0"
         self._ws: Dict[tuple, torch.Tensor] = {}
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self._sgd_tabs: Dict[int, tuple] = {}
@@ -71,6 +55,46 @@ class Stage1Step:
         # apply / backward, reductions, head) overlap the other group's tensor-bound GEMMs -- the persistent GEMM CTAs leave enough
         # registers / shared memory per SM for the small elementwise CTAs to co-reside.
         self.overlap = overlap
+        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap else []
+        self.g_params: List[torch.nn.Parameter] = []
+        self.n_rdb = 0
+
+    def _init_d(self, D, distributed):
+        self.D = D
+        self.Dstack = D.Discriminators[0]
+        self.d_params: List[torch.nn.Parameter] = self.Dstack._params()
+        # flat gradient buffer: param.grad are views, so one all-reduce per optimiser covers every parameter
+        self.d_sync = FlatGradSync(self.d_params, self.pg, distributed)
+        self.d_flat, self.d_grads = self.d_sync.flat, self.d_sync.views
+        self.distributed, self.world = self.d_sync.enabled, self.d_sync.world
+        self.d_mom = [torch.zeros_like(p) for p in self.d_params]
+        self.d_acc = _u8(self.lib.afi_d_gradacc_bytes(), self.dev)
+        self.d_packed = _u8(self.lib.afi_d_packed_bytes(self.prec), self.dev)
+
+    def _d_update(self):
+        """D's optimiser step (one multi-tensor launch; BatchNorm affine parameters without weight decay) + re-layout of its GEMM operands."""
+        self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
+        self._pack_d()
+        self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
+
+
+class Stage1Step(_StepBase):
+    def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
+                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
+                 reuse_g_forward: Optional[bool] = None, overlap_comm: bool = True):
+        self.G = G
+        g_params = G._params()
+        self._init_common(g_params[0].device, lr, momentum, weight_decay, weight_decay_norm, precision or G.precision or N.default_precision(),
+                          process_group, overlap, overlap_comm)
+        dev = self.dev
+        self.g_params = g_params
+        self.n_rdb = G.n_residual_dense_blocks
+        self.g_sync = FlatGradSync(self.g_params, process_group, distributed)
+        self.g_flat, self.g_grads = self.g_sync.flat, self.g_sync.views
+        self._init_d(D, distributed)
+        self.g_mom = [torch.zeros_like(p) for p in self.g_params]
+        self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
+        self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
         # The reference evaluates G(lr) twice per step -- detached for the D phase (:341-346), with a graph for the G phase (:390-395) --
         # with the SAME generator weights (G's optimiser only steps at the end of the G phase) and the same input, and G has no
         # normalisation, dropout or other state: the two evaluations are bit-identical.  One forward (kept for the backward) serves both.
@@ -79,7 +103,6 @@ class Stage1Step:
             import os
             reuse_g_forward = os.environ.get("AFIGAN_REUSE_G_FORWARD", "1") != "0"
         self.reuse_g_forward = reuse_g_forward
-        self.streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap else []
         self._pack_key = None
         self._refresh_packed()
 
@@ -91,7 +114,8 @@ class Stage1Step:
         external optimiser, a broadcast): the in-library SGD updates do not bump torch's version counters and re-pack explicitly."""
         key = self._param_key()
         if key != self._pack_key:
-            self._pack_g()
+            if self.g_params:
+                self._pack_g()
             self._pack_d()
             self._pack_key = key
 
@@ -306,9 +330,7 @@ class Stage1Step:
 
         def d_update():
             if apply_updates:
-                self._sgd(self.d_params, self.d_grads, self.d_mom, [i % 4 >= 2 and i < 12 for i in range(14)])
-                self._pack_d()
-                self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
+                self._d_update()
 
         def g_backward_pass():
             # L1(tr, hr) and its gradient; backward through G (reads the activations the ONE forward pass kept; does not read D)
@@ -379,6 +401,11 @@ class Stage1Step:
             out[f"adv_loss_p{l + 2}"] = float(v[2, l])
             out[f"content_loss_p{l + 2}"] = float(v[3, l])
         return out
+
+
+# helpers that only touch the shared / discriminator-side state are available to every step class
+for _name in ("_param_key", "_refresh_packed", "_ws_for", "_buf", "_ds", "_pack_d", "_d_calls", "_sub", "_d_phase", "_sgd"):
+    setattr(_StepBase, _name, getattr(Stage1Step, _name))
 
 
 class FeaturePrefetcher:

@@ -577,7 +577,7 @@ def run_stage2_c3(args):
     G phase (L1 + 2 D forwards), one backward through the whole top-down path."""
     import torch
     from afigan import native
-    from afigan.engine import stage2_discriminator_losses, stage2_generator_losses
+    from afigan.engine import Stage2Step
     from afigan.modeling import bifpn_feature_fusion
     rank, world, local_rank, dev = _dist_setup()
     barrier, timed = _timing_tools(world, dev)
@@ -588,6 +588,7 @@ def run_stage2_c3(args):
     wts = [torch.tensor([0.7, 1.3], device=dev, requires_grad=True) for _ in range(28)]
     guide = [torch.randn(N, 256, 2 * h + 1, 2 * w, generator=gen).to(dev) for h, w in C3_D_SIZES]
     lib = native.lib()
+    s2 = Stage2Step(D, lr=1e-3, momentum=0.9, weight_decay=1e-4, precision=args.precision, distributed=False)     # grouped D / G loss block
 
     def one():
         outs = []
@@ -600,11 +601,10 @@ def run_stage2_c3(args):
                 if layer == 6:
                     outs.append(top)
         model = [o[:, :, :h, :w] for o, (h, w) in zip(outs[::-1], C3_D_SIZES[:4])] + [feats[4][:, :, :3, :5]]
-        d_losses = stage2_discriminator_losses(D, guide, model)
-        sum(d_losses.values()).backward()
-        g_losses = stage2_generator_losses(D, guide, model)
+        s2.d_phase(guide, model)                                  # D forward x2 + backward over the five levels (grouped), all-reduce, SGD
+        g_losses = s2.g_losses(guide, model)                      # adv (grouped D forwards, no gradient) + L1 with autograd
         sum(g_losses.values()).backward()
-        for t in feats + wts + list(G.parameters()) + list(D.parameters()):
+        for t in feats + wts + list(G.parameters()):
             t.grad = None
 
     for _ in range(max(args.warmup, 3)):

@@ -107,3 +107,62 @@ def test_c3_stage2_discriminator_shapes(precision):
     tol = 1e-5 if precision in ("fp32", "split") else 6e-3
     for a, b in zip(got, ref):
         assert abs(a - b) <= tol * abs(b) + 1e-5, (got, ref)
+
+
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+def test_stage2_grouped_step_matches_the_per_level_autograd_path(precision):
+    """`Stage2Step` (grouped launches over the five levels, D gradients in one flat buffer, SGD in the library) against the per-level
+    autograd composition of the same loss block (`stage2_discriminator_losses` / `stage2_generator_losses`, themselves checked against
+    the oracle above): D losses, D gradients, the parameters after one SGD step, the G-side losses and their gradient w.r.t. the model's
+    features, and the BatchNorm buffers (20 calls) -- reference stage2_trainer.py:298-384."""
+    from afigan.engine import Stage2Step, stage2_discriminator_losses, stage2_generator_losses
+    from afigan.modeling import Discriminator, Generator
+    gen = torch.Generator().manual_seed(41)
+    sizes = [(28, 44), (14, 22), (7, 11), (3, 5)]
+    guide = [torch.randn(2, 256, 2 * h + 1, 2 * w, generator=gen).cuda() for h, w in sizes]
+    model = [torch.randn(2, 256, h + (l == 0), w, generator=gen).cuda() for l, (h, w) in enumerate(sizes)]     # level 0 over-sized: cropped
+    outs = {}
+    for kind in ("grouped", "autograd"):
+        torch.manual_seed(0)
+        Generator(n_residual_dense_blocks=3)
+        D = Discriminator(precision=precision).cuda()
+        D.Discriminators[0].train()
+        feats = [m.clone().requires_grad_(True) for m in model]
+        if kind == "grouped":
+            step = Stage2Step(D, lr=1e-2, precision=precision)
+            d_row = step.d_phase(guide, feats)
+            d_loss = [float(v) for v in d_row[:4].cpu()]
+            d_grads = [p.grad.clone() for p in step.d_params]
+            g = step.g_losses(guide, feats)
+        else:
+            params = D.Discriminators[0]._params()
+            opt = torch.optim.SGD([{"params": [p for i, p in enumerate(params) if not (i % 4 >= 2 and i < 12)], "weight_decay": 1e-4},
+                                   {"params": [p for i, p in enumerate(params) if i % 4 >= 2 and i < 12], "weight_decay": 0.0}], lr=1e-2, momentum=0.9)
+            dl = stage2_discriminator_losses(D, guide, feats)
+            d_loss = [float(v.detach()) for v in dl.values()]
+            opt.zero_grad()
+            sum(dl.values()).backward()
+            d_grads = [p.grad.clone() for p in params]
+            opt.step()
+            g = stage2_generator_losses(D, guide, feats)
+        sum(g.values()).backward()
+        outs[kind] = dict(d_loss=d_loss, d_grads=d_grads, g=[float(v.detach()) for v in g.values()], fgrad=[f.grad.clone() for f in feats],
+                          params=[p.detach().clone() for p in D.Discriminators[0]._params()], sd={k: v.clone() for k, v in D.state_dict().items() if "running" in k or "num_batches" in k})
+    a, b = outs["grouped"], outs["autograd"]
+    tol = 1e-5 if precision == "split" else 2e-2
+    assert list(outs["grouped"]["g"]) and len(a["g"]) == 4
+    for x, y in zip(a["d_loss"], b["d_loss"]):
+        assert abs(x - y) <= tol * abs(y)
+    for x, y in zip(a["g"], b["g"]):
+        assert abs(x - y) <= tol * abs(y) + 1e-6
+    for i, (x, y) in enumerate(zip(a["d_grads"], b["d_grads"])):
+        if float(y.norm()) < 1e-6:
+            continue
+        assert rel(x, y) < (2e-3 if precision == "split" else 0.1), i
+    for x, y in zip(a["params"], b["params"]):
+        assert rel(x, y) < (1e-5 if precision == "split" else 2e-3)
+    for x, y in zip(a["fgrad"], b["fgrad"]):
+        assert rel(x, y) < 1e-6
+    for k in a["sd"]:
+        assert rel(a["sd"][k].float(), b["sd"][k].float()) < (1e-5 if precision == "split" else 2e-2), k
+    assert int(a["sd"]["Discriminators.0.0.0.norm.num_batches_tracked"]) == 16
