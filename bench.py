@@ -402,9 +402,11 @@ def run_ours(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")   # DRAM bytes of the dominant kernel's largest launch (ncu --set full)
         traffic_detail = None
-        if os.path.exists(tpath) and dom == 4 and precision == "bf16":
+        if os.path.exists(tpath) and dom == 4 and precision in ("bf16", "split"):
             traffic_detail = json.load(open(tpath))
-            traffic = traffic_detail["bytes_per_launch"]
+            if precision == "split":
+                traffic_detail = traffic_detail.get("split")
+            traffic = traffic_detail["bytes_per_launch"] if traffic_detail else None
         roof = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"], "frac_of_burst_peak": achieved / pk["bf16_burst"], "peak_source": pk["source"] +
                 " sustained bf16 (kernel timed inside a long step)", "traffic": traffic, "traffic_detail": traffic_detail, "launches_per_step": cnt,
