@@ -25,6 +25,9 @@ class FlatGradSync:
             off += p.numel()
         self.pg = process_group
         active = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        import os
+        if os.environ.get("AFIGAN_NO_GRAD_SYNC") == "1":      # measurement aid: independent replicas (isolates rank skew from collective cost)
+            active = False
         self.enabled = active if enabled is None else enabled
         self.world = dist.get_world_size(process_group) if self.enabled else 1
         self._work = None
