@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libafigan_b200.so")
+LIB_PATH = os.environ.get("AFIGAN_LIB_PATH") or os.path.join(_HERE, "libafigan_b200.so")      # (override: A/B runs of kernel build variants)
 
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_SPLIT = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT, "split": PREC_SPLIT}

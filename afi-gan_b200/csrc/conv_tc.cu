@@ -663,7 +663,16 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 // with compile-time operand offsets and touch no dynamically indexed kernel parameter (a dependent LDC per tap cost ~300 cycles per
 // tap in the first version, measured with per-thread stall counters).
 // ---------------------------------------------------------------------------------------------------
-constexpr int HALO_SA = 3, HALO_SB_MAX = 8;
+// Ring depths (build-time overridable for A/B runs: AFI_EXTRA_NVCC_FLAGS="-DAFI_HALO_SA=4 -DAFI_HALO_SB_MAX=7").  Measured on the discriminator
+// shapes, kernel alone (tools/ab_conv.py): two halo slots cost 11 % (1700 -> 1515 TFLOP/s on 1024->1024: one chunk of look-ahead does not cover
+// the latency of the 180-row halo box), four or five are within noise of three, and 8 -> 11 weight slots change nothing.
+#ifndef AFI_HALO_SA
+#define AFI_HALO_SA 3
+#endif
+#ifndef AFI_HALO_SB_MAX
+#define AFI_HALO_SB_MAX 8
+#endif
+constexpr int HALO_SA = AFI_HALO_SA, HALO_SB_MAX = AFI_HALO_SB_MAX;
 constexpr int HALO_TH = 16, HALO_TW = 8;
 constexpr int HALO_BYTES = (HALO_TH + 2) * (HALO_TW + 2) * 128;           // 23040
 constexpr int HALO_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;              // 23552
