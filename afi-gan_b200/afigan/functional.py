@@ -448,5 +448,39 @@ def conv3x3s2_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     return Conv3x3S2Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])
 
 
+def sepconv_eval(x: torch.Tensor, dw_weight: torch.Tensor, pw_weight: torch.Tensor, pw_bias: Optional[torch.Tensor], pre_swish: bool,
+                 precision: Optional[str] = None) -> torch.Tensor:
+    """Forward-only depthwise-separable conv of the BiFPN neck in ONE library call (reference bifpn_layers/wrappers.py:166-206): the swish in
+    front of it, the depthwise 3x3 and the layout conversion are one HBM-bound pass, the pointwise conv (norm already folded into
+    pw_weight / pw_bias by the caller) runs on the tcgen05 engine."""
+    if not x.is_cuda:
+        raise RuntimeError("sepconv: input must live on an sm_100a CUDA device (no CPU fallback)")
+    prec = N.PRECISIONS[precision or N.default_precision()]
+    x = x.float()
+    n, c, h, w = x.shape
+    cout = pw_weight.shape[0]
+    lib, actx = N.lib(), N.context(x.device)
+    ws = _u8(lib.afi_sepconv_workspace_bytes(prec, n, c, h, w, cout), x.device)
+    y = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+    N.check(lib.afi_sepconv(actx, prec, N.view4(x), n, c, h, w, dw_weight.data_ptr(), pw_weight.data_ptr(), N.ptr(pw_bias), cout, int(pre_swish),
+                            y.data_ptr(), ws.data_ptr(), ws.numel(), N.stream_ptr()))
+    return y
+
+
+def bifpn_fuse_down(a: torch.Tensor, b: Optional[torch.Tensor], down: torch.Tensor, weight: Optional[torch.Tensor]) -> torch.Tensor:
+    """Forward-only bottom-up fusion site of the BiFPN neck (reference bifpn_sr.py:550-564): w[0]*a + w[1]*b + w[2]*pool(down) (or the two-term
+    form when b is None), pool = the zero-padded 3x3 / stride-2 max-pool of the reference's MaxPool2d wrapper -- one elementwise pass."""
+    if not a.is_cuda:
+        raise RuntimeError("bifpn_fuse_down: tensors must live on an sm_100a CUDA device (no CPU fallback)")
+    a, down = a.float(), down.float()
+    n, c, h, w = a.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=a.device)
+    bv = N.view4(b.float()) if b is not None else N.View4()
+    wt = weight.detach().float().contiguous() if weight is not None else None
+    N.check(N.lib().afi_bifpn_fuse_down(N.view4(a), bv, N.view4(down), N.ptr(wt), n, c, h, w, down.size(2), down.size(3), out.data_ptr(),
+                                        N.stream_ptr()))
+    return out
+
+
 def conv3x3_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
     return Conv3x3Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])

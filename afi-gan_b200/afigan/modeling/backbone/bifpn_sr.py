@@ -8,7 +8,10 @@ skip inputs from the ORIGINAL laterals (`lateral_features`, bifpn_sr.py:596-598,
 
 What runs where: the 28 fusion sites `w0 * cur + w1 * AFI(top)` go through the library (`bifpn_feature_fusion`: one call per site without
 autograd, the interpolator's autograd Function with it); every 1x1 conv (input laterals, skips, the pointwise half of the 56 separable
-convs) runs on the tcgen05 GEMM engine (`bifpn_layers.Conv2d`); depthwise 3x3, BatchNorm, swish and max-pool are HBM-bound torch ops.
+convs) runs on the tcgen05 GEMM engine (`bifpn_layers.Conv2d`).  At inference (no autograd, eval-mode norms) the rest of a layer is native
+too: `conv(swish(x))` is ONE library call per separable conv (swish + depthwise 3x3 + layout conversion in one HBM-bound pass, pointwise conv
+with the BatchNorm folded into its weights on the tensor cores) and the bottom-up fusion sites (weighted sum + zero-padded max-pool) are one
+elementwise pass each.  With autograd the depthwise 3x3, BatchNorm, swish and max-pool are torch ops.
 """
 from __future__ import annotations
 
@@ -143,6 +146,13 @@ class BiFPN_AFIGAN(Backbone):
         return bifpn_feature_fusion(self.srf_module, cur_feature, top_feature, w)
 
     def _feature_funsion2(self, layer_idx, skip_feature, cur_feature, bottom_feature, indice=-1):
+        if not torch.is_grad_enabled() and cur_feature.is_cuda and bottom_feature.size(2) >= 2 and bottom_feature.size(3) >= 2:
+            # inference: weighted sum + zero-padded 3x3 / stride-2 max-pool of the level below in ONE library pass
+            from ...functional import bifpn_fuse_down
+            w = getattr(self, f"BiFPNLayer_{layer_idx}_p{indice}_w2") if (self.attention and indice > 0) else None
+            if isinstance(skip_feature, torch.Tensor):
+                return bifpn_fuse_down(skip_feature, cur_feature, bottom_feature, w)
+            return bifpn_fuse_down(cur_feature, None, bottom_feature, w)
         down = self._downsample(bottom_feature)
         inputs = [skip_feature, cur_feature, down] if isinstance(skip_feature, torch.Tensor) else [cur_feature, down]
         if self.attention and indice > 0:
@@ -154,15 +164,16 @@ class BiFPN_AFIGAN(Backbone):
     def _layer(self, l, laterals, down_skips):
         conv = lambda name: getattr(self, f"BiFPNLayer_{l}_{name}")          # noqa: E731
         p3_in, p4_in, p5_in, p6_in, p7_in = laterals
-        p6_up = conv("conv6_up")(self._swish(self._feature_funsion(l, p6_in, p7_in, 6)))
-        p5_up = conv("conv5_up")(self._swish(self._feature_funsion(l, p5_in, p6_up, 5)))
-        p4_up = conv("conv4_up")(self._swish(self._feature_funsion(l, p4_in, p5_up, 4)))
-        p3_up = conv("conv3_up")(self._swish(self._feature_funsion(l, p3_in, p4_up, 3)))
+        # conv(swish(fused)): the swish is handed to the separable conv (fused into its depthwise pass on the native inference path)
+        p6_up = conv("conv6_up")(self._feature_funsion(l, p6_in, p7_in, 6), pre_swish=True)
+        p5_up = conv("conv5_up")(self._feature_funsion(l, p5_in, p6_up, 5), pre_swish=True)
+        p4_up = conv("conv4_up")(self._feature_funsion(l, p4_in, p5_up, 4), pre_swish=True)
+        p3_up = conv("conv3_up")(self._feature_funsion(l, p3_in, p4_up, 3), pre_swish=True)
         s4, s5, s6, s7 = down_skips
-        p4_out = conv("conv4_down")(self._swish(self._feature_funsion2(l, s4, p4_up, p3_up, 4)))
-        p5_out = conv("conv5_down")(self._swish(self._feature_funsion2(l, s5, p5_up, p4_out, 5)))
-        p6_out = conv("conv6_down")(self._swish(self._feature_funsion2(l, s6, p6_up, p5_out, 6)))
-        p7_out = conv("conv7_down")(self._swish(self._feature_funsion2(l, None, s7, p6_out, 7)))
+        p4_out = conv("conv4_down")(self._feature_funsion2(l, s4, p4_up, p3_up, 4), pre_swish=True)
+        p5_out = conv("conv5_down")(self._feature_funsion2(l, s5, p5_up, p4_out, 5), pre_swish=True)
+        p6_out = conv("conv6_down")(self._feature_funsion2(l, s6, p6_up, p5_out, 6), pre_swish=True)
+        p7_out = conv("conv7_down")(self._feature_funsion2(l, None, s7, p6_out, 7), pre_swish=True)
         return p3_up, p4_out, p5_out, p6_out, p7_out
 
     def forward(self, x):

@@ -5,7 +5,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..._compat import get_norm
-from ...functional import conv1x1_autograd
+from ...functional import conv1x1_autograd, sepconv_eval
 
 
 def _pair(v):
@@ -70,7 +70,38 @@ class SeparableConv2d(nn.Module):
             self.norm.eps, self.norm.momentum = eps, momentum
         self.activation = activation
 
-    def forward(self, x):
+    def _folded(self):
+        """Pointwise weight / bias with the eval-mode norm folded in: y = s * (W d + b - mean) + beta, s = gamma / sqrt(var + eps).  Cached on the
+        parameter / buffer versions (weights are static at inference)."""
+        n = self.norm
+        ts = [self.pointwise.weight] + ([self.pointwise.bias] if self.pointwise.bias is not None else []) + \
+             ([n.weight, n.bias, n.running_mean, n.running_var] if n is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if getattr(self, "_fold_key", None) != key:
+            with torch.no_grad():
+                w = self.pointwise.weight.float()
+                b = self.pointwise.bias.float() if self.pointwise.bias is not None else torch.zeros(w.shape[0], device=w.device)
+                if n is not None:
+                    s = n.weight.float() * torch.rsqrt(n.running_var.float() + n.eps)
+                    w, b = w * s.view(-1, 1, 1, 1), s * (b - n.running_mean.float()) + n.bias.float()
+                self._fold_w, self._fold_b, self._fold_key = w.contiguous(), b.contiguous(), key
+        return self._fold_w, self._fold_b
+
+    def _native_eval(self, x):
+        """Inference on CUDA with a BatchNorm-family norm in eval mode (or none): the whole block is one library call."""
+        n = self.norm
+        ok_norm = n is None or (isinstance(n, torch.nn.modules.batchnorm._BatchNorm) and not n.training and n.track_running_stats and n.affine)
+        return (not torch.is_grad_enabled() and x.is_cuda and ok_norm and self.activation is None and self.kernel_size == (3, 3)
+                and self.stride == (1, 1) and self.dilation == (1, 1) and self.padding_mode == "static_same" and x.dim() == 4
+                and self.in_channels % 32 == 0 and self.out_channels % 32 == 0 and x.size(0) * x.size(2) <= 65535)
+
+    def forward(self, x, pre_swish: bool = False):
+        """pre_swish: apply x * sigmoid(x) in front (the neck's `conv(self._swish(fused))`), fused into the depthwise pass on the native path."""
+        if self._native_eval(x):
+            w, b = self._folded()
+            return sepconv_eval(x, self.depthwise.weight, w, b, pre_swish, self.pointwise.precision)
+        if pre_swish:
+            x = x * torch.sigmoid(x)
         x = self.pointwise(self.depthwise(x))
         if self.norm is not None:
             x = self.norm(x)

@@ -1220,6 +1220,44 @@ int afi_conv3x3s2_backward(afi_ctx* ctx, int prec, afi_view4 x, afi_view4 dy, in
     return AFI_OK;
 }
 
+// ---- BiFPN neck at inference: depthwise-separable conv and bottom-up fusion site -----------------------------------------------------------
+size_t afi_sepconv_workspace_bytes(int prec, int n, int c, int h, int w, int cout) { return conv_single_ws_bytes(prec, 1, n, c, h, w, cout); }
+int afi_sepconv(afi_ctx* ctx, int prec, afi_view4 x, int n, int c, int h, int w, const float* dw_w, const float* pw_w, const float* pw_b, int cout,
+                int pre_swish, float* y, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    AFI_REQUIRE(ctx && x.ptr && dw_w && pw_w && y && ws && prec_ok(prec), "afi_sepconv: bad argument");
+    AFI_REQUIRE(c % 32 == 0 && cout % 32 == 0 && n >= 1 && h >= 1 && w >= 1, "afi_sepconv: channels must be multiples of 32");
+    if (ws_bytes < conv_single_ws_bytes(prec, 1, n, c, h, w, cout)) { set_error("afi_sepconv: workspace too small"); return AFI_ERR_WORKSPACE; }
+    const int dt = prec_dt(prec); const size_t es = dt_size(dt), wes = prec_wes(prec), P = (size_t)n * h * w;
+    Carver cv(ws);
+    void* X = cv.take(P * pad64(c) * es); void* Y = cv.take(P * pad64(cout) * es); cv.take(P * pad64(cout) * es);
+    void* Wp = cv.take((size_t)c * cout * wes); cv.take((size_t)c * cout * wes);
+    cv.take((size_t)c * cout * 4); cv.take(P * c * 4);
+    g_ss.k0 = 0; g_ss.n[0] = split_planes_bytes((long long)P, c) + split_planes_bytes((long long)P, cout); g_ss.p[0] = cv.take(g_ss.n[0]);
+    g_ss.pairs = split_pairs_env(3);                       // forward-only
+    // depthwise 3x3 (+ swish in front) straight into the pointwise GEMM's operand layout
+    if (dt == DT_F32) AFI_TRY(dw3x3_to_nhwc<float>(x, dw_w, n, c, h, w, pre_swish, pview(X, h, w, c), st));
+    else AFI_TRY(dw3x3_to_nhwc<bf16>(x, dw_w, n, c, h, w, pre_swish, pview(X, h, w, c), st));
+    AFI_TRY(pack_weights(pw_w, cout, c, pm(prec, 4), Wp, prec_wdt(prec), st));
+    ConvArgs a;
+    Dim3 d = {n, h, w};
+    conv_std(a, 1, &d, c, cout, Wp);
+    single_taps(a, 1);
+    a.bias = pw_b; a.out_dt = dt;
+    a.p[0].in[0] = pview(X, h, w, c); a.p[0].out = pview(Y, h, w, cout);
+    AFI_TRY(run_conv(ctx, prec, a, st));
+    afi_view4 none; memset(&none, 0, sizeof(none));
+    AFI_TRY(to_nchw(prec, pview(Y, h, w, cout), pview_null(), none, 0, 0, 1.f, n, cout, h, w, y, st));
+    return AFI_OK;
+}
+int afi_bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 down, const float* weights, int n, int c, int h, int w, int dh, int dw, float* out,
+                        void* stream) {
+    AFI_REQUIRE(a.ptr && down.ptr && out && n >= 1 && c >= 1 && h >= 1 && w >= 1, "afi_bifpn_fuse_down: bad argument");
+    AFI_REQUIRE(dh >= 2 && dw >= 2 && (dh - 2) / 2 + 1 == h && (dw - 2) / 2 + 1 == w,
+                "afi_bifpn_fuse_down: a %dx%d map is not the zero-padded 3x3 / stride-2 max-pool of a %dx%d one", h, w, dh, dw);
+    return bifpn_fuse_down(a, b, down, weights, b.ptr ? 3 : 2, n, c, h, w, dh, dw, out, (cudaStream_t)stream);
+}
+
 size_t afi_conv3x3_workspace_bytes(int prec, int n, int cin, int h, int w, int cout) { return conv_single_ws_bytes(prec, 3, n, cin, h, w, cout); }
 int afi_conv3x3(afi_ctx* ctx, int prec, afi_view4 x, int n, int cin, int h, int w, const float* weight, const float* bias, int cout,
                 int lrelu, float* y, void* ws, size_t ws_bytes, void* stream) {

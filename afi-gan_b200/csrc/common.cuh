@@ -175,6 +175,10 @@ int tc_init(afi_ctx* ctx);
 
 // ---- elementwise / layout kernels (elementwise.cu) ------------------------------------------------------
 template <typename T> int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st);
+// BiFPN inference building blocks (elementwise.cu): depthwise 3x3 (+ swish in front) fused with the NCHW -> NHWC conversion; bottom-up fusion site
+template <typename T> int dw3x3_to_nhwc(afi_view4 src, const float* wdw, int n, int c, int h, int w, int pre_swish, PView dst, cudaStream_t st);
+int bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 dn, const float* wts, int nw, int n, int c, int h, int w, int dh, int dw_, float* out,
+                    cudaStream_t st);
 // dst[n,c,y,x] (contiguous [n,c,oh,ow]) = scale * ( a[n,y,x,c] (T) [+ lat[n,y,x,c] (T)] [+ bilinear2x(skip)[n,c,y,x]] )
 // ... optionally followed by dst = fw[0] * add[n,c,y,x] + fw[1] * dst (fw: two device floats; the BiFPN fusion site)
 template <typename T> int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale,

@@ -117,6 +117,98 @@ template int nchw_to_nhwc<float>(afi_view4, int, int, int, int, PView, cudaStrea
 template int nchw_to_nhwc<bf16>(afi_view4, int, int, int, int, PView, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
+// BiFPN neck at inference (reference bifpn_sr.py:583-729, bifpn_layers/wrappers.py:166-252): the HBM-bound halves of its two building blocks.
+//   k_dw3x3_to_nhwc : dst[n,y,x,c] (NHWC T) = sum_{3x3} w[c][ky][kx] * act(src[n,c,y+ky-1,x+kx-1]), act = swish when pre_swish (zero padding =
+//                     'static_same' for k3 s1).  The depthwise half of a SeparableConv2d fused with the swish in front of it and with the
+//                     layout conversion the pointwise GEMM needs anyway: one pass instead of three.
+//   k_bifpn_fuse_down : out = w0 * a + w1 * b [+ w2 * maxpool3x3s2(c)], the bottom-up fusion site; the max-pool ZERO-pads right / bottom and the
+//                     padding takes part in the max ('static_same' of the reference's MaxPool2d wrapper).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_dw3x3_to_nhwc(afi_view4 src, const float* __restrict__ wdw, int c, int h, int w, int pre_swish, PView dst) {
+    __shared__ float tile[32][33];
+    const int x0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int n = blockIdx.z / h, y = blockIdx.z % h;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int cc = c0 + ty + 8 * i, xx = x0 + tx;
+        float acc = 0.f;
+        if (cc < c && xx < w) {
+            const float* sp = src.ptr + n * src.sn + cc * src.sc;
+            const float* wk = wdw + cc * 9;
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const int yy = y + ky - 1;
+                if (yy < 0 || yy >= h) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const int xs = xx + kx - 1;
+                    if (xs < 0 || xs >= w) continue;
+                    float v = sp[yy * src.sh + xs * src.sw];
+                    if (pre_swish) v = v / (1.f + __expf(-v));
+                    acc += __ldg(wk + ky * 3 + kx) * v;
+                }
+            }
+        }
+        tile[ty + 8 * i][tx] = acc;
+    }
+    __syncthreads();
+    T* d = reinterpret_cast<T*>(dst.ptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int xx = x0 + ty + 8 * i, cc = c0 + tx;
+        if (cc < c && xx < w) d[n * dst.sn + y * dst.sy + xx * dst.sx + cc] = (T)tile[tx][ty + 8 * i];
+    }
+}
+template <typename T>
+int dw3x3_to_nhwc(afi_view4 src, const float* wdw, int n, int c, int h, int w, int pre_swish, PView dst, cudaStream_t st) {
+    AFI_REQUIRE((long long)n * h <= 65535, "dw3x3_to_nhwc: n * h = %lld exceeds the grid limit", (long long)n * h);
+    dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
+    k_dw3x3_to_nhwc<T><<<grid, block, 0, st>>>(src, wdw, c, h, w, pre_swish, dst);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+template int dw3x3_to_nhwc<float>(afi_view4, const float*, int, int, int, int, int, PView, cudaStream_t);
+template int dw3x3_to_nhwc<bf16>(afi_view4, const float*, int, int, int, int, int, PView, cudaStream_t);
+
+__global__ void __launch_bounds__(256) k_bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 dn, const float* __restrict__ wts, int nw, int c, int h, int w,
+                                                         int dh, int dw_, float* __restrict__ out, long long total) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % w), y = (int)((i / w) % h), cc = (int)((i / ((long long)w * h)) % c), n = (int)(i / ((long long)w * h * c));
+    // max over the 3x3 window at stride 2 of `dn` padded with ZEROS on the right / bottom (F.pad(x, (0, 1, 0, 1)) then max_pool2d(3, 2))
+    const float* dp = dn.ptr + n * dn.sn + cc * dn.sc;
+    float m = -3.402823466e38f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            const int yy = 2 * y + ky, xx = 2 * x + kx;
+            const float v = (yy < dh && xx < dw_) ? dp[yy * dn.sh + xx * dn.sw] : 0.f;
+            m = fmaxf(m, v);
+        }
+    float r;
+    const float va = a.ptr[n * a.sn + cc * a.sc + y * a.sh + x * a.sw];
+    if (b.ptr) {
+        const float vb = b.ptr[n * b.sn + cc * b.sc + y * b.sh + x * b.sw];
+        r = wts ? wts[0] * va + wts[1] * vb + wts[2] * m : va + vb + m;
+    } else {
+        r = wts ? wts[0] * va + wts[1] * m : va + m;
+    }
+    (void)nw;
+    out[i] = r;
+}
+int bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 dn, const float* wts, int nw, int n, int c, int h, int w, int dh, int dw_, float* out,
+                    cudaStream_t st) {
+    const long long total = (long long)n * c * h * w;
+    if (total == 0) return AFI_OK;
+    k_bifpn_fuse_down<<<cdiv(total, 256), 256, 0, st>>>(a, b, dn, wts, nw, c, h, w, dh, dw_, out, total);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // NHWC T -> contiguous NCHW fp32, fused with the bilinear x2 skip (generator_rdb.py:125,130), the lateral
 // add and the merge scale (fpn_sr.py:154-157), and the top-left crop (stage1_trainer.py:437-443).
 // ---------------------------------------------------------------------------------------------------

@@ -223,6 +223,19 @@ int afi_conv3x3s2_backward(afi_ctx*, int prec, afi_view4 x, afi_view4 dy, int n,
                            int cout, float* dw, float* db, float* dxo, void* ws, size_t ws_bytes, void* stream);
 size_t afi_conv3x3s2_workspace_bytes(int prec, int n, int cin, int h, int w_, int cout);
 
+/* ---- BiFPN neck at inference (bifpn_sr.py:583-729) ------------------------------------------------------------------------------ */
+/* SeparableConv2d of bifpn_layers/wrappers.py:166-206 with its (eval-mode) norm folded into pw_w / pw_b by the caller, fused with the swish the
+ * neck applies in front of it: y = conv1x1(dw3x3(pre_swish ? swish(x) : x; dw_w); pw_w, pw_b).  x [n,c,h,w] view, dw_w [c,1,3,3],
+ * pw_w [cout,c,1,1], pw_b [cout] or NULL, y contiguous [n,cout,h,w].  Forward only. */
+int afi_sepconv(afi_ctx*, int prec, afi_view4 x, int n, int c, int h, int w_, const float* dw_w, const float* pw_w, const float* pw_b, int cout,
+                int pre_swish, float* y, void* ws, size_t ws_bytes, void* stream);
+size_t afi_sepconv_workspace_bytes(int prec, int n, int c, int h, int w_, int cout);
+/* Bottom-up fusion site `_feature_funsion2` (bifpn_sr.py:550-564): out [n,c,h,w] = w[0]*a + w[1]*b + w[2]*pool(down), or w[0]*a + w[1]*pool(down)
+ * when b.ptr == NULL; weights = device floats (the raw `BiFPNLayer_*_w2` parameter) or NULL for a plain sum; pool = the reference's 'static_same'
+ * MaxPool2d(3, 2): zero padding on the right / bottom that takes part in the max; down is [n,c,dh,dw]. */
+int afi_bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 down, const float* weights, int n, int c, int h, int w_, int dh, int dw, float* out,
+                        void* stream);
+
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
  * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05 per-tap
  * kernel, 1 wgrad tcgen05, 2 conv CUDA-core, 3 wgrad CUDA-core, 4 conv tcgen05 halo tiles on CTA pairs, 5 conv tcgen05 halo tiles on

@@ -131,3 +131,43 @@ def test_conv3x3_stride2_vs_torch(shape, precision):
     for name, a, r in (("y", y.detach(), y2.detach()), ("dx", x.grad, x2.grad), ("dw", wt.grad, w2.grad), ("db", b.grad, b2.grad)):
         e = float((a.double() - r).norm() / r.norm())
         assert e < tol, (name, e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["split", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 256, 16, 16), (2, 256, 7, 11), (1, 256, 1, 1), (1, 64, 5, 40)], ids=lambda s: "x".join(map(str, s)))
+def test_native_sepconv_and_fuse_down_vs_torch(shape, precision):
+    """The inference-only building blocks of the BiFPN neck against their torch composition (the reference's arithmetic): swish -> depthwise
+    3x3 ('static_same') -> pointwise 1x1 -> eval BatchNorm as ONE library call, and the bottom-up fusion site with the zero-padded max-pool."""
+    import torch.nn.functional as F
+    from afigan.functional import bifpn_fuse_down
+    from afigan.modeling.bifpn_layers import MaxPool2d, SeparableConv2d
+    n, c, h, w = shape
+    torch.manual_seed(11)
+    m = SeparableConv2d(c, c, 3, padding_mode="static_same", norm="BN", momentum=0.01, eps=1e-3, precision=precision).cuda().eval()
+    with torch.no_grad():
+        m.norm.running_mean.normal_(0, 0.2); m.norm.running_var.uniform_(0.5, 1.5); m.norm.weight.normal_(1, 0.2); m.norm.bias.normal_(0, 0.1)
+    x = torch.randn(n, c, h, w, device="cuda")
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            got = m(x, pre_swish=True)                                   # native path (no autograd, eval norm)
+            xs = (x * torch.sigmoid(x)).double()
+            ref = F.conv2d(F.pad(xs, (1, 1, 1, 1)), m.depthwise.weight.double(), None, 1, 0, 1, c)
+            ref = F.conv2d(ref, m.pointwise.weight.double(), m.pointwise.bias.double())
+            ref = F.batch_norm(ref, m.norm.running_mean.double(), m.norm.running_var.double(), m.norm.weight.double(), m.norm.bias.double(), False, 0.0, m.norm.eps)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    e = float((got.double() - ref).norm() / ref.norm())
+    assert e < (2e-5 if precision == "split" else 1e-2), e
+    if h >= 1 and w >= 1:
+        a, b = torch.randn(n, c, h, w, device="cuda"), torch.randn(n, c, h, w, device="cuda")
+        for dh, dw in ((2 * h, 2 * w), (2 * h + 1, 2 * w + 1)):        # even and odd source sizes give the same h x w output
+            dn = torch.randn(n, c, dh, dw, device="cuda") - 1.5          # mostly negative: the ZERO padding wins the max at the border
+            pool = MaxPool2d(3, 2)(dn)
+            assert pool.shape[2:] == (h, w)
+            w3, w2 = torch.tensor([0.4, 0.7, 0.9], device="cuda"), torch.tensor([0.6, 0.8], device="cuda")
+            assert torch.allclose(bifpn_fuse_down(a, b, dn, w3), w3[0] * a + w3[1] * b + w3[2] * pool, atol=1e-6)
+            assert torch.allclose(bifpn_fuse_down(a, None, dn, w2), w2[0] * a + w2[1] * pool, atol=1e-6)
+            assert torch.allclose(bifpn_fuse_down(a, b, dn, None), a + b + pool, atol=1e-6)
