@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc_bf16x2(afi_view4 src, int 
 }
 template <typename T>
 int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st) {
+    AFI_REQUIRE((long long)n * h <= 65535, "layout conversion: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * h);
     if (dt_of<T>::v == DT_BF16 && c % 2 == 0 && dst.sx % 2 == 0 && dst.sy % 2 == 0 && dst.sn % 2 == 0 && ((uintptr_t)dst.ptr & 3) == 0) {
         dim3 grid(cdiv(w, 32), cdiv(c, 64), n * h), block(32, 8);
         k_nchw_to_nhwc_bf16x2<<<grid, block, 0, st>>>(src, c, h, w, dst);
@@ -265,6 +266,7 @@ __global__ void k_nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int sh, int s
 template <typename T>
 int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale, int n, int c, int oh, int ow,
                  float* dst, cudaStream_t st, const afi_view4* add, const float* fw) {
+    AFI_REQUIRE((long long)n * oh <= 65535, "layout conversion: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * oh);
     dim3 grid(cdiv(ow, 32), cdiv(c, 32), n * oh), block(32, 8);
     afi_view4 addv; memset(&addv, 0, sizeof(addv));
     if (add && fw) addv = *add; else fw = nullptr;
@@ -322,6 +324,7 @@ __global__ void k_g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int c, i
     }
 }
 int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, int w, int oh, int ow, float* dst, cudaStream_t st) {
+    AFI_REQUIRE((long long)n * h <= 65535, "g_input_grad: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * h);
     dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
     k_g_input_grad<<<grid, block, 0, st>>>(dxb, dy, dy_scale, c, h, w, oh, ow, dst);
     AFI_LAUNCH_CHECK();
