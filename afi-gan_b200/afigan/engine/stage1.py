@@ -121,15 +121,27 @@ class Stage1Step(_StepBase):
 
     def load_optimizer_state(self, g_momentum: Sequence[torch.Tensor], d_momentum: Sequence[torch.Tensor], steps_done: int):
         """Resume: restored SGD momentum buffers (state-dict order) and the iteration count (detectron2 checkpoints carry both)."""
-        for dst, src in zip(self.g_mom, g_momentum):
+        for dst, src in zip(getattr(self, "g_mom", []), g_momentum):
             dst.copy_(src)
         for dst, src in zip(self.d_mom, d_momentum):
             dst.copy_(src)
         self.steps_done = int(steps_done)
         self._mom_restored = True
         if self.distributed:
-            self.g_sync.broadcast_parameters(self.g_mom)
+            if hasattr(self, "g_sync"):
+                self.g_sync.broadcast_parameters(self.g_mom)
             self.d_sync.broadcast_parameters(self.d_mom)
+
+    def optimizer_state_dict(self) -> Dict[str, object]:
+        """What a trainer checkpoints next to the two model files (detectron2 saves `optimizer` / `iteration` alongside `model`): the SGD
+        momentum buffers in state-dict order and the number of completed steps.  `AFCheckpointer(G, ..., optimizer=step)` stores it."""
+        return {"g_momentum": [m.detach().clone() for m in getattr(self, "g_mom", [])], "d_momentum": [m.detach().clone() for m in self.d_mom],
+                "steps_done": self.steps_done, "lr": self.lr, "momentum": self.momentum, "weight_decay": self.wd, "weight_decay_norm": self.wd_norm}
+
+    state_dict = optimizer_state_dict            # so that AFCheckpointer treats the step object as a checkpointable
+
+    def load_state_dict(self, state: Dict[str, object]) -> None:
+        self.load_optimizer_state(state.get("g_momentum", []), state["d_momentum"], int(state["steps_done"]))
 
     # ---- helpers --------------------------------------------------------------------------------------
     def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool, tag="") -> torch.Tensor:
@@ -404,7 +416,8 @@ class Stage1Step(_StepBase):
 
 
 # helpers that only touch the shared / discriminator-side state are available to every step class
-for _name in ("_param_key", "_refresh_packed", "_ws_for", "_buf", "_ds", "_pack_d", "_d_calls", "_sub", "_d_phase", "_sgd"):
+for _name in ("_param_key", "_refresh_packed", "_ws_for", "_buf", "_ds", "_pack_d", "_d_calls", "_sub", "_d_phase", "_sgd", "optimizer_state_dict",
+              "state_dict", "load_state_dict", "load_optimizer_state"):
     setattr(_StepBase, _name, getattr(Stage1Step, _name))
 
 

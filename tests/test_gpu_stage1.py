@@ -195,3 +195,42 @@ def test_single_and_double_generator_forward_are_identical():
         assert rel(a, b) < 1e-5 or float(b.norm()) < 1e-6
     for k in out[0][2]:
         assert rel(out[0][2][k].float(), out[1][2][k].float()) < 1e-6, k
+
+
+def test_resume_from_checkpoint_files_continues_the_trajectory(tmp_path):
+    """Three steps in one go vs two steps, checkpoint to files (model files + SGD momentum / iteration through AFCheckpointer), a fresh process
+    state (new modules, new Stage1Step), resume, one more step: same parameters, same BatchNorm buffers (reference stage1_trainer.py:129-174:
+    two DetectionCheckpointers G_0 / D_0 with `resume_or_load`).  Split mode; the weight-gradient reductions are fp32 atomics, hence 1e-4."""
+    from afigan.engine import AFCheckpointer
+    lr_shapes, hr_shapes = ((13, 21), (7, 11)), ((25, 42), (13, 21))
+    batches = [O.synthetic_features(2, it, lr_shapes, hr_shapes, seed=55) for it in range(3)]
+    to_dev = lambda b: ([t.cuda() for t in b[0]], [t.cuda() for t in b[1]])      # noqa: E731
+    G, D, step = _build("split")
+    step.lr = 1e-2
+    for b in batches:
+        step.run_step(*to_dev(b))
+    want = {**{"G." + k: v.clone() for k, v in G.state_dict().items()}, **{"D." + k: v.clone() for k, v in D.state_dict().items()}}
+    G1, D1, s1 = _build("split")
+    s1.lr = 1e-2
+    for b in batches[:2]:
+        s1.run_step(*to_dev(b))
+    AFCheckpointer(G1, str(tmp_path / "G_0"), optimizer=s1).save("model_0000001", iteration=1)
+    AFCheckpointer(D1, str(tmp_path / "D_0")).save("model_0000001", iteration=1)
+    torch.manual_seed(123)                                  # a "new process": different initial weights
+    from afigan.engine import Stage1Step
+    from afigan.modeling import Discriminator, Generator
+    G2, D2 = Generator(n_residual_dense_blocks=3, precision="split").cuda(), Discriminator(precision="split").cuda()
+    D2.Discriminators[0].train()
+    s2 = Stage1Step(G2, D2, lr=1e-2, precision="split")
+    rest = AFCheckpointer(G2, str(tmp_path / "G_0"), optimizer=s2).resume_or_load("", resume=True)
+    AFCheckpointer(D2, str(tmp_path / "D_0")).resume_or_load("", resume=True)
+    assert rest["iteration"] == 1 and s2.steps_done == 2
+    s2.run_step(*to_dev(batches[2]))                        # parameters changed behind its back: the step re-packs its GEMM operands
+    got = {**{"G." + k: v for k, v in G2.state_dict().items()}, **{"D." + k: v for k, v in D2.state_dict().items()}}
+    for k, v in want.items():
+        if "num_batches" in k:
+            assert int(got[k]) == int(v), k
+        elif k.endswith("0.bias") and k.startswith("D.Discriminators.0.") and not k.startswith("D.Discriminators.0.3."):
+            continue                                        # zero-gradient biases: rounding noise only
+        else:
+            assert rel(got[k].float(), v.float()) < 1e-4, k      # (two uninterrupted runs differ by ~1e-5 themselves: fp32 atomics; dropping the momentum costs ~1e-2)
