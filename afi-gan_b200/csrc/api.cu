@@ -686,20 +686,28 @@ int afi_g_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_g
     AFI_TRY(g_check(prec, 1, 1, 1, g->n_rdb));
     GGradAcc GL = g_gradacc_layout(g->n_rdb);
     int nk = prec_nk(prec) ? 1 : 0;
-    if (g->head_w) AFI_TRY(unpack_wgrad(gradacc + GL.head_w, C, C, nk, 0, g->head_w, scale, accumulate, st));
-    if (g->head_b) AFI_TRY(axpby_f32(gradacc + GL.head_b, g->head_b, C, scale, accumulate, st));
+    // every gradient tensor of the module in ONE launch
+    UnpackJob jobs[AFI_MAX_UNPACK]; int nj = 0;
+    auto wjob = [&](size_t off, float* dst, int co, int ci, int CO, int CI, int co_off, int kind) {
+        if (!dst) return;
+        UnpackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+        j.src = gradacc + off; j.dst = dst; j.kind = kind; j.nk = nk; j.co = co; j.ci = ci; j.CO = CO; j.CI = CI; j.co_off = co_off;
+        j.total = (long long)co * ci * (kind == UNPACK_DECONV ? 36 : 9);
+    };
+    auto cjob = [&](size_t off, float* dst, long long n) {
+        if (!dst) return;
+        UnpackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+        j.src = gradacc + off; j.dst = dst; j.kind = UNPACK_COPY; j.total = n;
+    };
+    wjob(GL.head_w, g->head_w, C, C, C, C, 0, UNPACK_STD); cjob(GL.head_b, g->head_b, C);
     for (int r = 0; r < g->n_rdb; r++) {
-        for (int i = 0; i < 4; i++)
-            if (g->rdb_w[r][i]) AFI_TRY(unpack_wgrad_sub(gradacc + GL.rdb_g[r], 4 * GR, C + 3 * GR, GR * i, GR, C + GR * i, nk, g->rdb_w[r][i], scale, accumulate, st));
-        if (g->rdb_w[r][4]) AFI_TRY(unpack_wgrad(gradacc + GL.rdb_w[r][4], C, CB, nk, 0, g->rdb_w[r][4], scale, accumulate, st));
+        for (int i = 0; i < 4; i++) wjob(GL.rdb_g[r], g->rdb_w[r][i], GR, C + GR * i, 4 * GR, C + 3 * GR, GR * i, UNPACK_STD);
+        wjob(GL.rdb_w[r][4], g->rdb_w[r][4], C, CB, C, CB, 0, UNPACK_STD);
     }
-    if (g->post_w) AFI_TRY(unpack_wgrad(gradacc + GL.post_w, C, C, nk, 0, g->post_w, scale, accumulate, st));
-    if (g->post_b) AFI_TRY(axpby_f32(gradacc + GL.post_b, g->post_b, C, scale, accumulate, st));
-    if (g->up_w) AFI_TRY(unpack_wgrad(gradacc + GL.up_w, C, C, nk, 1, g->up_w, scale, accumulate, st));
-    if (g->up_b) AFI_TRY(axpby_f32(gradacc + GL.up_b, g->up_b, C, scale, accumulate, st));
-    if (g->out_w) AFI_TRY(unpack_wgrad(gradacc + GL.out_w, C, C, nk, 0, g->out_w, scale, accumulate, st));
-    if (g->out_b) AFI_TRY(axpby_f32(gradacc + GL.out_b, g->out_b, C, scale, accumulate, st));
-    return AFI_OK;
+    wjob(GL.post_w, g->post_w, C, C, C, C, 0, UNPACK_STD); cjob(GL.post_b, g->post_b, C);
+    wjob(GL.up_w, g->up_w, C, C, C, C, 0, UNPACK_DECONV); cjob(GL.up_b, g->up_b, C);
+    wjob(GL.out_w, g->out_w, C, C, C, C, 0, UNPACK_STD); cjob(GL.out_b, g->out_b, C);
+    return unpack_group(nj, jobs, scale, accumulate, st);
 }
 
 }  // extern "C"
@@ -992,18 +1000,28 @@ int afi_d_unpack_grads(afi_ctx* ctx, int prec, const float* gradacc, const afi_d
     AFI_REQUIRE(ctx && gradacc && g && prec_ok(prec), "afi_d_unpack_grads: bad argument");
     DGradAcc GL = d_gradacc_layout();
     const int nk = prec_nk(prec) ? 1 : 0, head_tc = prec_tc(prec) ? 1 : 0;
+    UnpackJob jobs[AFI_MAX_UNPACK]; int nj = 0;
+    auto cjob = [&](size_t off, float* dst, long long n) {
+        if (!dst) return;
+        UnpackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+        j.src = gradacc + off; j.dst = dst; j.kind = UNPACK_COPY; j.total = n;
+    };
     for (int i = 0; i < 3; i++) {
-        if (g->w[i]) AFI_TRY(unpack_wgrad(gradacc + GL.w[i], DC[i + 1], DC[i], nk, 0, g->w[i], scale, accumulate, st));
-        if (g->b[i]) AFI_TRY(axpby_f32(gradacc + GL.b[i], g->b[i], DC[i + 1], scale, accumulate, st));
-        if (g->gamma[i]) AFI_TRY(axpby_f32(gradacc + GL.gamma[i], g->gamma[i], DC[i + 1], scale, accumulate, st));
-        if (g->beta[i]) AFI_TRY(axpby_f32(gradacc + GL.beta[i], g->beta[i], DC[i + 1], scale, accumulate, st));
+        if (g->w[i]) {
+            UnpackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+            j.src = gradacc + GL.w[i]; j.dst = g->w[i]; j.kind = UNPACK_STD; j.nk = nk; j.co = j.CO = DC[i + 1]; j.ci = j.CI = DC[i];
+            j.total = (long long)9 * DC[i] * DC[i + 1];
+        }
+        cjob(GL.b[i], g->b[i], DC[i + 1]); cjob(GL.gamma[i], g->gamma[i], DC[i + 1]); cjob(GL.beta[i], g->beta[i], DC[i + 1]);
     }
     if (g->w[3]) {
-        if (head_tc) AFI_TRY(dhead_unpack_tc(gradacc + GL.w[3], DC[3], g->w[3], scale, accumulate, st));
-        else AFI_TRY(axpby_f32(gradacc + GL.w[3], g->w[3], 9 * DC[3], scale, accumulate, st));
+        if (head_tc) {
+            UnpackJob& j = jobs[nj++]; memset(&j, 0, sizeof(j));
+            j.src = gradacc + GL.w[3]; j.dst = g->w[3]; j.kind = UNPACK_HEAD_TC; j.ci = DC[3]; j.total = (long long)9 * DC[3];
+        } else cjob(GL.w[3], g->w[3], 9 * DC[3]);
     }
-    if (g->b[3]) AFI_TRY(axpby_f32(gradacc + GL.b[3], g->b[3], 1, scale, accumulate, st));
-    return AFI_OK;
+    cjob(GL.b[3], g->b[3], 1);
+    return unpack_group(nj, jobs, scale, accumulate, st);
 }
 
 // =====================================================================================================

@@ -208,6 +208,13 @@ int unpack_wgrad(const float* packed, int co, int ci, int layout_nk, int deconv,
 // the [co][ci] sub-block starting at row co_off of a packed [slab][CO][CI] (nk) / [slab][CI][CO] gradient -> torch [co][ci][3][3]
 int unpack_wgrad_sub(const float* packed, int CO, int CI, int co_off, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st);
 int axpby_f32(const float* src, float* dst, long long n, float scale, int accumulate, cudaStream_t st);
+// grouped form of the un-layouts above: dst = [dst +] scale * unpack(src) for every job of a module in one launch.
+//   UNPACK_STD: packed [9][CO][CI] (nk) / [9][CI][CO] -> torch [co][ci][3][3], rows co_off .. co_off + co of the packed operand (CO x CI its extents)
+//   UNPACK_DECONV: packed 36 slabs -> torch ConvTranspose [ci][co][6][6];  UNPACK_COPY: total floats;  UNPACK_HEAD_TC: [16][ci] -> [ci][9]
+enum UnpackKind { UNPACK_STD = 0, UNPACK_DECONV = 1, UNPACK_COPY = 2, UNPACK_HEAD_TC = 3 };
+struct UnpackJob { const float* src; float* dst; int kind, nk, co, ci, CO, CI, co_off; long long total; };
+#define AFI_MAX_UNPACK 40
+int unpack_group(int njobs, const UnpackJob* jobs, float scale, int accumulate, cudaStream_t st);
 int unpack_1x1(const float* packed, int co, int ci, int layout_nk, float* dst, float scale, int accumulate, cudaStream_t st);
 // dx (contiguous NCHW) = dxb (NHWC fp32) + dy_scale * bilinear2x^T(dy)
 int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, int w, int oh, int ow, float* dst, cudaStream_t st);

@@ -1481,6 +1481,51 @@ int unpack_wgrad_sub(const float* packed, int CO, int CI, int co_off, int co, in
     AFI_LAUNCH_CHECK();
     return AFI_OK;
 }
+// all the gradient un-layouts of one module in ONE launch (the generator has 23 gradient tensors: one launch instead of 45)
+struct UnpackGroup { int njobs; int block_begin[AFI_MAX_UNPACK + 1]; UnpackJob j[AFI_MAX_UNPACK]; };
+__global__ void __launch_bounds__(256) k_unpack_group(const __grid_constant__ UnpackGroup G, float scale, int accumulate) {
+    int k = 0;
+    while (k + 1 < G.njobs && (int)blockIdx.x >= G.block_begin[k + 1]) k++;
+    const UnpackJob& q = G.j[k];
+    long long i = (long long)(blockIdx.x - G.block_begin[k]) * 1024 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < 4; u++, i += 256) {
+        if (i >= q.total) return;
+        long long src;
+        if (q.kind == UNPACK_COPY) src = i;
+        else if (q.kind == UNPACK_HEAD_TC) { const int cc = (int)(i / 9), t = (int)(i % 9); src = (long long)t * q.ci + cc; }
+        else {
+            int slab, c_o, c_i;
+            if (q.kind == UNPACK_DECONV) {
+                int kx = (int)(i % 6); long long t = i / 6; int ky = (int)(t % 6); t /= 6; c_o = (int)(t % q.co); c_i = (int)(t / q.co);
+                int a = ky & 1, b = kx & 1, d0 = 1 - (ky >> 1), d1 = 1 - (kx >> 1);
+                slab = (a * 2 + b) * 9 + (d0 + 1) * 3 + (d1 + 1);
+            } else {
+                slab = (int)(i % 9); long long t = i / 9; c_i = (int)(t % q.ci); c_o = (int)(t / q.ci);
+            }
+            c_o += q.co_off;
+            src = q.nk ? ((long long)slab * q.CO + c_o) * q.CI + c_i : ((long long)slab * q.CI + c_i) * q.CO + c_o;
+        }
+        const float v = q.src[src] * scale;
+        q.dst[i] = accumulate ? q.dst[i] + v : v;
+    }
+}
+int unpack_group(int njobs, const UnpackJob* jobs, float scale, int accumulate, cudaStream_t st) {
+    AFI_REQUIRE(njobs >= 0 && njobs <= AFI_MAX_UNPACK, "unpack_group: %d jobs (max %d)", njobs, AFI_MAX_UNPACK);
+    UnpackGroup G; memset(&G, 0, sizeof(G));
+    int b = 0, nj = 0;
+    for (int k = 0; k < njobs; k++) {
+        if (!jobs[k].dst || jobs[k].total == 0) continue;
+        G.j[nj] = jobs[k]; G.block_begin[nj] = b;
+        b += cdiv(jobs[k].total, 1024);
+        nj++;
+    }
+    if (nj == 0) return AFI_OK;
+    G.njobs = nj; G.block_begin[nj] = b;
+    k_unpack_group<<<b, 256, 0, st>>>(G, scale, accumulate);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
 // 1x1 weight gradient: packed [ci][co] (KN) or [co][ci] (NK) -> torch [co][ci]
 __global__ void k_unpack_1x1(const float* __restrict__ packed, int co, int ci, int nk, float* __restrict__ dst, float scale, int accumulate) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

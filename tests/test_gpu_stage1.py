@@ -80,9 +80,10 @@ def test_stage1_step_vs_oracle_and_golden(precision):
         assert int(sd[f"Discriminators.0.{n}.0.norm.num_batches_tracked"]) == 12   # 4 D calls x 3 levels
 
 
-def test_stage1_two_steps_with_sgd_fp32():
-    """Two consecutive steps WITH the optimiser updates (momentum, weight decay) against the oracle."""
-    G, D, step = _build("fp32")
+@pytest.mark.parametrize("precision", ["fp32", "split"])
+def test_stage1_two_steps_with_sgd_fp32(precision):
+    """Two consecutive steps WITH the optimiser updates (momentum, weight decay) against the oracle, in both fp32-accurate modes."""
+    G, D, step = _build(precision)
     lr_shapes, hr_shapes = ((7, 11), (4, 6)), ((13, 21), (7, 11))
     g_sd, d_sd = O.init_states(0)
     g_mom, d_mom = {}, {}
