@@ -77,35 +77,6 @@ class _StepBase:
         self._pack_d()
         self.Dstack._native.packed.key = None      # the module's own packed copy (autograd path) is stale now
 
-
-class Stage1Step(_StepBase):
-    def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
-                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
-                 reuse_g_forward: Optional[bool] = None, overlap_comm: bool = True):
-        self.G = G
-        g_params = G._params()
-        self._init_common(g_params[0].device, lr, momentum, weight_decay, weight_decay_norm, precision or G.precision or N.default_precision(),
-                          process_group, overlap, overlap_comm)
-        dev = self.dev
-        self.g_params = g_params
-        self.n_rdb = G.n_residual_dense_blocks
-        self.g_sync = FlatGradSync(self.g_params, process_group, distributed)
-        self.g_flat, self.g_grads = self.g_sync.flat, self.g_sync.views
-        self._init_d(D, distributed)
-        self.g_mom = [torch.zeros_like(p) for p in self.g_params]
-        self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
-        self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
-        # The reference evaluates G(lr) twice per step -- detached for the D phase (:341-346), with a graph for the G phase (:390-395) --
-        # with the SAME generator weights (G's optimiser only steps at the end of the G phase) and the same input, and G has no
-        # normalisation, dropout or other state: the two evaluations are bit-identical.  One forward (kept for the backward) serves both.
-        # AFIGAN_REUSE_G_FORWARD=0 restores the literal second evaluation.
-        if reuse_g_forward is None:
-            import os
-            reuse_g_forward = os.environ.get("AFIGAN_REUSE_G_FORWARD", "1") != "0"
-        self.reuse_g_forward = reuse_g_forward
-        self._pack_key = None
-        self._refresh_packed()
-
     def _param_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.g_params + self.d_params)
 
@@ -143,7 +114,6 @@ class Stage1Step(_StepBase):
     def load_state_dict(self, state: Dict[str, object]) -> None:
         self.load_optimizer_state(state.get("g_momentum", []), state["d_momentum"], int(state["steps_done"]))
 
-    # ---- helpers --------------------------------------------------------------------------------------
     def _ws_for(self, kind: str, n: int, h: int, w: int, save: bool, tag="") -> torch.Tensor:
         key = (kind, n, h, w, save, tag)
         if key not in self._ws:
@@ -160,54 +130,12 @@ class Stage1Step(_StepBase):
             self._bufs[key] = torch.empty(shape, dtype=torch.float32, device=self.dev)
         return self._bufs[key]
 
-    def _gs(self):
-        return g_param_struct(self.g_params, self.n_rdb)
-
     def _ds(self):
         return d_param_struct(self.d_params, self.Dstack._buffers_list())
-
-    def _pack_g(self):
-        ps = self._gs()
-        N.check(self.lib.afi_g_pack(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.stream_ptr()))
 
     def _pack_d(self):
         ps = self._ds()
         N.check(self.lib.afi_d_pack(self.ctx, self.prec, C.byref(ps), self.d_packed.data_ptr(), N.stream_ptr()))
-
-    # ---- grouped calls: ONE kernel launch per layer covers all pyramid levels (and real + fake for the discriminator)
-    def _g_calls(self, lr_feats, hr_feats, save: bool, tag: str, dys=None):
-        calls = (N.GCall * len(lr_feats))()
-        outs = []
-        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
-            n, _, h, w = lo.shape
-            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))          # _reshape_stage1: crop to the element-wise min
-            ws = self._ws_for("g", n, h, w, save, l)
-            y = self._buf(f"tr{tag}{l}", (n, CH, oh, ow))
-            c = calls[l]
-            c.x, c.n, c.h, c.w, c.y, c.oh, c.ow = N.view4(lo), n, h, w, y.data_ptr(), oh, ow
-            c.ws, c.ws_bytes = ws.data_ptr(), ws.numel()
-            if dys is not None:
-                c.dy = N.view4(dys[l])
-            outs.append(y)
-        return calls, outs
-
-    def _g_forward(self, lr_feats, hr_feats, save: bool, tag: str):
-        calls, outs = self._g_calls(lr_feats, hr_feats, save, tag)
-        ps = self._gs()
-        for i in range(0, len(calls), N.MAX_CALLS):
-            k = min(N.MAX_CALLS, len(calls) - i)
-            N.check(self.lib.afi_g_forward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
-                                           C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, int(save), N.stream_ptr()))
-        return outs
-
-    def _g_backward(self, lr_feats, hr_feats, dys, tag: str):
-        calls, _ = self._g_calls(lr_feats, hr_feats, True, tag, dys)
-        ps = self._gs()
-        for i in range(0, len(calls), N.MAX_CALLS):
-            k = min(N.MAX_CALLS, len(calls) - i)
-            N.check(self.lib.afi_g_backward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
-                                            C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, self.g_acc.data_ptr(),
-                                            N.stream_ptr()))
 
     def _d_calls(self, xs, tags, save: bool, dlogits=None, stats_only=None, staged: bool = False):
         calls = (N.DCall * len(xs))()
@@ -296,6 +224,78 @@ class Stage1Step(_StepBase):
             self._sgd_tabs[id(params)] = tab
         _, P, G, M, cnt, wd = tab
         N.check(self.lib.afi_sgd_step_multi(n, P, G, M, cnt, wd, self.lr, self.momentum, 1.0 / self.world, first, N.stream_ptr()))
+
+
+class Stage1Step(_StepBase):
+    def __init__(self, G, D, lr: float = 1e-3, momentum: float = 0.9, weight_decay: float = 1e-4, weight_decay_norm: float = 0.0,
+                 precision: Optional[str] = None, process_group=None, distributed: Optional[bool] = None, overlap: bool = True,
+                 reuse_g_forward: Optional[bool] = None, overlap_comm: bool = True):
+        self.G = G
+        g_params = G._params()
+        self._init_common(g_params[0].device, lr, momentum, weight_decay, weight_decay_norm, precision or G.precision or N.default_precision(),
+                          process_group, overlap, overlap_comm)
+        dev = self.dev
+        self.g_params = g_params
+        self.n_rdb = G.n_residual_dense_blocks
+        self.g_sync = FlatGradSync(self.g_params, process_group, distributed)
+        self.g_flat, self.g_grads = self.g_sync.flat, self.g_sync.views
+        self._init_d(D, distributed)
+        self.g_mom = [torch.zeros_like(p) for p in self.g_params]
+        self.g_acc = _u8(self.lib.afi_g_gradacc_bytes(self.n_rdb), dev)
+        self.g_packed = _u8(self.lib.afi_g_packed_bytes(self.prec, self.n_rdb), dev)
+        # The reference evaluates G(lr) twice per step -- detached for the D phase (:341-346), with a graph for the G phase (:390-395) --
+        # with the SAME generator weights (G's optimiser only steps at the end of the G phase) and the same input, and G has no
+        # normalisation, dropout or other state: the two evaluations are bit-identical.  One forward (kept for the backward) serves both.
+        # AFIGAN_REUSE_G_FORWARD=0 restores the literal second evaluation.
+        if reuse_g_forward is None:
+            import os
+            reuse_g_forward = os.environ.get("AFIGAN_REUSE_G_FORWARD", "1") != "0"
+        self.reuse_g_forward = reuse_g_forward
+        self._pack_key = None
+        self._refresh_packed()
+
+    # ---- helpers --------------------------------------------------------------------------------------
+    def _gs(self):
+        return g_param_struct(self.g_params, self.n_rdb)
+
+    def _pack_g(self):
+        ps = self._gs()
+        N.check(self.lib.afi_g_pack(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(), N.stream_ptr()))
+
+    # ---- grouped calls: ONE kernel launch per layer covers all pyramid levels (and real + fake for the discriminator)
+    def _g_calls(self, lr_feats, hr_feats, save: bool, tag: str, dys=None):
+        calls = (N.GCall * len(lr_feats))()
+        outs = []
+        for l, (lo, hi) in enumerate(zip(lr_feats, hr_feats)):
+            n, _, h, w = lo.shape
+            oh, ow = min(2 * h, hi.size(2)), min(2 * w, hi.size(3))          # _reshape_stage1: crop to the element-wise min
+            ws = self._ws_for("g", n, h, w, save, l)
+            y = self._buf(f"tr{tag}{l}", (n, CH, oh, ow))
+            c = calls[l]
+            c.x, c.n, c.h, c.w, c.y, c.oh, c.ow = N.view4(lo), n, h, w, y.data_ptr(), oh, ow
+            c.ws, c.ws_bytes = ws.data_ptr(), ws.numel()
+            if dys is not None:
+                c.dy = N.view4(dys[l])
+            outs.append(y)
+        return calls, outs
+
+    def _g_forward(self, lr_feats, hr_feats, save: bool, tag: str):
+        calls, outs = self._g_calls(lr_feats, hr_feats, save, tag)
+        ps = self._gs()
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_g_forward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
+                                           C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, int(save), N.stream_ptr()))
+        return outs
+
+    def _g_backward(self, lr_feats, hr_feats, dys, tag: str):
+        calls, _ = self._g_calls(lr_feats, hr_feats, True, tag, dys)
+        ps = self._gs()
+        for i in range(0, len(calls), N.MAX_CALLS):
+            k = min(N.MAX_CALLS, len(calls) - i)
+            N.check(self.lib.afi_g_backward(self.ctx, self.prec, C.byref(ps), self.g_packed.data_ptr(),
+                                            C.cast(C.byref(calls, i * C.sizeof(N.GCall)), C.POINTER(N.GCall)), k, self.g_acc.data_ptr(),
+                                            N.stream_ptr()))
 
     def _allreduce(self, flat: torch.Tensor):
         (self.g_sync if flat is self.g_flat else self.d_sync).all_reduce()
@@ -413,12 +413,6 @@ class Stage1Step(_StepBase):
             out[f"adv_loss_p{l + 2}"] = float(v[2, l])
             out[f"content_loss_p{l + 2}"] = float(v[3, l])
         return out
-
-
-# helpers that only touch the shared / discriminator-side state are available to every step class
-for _name in ("_param_key", "_refresh_packed", "_ws_for", "_buf", "_ds", "_pack_d", "_d_calls", "_sub", "_d_phase", "_sgd", "optimizer_state_dict",
-              "state_dict", "load_state_dict", "load_optimizer_state"):
-    setattr(_StepBase, _name, getattr(Stage1Step, _name))
 
 
 class FeaturePrefetcher:
