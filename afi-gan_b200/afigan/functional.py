@@ -104,7 +104,7 @@ class AFInterpolatorFn(torch.autograd.Function):
             call.lateral = C.pointer(lat)
         N.check(lib.afi_g_forward(actx, prec, C.byref(ps), packed.data_ptr(), C.byref(call), 1, int(need_bwd), N.stream_ptr()))
         ctx.prec, ctx.shape, ctx.n_rdb, ctx.scale, ctx.lat_c = prec, (n, h, w, oh, ow), n_rdb, scale, lat_c
-        ctx.ws, ctx.packed = ws, packed
+        ctx.ws, ctx.packed, ctx.holder = ws, packed, holder
         ctx.has_lat_b = lat_b is not None
         ctx.save_for_backward(lat_x if lat_x is not None else x.new_empty(0), lat_w if lat_w is not None else x.new_empty(0),
                               lat_b if lat_b is not None else x.new_empty(0), *params)
@@ -117,8 +117,21 @@ class AFInterpolatorFn(torch.autograd.Function):
         dev = dy.device
         lib, actx = N.lib(), N.context(dev)
         dy = dy.float()
-        acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
-        N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
+        holder = ctx.holder
+        want = [bool(ctx.needs_input_grad[9 + i]) for i in range(len(params))]
+        deferred = holder.deferred and all(want)
+        if deferred:
+            # ONE packed accumulator for every call of this backward pass; un-packed into .grad by a callback when the pass ends
+            if holder.acc is None or holder.acc.device != dev:
+                holder.acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
+            acc = holder.acc
+            if holder.pending is None:
+                N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
+                holder.pending = (ctx.prec, ctx.n_rdb, list(params), torch.cuda.current_stream(dev))
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_deferred(holder))
+        else:
+            acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
+            N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
         ps = g_param_struct(params, ctx.n_rdb)
         call = N.GCall(n=n, h=h, w=w, oh=oh, ow=ow, dy=N.view4(dy), ws=ctx.ws.data_ptr(), ws_bytes=ctx.ws.numel())
         dx = d_lat_x = d_lat_w = d_lat_b = None
@@ -140,11 +153,37 @@ class AFInterpolatorFn(torch.autograd.Function):
                 d_lat_b = torch.empty_like(lat_b)
                 call.lat_gb = d_lat_b.data_ptr()
         N.check(lib.afi_g_backward(actx, ctx.prec, C.byref(ps), ctx.packed.data_ptr(), C.byref(call), 1, acc.data_ptr(), N.stream_ptr()))
-        grads = [torch.empty_like(p) if ctx.needs_input_grad[9 + i] else None for i, p in enumerate(params)]
-        gs = g_param_struct(grads, ctx.n_rdb)
-        N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
+        if deferred:
+            grads = [None] * len(params)
+        else:
+            grads = [torch.empty_like(p) if w_ else None for p, w_ in zip(params, want)]
+            gs = g_param_struct(grads, ctx.n_rdb)
+            N.check(lib.afi_g_unpack_grads(actx, ctx.prec, acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
         ctx.ws = None
         return (dx, d_lat_x, d_lat_w, d_lat_b, None, None, None, None, None, *grads)
+
+
+def _flush_deferred(holder) -> None:
+    """End-of-backward callback of the deferred weight gradients: p.grad (+)= unpack(accumulator), one launch for all 23 tensors."""
+    prec, n_rdb, params, stream = holder.pending
+    holder.pending = None
+    lib = N.lib()
+    dev = params[0].device
+    with torch.no_grad(), torch.cuda.device(dev), torch.cuda.stream(stream):     # the stream the backward calls were issued on
+        actx = N.context(dev)
+        if all(p.grad is not None for p in params):
+            gs = g_param_struct([p.grad for p in params], n_rdb)
+            N.check(lib.afi_g_unpack_grads(actx, prec, holder.acc.data_ptr(), C.byref(gs), 1.0, 1, N.stream_ptr()))
+        else:
+            flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for p in params:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            gs = g_param_struct(views, n_rdb)
+            N.check(lib.afi_g_unpack_grads(actx, prec, holder.acc.data_ptr(), C.byref(gs), 1.0, 0, N.stream_ptr()))
+            for p, v in zip(params, views):
+                p.grad = v if p.grad is None else p.grad + v
 
 
 class InferenceGraphs:

@@ -82,6 +82,17 @@ class Generator(nn.Module):
         self.Generators = nn.ModuleList([nn.Sequential(*stages)])
         self._native = _holder.Holder(n_rdb=n_residual_dense_blocks)
 
+    @property
+    def deferred_weight_grads(self) -> bool:
+        """Opt-in: accumulate this module's weight gradients over ALL its calls of a backward pass in one packed buffer and write .grad once when
+        the pass ends (a BiFPN calls the interpolator 28 times per step).  Not for torch DistributedDataParallel (its per-parameter hooks do not
+        fire); see `_holder.Holder`."""
+        return self._native.deferred
+
+    @deferred_weight_grads.setter
+    def deferred_weight_grads(self, on: bool) -> None:
+        self._native.deferred = bool(on)
+
     def _params(self) -> List[nn.Parameter]:
         g = self.Generators[0]
         ps = [g[0][0].weight, g[0][0].bias]

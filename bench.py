@@ -536,6 +536,7 @@ def run_pafpn_c4(args):
     barrier, timed = _timing_tools(world, dev)
     N = 16
     G, _ = _models(args.precision, dev)
+    G.deferred_weight_grads = True          # one packed gradient accumulator for the three calls of a backward pass
     gen = torch.Generator().manual_seed(33 + rank)
     c5 = torch.randn(N, 256, 13, 21, generator=gen).to(dev).requires_grad_(True)
     lat_in = [torch.randn(N, c, h, w, generator=gen).to(dev).requires_grad_(True) for c, h, w in ((1024, 25, 42), (512, 50, 84), (256, 100, 168))]
@@ -585,6 +586,7 @@ def run_stage2_c3(args):
     barrier, timed = _timing_tools(world, dev)
     N = PER_GPU_BATCH
     G, D = _models(args.precision, dev)
+    G.deferred_weight_grads = True          # one packed gradient accumulator for the 28 calls of a backward pass (no per-call un-pack / adds)
     gen = torch.Generator().manual_seed(35 + rank)
     feats = [torch.randn(N, 256, h, w, generator=gen).to(dev).requires_grad_(True) for h, w in C3_LEVELS]
     wts = [torch.tensor([0.7, 1.3], device=dev, requires_grad=True) for _ in range(28)]

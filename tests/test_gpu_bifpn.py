@@ -171,3 +171,34 @@ def test_native_sepconv_and_fuse_down_vs_torch(shape, precision):
             assert torch.allclose(bifpn_fuse_down(a, b, dn, w3), w3[0] * a + w3[1] * b + w3[2] * pool, atol=1e-6)
             assert torch.allclose(bifpn_fuse_down(a, None, dn, w2), w2[0] * a + w2[1] * pool, atol=1e-6)
             assert torch.allclose(bifpn_fuse_down(a, b, dn, None), a + b + pool, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_deferred_weight_grads_equal_per_call_accumulation():
+    """`Generator.deferred_weight_grads`: 8 interpolator calls in one graph (two BiFPN-like top-down sweeps), two backward passes in a row
+    (so that the second one ADDS into existing .grad): same parameter gradients and same input gradients as autograd's per-call accumulation."""
+    from afigan.modeling import Generator, bifpn_feature_fusion
+    shapes = [(4, 6), (8, 12), (16, 24), (32, 48), (64, 96)]
+    gen = torch.Generator().manual_seed(9)
+    base = [torch.randn(1, 256, h, w, generator=gen).cuda() for h, w in shapes]
+    res = {}
+    for deferred in (False, True):
+        torch.manual_seed(0)
+        G = Generator(n_residual_dense_blocks=3, precision="split").cuda()
+        G.deferred_weight_grads = deferred
+        feats = [t.clone().requires_grad_(True) for t in base]
+        wt = torch.tensor([0.7, 1.3], device="cuda", requires_grad=True)
+        for rep in range(2):
+            top = feats[0]
+            for sweep in range(2):
+                for f in feats[1:]:
+                    s = bifpn_feature_fusion(G, f, top, wt)
+                    top = s * torch.sigmoid(s)
+                top = top[:, :, ::16, ::16]                      # back to the 4 x 6 level for the second sweep
+            top.square().mean().backward()
+        res[deferred] = ([p.grad.clone() for p in G.parameters()], [f.grad.clone() for f in feats], wt.grad.clone())
+    for a, b in zip(res[True][0], res[False][0]):
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12
+    for a, b in zip(res[True][1], res[False][1]):
+        assert float((a - b).norm()) <= 1e-6 * float(b.norm())
+    assert torch.allclose(res[True][2], res[False][2], rtol=1e-6)
