@@ -61,6 +61,7 @@ struct Tiling {
     int nstages, stage_bytes;         // per-tap conv and wgrad: operand ring (a narrow N tile leaves room for more, smaller stages)
     // halo-tile convolution only: B ring of `sb` slots of b_slot bytes (one (tap, chunk) weight tile, or half of it in pair mode)
     int sb, b_slot, nviews;
+    int tb;                           // taps per weight slot (1, 3 or 9): one TMA box / one full-empty barrier pair covers tb consecutive taps
     int view_slab0[4];                // first weight slab of view v (its nine taps use slab0 .. slab0 + 8 in standard order)
     // split-precision operands (ConvArgs.split): the K loop runs once per plane pair (pa[i], pb[i]); plane p of image n of an A view
     // is image p * N + n, plane p of weight slab s is slab p * nslab_total + s.  npairs = 1, pa = pb = {0} for plain bf16 operands.
@@ -111,11 +112,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
 // environment has AFIGAN_HALO_DBG -- the instrument behind the pipeline notes in DESIGN.md.  Off in the shipped library: every
 // instruction in those single-thread loops is on the critical path.
 #ifdef AFI_STALL_COUNTERS
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define AFI_TSTAMP(slot) do { if (tl.dbg) tl.dbg[2048 + blockIdx.x * 8 + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long& acc, bool on) {
     if (on) { long long t0 = clock64(); mbar_wait(bar, parity, who); acc += clock64() - t0; }
     else mbar_wait(bar, parity, who);
 }
 #else
+#define AFI_TSTAMP(slot) do { } while (0)
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long&, bool) { mbar_wait(bar, parity, who); }
 #endif
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
@@ -246,6 +250,7 @@ struct Smem {
 __device__ __forceinline__ uint32_t setup(Smem& s, const Maps& maps, int epi_warps, int warp, int lane) {
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.b);
+        prefetch_tmap(&maps.a[0][0]);
         for (int i = 0; i < STAGES_MAX; i++) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), epi_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -694,6 +699,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
+    if (threadIdx.x == 0) AFI_TSTAMP(0);
     for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t a0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b0 = a0 + HALO_SA * HALO_SLOT;
@@ -701,6 +707,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     const uint32_t b_slot = tl.b_slot;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.b);
+        prefetch_tmap(&maps.a[tl.p[0].prob][0]);
         for (int i = 0; i < HALO_SA; i++) { mbar_init(smem_u32(&s.a_full[i]), 1); mbar_init(smem_u32(&s.a_empty[i]), 1); }
         for (int i = 0; i < sb; i++) { mbar_init(smem_u32(&s.b_full[i]), 1); mbar_init(smem_u32(&s.b_empty[i]), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.acc_empty[i]), (PAIR ? 2 : 1) * EPI_WARPS); }
@@ -720,8 +727,10 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
+    if (threadIdx.x == 0) AFI_TSTAMP(1);
     pdl_launch();
     if (warp != 1) pdl_wait();        // the producer and epilogue warps touch global memory; the MMA warp does not
+    if (threadIdx.x == 0) AFI_TSTAMP(2);
     const int kchunks = tl.kchunks;
     const int nchunks = tl.npairs * tl.nviews * kchunks;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -732,7 +741,8 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
         {
             long long w_ae = 0, w_be = 0; const long long t_start = clock64();
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0;
-            const uint32_t b_tx = (uint32_t)tl.bn * 128u;               // bytes of a whole weight tile (both halves in pair mode)
+            const int tb = tl.tb;
+            const uint32_t b_tx = (uint32_t)tl.bn * 128u * (uint32_t)tb;   // bytes of a whole weight slot (both halves in pair mode)
             const int brow = PAIR ? rank * (tl.bn >> 1) : 0;
             const uint32_t bar_af = smem_u32(&s.a_full[0]), bar_ae = smem_u32(&s.a_empty[0]);
             const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
@@ -788,8 +798,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                     // the halo of the NEXT chunk is requested before this chunk's weight tiles (three A slots: its slot was released long ago)
                     if (chunk + 1 < nchunks) issue_a(cur, nview, nkc, tl.pa[npr]);
                     else if (has_next) issue_a(nxt, 0, 0, tl.pa[0]);
-#pragma unroll
-                    for (int j = 0; j < 9; j++) {
+                    for (int j = 0; j < 9; j += tb) {       // one box of tb taps per slot
                         mbar_wait_t(bar_be + 8 * bi, bph ^ 1, 22, w_be, dbg_on);
                         const uint32_t fb = bar_bf + 8 * bi;
                         const uint32_t dst = b0 + bi * b_slot;
@@ -827,6 +836,11 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             const uint32_t bar_bf = smem_u32(&s.b_full[0]), bar_be = smem_u32(&s.b_empty[0]);
             const int cin = a.cin;
             const bool dual = AUX32 && tl.dual;
+            // taps that open / close a weight slot (tb taps per slot): tb = 1 -> every tap, 3 -> taps 0, 3, 6 / 2, 5, 8, 9 -> tap 0 / 8
+            const uint32_t slot_first = tl.tb == 1 ? 0x1FFu : (tl.tb == 3 ? 0x49u : 0x1u);
+            const uint32_t slot_last = tl.tb == 1 ? 0x1FFu : (tl.tb == 3 ? 0x124u : 0x100u);
+            const uint32_t b_tile = (uint32_t)tl.b_slot / (uint32_t)tl.tb;
+            uint32_t bbase = b0;
             auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int ti = 0;
             for (int item = item0; item < total; item += item_stride) {
@@ -843,14 +857,19 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                     int nk = (cin - kc * 64 + 15) >> 4;              // 16-channel MMA steps with data in this chunk
                     if (++kc == kchunks) kc = 0;
                     mbar_wait_t(bar_af + 8 * ai, aph, 24, w_af, dbg_on);
+                    if (item == item0 && chunk == 0 && lane == 0) AFI_TSTAMP(3);
                     const uint32_t abase = a0 + ai * HALO_SLOT;
 #pragma unroll
                     for (int j = 0; j < 9; j++) {
                         // tap j = (dy, dx) = (j/3 - 1, j%3 - 1): shift of dy halo lines + dx pixels (orient 0) or dx lines + dy pixels (orient 1)
                         const uint32_t aaddr = abase + (orient ? (uint32_t)(((j % 3) * 10 + (j / 3)) * 128) : (uint32_t)(((j / 3) * 10 + (j % 3)) * 128));
-                        const uint32_t baddr = b0 + bi * b_slot;
-                        mbar_wait_t(bar_bf + 8 * bi, bph, 25, w_bf, dbg_on);
-                        tc_fence_after();
+                        if ((slot_first >> j) & 1u) {             // tap j opens a weight slot
+                            mbar_wait_t(bar_bf + 8 * bi, bph, 25, w_bf, dbg_on);
+                            tc_fence_after();
+                            bbase = b0 + bi * b_slot;
+                        }
+                        const uint32_t baddr = bbase;
+                        bbase += b_tile;
                         const uint64_t ad = adesc0 | (uint64_t)((aaddr >> 4) & 0x3FFFu), bd = bdesc0 | (uint64_t)((baddr >> 4) & 0x3FFFu);
                         if (elect_one()) {
                         if (nk >= 4) {
@@ -865,10 +884,10 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                                 else umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum | (uint32_t)(j | k));
                             }
                         }
-                        commit(bar_be + 8 * bi);
+                        if ((slot_last >> j) & 1u) commit(bar_be + 8 * bi);
                         }
                         __syncwarp();
-                        if (++bi == sb) { bi = 0; bph ^= 1; }
+                        if ((slot_last >> j) & 1u) { if (++bi == sb) { bi = 0; bph ^= 1; } }
                     }
                     accum = 1;
                     if (elect_one()) commit(bar_ae + 8 * ai);
@@ -877,6 +896,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
                 }
                 if (elect_one()) commit(smem_u32(&s.acc_full[as]));
                 __syncwarp();
+                if (lane == 0) AFI_TSTAMP(4);
                 if (dual) aphase ^= 1;
                 else if (++as == 2) { as = 0; aphase ^= 1; }
             }
@@ -884,15 +904,18 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
         }
     } else {
         conv_epilogue<EPI_WARPS, PAIR, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
+        if (warp == 2 && lane == 0) AFI_TSTAMP(6);
     }
     tc_fence_before();
     __syncwarp();
+    if (threadIdx.x == 0) AFI_TSTAMP(5);
     if (PAIR) cluster_sync_all();      // neither CTA frees TMEM / exits while the other may still read its shared memory or signal it
     else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (lane == 0) AFI_TSTAMP(7);
     }
 }
 
@@ -1266,6 +1289,9 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     int hmode = halo_eligible(a) ? halo_mode() : 0;
     if (a.aux_f32 && hmode == 1) hmode = 2;                // (the single-CTA halo kernel has no fp32-operand instantiation)
     if (hmode == 2 && K < 4096 && (tl.bn < 128 || a.cin < 64) && !getenv("AFIGAN_PAIR_ALL")) hmode = 0;
+    // (Negative result, inference pyramid levels with fewer tiles than SMs: single-CTA halo tiles with 32/64-column N tiles and all nine
+    // taps per weight slot instead of the per-tap kernel changed a 28-call image by < 2 %: those calls are bound by the ~7 us of
+    // set-up, first TMA round trip, epilogue and exit of each of their 21 dependent kernels, not by the K loops.)
     const bool pair = hmode == 2;
 #ifdef AFI_STALL_COUNTERS
     if (getenv("AFIGAN_HALO_DBG")) {
@@ -1277,8 +1303,17 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
 #endif
     if (hmode) {
         tl.nviews = nviews;
-        tl.b_slot = ((pair ? tl.bn * 64 : tl.bn * 128) + 1023) / 1024 * 1024;
+        const int b_tile = pair ? tl.bn * 64 : tl.bn * 128;            // bytes of one tap's weight tile in this CTA (rows x 128 B: a multiple of 1024)
+        // Taps per weight slot.  What the single producer / MMA threads spend per slot on barrier waits, expect_tx, TMA issue and commit
+        // (~300 cycles) is more than the 4 MMAs of a 128-column tap (256 cycles) and not far below those of a 256-column tap (512): a slot
+        // holds a whole kernel row (three taps, one TMA box, one barrier round trip).  Measured alone on 2 x 200 x 336: 256->128 766 -> 910,
+        // 128->128 614 -> 677, 1024->1024 1728 -> 1769 TFLOP/s.
+        tl.tb = 3;
+        if (const char* e = getenv("AFIGAN_HALO_TB")) { int v = atoi(e); if (v == 1 || v == 3 || v == 9) tl.tb = v; }
+        tl.b_slot = b_tile * tl.tb;
         const int room = g_halo_dyn_max[epi8] - 1024 - HALO_SA * HALO_SLOT;
+        if (tl.tb == 9 && room / tl.b_slot < 2) { tl.tb = 3; tl.b_slot = b_tile * 3; }
+        if (tl.tb == 3 && room / tl.b_slot < 3) { tl.tb = 1; tl.b_slot = b_tile; }
         tl.sb = room / tl.b_slot;
         if (tl.sb > HALO_SB_MAX) tl.sb = HALO_SB_MAX;
         AFI_REQUIRE(tl.sb >= 2, "conv_tc: shared memory budget leaves %d weight stages", tl.sb);
@@ -1323,7 +1358,7 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
     {
         cuuint64_t dims[3] = {(cuuint64_t)a.cin, (cuuint64_t)a.cout, (cuuint64_t)nslab * (a.split ? 3 : 1)};
         cuuint64_t strides[2] = {(cuuint64_t)a.cin * 2, (cuuint64_t)a.cin * a.cout * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)(pair ? tl.bn / 2 : tl.bn), (cuuint32_t)(hmode ? tl.tb : 1)};
         AFI_TRY(encode_map(ctx, &maps.b, const_cast<void*>(a.w), 3, dims, strides, box));
     }
     tl.stage_bytes = A_BYTES + (tl.bn * 128 + 1023) / 1024 * 1024;
@@ -1382,6 +1417,17 @@ int conv_tc(afi_ctx* ctx, const ConvArgs& a, cudaStream_t st) {
             for (int b = 0; b < grid; b++) for (int i = 0; i < 8; i++) sum[i] += (double)h[b * 8 + i];
             fprintf(stderr, "[halo dbg] cin %d cout %d sa %d sb %d tiles %d: producer wait a_empty %.0f b_empty %.0f of %.0f | mma wait a_full %.0f b_full %.0f acc_empty %.0f of %.0f (avg cycles per CTA)\n",
                     a.cin, a.cout, hmode ? HALO_SA : 0, tl.sb, tl.total, sum[0] / grid, sum[1] / grid, sum[2] / grid, sum[3] / mg, sum[4] / mg, sum[5] / mg, sum[6] / mg);
+            if (hmode && grid <= 16) {      // timeline (ns since the first CTA's entry): entry, setup done, dependency wait done, first halo landed, MMAs issued, producer done, epilogue done, exit
+                long long ts[16 * 8];
+                cudaMemcpy(ts, tl.dbg + 2048, sizeof(ts), cudaMemcpyDeviceToHost);
+                long long t0 = ts[0];
+                for (int b = 0; b < grid; b++) if (ts[b * 8] && ts[b * 8] < t0) t0 = ts[b * 8];
+                for (int b = 0; b < grid; b++) {
+                    fprintf(stderr, "[halo timeline] cta %d:", b);
+                    for (int i = 0; i < 8; i++) fprintf(stderr, " %lld", ts[b * 8 + i] ? ts[b * 8 + i] - t0 : -1);
+                    fprintf(stderr, "\n");
+                }
+            }
         }
     }
 #endif
