@@ -338,14 +338,15 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 // accumulator stage on the LEADER's barrier, which counts the epilogue warps of both CTAs.
 template <int EPI_WARPS, bool PAIR = false, bool AUX32 = false>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& tl, uint64_t* acc_full, uint64_t* acc_empty,
-                                              float (*sstat)[2][ACC_COLS], const uint32_t tmem_base, const int warp, const int lane,
-                                              const int rank = 0) {
+                                              float (*sstat)[2][ACC_COLS], float (*sbias)[ACC_COLS], const uint32_t tmem_base, const int warp,
+                                              const int lane, const int rank = 0) {
     constexpr int HALVES = EPI_WARPS / 4;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;       // 0 .. HALVES-1
     const int row = q * 32 + lane;
     int as = 0; uint32_t aphase = 0;
+    int bias_buf = 0;
     // Column statistics stay in shared memory across the tiles of this CTA for as long as (problem, N tile) does not change
     // (with gridDim a multiple of n_tiles that is the whole run of a problem) and are published with ONE fp64 atomic per
     // column per run: same-address fp64 atomics from 148 CTAs on every tile were the bottleneck of the first version.
@@ -464,10 +465,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
             const int col = n0 + c0;
             const bool valid = ok && col < a.cout;
             if (valid) {
-                if (a.bias) {
-                    const float4* b4 = reinterpret_cast<const float4*>(a.bias + col);
+                if (a.bias) {       // staged in shared memory while the MMAs of this tile ran (a dependent global load per chunk otherwise)
+                    const float4* b4 = reinterpret_cast<const float4*>(&sbias[bias_buf][c0]);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) { float4 b = __ldg(b4 + i); v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w; }
+                    for (int i = 0; i < 4; i++) { float4 b = b4[i]; v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w; }
                 }
                 if (a.act && !a.act_post) {
 #pragma unroll
@@ -525,6 +526,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         bB = bA;
         aux_load(half, bA);
         aux_load(half + HALVES, bB);
+        if (a.bias) {           // this tile's bias columns -> shared memory (double-buffered over tiles: one barrier per tile is enough)
+            bias_buf ^= 1;
+            for (int c = row + half * 128; c < tl.bn; c += 32 * EPI_WARPS) sbias[bias_buf][c] = n0 + c < a.cout ? __ldg(a.bias + n0 + c) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        }
         mbar_wait(smem_u32(&acc_full[as]), aphase, 4);
         tc_fence_after();
         for (int ch = half; ch < nchunks; ch += 2 * HALVES) {
@@ -557,6 +563,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
     __shared__ float sstat[EPI_WARPS][2][ACC_COLS];   // per epilogue warp: no atomics (fp32 smem atomics are CAS loops)
+    __shared__ __align__(16) float sbias[2][ACC_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -642,7 +649,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[4] = w_f; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
-        conv_epilogue<EPI_WARPS, false, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane);
+        conv_epilogue<EPI_WARPS, false, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, sbias, tmem_base, warp, lane);
     }
     teardown(tmem_base, warp);
 }
@@ -696,6 +703,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     extern __shared__ uint8_t smem_raw[];
     __shared__ SmemH s;
     __shared__ float sstat[EPI_WARPS][2][ACC_COLS];
+    __shared__ __align__(16) float sbias[2][ACC_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
@@ -903,7 +911,7 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
             if (dbg_on && lane == 0) { long long* d = tl.dbg + blockIdx.x * 8; d[3] = w_af; d[4] = w_bf; d[5] = w_acc; d[6] = clock64() - t_start; }
         }
     } else {
-        conv_epilogue<EPI_WARPS, PAIR, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, tmem_base, warp, lane, rank);
+        conv_epilogue<EPI_WARPS, PAIR, AUX32>(a, tl, s.acc_full, s.acc_empty, sstat, sbias, tmem_base, warp, lane, rank);
         if (warp == 2 && lane == 0) AFI_TSTAMP(6);
     }
     tc_fence_before();

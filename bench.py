@@ -652,7 +652,7 @@ def run_infer_c5(args):
     G, _ = _models(args.precision, dev)
     G.eval()
     # IN_FLIGHT - 1 further lanes (own workspace, own graphs, own stream, the same weights) for the "several images in flight" leg
-    IN_FLIGHT = 4
+    IN_FLIGHT = max(2, int(os.environ.get("AFIGAN_IN_FLIGHT", "4")))
     lanes = [G]
     for _ in range(IN_FLIGHT - 1):
         g2 = Generator(n_residual_dense_blocks=3, precision=args.precision).to(dev).eval()
