@@ -242,6 +242,13 @@ def _timing_tools(world, dev):
     return barrier, timed
 
 
+def _dist_teardown(world):
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def _models(precision, dev):
     import torch
     from afigan.modeling import Discriminator, Generator
@@ -534,6 +541,7 @@ def run_g_only(args):
                                roofline={"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
                                          "frac_of_burst_peak": tf / pk["bf16_burst"], "traffic": None,
                                          "note": "whole fwd+bwd incl. layout conversions and elementwise passes; algorithmic FLOPs (SURVEY.md §8d)"})))
+    _dist_teardown(world)
 
 
 def run_pafpn_c4(args):
@@ -578,6 +586,7 @@ def run_pafpn_c4(args):
                                per_gpu_batch=N, step_tflops_per_gpu=tf, gpu_launches=launches,
                                roofline={"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
                                          "traffic": None, "note": "AFI fwd + 2x bwd + laterals fwd/dgrad/wgrad, algorithmic FLOPs over the whole autograd step"})))
+    _dist_teardown(world)
 
 
 C3_LEVELS = ((64, 96), (32, 48), (16, 24), (8, 12), (4, 6))             # p3 .. p7 of a 512x768 (0.5x) image
@@ -638,6 +647,7 @@ def run_stage2_c3(args):
                                per_gpu_batch=N, step_tflops_per_gpu=tf, gpu_launches=launches,
                                roofline={"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
                                          "traffic": None, "note": "small maps: launch / tile-latency bound (14 280 AFI pixels and 6 560 D pixels per image)"})))
+    _dist_teardown(world)
 
 
 def run_infer_c5(args):
@@ -737,6 +747,7 @@ def run_infer_c5(args):
                                                   "`value` is the strict one-image-at-a-time reading of config 5" % IN_FLIGHT},
                                roofline={"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
                                          "traffic": None})))
+    _dist_teardown(world)
 
 
 def main():

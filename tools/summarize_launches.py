@@ -9,6 +9,8 @@ lines = [l for l in open(path) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 n = len(rows)
 half = rows[n // 2:] if "--all" not in sys.argv else rows
+if "--last" in sys.argv:      # the last N launches (N = launches/step printed by quick_time.py: the first step also packs and initialises)
+    half = rows[n - int(sys.argv[sys.argv.index("--last") + 1]):]
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for row in half:
     name = re.sub(r"\(.*", "", row["Kernel Name"])
