@@ -81,7 +81,7 @@ class AFInterpolatorFn(torch.autograd.Function):
             raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
         if x.dim() != 4 or x.size(1) != CH:
             raise ValueError(f"AF interpolator expects [N,{CH},H,W], got {tuple(x.shape)}")
-        x = x.float()
+        x = N.boundary(x)
         n, _, h, w = x.shape
         oh, ow = out_hw if out_hw is not None else (2 * h, 2 * w)
         n_rdb = holder.n_rdb
@@ -92,7 +92,7 @@ class AFInterpolatorFn(torch.autograd.Function):
         lib, actx = N.lib(), N.context(dev)
         lat_c, lat = 0, None
         if lat_x is not None:
-            lat_x, lat_w = lat_x.float(), lat_w.float().contiguous()
+            lat_x, lat_w = N.boundary(lat_x), lat_w.float().contiguous()
             lat_c = lat_x.size(1)
             if tuple(lat_x.shape) != (n, lat_c, oh, ow) or tuple(lat_w.shape[:2]) != (CH, lat_c):
                 raise ValueError(f"lateral input {tuple(lat_x.shape)} / weight {tuple(lat_w.shape)} do not match the output [{n},{CH},{oh},{ow}]")
@@ -106,7 +106,7 @@ class AFInterpolatorFn(torch.autograd.Function):
         ctx.prec, ctx.shape, ctx.n_rdb, ctx.scale, ctx.lat_c = prec, (n, h, w, oh, ow), n_rdb, scale, lat_c
         ctx.ws, ctx.packed, ctx.holder = ws, packed, holder
         ctx.has_lat_b = lat_b is not None
-        ctx.save_for_backward(lat_x if lat_x is not None else x.new_empty(0), lat_w if lat_w is not None else x.new_empty(0),
+        ctx.save_for_backward(lat_x if lat_x is not None else x.new_empty(0), lat_w if lat_w is not None else x.new_empty(0, dtype=torch.float32),
                               lat_b if lat_b is not None else x.new_empty(0), *params)
         return y
 
@@ -116,7 +116,7 @@ class AFInterpolatorFn(torch.autograd.Function):
         n, h, w, oh, ow = ctx.shape
         dev = dy.device
         lib, actx = N.lib(), N.context(dev)
-        dy = dy.float()
+        dy = N.boundary(dy)
         holder = ctx.holder
         want = [bool(ctx.needs_input_grad[9 + i]) for i in range(len(params))]
         deferred = holder.deferred and all(want)
@@ -216,7 +216,7 @@ class InferenceGraphs:
         """lat = (lat_x, lat_w [256, lat_c], lat_b or None, scale); fuse = (cur, weight[2] or None)."""
         if not x.is_cuda:
             raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
-        x = x.float()
+        x = N.boundary(x)
         n, c, h, w = x.shape
         if c != CH:
             raise ValueError(f"AF interpolator expects [N,{CH},H,W], got {tuple(x.shape)}")
@@ -225,16 +225,16 @@ class InferenceGraphs:
         ps = g_param_struct(params, holder.n_rdb)
         packed = holder.packed.get("g", prec, params, ps, holder.n_rdb)
         key = (prec, dev, n, h, w, oh, ow, packed.data_ptr(), tuple(p.data_ptr() for p in params),
-               None if lat is None else (lat[0].size(1), lat[1].data_ptr(), N.ptr(lat[2]) if lat[2] is not None else 0, float(lat[3])),
-               fuse is not None)
+               None if lat is None else (lat[0].size(1), lat[1].data_ptr(), N.ptr(lat[2]) if lat[2] is not None else 0, float(lat[3]), lat[0].dtype),
+               None if fuse is None else fuse[0].dtype, x.dtype)
         e = self.entries.get(key)
         if e is None:
             lat_c = 0 if lat is None else lat[0].size(1)
-            e = {"x": torch.empty((n, CH, h, w), dtype=torch.float32, device=dev),
+            e = {"x": torch.empty((n, CH, h, w), dtype=x.dtype, device=dev),
                  "y": torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev),
                  "ws": _u8(N.lib().afi_g_workspace_bytes(prec, n, h, w, holder.n_rdb, lat_c, 0), dev),
-                 "lat_x": None if lat is None else torch.empty((n, lat_c, oh, ow), dtype=torch.float32, device=dev),
-                 "cur": None if fuse is None else torch.empty((n, CH, oh, ow), dtype=torch.float32, device=dev),
+                 "lat_x": None if lat is None else torch.empty((n, lat_c, oh, ow), dtype=lat[0].dtype, device=dev),
+                 "cur": None if fuse is None else torch.empty((n, CH, oh, ow), dtype=fuse[0].dtype, device=dev),
                  "fw": None if fuse is None else torch.ones(2, dtype=torch.float32, device=dev)}
             e["x"].zero_()
             lat_s = None if lat is None else (e["lat_x"].zero_(), lat[1], lat[2], lat[3])
@@ -268,7 +268,7 @@ def afi_bifpn_fuse(x: torch.Tensor, cur: torch.Tensor, weight: Optional[torch.Te
     weight[0] * cur + weight[1] * (Generators[0](x) + bilinear2x(x))[:, :, :H, :W]  (weight None: plain sum)."""
     if not x.is_cuda:
         raise RuntimeError("AF interpolator: input must live on an sm_100a CUDA device (no CPU fallback)")
-    x, cur = x.float(), cur.float()
+    x, cur = N.boundary(x), N.boundary(cur)
     n, _, h, w = x.shape
     oh, ow = cur.shape[2:]
     if tuple(cur.shape[:2]) != (n, CH) or oh > 2 * h or ow > 2 * w:
@@ -296,7 +296,7 @@ class PatchDiscriminatorFn(torch.autograd.Function):
             raise RuntimeError("feature-patch discriminator: input must live on an sm_100a CUDA device (no CPU fallback)")
         if x.dim() != 4 or x.size(1) != CH:
             raise ValueError(f"discriminator expects [N,{CH},H,W], got {tuple(x.shape)}")
-        x = x.float()
+        x = N.boundary(x)
         n, _, h, w = x.shape
         dev = x.device
         ps = d_param_struct(params, buffers)
@@ -364,7 +364,7 @@ def conv3x3_backward(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, pr
     lib, actx = N.lib(), N.context(x.device)
     ws = _u8(lib.afi_conv3x3_workspace_bytes(prec, n, cin, h, w, cout), x.device)
     dw = torch.empty_like(weight)
-    dx = torch.empty_like(x) if need_dx else None
+    dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if need_dx else None
     N.check(lib.afi_conv3x3_backward(actx, prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), None, N.ptr(dx),
                                      ws.data_ptr(), ws.numel(), N.stream_ptr()))
     return dw, dx
@@ -378,7 +378,7 @@ class Conv3x3Fn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, prec: int):
         if not x.is_cuda:
             raise RuntimeError("conv3x3: input must live on an sm_100a CUDA device (no CPU fallback)")
-        x, weight = x.float(), weight.float().contiguous()
+        x, weight = N.boundary(x), weight.float().contiguous()
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
@@ -393,14 +393,14 @@ class Conv3x3Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dy = dy.float()
+        dy = N.boundary(dy)
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
         ws = _u8(lib.afi_conv3x3_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
         dw = torch.empty_like(weight)
         db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
         N.check(lib.afi_conv3x3_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(db),
                                          N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
         return dx, dw, db, None
@@ -415,7 +415,7 @@ class Conv1x1Fn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, prec: int):
         if not x.is_cuda:
             raise RuntimeError("conv1x1: input must live on an sm_100a CUDA device (no CPU fallback)")
-        x, weight = x.float(), weight.float().contiguous()
+        x, weight = N.boundary(x), weight.float().contiguous()
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
@@ -430,14 +430,14 @@ class Conv1x1Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dy = dy.float()
+        dy = N.boundary(dy)
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
         ws = _u8(lib.afi_conv1x1_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
         dw = torch.empty_like(weight)
         db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
         N.check(lib.afi_conv1x1_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(), N.ptr(db),
                                          N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
         return dx, dw, db, None
@@ -455,7 +455,7 @@ class Conv3x3S2Fn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, prec: int):
         if not x.is_cuda:
             raise RuntimeError("conv3x3s2: input must live on an sm_100a CUDA device (no CPU fallback)")
-        x, weight = x.float(), weight.float().contiguous()
+        x, weight = N.boundary(x), weight.float().contiguous()
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
@@ -470,14 +470,14 @@ class Conv3x3S2Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dy = dy.float()
+        dy = N.boundary(dy)
         n, cin, h, w = x.shape
         cout = weight.shape[0]
         lib, actx = N.lib(), N.context(x.device)
         ws = _u8(lib.afi_conv3x3s2_workspace_bytes(ctx.prec, n, cin, h, w, cout), x.device)
         dw = torch.empty_like(weight)
         db = torch.empty(cout, dtype=torch.float32, device=x.device) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
         N.check(lib.afi_conv3x3s2_backward(actx, ctx.prec, N.view4(x), N.view4(dy), n, cin, h, w, weight.data_ptr(), cout, dw.data_ptr(),
                                            N.ptr(db), N.ptr(dx), ws.data_ptr(), ws.numel(), N.stream_ptr()))
         return dx, dw, db, None
@@ -495,7 +495,7 @@ def sepconv_eval(x: torch.Tensor, dw_weight: torch.Tensor, pw_weight: torch.Tens
     if not x.is_cuda:
         raise RuntimeError("sepconv: input must live on an sm_100a CUDA device (no CPU fallback)")
     prec = N.PRECISIONS[precision or N.default_precision()]
-    x = x.float()
+    x = N.boundary(x)
     n, c, h, w = x.shape
     cout = pw_weight.shape[0]
     lib, actx = N.lib(), N.context(x.device)
@@ -511,10 +511,10 @@ def bifpn_fuse_down(a: torch.Tensor, b: Optional[torch.Tensor], down: torch.Tens
     form when b is None), pool = the zero-padded 3x3 / stride-2 max-pool of the reference's MaxPool2d wrapper -- one elementwise pass."""
     if not a.is_cuda:
         raise RuntimeError("bifpn_fuse_down: tensors must live on an sm_100a CUDA device (no CPU fallback)")
-    a, down = a.float(), down.float()
+    a, down = N.boundary(a), N.boundary(down)
     n, c, h, w = a.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=a.device)
-    bv = N.view4(b.float()) if b is not None else N.View4()
+    bv = N.view4(N.boundary(b)) if b is not None else N.View4()
     wt = weight.detach().float().contiguous() if weight is not None else None
     N.check(N.lib().afi_bifpn_fuse_down(N.view4(a), bv, N.view4(down), N.ptr(wt), n, c, h, w, down.size(2), down.size(3), out.data_ptr(),
                                         N.stream_ptr()))

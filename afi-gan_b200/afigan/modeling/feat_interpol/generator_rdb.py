@@ -123,7 +123,7 @@ class Generator(nn.Module):
         with torch.no_grad():
             if self._use_graphs(top_feature):
                 oh, ow = cur_feature.shape[2:]
-                return self._native.graphs.run(self._native, prec, self._params(), top_feature, (oh, ow), fuse=(cur_feature.float(), weight))
+                return self._native.graphs.run(self._native, prec, self._params(), top_feature, (oh, ow), fuse=(native.boundary(cur_feature), weight))
             return afi_bifpn_fuse(top_feature, cur_feature, weight, self._native, prec, self._params())
 
     def merge(self, prev_features: torch.Tensor, bottom_up: torch.Tensor, lateral_weight: torch.Tensor,
@@ -136,6 +136,6 @@ class Generator(nn.Module):
         w2 = lateral_weight.reshape(lateral_weight.shape[0], lateral_weight.shape[1])
         if self._use_graphs(prev_features) and lateral_weight.is_contiguous() and lateral_weight.dtype == torch.float32:
             return self._native.graphs.run(self._native, prec, self._params(), prev_features, (oh, ow),
-                                           lat=(bottom_up.float(), w2, lateral_bias, 0.5 if fuse_type == "avg" else 1.0))
+                                           lat=(native.boundary(bottom_up), w2, lateral_bias, 0.5 if fuse_type == "avg" else 1.0))
         return AFInterpolatorFn.apply(prev_features, bottom_up, w2, lateral_bias, self._native, prec, (oh, ow),
                                       0.5 if fuse_type == "avg" else 1.0, torch.is_grad_enabled(), *self._params())

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("AFIGAN_LIB_PATH") or os.path.join(_HERE, "libafigan_b
 PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_SPLIT = 0, 1, 2, 3
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16_simt": PREC_BF16_SIMT, "split": PREC_SPLIT}
 MAX_RDB = 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def default_precision() -> str:
@@ -31,7 +31,8 @@ def default_precision() -> str:
 
 
 class View4(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("sn", C.c_longlong), ("sc", C.c_longlong), ("sh", C.c_longlong), ("sw", C.c_longlong)]
+    _fields_ = [("ptr", C.c_void_p), ("sn", C.c_longlong), ("sc", C.c_longlong), ("sh", C.c_longlong), ("sw", C.c_longlong),
+                ("dtype", C.c_int), ("reserved", C.c_int)]
 
 
 class GParams(C.Structure):
@@ -179,11 +180,20 @@ def stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+DT_F32, DT_BF16 = 0, 1
+
+
 def view4(t: torch.Tensor) -> View4:
-    if t.dtype != torch.float32 or t.dim() != 4:
-        raise TypeError(f"expected a 4-D float32 tensor, got {tuple(t.shape)} {t.dtype}")
+    """Strided view of a 4-D fp32 or bf16 tensor (any strides: contiguous, channels_last, crops) -- no copy, no up-cast."""
+    if t.dtype not in (torch.float32, torch.bfloat16) or t.dim() != 4:
+        raise TypeError(f"expected a 4-D float32 / bfloat16 tensor, got {tuple(t.shape)} {t.dtype}")
     s = t.stride()
-    return View4(t.data_ptr(), s[0], s[1], s[2], s[3])
+    return View4(t.data_ptr(), s[0], s[1], s[2], s[3], DT_BF16 if t.dtype == torch.bfloat16 else DT_F32, 0)
+
+
+def boundary(t: torch.Tensor) -> torch.Tensor:
+    """What crosses the boundary as it is: fp32 and bf16 tensors.  Anything else (fp16 under autocast, fp64) is cast to fp32 once."""
+    return t if t.dtype in (torch.float32, torch.bfloat16) else t.float()
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

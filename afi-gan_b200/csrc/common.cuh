@@ -174,6 +174,13 @@ int split3_group(int njobs, const SplitJob* jobs, cudaStream_t st);
 int tc_init(afi_ctx* ctx);
 
 // ---- elementwise / layout kernels (elementwise.cu) ------------------------------------------------------
+// element `off` of a boundary view as fp32 (the dtype branch is uniform over a launch)
+#ifdef __CUDACC__
+__device__ __forceinline__ float vld(const afi_view4& v, long long off) {
+    return v.dtype == AFI_DT_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(v.ptr)[off]) : reinterpret_cast<const float*>(v.ptr)[off];
+}
+#endif
+static inline bool view_dtype_ok(const afi_view4& v) { return (v.dtype == AFI_DT_F32 || v.dtype == AFI_DT_BF16) && v.reserved == 0; }
 template <typename T> int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st);
 // BiFPN inference building blocks (elementwise.cu): depthwise 3x3 (+ swish in front) fused with the NCHW -> NHWC conversion; bottom-up fusion site
 template <typename T> int dw3x3_to_nhwc(afi_view4 src, const float* wdw, int n, int c, int h, int w, int pre_swish, PView dst, cudaStream_t st);

@@ -66,7 +66,7 @@ __global__ void k_nchw_to_nhwc(afi_view4 src, int c, int h, int w, PView dst) {
     for (int i = 0; i < 4; i++) {
         int cc = c0 + ty + 8 * i, xx = x0 + tx;
         float v = 0.f;
-        if (cc < c && xx < w) v = src.ptr[n * src.sn + cc * src.sc + y * src.sh + xx * src.sw];
+        if (cc < c && xx < w) v = vld(src, n * src.sn + cc * src.sc + y * src.sh + xx * src.sw);
         tile[ty + 8 * i][tx] = v;
     }
     __syncthreads();
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc_bf16x2(afi_view4 src, int 
     for (int i = 0; i < 8; i++) {
         const int cc = c0 + ty + 8 * i, xx = x0 + tx;
         float v = 0.f;
-        if (cc < c && xx < w) v = src.ptr[n * src.sn + cc * src.sc + y * src.sh + xx * src.sw];
+        if (cc < c && xx < w) v = vld(src, n * src.sn + cc * src.sc + y * src.sh + xx * src.sw);
         tile[tx][ty + 8 * i] = v;
     }
     __syncthreads();
@@ -100,8 +100,43 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc_bf16x2(afi_view4 src, int 
             *reinterpret_cast<uint32_t*>(d + n * dst.sn + y * dst.sy + xx * dst.sx + cc) = pack_bf16x2(tile[xl][2 * tx], tile[xl][2 * tx + 1]);
     }
 }
+// channels_last source (sc == 1: the view is NHWC already): a straight copy / conversion, four channels per thread
+template <typename T, typename S>
+__global__ void __launch_bounds__(256) k_nhwc_view_to_nhwc(afi_view4 src, int c4, int h, int w, long long total, PView dst) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cc = (int)(i % c4) * 4;
+    const long long p = i / c4;
+    const int x = (int)(p % w), y = (int)((p / w) % h), n = (int)(p / ((long long)w * h));
+    const S* sp = reinterpret_cast<const S*>(src.ptr) + n * src.sn + y * src.sh + x * src.sw + cc;
+    float v[4];
+    if constexpr (sizeof(S) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(sp);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(sp);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u); v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    T* dp = reinterpret_cast<T*>(dst.ptr) + n * dst.sn + y * dst.sy + x * dst.sx + cc;
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<uint2*>(dp) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
 template <typename T>
 int nchw_to_nhwc(afi_view4 src, int n, int c, int h, int w, PView dst, cudaStream_t st) {
+    AFI_REQUIRE(view_dtype_ok(src), "layout conversion: unknown view dtype %d", src.dtype);
+    {
+        const int ses = src.dtype == AFI_DT_BF16 ? 2 : 4;
+        const uintptr_t salign = (uintptr_t)(4 * ses) - 1, dalign = (uintptr_t)(4 * sizeof(T)) - 1;
+        if (src.sc == 1 && c % 4 == 0 && src.sn % 4 == 0 && src.sh % 4 == 0 && src.sw % 4 == 0 && ((uintptr_t)src.ptr & salign) == 0 &&
+            dst.sn % 4 == 0 && dst.sy % 4 == 0 && dst.sx % 4 == 0 && ((uintptr_t)dst.ptr & dalign) == 0) {
+            const long long total = (long long)n * h * w * (c / 4);
+            const int grid = (int)cdiv(total, 256);
+            if (src.dtype == AFI_DT_BF16) k_nhwc_view_to_nhwc<T, bf16><<<grid, 256, 0, st>>>(src, c / 4, h, w, total, dst);
+            else k_nhwc_view_to_nhwc<T, float><<<grid, 256, 0, st>>>(src, c / 4, h, w, total, dst);
+            AFI_LAUNCH_CHECK();
+            return AFI_OK;
+        }
+    }
     AFI_REQUIRE((long long)n * h <= 65535, "layout conversion: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * h);
     if (dt_of<T>::v == DT_BF16 && c % 2 == 0 && dst.sx % 2 == 0 && dst.sy % 2 == 0 && dst.sn % 2 == 0 && ((uintptr_t)dst.ptr & 3) == 0) {
         dim3 grid(cdiv(w, 32), cdiv(c, 64), n * h), block(32, 8);
@@ -136,7 +171,7 @@ __global__ void __launch_bounds__(256) k_dw3x3_to_nhwc(afi_view4 src, const floa
         const int cc = c0 + ty + 8 * i, xx = x0 + tx;
         float acc = 0.f;
         if (cc < c && xx < w) {
-            const float* sp = src.ptr + n * src.sn + cc * src.sc;
+            const long long sp = n * src.sn + cc * src.sc;
             const float* wk = wdw + cc * 9;
 #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
@@ -146,7 +181,7 @@ __global__ void __launch_bounds__(256) k_dw3x3_to_nhwc(afi_view4 src, const floa
                 for (int kx = 0; kx < 3; kx++) {
                     const int xs = xx + kx - 1;
                     if (xs < 0 || xs >= w) continue;
-                    float v = sp[yy * src.sh + xs * src.sw];
+                    float v = vld(src, sp + yy * src.sh + xs * src.sw);
                     if (pre_swish) v = v / (1.f + __expf(-v));
                     acc += __ldg(wk + ky * 3 + kx) * v;
                 }
@@ -164,6 +199,7 @@ __global__ void __launch_bounds__(256) k_dw3x3_to_nhwc(afi_view4 src, const floa
 }
 template <typename T>
 int dw3x3_to_nhwc(afi_view4 src, const float* wdw, int n, int c, int h, int w, int pre_swish, PView dst, cudaStream_t st) {
+    AFI_REQUIRE(view_dtype_ok(src), "dw3x3: unknown view dtype %d", src.dtype);
     AFI_REQUIRE((long long)n * h <= 65535, "dw3x3_to_nhwc: n * h = %lld exceeds the grid limit", (long long)n * h);
     dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
     k_dw3x3_to_nhwc<T><<<grid, block, 0, st>>>(src, wdw, c, h, w, pre_swish, dst);
@@ -179,20 +215,20 @@ __global__ void __launch_bounds__(256) k_bifpn_fuse_down(afi_view4 a, afi_view4 
     if (i >= total) return;
     const int x = (int)(i % w), y = (int)((i / w) % h), cc = (int)((i / ((long long)w * h)) % c), n = (int)(i / ((long long)w * h * c));
     // max over the 3x3 window at stride 2 of `dn` padded with ZEROS on the right / bottom (F.pad(x, (0, 1, 0, 1)) then max_pool2d(3, 2))
-    const float* dp = dn.ptr + n * dn.sn + cc * dn.sc;
+    const long long dp = n * dn.sn + cc * dn.sc;
     float m = -3.402823466e38f;
 #pragma unroll
     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
             const int yy = 2 * y + ky, xx = 2 * x + kx;
-            const float v = (yy < dh && xx < dw_) ? dp[yy * dn.sh + xx * dn.sw] : 0.f;
+            const float v = (yy < dh && xx < dw_) ? vld(dn, dp + yy * dn.sh + xx * dn.sw) : 0.f;
             m = fmaxf(m, v);
         }
     float r;
-    const float va = a.ptr[n * a.sn + cc * a.sc + y * a.sh + x * a.sw];
+    const float va = vld(a, n * a.sn + cc * a.sc + y * a.sh + x * a.sw);
     if (b.ptr) {
-        const float vb = b.ptr[n * b.sn + cc * b.sc + y * b.sh + x * b.sw];
+        const float vb = vld(b, n * b.sn + cc * b.sc + y * b.sh + x * b.sw);
         r = wts ? wts[0] * va + wts[1] * vb + wts[2] * m : va + vb + m;
     } else {
         r = wts ? wts[0] * va + wts[1] * m : va + m;
@@ -204,6 +240,7 @@ int bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 dn, const float* wts, in
                     cudaStream_t st) {
     const long long total = (long long)n * c * h * w;
     if (total == 0) return AFI_OK;
+    AFI_REQUIRE(view_dtype_ok(a) && view_dtype_ok(b) && view_dtype_ok(dn), "bifpn_fuse_down: unknown view dtype");
     k_bifpn_fuse_down<<<cdiv(total, 256), 256, 0, st>>>(a, b, dn, wts, nw, c, h, w, dh, dw_, out, total);
     AFI_LAUNCH_CHECK();
     return AFI_OK;
@@ -252,13 +289,13 @@ __global__ void k_nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int sh, int s
             if (skip.ptr) {
                 int xa, xb; float lx0, lx1;
                 bilin_coord(xx, sw_, xa, xb, lx0, lx1);
-                const float* s = skip.ptr + n * skip.sn + cc * skip.sc;
-                float v00 = s[y0 * skip.sh + xa * skip.sw], v01 = s[y0 * skip.sh + xb * skip.sw];
-                float v10 = s[y1 * skip.sh + xa * skip.sw], v11 = s[y1 * skip.sh + xb * skip.sw];
+                const long long s = n * skip.sn + cc * skip.sc;
+                float v00 = vld(skip, s + y0 * skip.sh + xa * skip.sw), v01 = vld(skip, s + y0 * skip.sh + xb * skip.sw);
+                float v10 = vld(skip, s + y1 * skip.sh + xa * skip.sw), v11 = vld(skip, s + y1 * skip.sh + xb * skip.sw);
                 v += ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
             }
             v *= scale;
-            if (fw) v = fw[0] * add.ptr[n * add.sn + cc * add.sc + y * add.sh + xx * add.sw] + fw[1] * v;
+            if (fw) v = fw[0] * vld(add, n * add.sn + cc * add.sc + y * add.sh + xx * add.sw) + fw[1] * v;
             dst[(((long long)n * c + cc) * oh + y) * ow + xx] = v;
         }
     }
@@ -267,6 +304,7 @@ template <typename T>
 int nhwc_to_nchw(PView a, PView lat, afi_view4 skip, int skip_h, int skip_w, float scale, int n, int c, int oh, int ow,
                  float* dst, cudaStream_t st, const afi_view4* add, const float* fw) {
     AFI_REQUIRE((long long)n * oh <= 65535, "layout conversion: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * oh);
+    AFI_REQUIRE(view_dtype_ok(skip) && (!add || view_dtype_ok(*add)), "layout conversion: unknown view dtype");
     dim3 grid(cdiv(ow, 32), cdiv(c, 32), n * oh), block(32, 8);
     afi_view4 addv; memset(&addv, 0, sizeof(addv));
     if (add && fw) addv = *add; else fw = nullptr;
@@ -305,7 +343,7 @@ __global__ void k_g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int c, i
         int cc = c0 + ty + 8 * i, xx = x0 + tx;
         if (cc < c && xx < w) {
             float v = tile[tx][ty + 8 * i];
-            const float* g = dy.ptr + n * dy.sn + cc * dy.sc;
+            const long long g = n * dy.sn + cc * dy.sc;
             float acc = 0.f;
 #pragma unroll
             for (int a = -1; a <= 2; a++) {
@@ -316,7 +354,7 @@ __global__ void k_g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int c, i
                 for (int b = -1; b <= 2; b++) {
                     int ox = 2 * xx + b;
                     if (ox < 0 || ox >= ow || ox >= 2 * w) continue;
-                    acc += wy * bilin_adj_w(xx, ox, w) * g[oy * dy.sh + ox * dy.sw];
+                    acc += wy * bilin_adj_w(xx, ox, w) * vld(dy, g + oy * dy.sh + ox * dy.sw);
                 }
             }
             dst[(((long long)n * c + cc) * h + y) * w + xx] = v + dy_scale * acc;
@@ -324,6 +362,7 @@ __global__ void k_g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int c, i
     }
 }
 int g_input_grad(PView dxb, afi_view4 dy, float dy_scale, int n, int c, int h, int w, int oh, int ow, float* dst, cudaStream_t st) {
+    AFI_REQUIRE(view_dtype_ok(dy), "input gradient: unknown view dtype %d", dy.dtype);
     AFI_REQUIRE((long long)n * h <= 65535, "g_input_grad: n * h = %lld exceeds the 65535-block grid limit (split the batch)", (long long)n * h);
     dim3 grid(cdiv(w, 32), cdiv(c, 32), n * h), block(32, 8);
     k_g_input_grad<<<grid, block, 0, st>>>(dxb, dy, dy_scale, c, h, w, oh, ow, dst);
@@ -1587,7 +1626,7 @@ __global__ void k_l1(afi_view4 a, afi_view4 b, int c, int h, int w, long long to
     float ginv = gscale / (float)total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int x = (int)(i % w); long long t = i / w; int y = (int)(t % h); t /= h; int cc = (int)(t % c); int n = (int)(t / c);
-        float d = a.ptr[n * a.sn + cc * a.sc + y * a.sh + x * a.sw] - b.ptr[n * b.sn + cc * b.sc + y * b.sh + x * b.sw];
+        float d = vld(a, n * a.sn + cc * a.sc + y * a.sh + x * a.sw) - vld(b, n * b.sn + cc * b.sc + y * b.sh + x * b.sw);
         acc += (double)fabsf(d);
         if (da) da[i] = d > 0.f ? ginv : (d < 0.f ? -ginv : 0.f);
     }
@@ -1634,8 +1673,9 @@ extern "C" int afi_l1_loss(afi_view4 a, afi_view4 b, int n, int c, int h, int w,
     cudaStream_t st = (cudaStream_t)stream;
     long long total = (long long)n * c * h * w;
     AFI_REQUIRE(total > 0, "l1: empty tensors");
+    AFI_REQUIRE(view_dtype_ok(a) && view_dtype_ok(b), "l1: unknown view dtype");
     if (loss_out) AFI_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-    if (total % 4 == 0 && view4_contiguous(a, c, h, w) && view4_contiguous(b, c, h, w) && ((uintptr_t)a.ptr & 15) == 0 &&
+    if (total % 4 == 0 && a.dtype == AFI_DT_F32 && b.dtype == AFI_DT_F32 && view4_contiguous(a, c, h, w) && view4_contiguous(b, c, h, w) && ((uintptr_t)a.ptr & 15) == 0 &&
         ((uintptr_t)b.ptr & 15) == 0 && (!da || ((uintptr_t)da & 15) == 0)) {
         long long n4 = total / 4;
         int grid = cdiv(n4, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;

@@ -576,6 +576,15 @@ def run_pafpn_c4(args):
     lib.afi_launch_count(1)
     ms = timed(one, args.steps) / args.steps
     launches = int(lib.afi_launch_count(0))
+    # the same step fed with bf16 channels_last bottom-up maps (what an autocast backbone hands the neck): the boundary takes them as they
+    # are (afi_view4.dtype, any strides) -- no up-cast copy, no transpose
+    fp32_inputs = (c5, lat_in)
+    c5 = c5.detach().bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lat_in = [t.detach().bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True) for t in lat_in]
+    for _ in range(3):
+        one()
+    ms_bf16_in = timed(one, args.steps) / args.steps
+    c5, lat_in = fp32_inputs
     afi_px = N * (13 * 21 + 25 * 42 + 50 * 84)
     flops = 3 * G_FWD_FLOP_PER_INPUT_PX * afi_px + 3 * 2 * 256 * sum(c * h * w for c, h, w in ((1024, 25, 42), (512, 50, 84), (256, 100, 168))) * N
     tf = flops / ms / 1e9
@@ -584,6 +593,7 @@ def run_pafpn_c4(args):
         print(json.dumps(_line("pafpn_topdown_afi_fwd_bwd_img_per_s", world * N / (ms * 1e-3), "img/s", world, args, ms, args.precision,
                                "config 4: PAFPN top-down path, 3 AF-interpolator merges + 1x1 laterals, batch 16 per GPU, fwd + full bwd via autograd",
                                per_gpu_batch=N, step_tflops_per_gpu=tf, gpu_launches=launches,
+                               bf16_channels_last_inputs={"ms_per_step": ms_bf16_in, "img_per_s": world * N / (ms_bf16_in * 1e-3)},
                                roofline={"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_sustained"],
                                          "traffic": None, "note": "AFI fwd + 2x bwd + laterals fwd/dgrad/wgrad, algorithmic FLOPs over the whole autograd step"})))
     _dist_teardown(world)

@@ -12,8 +12,9 @@
  *    (thread-local).  Unsupported shapes / precision / architecture are hard errors: there is no fallback.
  *  - all work is enqueued on the caller's stream; nothing synchronises; nothing is allocated: the caller
  *    provides workspaces sized by the *_bytes() queries (torch owns all memory).
- *  - tensors cross the boundary as strided fp32 NCHW-logical views (afi_view4: element strides), so both
- *    contiguous and channels_last torch tensors and top-left crops are accepted without copies.
+ *  - input tensors cross the boundary as strided fp32 or bf16 NCHW-logical views (afi_view4: element strides and a dtype
+ *    tag), so contiguous and channels_last torch tensors, top-left crops and autocast (bf16) activations are accepted
+ *    without copies or up-casts; outputs and gradients are contiguous fp32 NCHW.
  *  - parameters and gradients use the reference's state-dict layouts.
  */
 #ifndef AFIGAN_B200_H
@@ -25,8 +26,9 @@
 extern "C" {
 #endif
 
-#define AFI_ABI_VERSION 3   /* 2: afi_d_call.input_staged, afi_g_call.fuse_cur / fuse_w, afi_sgd_step_multi, afi_sizeof
-                             * 3: AFI_PREC_SPLIT, afi_conv1x1*, afi_conv3x3s2* (struct layouts unchanged since 2) */
+#define AFI_ABI_VERSION 4   /* 2: afi_d_call.input_staged, afi_g_call.fuse_cur / fuse_w, afi_sgd_step_multi, afi_sizeof
+                             * 3: AFI_PREC_SPLIT, afi_conv1x1*, afi_conv3x3s2* (struct layouts unchanged since 2)
+                             * 4: afi_view4.dtype (fp32 or bf16 input views): afi_view4 and every struct that embeds one grew */
 
 #define AFI_OK 0
 #define AFI_ERR_INVALID (-1)   /* bad argument / unsupported shape */
@@ -48,10 +50,14 @@ extern "C" {
 
 typedef struct afi_ctx afi_ctx;
 
-/* Strided fp32 view of a logical [N, C, H, W] tensor; strides in elements. */
+/* Strided view of a logical [N, C, H, W] tensor; strides in ELEMENTS of its dtype. */
+#define AFI_DT_F32 0
+#define AFI_DT_BF16 1
 typedef struct {
-    const float* ptr;
+    const void* ptr;
     long long sn, sc, sh, sw;
+    int dtype;                  /* AFI_DT_F32 | AFI_DT_BF16 (a zeroed struct is an absent fp32 view) */
+    int reserved;               /* must be 0 */
 } afi_view4;
 
 /* ---- library ------------------------------------------------------------------------------------ */

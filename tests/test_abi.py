@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/afigan_b200.h but not exported"
     assert set(native.EXPORTED_SYMBOLS) == set(names), set(native.EXPORTED_SYMBOLS) ^ set(names)
-    assert native.lib().afi_abi_version() == 3
+    assert native.lib().afi_abi_version() == 4
 
 
 def test_ctypes_structs_match_the_library():
