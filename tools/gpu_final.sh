@@ -9,6 +9,7 @@ python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/final_bench_
 for w in g_only pafpn_c4 stage2_c3 infer_c5; do python bench.py --workload $w > gpurun_out/final_bench_$w.json 2> gpurun_out/final_bench_$w.err; echo "$w exit $?"; done
 python bench.py --precision split --no-cpu-baseline > gpurun_out/final_bench_split.json 2> gpurun_out/final_bench_split.err; echo "split exit $?"
 AFIGAN_IN_FLIGHT=8 python bench.py --workload infer_c5 > gpurun_out/final_bench_infer_c5_8_in_flight.json 2> /dev/null; echo "infer_c5 x8 exit $?"
+TAILN=3 run soak_bf16 python tools/quick_time.py bf16 200
 TAILN=24 run gprof_bf16 python tools/g_profile.py bf16
 TAILN=34 run stepprof_bf16 python tools/step_profile.py bf16
 TAILN=34 run stepprof_split python tools/step_profile.py split
