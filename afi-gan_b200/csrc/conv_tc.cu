@@ -666,7 +666,7 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 // PAIR = true: the two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 stream, M = 256 = two patches (one
 // per CTA), N = bn.  Each CTA stages its own halo and only HALF of the weight tile (bn/2 rows); the tensor cores read the other half
 // from the peer's shared memory.  Per SM that halves the weight bytes read from L2 and the shared-memory fill, cuts the operand reads
-// per MMA from 12 KB to 8 KB, and gives the B ring 8 stages of 16 KB.  Protocol (as CUTLASS' 2-SM pipelines): both producers wait on
+// per MMA from 12 KB to 8 KB, and gives the B ring three slots of a kernel ROW each (three taps: 48 KB at N = 256; see Tiling.tb).  Protocol (as CUTLASS' 2-SM pipelines): both producers wait on
 // their OWN empty barriers and issue cta_group::2 TMA loads that complete bytes on the LEADER's full barrier (the leader's producer
 // posts the expected bytes of both CTAs); the leader's MMA thread issues the MMAs and multicasts its commits to the empty /
 // accumulator-full barriers of both CTAs; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
@@ -677,7 +677,9 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
 // ---------------------------------------------------------------------------------------------------
 // Ring depths (build-time overridable for A/B runs: AFI_EXTRA_NVCC_FLAGS="-DAFI_HALO_SA=4 -DAFI_HALO_SB_MAX=7").  Measured on the discriminator
 // shapes, kernel alone (tools/ab_conv.py): two halo slots cost 11 % (1700 -> 1515 TFLOP/s on 1024->1024: one chunk of look-ahead does not cover
-// the latency of the 180-row halo box), four or five are within noise of three, and 8 -> 11 weight slots change nothing.
+// the latency of the 180-row halo box), four or five are within noise of three, and 8 -> 11 (or 18, for 8 KB tiles) weight slots change nothing:
+// what the weight ring was short of was not depth but the ~300 cycles the single producer / MMA threads spend per SLOT -- hence three taps per
+// slot (conv_tc(): Tiling.tb).
 #ifndef AFI_HALO_SA
 #define AFI_HALO_SA 3
 #endif
