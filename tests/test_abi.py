@@ -38,6 +38,27 @@ def test_ctypes_structs_match_the_library():
     assert lib.afi_sizeof(99) == 0
 
 
+def test_view4_carries_strides_and_the_dtype_tag():
+    """ABI 4: a boundary view is (pointer, four element strides, dtype tag); fp32 and bf16 tensors of any layout map onto it without a copy,
+    anything else is refused by the binding (the callers cast such tensors to fp32 once: native.boundary)."""
+    import torch
+    from afigan import native
+    x = torch.zeros(2, 8, 3, 5)
+    v = native.view4(x)
+    assert (v.ptr, v.sn, v.sc, v.sh, v.sw, v.dtype, v.reserved) == (x.data_ptr(), 120, 15, 5, 1, native.DT_F32, 0)
+    xc = x.bfloat16().contiguous(memory_format=torch.channels_last)[:, :, :2, :4]          # bf16, NHWC strides, top-left crop
+    v = native.view4(xc)
+    assert (v.ptr, v.sn, v.sc, v.sh, v.sw, v.dtype) == (xc.data_ptr(), 120, 1, 40, 8, native.DT_BF16)
+    for bad in (x.half(), x.double(), x[0]):
+        try:
+            native.view4(bad)
+        except TypeError:
+            continue
+        raise AssertionError("view4 accepted an unsupported tensor")
+    assert native.boundary(x) is x and native.boundary(xc) is xc and native.boundary(x.half()).dtype == torch.float32
+    assert ctypes.sizeof(native.View4) == 48
+
+
 def test_integration_snippet():
     """the ctypes stub printed in INTEGRATION.md must be the struct layout the library was built with -- the block between the
     binding-begin / binding-end markers is executed as is and its own check_binding() is run against the built library."""
