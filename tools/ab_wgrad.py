@@ -34,4 +34,4 @@ for i in range(cnt.value):
         ts.append((ms.value, fl.value))
 ts.sort()
 med = ts[len(ts) // 2]
-print(f"[{prec}] korder={os.environ.get('AFIGAN_WGRAD_KORDER', 'default')} wgrad n{n} {cin}->{cout} {h}x{w}: median {med[0]:.4f} ms = {med[1] / med[0] / 1e9:7.1f} TFLOP/s")
+print(f"[{prec}] wgrad n{n} {cin}->{cout} {h}x{w}: median {med[0]:.4f} ms = {med[1] / med[0] / 1e9:7.1f} TFLOP/s")
