@@ -125,10 +125,11 @@ class AFInterpolatorFn(torch.autograd.Function):
             if holder.acc is None or holder.acc.device != dev:
                 holder.acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
             acc = holder.acc
-            if holder.pending is None:
+            task = torch._C._current_graph_task_id()
+            if holder.pending is None or holder.pending[4] != task:      # first call of this pass (a pass that raised leaves a stale entry)
                 N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
-                holder.pending = (ctx.prec, ctx.n_rdb, list(params), torch.cuda.current_stream(dev))
-                torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_deferred(holder))
+                holder.pending = (ctx.prec, ctx.n_rdb, list(params), torch.cuda.current_stream(dev), task)
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_deferred(holder, task))
         else:
             acc = _u8(lib.afi_g_gradacc_bytes(ctx.n_rdb), dev)
             N.check(lib.afi_zero(acc.data_ptr(), acc.numel(), N.stream_ptr()))
@@ -163,9 +164,11 @@ class AFInterpolatorFn(torch.autograd.Function):
         return (dx, d_lat_x, d_lat_w, d_lat_b, None, None, None, None, None, *grads)
 
 
-def _flush_deferred(holder) -> None:
+def _flush_deferred(holder, task: int) -> None:
     """End-of-backward callback of the deferred weight gradients: p.grad (+)= unpack(accumulator), one launch for all 23 tensors."""
-    prec, n_rdb, params, stream = holder.pending
+    if holder.pending is None or holder.pending[4] != task:
+        return
+    prec, n_rdb, params, stream, _ = holder.pending
     holder.pending = None
     lib = N.lib()
     dev = params[0].device
