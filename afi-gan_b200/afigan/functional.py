@@ -524,5 +524,43 @@ def bifpn_fuse_down(a: torch.Tensor, b: Optional[torch.Tensor], down: torch.Tens
     return out
 
 
+class FuseActFn(torch.autograd.Function):
+    """Top-down BiFPN fusion site with autograd (reference bifpn_sr.py:542-548, swish of :591-594): act(w0 * cur + w1 * up) in one pass."""
+
+    @staticmethod
+    def forward(ctx, cur, up, weight, act: bool):
+        if not cur.is_cuda:
+            raise RuntimeError("bifpn fusion: tensors must live on an sm_100a CUDA device (no CPU fallback)")
+        cur, up = N.boundary(cur), N.boundary(up)
+        if cur.shape != up.shape or cur.dim() != 4:
+            raise ValueError(f"bifpn fusion: shapes {tuple(cur.shape)} / {tuple(up.shape)}")
+        n, c, h, w = cur.shape
+        wt = weight.detach().float().contiguous() if weight is not None else None
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=cur.device)
+        s = torch.empty_like(out) if act else None
+        N.check(N.lib().afi_bifpn_fuse_act(N.view4(cur), N.view4(up), N.ptr(wt), int(act), n, c, h, w, N.ptr(s), out.data_ptr(), N.stream_ptr()))
+        ctx.act, ctx.has_w = bool(act), weight is not None
+        ctx.save_for_backward(cur, up, wt if wt is not None else out.new_empty(0), s if s is not None else out.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cur, up, wt, s = ctx.saved_tensors
+        dout = N.boundary(dout)
+        n, c, h, w = cur.shape
+        dev = cur.device
+        d_cur = torch.empty((n, c, h, w), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        d_up = torch.empty((n, c, h, w), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        d_w = torch.empty(2, dtype=torch.float32, device=dev) if (ctx.has_w and ctx.needs_input_grad[2]) else None
+        N.check(N.lib().afi_bifpn_fuse_act_backward(N.view4(dout), N.ptr(s) if ctx.act else None, N.view4(cur), N.view4(up),
+                                                    N.ptr(wt) if ctx.has_w else None, int(ctx.act), n, c, h, w, N.ptr(d_cur), N.ptr(d_up),
+                                                    N.ptr(d_w), N.stream_ptr()))
+        return d_cur, d_up, d_w, None
+
+
+def bifpn_fuse_act(cur: torch.Tensor, up: torch.Tensor, weight: Optional[torch.Tensor], swish: bool) -> torch.Tensor:
+    return FuseActFn.apply(cur, up, weight, bool(swish))
+
+
 def conv3x3_autograd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: Optional[str] = None) -> torch.Tensor:
     return Conv3x3Fn.apply(x, weight, bias, N.PRECISIONS[precision or N.default_precision()])

@@ -30,18 +30,22 @@ __all__ = ["build_swint_bifpn_sr_backbone", "BiFPN_AFIGAN", "BeforeBiFPNLayer", 
 
 
 def bifpn_feature_fusion(srf_module, cur_feature: torch.Tensor, top_feature: torch.Tensor,
-                         weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         weight: Optional[torch.Tensor] = None, swish: bool = False) -> torch.Tensor:
     """`BiFPN_AFIGAN._feature_funsion` (bifpn_sr.py:542-548).  weight is the 2-element `..._w1` parameter (or None when attention is
-    disabled): w[0]*cur + w[1]*AFI(top).  Without autograd (inference, BASELINE config C5: 28 of these per image) the whole site is one
-    library call; with autograd the interpolator is the library's autograd Function and the two-term fusion stays in torch."""
+    disabled): w[0]*cur + w[1]*AFI(top); swish=True also applies the x * sigmoid(x) the neck puts behind every fusion (bifpn_sr.py:591-594).
+    Without autograd (inference, BASELINE config C5: 28 of these per image) the whole site is one library call; with autograd the
+    interpolator is the library's autograd Function and the fusion (+ swish) ONE elementwise pass each way (`functional.FuseActFn`)."""
     needs_grad = torch.is_grad_enabled() and (cur_feature.requires_grad or top_feature.requires_grad or (weight is not None and weight.requires_grad)
                                               or any(p.requires_grad for p in srf_module.parameters()))
     if not needs_grad and top_feature.is_cuda and hasattr(srf_module, "fuse"):
-        return srf_module.fuse(top_feature, cur_feature, weight)
+        out = srf_module.fuse(top_feature, cur_feature, weight)
+        return out * torch.sigmoid(out) if swish else out
     up = srf_module(top_feature, out_hw=tuple(cur_feature.shape[2:]))
-    if weight is None:
-        return cur_feature + up
-    return cur_feature * weight[0] + up * weight[1]
+    if up.is_cuda:
+        from ...functional import bifpn_fuse_act
+        return bifpn_fuse_act(cur_feature, up, weight, swish)
+    out = cur_feature + up if weight is None else cur_feature * weight[0] + up * weight[1]
+    return out * torch.sigmoid(out) if swish else out
 
 
 class ResampleFeature(nn.Module):
@@ -141,9 +145,9 @@ class BiFPN_AFIGAN(Backbone):
         return self._size_divisibility
 
     # ---- fusion sites (bifpn_sr.py:535-564)
-    def _feature_funsion(self, layer_idx, cur_feature, top_feature, indice=-1):
+    def _feature_funsion(self, layer_idx, cur_feature, top_feature, indice=-1, swish=False):
         w = getattr(self, f"BiFPNLayer_{layer_idx}_p{indice}_w1") if (self.attention and indice > 0) else None
-        return bifpn_feature_fusion(self.srf_module, cur_feature, top_feature, w)
+        return bifpn_feature_fusion(self.srf_module, cur_feature, top_feature, w, swish)
 
     def _feature_funsion2(self, layer_idx, skip_feature, cur_feature, bottom_feature, indice=-1):
         if not torch.is_grad_enabled() and cur_feature.is_cuda and bottom_feature.size(2) >= 2 and bottom_feature.size(3) >= 2:
@@ -164,11 +168,17 @@ class BiFPN_AFIGAN(Backbone):
     def _layer(self, l, laterals, down_skips):
         conv = lambda name: getattr(self, f"BiFPNLayer_{l}_{name}")          # noqa: E731
         p3_in, p4_in, p5_in, p6_in, p7_in = laterals
-        # conv(swish(fused)): the swish is handed to the separable conv (fused into its depthwise pass on the native inference path)
-        p6_up = conv("conv6_up")(self._feature_funsion(l, p6_in, p7_in, 6), pre_swish=True)
-        p5_up = conv("conv5_up")(self._feature_funsion(l, p5_in, p6_up, 5), pre_swish=True)
-        p4_up = conv("conv4_up")(self._feature_funsion(l, p4_in, p5_up, 4), pre_swish=True)
-        p3_up = conv("conv3_up")(self._feature_funsion(l, p3_in, p4_up, 3), pre_swish=True)
+        # conv(swish(fused)).  Inference: the swish is handed to the separable conv (fused into its depthwise pass on the native path).
+        # With autograd: fusion + swish are ONE elementwise pass each way (functional.FuseActFn) and the conv gets the activated map.
+        tr = torch.is_grad_enabled()
+
+        def td(name, cur, top, idx):
+            return conv(name)(self._feature_funsion(l, cur, top, idx, swish=tr), pre_swish=not tr)
+
+        p6_up = td("conv6_up", p6_in, p7_in, 6)
+        p5_up = td("conv5_up", p5_in, p6_up, 5)
+        p4_up = td("conv4_up", p4_in, p5_up, 4)
+        p3_up = td("conv3_up", p3_in, p4_up, 3)
         s4, s5, s6, s7 = down_skips
         p4_out = conv("conv4_down")(self._feature_funsion2(l, s4, p4_up, p3_up, 4), pre_swish=True)
         p5_out = conv("conv5_down")(self._feature_funsion2(l, s5, p5_up, p4_out, 5), pre_swish=True)

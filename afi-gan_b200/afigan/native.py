@@ -122,6 +122,9 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "afi_sepconv_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
     "afi_bifpn_fuse_down": (C.c_int, [View4, View4, View4, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "afi_bifpn_fuse_act": (C.c_int, [View4, View4, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "afi_bifpn_fuse_act_backward": (C.c_int, [View4, C.c_void_p, View4, View4, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "afi_launch_count": (C.c_longlong, [C.c_int]),
     "afi_profile_begin": (C.c_int, [C.c_int]),
     "afi_profile_end": (C.c_int, [C.POINTER(C.c_int)]),

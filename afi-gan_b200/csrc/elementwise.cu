@@ -318,6 +318,80 @@ template int nhwc_to_nchw<float>(PView, PView, afi_view4, int, int, float, int, 
 template int nhwc_to_nchw<bf16>(PView, PView, afi_view4, int, int, float, int, int, int, int, float*, cudaStream_t, const afi_view4*, const float*);
 
 // ---------------------------------------------------------------------------------------------------
+// Top-down fusion site of the BiFPN neck WITH autograd (reference bifpn_sr.py:542-548 + the swish of :591-594):
+//   s = w0 * cur + w1 * up,  out = act ? s * sigmoid(s) : s          (w = NULL: plain sum)
+// One elementwise pass forward (five torch kernels otherwise) and one backward:
+//   ds = dout * (act ? sig(s) * (1 + s * (1 - sig(s))) : 1),  d_cur = w0 * ds,  d_up = w1 * ds,  d_w += (sum ds * cur, sum ds * up)
+// Views carry their own strides / dtype; s, out and the gradients are contiguous fp32 NCHW.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fuse_act_fwd(afi_view4 cur, afi_view4 up, const float* __restrict__ wts, int act, int c, int h, int w,
+                                                      long long total, float* __restrict__ s_out, float* __restrict__ out) {
+    const float w0 = wts ? wts[0] : 1.f, w1 = wts ? wts[1] : 1.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w), y = (int)((i / w) % h), cc = (int)((i / ((long long)w * h)) % c), n = (int)(i / ((long long)w * h * c));
+        const float s = w0 * vld(cur, n * cur.sn + cc * cur.sc + y * cur.sh + x * cur.sw) + w1 * vld(up, n * up.sn + cc * up.sc + y * up.sh + x * up.sw);
+        if (s_out) s_out[i] = s;
+        out[i] = act ? s / (1.f + __expf(-s)) : s;
+    }
+}
+__global__ void __launch_bounds__(256) k_fuse_act_bwd(afi_view4 dout, const float* __restrict__ s_in, afi_view4 cur, afi_view4 up,
+                                                      const float* __restrict__ wts, int act, int c, int h, int w, long long total,
+                                                      float* __restrict__ d_cur, float* __restrict__ d_up, float* d_w) {
+    __shared__ float red[2][8];
+    const float w0 = wts ? wts[0] : 1.f, w1 = wts ? wts[1] : 1.f;
+    float a0 = 0.f, a1 = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w), y = (int)((i / w) % h), cc = (int)((i / ((long long)w * h)) % c), n = (int)(i / ((long long)w * h * c));
+        float ds = vld(dout, n * dout.sn + cc * dout.sc + y * dout.sh + x * dout.sw);
+        if (act) {
+            const float s = s_in[i], sg = 1.f / (1.f + __expf(-s));
+            ds *= sg * (1.f + s * (1.f - sg));
+        }
+        if (d_cur) d_cur[i] = w0 * ds;
+        if (d_up) d_up[i] = w1 * ds;
+        if (d_w) {
+            a0 += ds * vld(cur, n * cur.sn + cc * cur.sc + y * cur.sh + x * cur.sw);
+            a1 += ds * vld(up, n * up.sn + cc * up.sc + y * up.sh + x * up.sw);
+        }
+    }
+    if (d_w) {      // uniform branch
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a0; red[1][threadIdx.x >> 5] = a1; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t += red[threadIdx.x][j];
+            atomicAdd(d_w + threadIdx.x, t);
+        }
+    }
+}
+extern "C" int afi_bifpn_fuse_act(afi_view4 cur, afi_view4 up, const float* weights, int act, int n, int c, int h, int w, float* s_out, float* out,
+                                  void* stream) {
+    const long long total = (long long)n * c * h * w;
+    AFI_REQUIRE(cur.ptr && up.ptr && out && total > 0, "afi_bifpn_fuse_act: bad argument");
+    AFI_REQUIRE(view_dtype_ok(cur) && view_dtype_ok(up), "afi_bifpn_fuse_act: unknown view dtype");
+    long long grid = cdiv(total, 256 * 4); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    k_fuse_act_fwd<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(cur, up, weights, act, c, h, w, total, act ? s_out : nullptr, out);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+extern "C" int afi_bifpn_fuse_act_backward(afi_view4 dout, const float* s, afi_view4 cur, afi_view4 up, const float* weights, int act, int n, int c,
+                                           int h, int w, float* d_cur, float* d_up, float* d_w, void* stream) {
+    const long long total = (long long)n * c * h * w;
+    AFI_REQUIRE(dout.ptr && total > 0 && (!act || s), "afi_bifpn_fuse_act_backward: bad argument");
+    AFI_REQUIRE(!d_w || (cur.ptr && up.ptr), "afi_bifpn_fuse_act_backward: the weight gradient needs both operands");
+    AFI_REQUIRE(view_dtype_ok(dout) && view_dtype_ok(cur) && view_dtype_ok(up), "afi_bifpn_fuse_act_backward: unknown view dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_w) AFI_CUDA(cudaMemsetAsync(d_w, 0, 2 * sizeof(float), st));
+    long long grid = cdiv(total, 256 * 4); if (grid > 148 * 8) grid = 148 * 8; if (grid < 1) grid = 1;
+    k_fuse_act_bwd<<<(int)grid, 256, 0, st>>>(dout, s, cur, up, weights, act, c, h, w, total, d_cur, d_up, d_w);
+    AFI_LAUNCH_CHECK();
+    return AFI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Input gradient of the interpolator: dx[n,c,i,j] = dXb[n,i,j,c] (head-conv dgrad, NHWC fp32) + bilinear2x^T(dy)[n,c,i,j].
 // Adjoint of the x2 bilinear upsample (align_corners=False): x[i] feeds out[2i-1] (1/4), out[2i], out[2i+1] (3/4), out[2i+2] (1/4);
 // the edge clamps fold the missing neighbour's 1/4 onto out[0] / out[2H-1] (weight 1).  dy is only defined on the oh x ow crop.

@@ -638,8 +638,7 @@ def run_stage2_c3(args):
         for layer in range(7):
             top = feats[4]
             for l in (3, 2, 1, 0):
-                s = bifpn_feature_fusion(G, feats[l], top, wts[k]); k += 1
-                top = s * torch.sigmoid(s)
+                top = bifpn_feature_fusion(G, feats[l], top, wts[k], swish=True); k += 1      # fusion + swish: one pass each way
                 if layer == 6:
                     outs.append(top)
         model = [o[:, :, :h, :w] for o, (h, w) in zip(outs[::-1], C3_D_SIZES[:4])] + [feats[4][:, :, :3, :5]]

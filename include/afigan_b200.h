@@ -242,6 +242,15 @@ size_t afi_sepconv_workspace_bytes(int prec, int n, int c, int h, int w_, int co
 int afi_bifpn_fuse_down(afi_view4 a, afi_view4 b, afi_view4 down, const float* weights, int n, int c, int h, int w_, int dh, int dw, float* out,
                         void* stream);
 
+/* Top-down fusion site `_feature_funsion` WITH autograd (bifpn_sr.py:542-548) and the swish the neck applies to it (:591-594) in one
+ * elementwise pass each way:  s = w[0]*cur + w[1]*up (weights NULL: 1, 1);  out = act ? s*sigmoid(s) : s.  cur / up [n,c,h,w] views; s_out
+ * (pre-activation, needed by the backward when act; may be NULL otherwise) and out contiguous fp32.
+ * backward: ds = dout * d act(s);  d_cur = w[0]*ds, d_up = w[1]*ds (each may be NULL), d_w[2] = (sum ds*cur, sum ds*up) (may be NULL; overwritten). */
+int afi_bifpn_fuse_act(afi_view4 cur, afi_view4 up, const float* weights, int act, int n, int c, int h, int w_, float* s_out, float* out,
+                       void* stream);
+int afi_bifpn_fuse_act_backward(afi_view4 dout, const float* s, afi_view4 cur, afi_view4 up, const float* weights, int act, int n, int c, int h,
+                                int w_, float* d_cur, float* d_up, float* d_w, void* stream);
+
 /* Per-launch CUDA-event timing of the implicit-GEMM kernels (bench.py's roofline leg).  begin: start recording up to
  * max_launches GEMM launches; end: device-synchronise and resolve the durations; get: record i = kind (0 conv tcgen05 per-tap
  * kernel, 1 wgrad tcgen05, 2 conv CUDA-core, 3 wgrad CUDA-core, 4 conv tcgen05 halo tiles on CTA pairs, 5 conv tcgen05 halo tiles on

@@ -202,3 +202,58 @@ def test_deferred_weight_grads_equal_per_call_accumulation():
     for a, b in zip(res[True][1], res[False][1]):
         assert float((a - b).norm()) <= 1e-6 * float(b.norm())
     assert torch.allclose(res[True][2], res[False][2], rtol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("swish", [False, True])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fused_topdown_site_matches_the_torch_composition(swish, weighted):
+    """`functional.FuseActFn` (w0 * cur + w1 * up, optional swish; reference bifpn_sr.py:542-548, 591-594) against the torch ops it replaces:
+    output, both input gradients and the gradient of the 2-element fusion weight; `cur` as a channels_last crop, `up` contiguous."""
+    from afigan.functional import bifpn_fuse_act
+    gen = torch.Generator().manual_seed(21)
+    cur0 = torch.randn(2, 256, 15, 23, generator=gen).cuda().contiguous(memory_format=torch.channels_last)[:, :, :13, :21]
+    up0 = torch.randn(2, 256, 13, 21, generator=gen).cuda()
+    w0 = torch.tensor([0.7, 1.3], device="cuda")
+    dy = torch.randn(2, 256, 13, 21, generator=gen).cuda()
+    res = []
+    for fused in (True, False):
+        cur, up = cur0.clone().requires_grad_(True), up0.clone().requires_grad_(True)
+        w = w0.clone().requires_grad_(True) if weighted else None
+        if fused:
+            out = bifpn_fuse_act(cur, up, w, swish)
+        else:
+            s = (cur.double() * w[0].double() + up.double() * w[1].double()) if weighted else cur.double() + up.double()
+            out = (s * torch.sigmoid(s) if swish else s)
+        out.backward(dy.to(out.dtype))
+        res.append((out.detach().double(), cur.grad.double(), up.grad.double(), None if w is None else w.grad.double()))
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert float((a - b).norm()) <= 2e-6 * float(b.norm())
+    if weighted:
+        assert float((res[0][3] - res[1][3]).norm()) <= 1e-4 * float(res[1][3].norm())
+
+
+@pytest.mark.gpu
+def test_bifpn_class_training_path_uses_one_pass_per_fusion_site():
+    """BiFPN_AFIGAN with autograd: the top-down sites run through FuseActFn (fusion + swish fused), the result equals the composition
+    `conv(swish(w0 * cur + w1 * AFI(top)))` evaluated with torch ops around the same interpolator call."""
+    from afigan.modeling import Generator, bifpn_feature_fusion
+    torch.manual_seed(0)
+    G = Generator(n_residual_dense_blocks=3, precision="split").cuda()
+    gen = torch.Generator().manual_seed(22)
+    cur = torch.randn(1, 256, 16, 24, generator=gen).cuda().requires_grad_(True)
+    top = torch.randn(1, 256, 8, 12, generator=gen).cuda().requires_grad_(True)
+    w = torch.tensor([0.9, 1.1], device="cuda", requires_grad=True)
+    a = bifpn_feature_fusion(G, cur, top, w, swish=True)
+    a.square().mean().backward()
+    ga = [cur.grad.clone(), top.grad.clone(), w.grad.clone(), G.Generators[0][4][0].weight.grad.clone()]
+    for t in (cur, top, w, *G.parameters()):
+        t.grad = None
+    up = G(top, out_hw=(16, 24))
+    s = cur * w[0] + up * w[1]
+    b = s * torch.sigmoid(s)
+    b.square().mean().backward()
+    gb = [cur.grad, top.grad, w.grad, G.Generators[0][4][0].weight.grad]
+    assert float((a - b).detach().norm()) <= 2e-6 * float(b.detach().norm())
+    for x, y in zip(ga, gb):
+        assert float((x - y).norm()) <= 2e-5 * float(y.norm())

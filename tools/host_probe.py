@@ -19,8 +19,7 @@ def one():
     for layer in range(7):
         top = feats[4]
         for l in (3, 2, 1, 0):
-            s = bifpn_feature_fusion(G, feats[l], top, wts[k]); k += 1
-            top = s * torch.sigmoid(s)
+            top = bifpn_feature_fusion(G, feats[l], top, wts[k], swish=True); k += 1
             if layer == 6: outs.append(top)
     model = [o[:, :, :h, :w] for o, (h, w) in zip(outs[::-1], bench.C3_D_SIZES[:4])] + [feats[4][:, :, :3, :5]]
     s2.d_phase(guide, model)
