@@ -431,6 +431,9 @@ def run_ours(args):
                 "per_kernel": {names[k]: {"launches": v[0], "ms": v[2], "tflops": v[1] / max(v[2], 1e-9) / 1e9} for k, v in agg.items()},
                 "largest_launch": None if top is None else {"ms": top[0], "tflops": top[1] / top[0] / 1e9, "cin": top[2], "cout": top[3],
                                                             "pixels": top[4]}}
+        if roof["frac"] > 1.0:
+            roof["note"] = ("frac > 1: the kernel's average over the step exceeds the driver-measured SUSTAINED cuBLAS bf16 figure used as `peak` "
+                            "(MEASURED_PEAKS.json); against the burst figure it is frac_of_burst_peak")
         if precision == "split":
             roof["note"] = ("split-precision mode: achieved counts ALGORITHMIC FLOPs; the tensor cores execute 3 (backward, forward-only) to 6 "
                             "(training forward) bf16 MMA passes per algorithmic product, so the MMA pipe runs at 3-6x this figure")
