@@ -338,7 +338,7 @@ __device__ __forceinline__ int butterfly_col(int lane) { return ((lane >> 4) & 1
 // accumulator stage on the LEADER's barrier, which counts the epilogue warps of both CTAs.
 template <int EPI_WARPS, bool PAIR = false, bool AUX32 = false>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& tl, uint64_t* acc_full, uint64_t* acc_empty,
-                                              float (*sstat)[2][ACC_COLS], float (*sbias)[ACC_COLS], const uint32_t tmem_base, const int warp,
+                                              float (*sstat)[2][ACC_COLS / (EPI_WARPS / 4)], float (*sbias)[ACC_COLS], const uint32_t tmem_base, const int warp,
                                               const int lane, const int rank = 0) {
     constexpr int HALVES = EPI_WARPS / 4;
     const int item0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -357,11 +357,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
         const int fn0 = nt_ * tl.bn;
         for (int c = row + half * 128; c < tl.bn; c += 32 * EPI_WARPS) {
             const int w0 = ((c >> 4) % HALVES) * 4;      // the four warps (one per lane quarter) that own this column's chunk
+            const int lc = (((c >> 4) / HALVES) << 4) | (c & 15);      // ... and its slot in their compacted (every HALVES-th chunk) arrays
             float t0 = 0.f, t1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                t0 += sstat[w0 + j][0][c]; t1 += sstat[w0 + j][1][c];
-                sstat[w0 + j][0][c] = 0.f; sstat[w0 + j][1][c] = 0.f;
+                t0 += sstat[w0 + j][0][lc]; t1 += sstat[w0 + j][1][lc];
+                sstat[w0 + j][0][lc] = 0.f; sstat[w0 + j][1][lc] = 0.f;
             }
             if (fn0 + c < a.cout) {
                 atomicAdd(fp.stat0 + fn0 + c, (double)t0);
@@ -512,7 +513,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, const Tiling& t
                 butterfly16(s0, lane);
                 butterfly16(s1, lane);
                 if ((lane & 1) == 0) {      // 16 lanes own 16 distinct columns of this warp's private accumulator
-                    int cc = c0 + butterfly_col(lane);
+                    int cc = ((ch / HALVES) << 4) + butterfly_col(lane);      // this warp owns every HALVES-th chunk: compacted index
                     sstat[warp - 2][0][cc] += s0[0];
                     sstat[warp - 2][1][cc] += s1[0];
                 }
@@ -562,10 +563,12 @@ k_conv_tc(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs a,
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ Smem s;
-    __shared__ float sstat[EPI_WARPS][2][ACC_COLS];   // per epilogue warp: no atomics (fp32 smem atomics are CAS loops)
+    // per epilogue warp: no atomics (fp32 smem atomics are CAS loops); with eight warps each owns every second 16-column chunk, so the
+    // arrays are half as long (8 KB either way: the halo kernel's weight ring gets the same three 48 KB slots in both instantiations)
+    __shared__ float sstat[EPI_WARPS][2][ACC_COLS / (EPI_WARPS / 4)];
     __shared__ __align__(16) float sbias[2][ACC_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t tmem_base = setup(s, maps, EPI_WARPS, warp, lane);
     const int iters = tl.npairs * a.ntaps * tl.kchunks;
@@ -704,13 +707,13 @@ k_conv_halo(const __grid_constant__ Maps maps, const __grid_constant__ ConvArgs 
     constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ SmemH s;
-    __shared__ float sstat[EPI_WARPS][2][ACC_COLS];
+    __shared__ float sstat[EPI_WARPS][2][ACC_COLS / (EPI_WARPS / 4)];
     __shared__ __align__(16) float sbias[2][ACC_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = PAIR ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     if (threadIdx.x == 0) AFI_TSTAMP(0);
-    for (int i = threadIdx.x; i < EPI_WARPS * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * ACC_COLS; i += NTHREADS) (&sstat[0][0][0])[i] = 0.f;
     const uint32_t a0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b0 = a0 + HALO_SA * HALO_SLOT;
     const int sb = tl.sb;
