@@ -257,3 +257,34 @@ def test_bifpn_class_training_path_uses_one_pass_per_fusion_site():
     assert float((a - b).detach().norm()) <= 2e-6 * float(b.detach().norm())
     for x, y in zip(ga, gb):
         assert float((x - y).norm()) <= 2e-5 * float(y.norm())
+
+
+@pytest.mark.gpu
+def test_deferred_weight_grads_survive_a_backward_pass_that_raised():
+    """The packed accumulator of `deferred_weight_grads` is keyed by the autograd graph task: a backward pass that raises after some
+    interpolator calls (its end-of-pass callback never runs) must not leak into the next pass."""
+    from afigan.modeling import Generator
+    gen = torch.Generator().manual_seed(23)
+    x = torch.randn(1, 256, 8, 12, generator=gen).cuda()
+
+    def run(G, poison):
+        xin = x.clone().requires_grad_(True)
+        y = G(G(xin)[:, :, ::2, ::2])                      # two interpolator calls in one graph
+        if poison:
+            xin.register_hook(lambda g: (_ for _ in ()).throw(RuntimeError("boom")))
+        (y.square().mean()).backward()
+
+    torch.manual_seed(0)
+    G = Generator(n_residual_dense_blocks=3, precision="split").cuda()
+    G.deferred_weight_grads = True
+    with pytest.raises(RuntimeError, match="boom"):
+        run(G, True)
+    for p in G.parameters():
+        p.grad = None
+    run(G, False)
+    got = [p.grad.clone() for p in G.parameters()]
+    torch.manual_seed(0)
+    R = Generator(n_residual_dense_blocks=3, precision="split").cuda()
+    run(R, False)
+    for a, b in zip(got, [p.grad for p in R.parameters()]):
+        assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12
